@@ -1,0 +1,964 @@
+"""World-model learner engine: the whole `Agent.train` step of the reference
+(/root/reference/embodied/agents/dreamerv2plus/agent.py:67-93) laid out as a
+static sequence of kernel launches with hand-derived backward passes.
+
+The engine owns every device buffer (parameters, Adam state, controllers,
+saved activations) and only ever calls `self.be.<primitive>(...)`; the product
+backend (backend.CudaBackend) turns each call into one sm_100a kernel launch
+through the C-ABI in include/dd_kernels.h.  Shapes are fixed at construction
+(B sequences x L steps, horizon H) so the launch sequence can be captured into
+a CUDA graph and replayed.
+
+Internal layout: time-major everywhere.  Row n = l*B + b of any [N, .] buffer
+is sequence b at step l; trajectories are [H+1, N, .].
+
+Reference map (A/ = embodied/agents/dreamerv2plus):
+  observe scan ........ A/nets.py:66-117   (obs_step), :119-160 (img_step, GRU)
+  KL balance .......... A/nets.py:178-183
+  world-model loss .... A/agent.py:165-212
+  optimizer ........... A/tfutils.py:180-302
+  imagination ......... A/agent.py:234-261
+  critic / lambda ..... A/agent.py:398-454
+  actor loss .......... A/agent.py:326-381
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+
+
+# ----------------------------------------------------------------------------
+# Spec (sizes + hyper-parameters, resolved from the embodied.Config)
+# ----------------------------------------------------------------------------
+
+@dataclasses.dataclass
+class Spec:
+  obs_dims: Dict[str, int]
+  act_dim: int = 12
+  discrete: bool = False
+  deter: int = 512
+  units: int = 512
+  stoch: int = 32
+  classes: int = 32
+  prior_layers: int = 3
+  rssm_unimix: float = 0.01
+  enc_layers: int = 4
+  enc_units: int = 512
+  head_layers: int = 4
+  head_units: int = 512
+  horizon: int = 15
+  discount: float = 0.995
+  lam: float = 0.95
+  kl_balance: float = 0.8
+  wmkl_target: float = 3.5
+  wmkl_min: float = 1e-3
+  wmkl_max: float = 1.0
+  actent_target: float = 0.5
+  actent_min: float = 1e-5
+  actent_max: float = 1.0
+  ctrl_vel: float = 0.1
+  ctrl_thres: float = 0.1
+  actor_minstd: float = 0.1
+  actor_maxstd: float = 1.0
+  actor_unimix: float = 0.1
+  lr: float = 1e-4
+  adam_eps: float = 1e-6
+  clip: float = 100.0
+  wd: float = 1e-2
+  beta1: float = 0.9
+  beta2: float = 0.999
+  slow_every: int = 100
+  advnorm_decay: float = 0.99
+  advnorm_max: float = 1e8
+
+  @property
+  def sc(self):
+    return self.stoch * self.classes
+
+  @property
+  def feat(self):
+    return self.deter + self.sc
+
+  @property
+  def obs_total(self):
+    return int(sum(self.obs_dims.values()))
+
+
+def param_shapes(spec: Spec) -> Dict[str, Tuple[int, ...]]:
+  """Every trainable tensor (+ slow critic), reference names and shapes
+  (Linear has no bias when LayerNorm follows, A/nets.py:563)."""
+  s = {}
+
+  def dense(prefix, fin, fout):
+    s[f'{prefix}/kernel'] = (fin, fout)
+    s[f'{prefix}/norm/scale'] = (fout,)
+    s[f'{prefix}/norm/bias'] = (fout,)
+
+  def out(prefix, fin, fout):
+    s[f'{prefix}/kernel'] = (fin, fout)
+    s[f'{prefix}/bias'] = (fout,)
+
+  def mlp(prefix, fin, layers, units):
+    for i in range(layers):
+      dense(f'{prefix}/dense{i}', fin if i == 0 else units, units)
+
+  D, U, SC, A = spec.deter, spec.units, spec.sc, spec.act_dim
+  mlp('enc', spec.obs_total, spec.enc_layers, spec.enc_units)
+  dense('rssm/img_in', SC + A, U)
+  dense('rssm/gru_out', D + U, 3 * D)
+  for i in range(spec.prior_layers):
+    dense(f'rssm/img_out_{i}', D if i == 0 else U, U)
+  out('rssm/img_stats', U, SC)
+  dense('rssm/obs_out', D + spec.enc_units, U)
+  out('rssm/obs_stats', U, SC)
+  s['rssm/initial_deter'] = (D,)
+  mlp('dec', spec.feat, spec.head_layers, spec.head_units)
+  out('dec/dist_out/out', spec.head_units, spec.obs_total)
+  for name in ('reward', 'cont'):
+    mlp(name, spec.feat, spec.head_layers, spec.head_units)
+    out(f'{name}/dist_out/out', spec.head_units, 1)
+  mlp('actor', spec.feat, spec.head_layers, spec.head_units)
+  out('actor/dist_out/out', spec.head_units, A)
+  if not spec.discrete:
+    out('actor/dist_out/std', spec.head_units, A)
+  for name in ('critic', 'slow_critic'):
+    mlp(name, spec.feat, spec.head_layers, spec.head_units)
+    out(f'{name}/dist_out/out', spec.head_units, 1)
+  return s
+
+
+GROUP_PREFIXES = {
+    'model': ('enc/', 'rssm/', 'dec/', 'reward/', 'cont/'),
+    'actor': ('actor/',),
+    'critic': ('critic/',),
+    'slow_critic': ('slow_critic/',),
+}
+
+
+def init_params(spec: Spec, seed=1) -> Dict[str, np.ndarray]:
+  """Reference initialisers: kernels U(+-sqrt(3*outscale/mean(fan_in,fan_out)))
+  (A/nets.py:568-569), DistLayer 'out' outscale 0.1 (A/nets.py:448-450),
+  LayerNorm scale 1 / bias 0, biases 0, initial_deter 0."""
+  rng = np.random.default_rng(seed)
+  out = {}
+  for name, shape in param_shapes(spec).items():
+    if name.endswith('/kernel'):
+      outscale = 0.1 if name.endswith('dist_out/out/kernel') else 1.0
+      limit = math.sqrt(3.0 * outscale / ((shape[0] + shape[1]) / 2.0))
+      out[name] = rng.uniform(-limit, limit, shape).astype(np.float32)
+    elif name.endswith('norm/scale'):
+      out[name] = np.ones(shape, np.float32)
+    else:
+      out[name] = np.zeros(shape, np.float32)
+  return out
+
+
+class ParamGroup:
+  """One optimizer group as flat fp32 buffers [params | grads | m | v]; tensors
+  matching the weight-decay pattern 'kernel' (A/tfutils.py:292) come first so
+  the fused Adam kernel decays a prefix."""
+
+  def __init__(self, be, names_shapes: List[Tuple[str, Tuple[int, ...]]], opt=True):
+    decayed = [(n, s) for n, s in names_shapes if 'kernel' in n]
+    rest = [(n, s) for n, s in names_shapes if 'kernel' not in n]
+    self.order = decayed + rest
+    self.offsets = {}
+    off = 0
+    self.n_decay = 0
+    for i, (n, s) in enumerate(self.order):
+      off = (off + 3) // 4 * 4        # 16-byte alignment for vectorised kernels
+      self.offsets[n] = (off, s)
+      off += int(np.prod(s))
+      if i == len(decayed) - 1:
+        self.n_decay = (off + 3) // 4 * 4
+    self.size = (off + 3) // 4 * 4
+    self.p = be.zeros(self.size)
+    self.g = be.zeros(self.size) if opt else None
+    self.m = be.zeros(self.size) if opt else None
+    self.v = be.zeros(self.size) if opt else None
+    self.sumsq = be.zeros(1, dtype=torch.float64) if opt else None
+
+  def view(self, flat, name):
+    off, shape = self.offsets[name]
+    return flat[off:off + int(np.prod(shape))].view(*shape)
+
+  def P(self, name):
+    return self.view(self.p, name)
+
+  def G(self, name):
+    return self.view(self.g, name)
+
+
+# ----------------------------------------------------------------------------
+# MLP trunk with saved activations
+# ----------------------------------------------------------------------------
+
+class Trunk:
+  """`layers` x (Linear(no bias) -> LayerNorm(eps 1e-3) -> elu) over a fixed
+  number of rows, keeping pre-norm Z, output H and (mean, rstd) per layer for
+  the backward pass (A/nets.py:408-416, :566-582)."""
+
+  def __init__(self, eng, group, prefix, layers, units, rows, param_prefix=None):
+    be = eng.be
+    self.eng, self.group, self.prefix = eng, group, prefix
+    self.pp = param_prefix or prefix
+    self.layers, self.units, self.rows = layers, units, rows
+    self.Z = [be.zeros(rows, units) for _ in range(layers)]
+    self.H = [be.zeros(rows, units) for _ in range(layers)]
+    self.st = [be.zeros(rows, 2) for _ in range(layers)]
+
+  def _names(self, i):
+    b = f'{self.pp}/dense{i}'
+    return f'{b}/kernel', f'{b}/norm/scale', f'{b}/norm/bias'
+
+  def fwd(self, xs, r0, r1, group=None):
+    """xs: list of (X[r1-r0, k], first weight row).  Returns H[-1][r0:r1]."""
+    be, g = self.eng.be, group or self.group
+    for i in range(self.layers):
+      kn, sn, bn = self._names(i)
+      W = g.P(kn)
+      Z = self.Z[i][r0:r1]
+      if i == 0:
+        beta = 0.0
+        for X, w0 in xs:
+          be.gemm(X, W[w0:w0 + X.shape[1]], Z, beta=beta)
+          beta = 1.0
+      else:
+        be.gemm(self.H[i - 1][r0:r1], W, Z)
+      be.ln_fwd(Z, g.P(sn), g.P(bn), self.H[i][r0:r1], self.st[i][r0:r1], 1)
+    return self.H[-1][r0:r1]
+
+  def bwd(self, dH, r0, r1, xs, dxs, wgrad, group=None):
+    """dH: grad wrt H[-1][r0:r1] (clobbered).  xs as in fwd (needed for the
+    first layer's weight grad); dxs: list of (dX, first weight row, beta) input
+    grads to produce.  wgrad: accumulate parameter grads into the group."""
+    eng, be, g = self.eng, self.eng.be, group or self.group
+    n = r1 - r0
+    tA = dH
+    for i in reversed(range(self.layers)):
+      kn, sn, bn = self._names(i)
+      W = g.P(kn)
+      tB = eng.tmp_other(tA, n, self.units)
+      be.ln_bwd(tA, self.Z[i][r0:r1], self.st[i][r0:r1], g.P(sn), g.P(bn), tB,
+                g.G(sn) if wgrad else None, g.G(bn) if wgrad else None, 1)
+      if wgrad:
+        GW = g.G(kn)
+        if i == 0:
+          for X, w0 in xs:
+            be.gemm(X, tB, GW[w0:w0 + X.shape[1]], ta=True, beta=1.0)
+        else:
+          be.gemm(self.H[i - 1][r0:r1], tB, GW, ta=True, beta=1.0)
+      if i == 0:
+        for dX, w0, beta in dxs:
+          be.gemm(tB, W[w0:w0 + dX.shape[1]], dX, tb=True, beta=beta)
+      else:
+        tA = eng.tmp_other(tB, n, self.units)
+        be.gemm(tB, W, tA, tb=True)
+
+
+# ----------------------------------------------------------------------------
+# Engine
+# ----------------------------------------------------------------------------
+
+C_MODEL, C_CRITIC, C_ACTOR, C_SLOW, C_RNG = 0, 1, 2, 3, 4
+STREAM_OBS, STREAM_IMG, STREAM_ACT = 1, 2, 3
+
+
+class Engine:
+
+  def __init__(self, spec: Spec, be, B: int, L: int, seed: int = 0,
+               world: int = 1, allreduce=None):
+    assert not spec.discrete, 'discrete (one-hot) actor is not built yet'
+    self.spec, self.be = spec, be
+    self.B, self.L, self.N, self.H = B, L, B * L, spec.horizon
+    self.seed = seed
+    self.world = world
+    self.allreduce = allreduce            # callable(flat tensor) -> sum over ranks
+    s, N, H = spec, self.N, self.H
+    D, U, SC, A, E = s.deter, s.units, s.sc, s.act_dim, s.enc_units
+    z = be.zeros
+    shapes = param_shapes(spec)
+    self.groups = {
+        g: ParamGroup(be, [(n, sh) for n, sh in shapes.items() if n.startswith(pre)],
+                      opt=(g != 'slow_critic'))
+        for g, pre in GROUP_PREFIXES.items()}
+    gm = self.groups['model']
+
+    # controllers / counters (device-resident so the step is one static graph)
+    self.counters = z(8, dtype=torch.int64)
+    self.wmkl_scale = z(1)
+    self.actent_scale = z(A)
+    self.norm_state = z(3, 3, dtype=torch.float64)     # adv / ret / score
+    self.adv = z(2)                                    # (mean, scale) transform
+    self.scratch2 = z(2)
+    self.reset_state()
+
+    # inputs (time-major)
+    self.obs = z(N, s.obs_total)
+    self.action = z(N, A)
+    self.first = z(N)
+    self.reward = z(N, 1)
+    self.cont = z(N, 1)
+    self.prev_deter = z(B, D)
+    self.prev_stoch = z(B, SC)
+    self.first0 = z(B)            # is_first at t=0, or all ones when no state is carried
+
+    # noise
+    self.g_obs = z(self.L, B, SC)
+    self.g_img = z(H, N, SC)
+    self.eps_act = z(H + 1, N, A)
+
+    # shared temporaries for backward ping-pong (largest row count x widest)
+    R = (H + 1) * N
+    wide = max(3 * D, SC, U, s.head_units, E)
+    self._tmp = [z(R * wide) for _ in range(3)]
+
+    # -- world model buffers -------------------------------------------------
+    self.enc = Trunk(self, gm, 'enc', s.enc_layers, E, N)
+    self.init_deter = z(1, D)
+    self.init_trunk = Trunk(self, gm, 'rssm/initp', s.prior_layers, U, 1)
+    self.init_zs = z(1, SC)
+    self.init_logit = z(1, SC)
+    self.init_stoch = z(1, SC)
+    self.m_deter = z(N, D)          # masked previous deter per step
+    self.m_stoch = z(N, SC)
+    self.m_act = z(N, A)
+    self.z_in = z(N, U)
+    self.x_in = z(N, U)
+    self.st_in = z(N, 2)
+    self.z_gru = z(N, 3 * D)
+    self.y_gru = z(N, 3 * D)
+    self.st_gru = z(N, 2)
+    self.feat = z(N, D + SC)        # [post.deter | post.stoch]
+    self.z_obs = z(N, U)
+    self.h_obs = z(N, U)
+    self.st_obs = z(N, 2)
+    self.zs_tmp = z(N, SC)
+    self.post_logit = z(N, SC)
+    self.post_idx = z(N, s.stoch, dtype=torch.int32)
+    self.prior = Trunk(self, gm, 'rssm/priorp', s.prior_layers, U, N)
+    self.prior_logit = z(N, SC)
+    self.heads = {k: Trunk(self, gm, k, s.head_layers, s.head_units, N)
+                  for k in ('dec', 'reward', 'cont')}
+    self.out_dec = z(N, s.obs_total)
+    self.out_rew = z(N, 1)
+    self.out_con = z(N, 1)
+    self.d_dec = z(N, s.obs_total)
+    self.d_rew = z(N, 1)
+    self.d_con = z(N, 1)
+    self.kl_row = z(N)
+    self.ent_post = z(N)
+    self.ent_prior = z(N)
+    self.loss_rows = {k: z(N) for k in list(s.obs_dims) + ['reward', 'cont', 'total']}
+    self.kl_sum = z(1)
+    self.dfeat = z(N, D + SC)
+    self.dpost_logit = z(N, SC)
+    self.dprior_logit = z(N, SC)
+    self.dzs = z(N, SC)
+    self.dz_obs = z(N, U)
+    self.dz_gru = z(N, 3 * D)
+    self.dz_in = z(N, U)
+    self.d_embed = z(N, E)
+    self.d_initdeter = z(1, D)
+
+    # -- imagination buffers ------------------------------------------------
+    ga, gc, gs = self.groups['actor'], self.groups['critic'], self.groups['slow_critic']
+    T = H + 1
+    self.tfeat = z(T, N, D + SC)
+    self.tlogit = z(T, N, SC)
+    self.taction = z(T, N, A)
+    self.tmean = z(T, N, A)
+    self.tstd = z(T, N, A)
+    self.a_mraw = z(T * N, A)
+    self.a_sraw = z(T * N, A)
+    self.actor = Trunk(self, ga, 'actor', s.head_layers, s.head_units, T * N)
+    self.i_zin = z(H, N, U)
+    self.i_xin = z(H, N, U)
+    self.i_stin = z(H, N, 2)
+    self.i_zgru = z(H, N, 3 * D)
+    self.i_ygru = z(H, N, 3 * D)
+    self.i_stgru = z(H, N, 2)
+    self.i_prior = Trunk(self, gm, 'rssm/priorp', s.prior_layers, U, H * N)
+    self.i_zs = z(N, SC)
+    self.t_reward = Trunk(self, gm, 'reward', s.head_layers, s.head_units, T * N)
+    self.t_cont = Trunk(self, gm, 'cont', s.head_layers, s.head_units, T * N)
+    self.t_slow = Trunk(self, gs, 'critic', s.head_layers, s.head_units, T * N,
+                        param_prefix='slow_critic')
+    self.t_critic = Trunk(self, gc, 'critic', s.head_layers, s.head_units, H * N)
+    self.rho = z(T, N)
+    self.vraw = z(T, N)
+    self.kraw = z(T, N)
+    self.vpred = z(H * N, 1)
+    self.d_vpred = z(H * N, 1)
+    self.r_reward = z(H, N)
+    self.r_value = z(T, N)
+    self.r_cont = z(T, N)
+    self.r_weight = z(T, N)
+    self.r_ret = z(H, N)
+    self.cont0 = z(N)
+    self.closs_row = z(H * N)
+    self.score = z(H, N)
+    self.vsym = z(H * N, 1)
+    self.ent = z(H * N, A)
+    self.ent_sum = z(A)
+    self.aloss_row = z(H * N)
+    self.d_rho = z(T, N)
+    self.d_vraw = z(T, N)
+    self.d_kraw = z(T, N)
+    self.dtfeat = z(T, N, D + SC)
+    self.da = z(H * N, A)
+    self.d_mraw = z(H * N, A)
+    self.d_sraw = z(H * N, A)
+
+    # metrics: rows of 8 doubles written by `stats`/`balance`
+    self.mnames = [
+        'kl', 'ent_post', 'ent_prior', 'reward_loss', 'cont_loss', 'total_loss',
+        *[f'loss_{k}' for k in s.obs_dims], 'bal_reward', 'bal_cont',
+        'imag_reward', 'imag_critic', 'imag_return', 'closs', 'score', 'ret_ctrl',
+        'score_ctrl', 'ent', 'aloss']
+    self.mstat = z(len(self.mnames), 8, dtype=torch.float64)
+    self.midx = {k: i for i, k in enumerate(self.mnames)}
+
+  # -- small helpers --------------------------------------------------------
+  def tmp(self, i, rows, cols):
+    return self._tmp[i][:rows * cols].view(rows, cols)
+
+  def tmp_other(self, cur, rows, cols):
+    """Ping-pong between shared temporaries 0 and 1 (2 is free for callers)."""
+    i = 1 if cur.data_ptr() == self._tmp[0].data_ptr() else 0
+    return self.tmp(i, rows, cols)
+
+  def reset_state(self):
+    be = self.be
+    be.fill_(self.wmkl_scale, 1.0)
+    be.fill_(self.actent_scale, 1.0)
+    be.fill_(self.norm_state, 0.0)
+    self.counters.copy_(torch.tensor([0, 0, 0, -1, 0, 0, 0, 0], dtype=torch.int64))
+
+  def load_params(self, params: Dict[str, np.ndarray]):
+    for g in self.groups.values():
+      for n, _ in g.order:
+        g.P(n).copy_(torch.as_tensor(np.asarray(params[n], np.float32)).to(g.p.device))
+
+  def get_params(self) -> Dict[str, np.ndarray]:
+    out = {}
+    for g in self.groups.values():
+      for n, _ in g.order:
+        out[n] = g.P(n).detach().cpu().numpy().copy()
+    return out
+
+  def get_grads(self, group) -> Dict[str, np.ndarray]:
+    g = self.groups[group]
+    return {n: g.G(n).detach().cpu().numpy().copy() for n, _ in g.order}
+
+  def P(self, name):
+    for g, pre in GROUP_PREFIXES.items():
+      if name.startswith(pre):
+        return self.groups[g].P(name)
+    raise KeyError(name)
+
+  def _stat(self, X, key):
+    self.be.stats(X, self.mstat[self.midx[key]])
+
+  def _out_fwd(self, g, prefix, X, out):
+    self.be.gemm(X, g.P(f'{prefix}/kernel'), out, bias=g.P(f'{prefix}/bias'))
+
+  def _out_bwd(self, g, prefix, X, dOut, dX, wgrad):
+    be = self.be
+    if wgrad:
+      be.gemm(X, dOut, g.G(f'{prefix}/kernel'), ta=True, beta=1.0)
+      be.colsum(dOut, g.G(f'{prefix}/bias'), acc=True)
+    be.gemm(dOut, g.P(f'{prefix}/kernel'), dX, tb=True)
+
+  def _prior_stats_fwd(self, trunk, r0, r1, X, zs, G, logit, stoch, idx, mode):
+    """img_out_0..k -> img_stats -> unimix logits (+ draw)  (A/nets.py:132-137)."""
+    s, gm = self.spec, self.groups['model']
+    h = self._prior_trunk_fwd(trunk, r0, r1, X)
+    self._out_fwd(gm, 'rssm/img_stats', h, zs)
+    self.be.stats_fwd(zs, G, logit, stoch, idx, s.stoch, s.classes, s.rssm_unimix, mode)
+
+  def _prior_names(self, i):
+    b = f'rssm/img_out_{i}'
+    return f'{b}/kernel', f'{b}/norm/scale', f'{b}/norm/bias'
+
+  def _prior_trunk_fwd(self, trunk, r0, r1, X):
+    be, gm = self.be, self.groups['model']
+    for i in range(trunk.layers):
+      kn, sn, bn = self._prior_names(i)
+      src = X if i == 0 else trunk.H[i - 1][r0:r1]
+      be.gemm(src, gm.P(kn), trunk.Z[i][r0:r1])
+      be.ln_fwd(trunk.Z[i][r0:r1], gm.P(sn), gm.P(bn), trunk.H[i][r0:r1],
+                trunk.st[i][r0:r1], 1)
+    return trunk.H[-1][r0:r1]
+
+  def _prior_trunk_bwd(self, trunk, r0, r1, X, dH, dX, beta, wgrad):
+    """Backward of img_out_* trunk; dH clobbered; dX (+)= grad wrt X."""
+    be, gm = self.be, self.groups['model']
+    n = r1 - r0
+    tA = dH
+    for i in reversed(range(trunk.layers)):
+      kn, sn, bn = self._prior_names(i)
+      tB = self.tmp_other(tA, n, trunk.units)
+      be.ln_bwd(tA, trunk.Z[i][r0:r1], trunk.st[i][r0:r1], gm.P(sn), gm.P(bn), tB,
+                gm.G(sn) if wgrad else None, gm.G(bn) if wgrad else None, 1)
+      src = X if i == 0 else trunk.H[i - 1][r0:r1]
+      if wgrad:
+        be.gemm(src, tB, gm.G(kn), ta=True, beta=1.0)
+      if i == 0:
+        if dX is not None:
+          be.gemm(tB, gm.P(kn), dX, tb=True, beta=beta)
+      else:
+        tA = self.tmp_other(tB, n, trunk.units)
+        be.gemm(tB, gm.P(kn), tA, tb=True)
+
+  # -- noise ------------------------------------------------------------------
+  def draw_noise(self):
+    be = self.be
+    be.fill_gumbel(self.g_obs, self.seed, STREAM_OBS, self.counters, C_RNG)
+    be.fill_gumbel(self.g_img, self.seed, STREAM_IMG, self.counters, C_RNG)
+    be.fill_normal(self.eps_act, self.seed, STREAM_ACT, self.counters, C_RNG)
+    be.counter_inc(self.counters, C_RNG)
+
+  # ==========================================================================
+  # 1. world model: forward
+  # ==========================================================================
+  def wm_forward(self):
+    s, be, gm = self.spec, self.be, self.groups['model']
+    B, L, N = self.B, self.L, self.N
+    D, U, SC, A, E = s.deter, s.units, s.sc, s.act_dim, s.enc_units
+    feat = self.feat
+
+    embed = self.enc.fwd([(self.obs, 0)], 0, N)
+    # embed part of obs_out's pre-activation, all steps at once
+    Wobs = gm.P('rssm/obs_out/kernel')
+    be.gemm(embed, Wobs[D:], self.z_obs)
+
+    # learned initial state (A/nets.py:54-62): deter0 = tanh(v), stoch0 = mode
+    be.tanh_fwd(gm.P('rssm/initial_deter').view(1, D), self.init_deter)
+    self._prior_stats_fwd(self.init_trunk, 0, 1, self.init_deter, self.init_zs,
+                          None, self.init_logit, self.init_stoch, None, 1)
+
+    Win = gm.P('rssm/img_in/kernel')
+    Wgru = gm.P('rssm/gru_out/kernel')
+    for t in range(L):
+      r = slice(t * B, (t + 1) * B)
+      if t == 0:
+        pd, ps, first = self.prev_deter, self.prev_stoch, self.first0
+      else:
+        q = slice((t - 1) * B, t * B)
+        pd, ps, first = feat[q, :D], feat[q, D:], self.first[r]
+      be.mask_fwd(pd, ps, self.action[r], first, self.init_deter[0],
+                  self.init_stoch[0], self.m_deter[r], self.m_stoch[r], self.m_act[r])
+      # img_in
+      be.gemm(self.m_stoch[r], Win[:SC], self.z_in[r])
+      be.gemm(self.m_act[r], Win[SC:], self.z_in[r], beta=1.0)
+      be.ln_fwd(self.z_in[r], gm.P('rssm/img_in/norm/scale'),
+                gm.P('rssm/img_in/norm/bias'), self.x_in[r], self.st_in[r], 1)
+      # GRU (A/nets.py:149-160)
+      be.gemm(self.m_deter[r], Wgru[:D], self.z_gru[r])
+      be.gemm(self.x_in[r], Wgru[D:], self.z_gru[r], beta=1.0)
+      be.ln_fwd(self.z_gru[r], gm.P('rssm/gru_out/norm/scale'),
+                gm.P('rssm/gru_out/norm/bias'), self.y_gru[r], self.st_gru[r], 0)
+      be.gru_fwd(self.y_gru[r], self.m_deter[r], feat[r, :D])
+      # posterior
+      be.gemm(feat[r, :D], Wobs[:D], self.z_obs[r], beta=1.0)
+      be.ln_fwd(self.z_obs[r], gm.P('rssm/obs_out/norm/scale'),
+                gm.P('rssm/obs_out/norm/bias'), self.h_obs[r], self.st_obs[r], 1)
+      self._out_fwd(gm, 'rssm/obs_stats', self.h_obs[r], self.zs_tmp[r])
+      be.stats_fwd(self.zs_tmp[r], self.g_obs[t], self.post_logit[r], feat[r, D:],
+                   self.post_idx[r], s.stoch, s.classes, s.rssm_unimix, 0)
+
+    # prior logits for every step at once (the prior draw is unused by observe)
+    self._prior_stats_fwd(self.prior, 0, N, feat[:, :D], self.zs_tmp, None,
+                          self.prior_logit, None, None, 2)
+
+    # heads on the posterior features (A/agent.py:170-176)
+    xs = [(feat, 0)]
+    self._out_fwd(gm, 'dec/dist_out/out', self.heads['dec'].fwd(xs, 0, N), self.out_dec)
+    self._out_fwd(gm, 'reward/dist_out/out', self.heads['reward'].fwd(xs, 0, N), self.out_rew)
+    self._out_fwd(gm, 'cont/dist_out/out', self.heads['cont'].fwd(xs, 0, N), self.out_con)
+
+  # ==========================================================================
+  # 1b. world model: losses, backward, optimizer
+  # ==========================================================================
+  def wm_losses(self):
+    s, be = self.spec, self.be
+    N = self.N
+    coef = 1.0 / (N * self.world)
+    be.kl_fwd(self.post_logit, self.prior_logit, s.stoch, s.classes, s.kl_balance,
+              self.kl_row, self.ent_post, self.ent_prior)
+    be.colsum(self.kl_row.view(N, 1), self.kl_sum)
+    if self.allreduce and self.world > 1:
+      self.allreduce(self.kl_sum)
+    be.autoadapt(self.wmkl_scale, self.kl_sum, float(N * self.world), s.wmkl_target,
+                 s.wmkl_min, s.wmkl_max, s.ctrl_vel, s.ctrl_thres, False)
+    off = 0
+    tot = self.loss_rows['total']
+    be.fill_(tot, 0.0)
+    for k, d in s.obs_dims.items():
+      be.head_loss(0, self.out_dec[:, off:off + d], self.obs[:, off:off + d], None,
+                   coef, self.loss_rows[k], self.d_dec[:, off:off + d])
+      be.add_(tot, self.loss_rows[k])
+      off += d
+    be.head_loss(1, self.out_rew, self.reward, None, coef, self.loss_rows['reward'], self.d_rew)
+    be.head_loss(2, self.out_con, self.cont, None, coef, self.loss_rows['cont'], self.d_con)
+    be.add_(tot, self.loss_rows['reward'])
+    be.add_(tot, self.loss_rows['cont'])
+    be.axpy_(tot, self.kl_row, self.wmkl_scale)
+    be.kl_bwd(self.post_logit, self.prior_logit, s.stoch, s.classes, s.kl_balance,
+              coef, self.wmkl_scale, self.dpost_logit, self.dprior_logit)
+    # metrics
+    self._stat(self.kl_row, 'kl')
+    self._stat(self.ent_post, 'ent_post')
+    self._stat(self.ent_prior, 'ent_prior')
+    self._stat(self.loss_rows['reward'], 'reward_loss')
+    self._stat(self.loss_rows['cont'], 'cont_loss')
+    self._stat(tot, 'total_loss')
+    for k in s.obs_dims:
+      self._stat(self.loss_rows[k], f'loss_{k}')
+    be.balance(1, self.out_rew, self.loss_rows['reward'], self.reward, 0.1,
+               self.mstat[self.midx['bal_reward']])
+    be.balance(2, self.out_con, self.loss_rows['cont'], self.cont, 0.5,
+               self.mstat[self.midx['bal_cont']])
+
+  def wm_backward(self):
+    s, be, gm = self.spec, self.be, self.groups['model']
+    B, L, N = self.B, self.L, self.N
+    D, U, SC, A, E = s.deter, s.units, s.sc, s.act_dim, s.enc_units
+    feat, dfeat = self.feat, self.dfeat
+    be.fill_(gm.g, 0.0)
+    be.fill_(self.d_initdeter, 0.0)
+    hu = s.head_units
+
+    # heads -> dfeat
+    beta = 0.0
+    for name, dOut in (('dec', self.d_dec), ('reward', self.d_rew), ('cont', self.d_con)):
+      tr = self.heads[name]
+      dH = self.tmp(0, N, hu)
+      self._out_bwd(gm, f'{name}/dist_out/out', tr.H[-1], dOut, dH, True)
+      tr.bwd(dH, 0, N, [(feat, 0)], [(dfeat, 0, beta)], True)
+      beta = 1.0
+
+    # prior chain (all steps at once): dprior_logit -> ... -> dfeat[:, :D]
+    be.stats_bwd(None, self.dprior_logit, self.prior_logit, self.dzs, s.stoch,
+                 s.classes, s.rssm_unimix)
+    dH = self.tmp(0, N, U)
+    self._out_bwd(gm, 'rssm/img_stats', self.prior.H[-1], self.dzs, dH, True)
+    self._prior_trunk_bwd(self.prior, 0, N, feat[:, :D], dH, dfeat[:, :D], 1.0, True)
+
+    # reverse scan (BPTT)
+    Win = gm.P('rssm/img_in/kernel')
+    Wgru = gm.P('rssm/gru_out/kernel')
+    Wobs = gm.P('rssm/obs_out/kernel')
+    Wst = gm.P('rssm/obs_stats/kernel')
+    for t in reversed(range(L)):
+      r = slice(t * B, (t + 1) * B)
+      dh = self.tmp(0, B, U)
+      dd = self.tmp(1, B, D)
+      ds = self.tmp(2, B, SC)
+      # posterior
+      be.stats_bwd(dfeat[r, D:], self.dpost_logit[r], self.post_logit[r], self.dzs[r],
+                   s.stoch, s.classes, s.rssm_unimix)
+      be.gemm(self.dzs[r], Wst, dh, tb=True)
+      be.ln_bwd(dh, self.z_obs[r], self.st_obs[r], gm.P('rssm/obs_out/norm/scale'),
+                gm.P('rssm/obs_out/norm/bias'), self.dz_obs[r],
+                gm.G('rssm/obs_out/norm/scale'), gm.G('rssm/obs_out/norm/bias'), 1)
+      be.gemm(self.dz_obs[r], Wobs[:D], dfeat[r, :D], tb=True, beta=1.0)
+      # GRU
+      dy = self.tmp(0, B, 3 * D)
+      be.gru_bwd(dfeat[r, :D], self.y_gru[r], self.m_deter[r], dy, dd, False)
+      be.ln_bwd(dy, self.z_gru[r], self.st_gru[r], gm.P('rssm/gru_out/norm/scale'),
+                gm.P('rssm/gru_out/norm/bias'), self.dz_gru[r],
+                gm.G('rssm/gru_out/norm/scale'), gm.G('rssm/gru_out/norm/bias'), 0)
+      be.gemm(self.dz_gru[r], Wgru[:D], dd, tb=True, beta=1.0)
+      dx = self.tmp(0, B, U)
+      be.gemm(self.dz_gru[r], Wgru[D:], dx, tb=True)
+      # img_in
+      be.ln_bwd(dx, self.z_in[r], self.st_in[r], gm.P('rssm/img_in/norm/scale'),
+                gm.P('rssm/img_in/norm/bias'), self.dz_in[r],
+                gm.G('rssm/img_in/norm/scale'), gm.G('rssm/img_in/norm/bias'), 1)
+      be.gemm(self.dz_in[r], Win[:SC], ds, tb=True)
+      if t == 0:
+        be.mask_bwd(dd, ds, self.first0, None, None, self.d_initdeter[0])
+      else:
+        q = slice((t - 1) * B, t * B)
+        be.mask_bwd(dd, ds, self.first[r], dfeat[q, :D], dfeat[q, D:], self.d_initdeter[0])
+
+    # weight grads of the scan layers, all steps at once
+    be.gemm(self.h_obs, self.dzs, gm.G('rssm/obs_stats/kernel'), ta=True, beta=1.0)
+    be.colsum(self.dzs, gm.G('rssm/obs_stats/bias'), acc=True)
+    Gobs = gm.G('rssm/obs_out/kernel')
+    be.gemm(feat[:, :D], self.dz_obs, Gobs[:D], ta=True, beta=1.0)
+    embed = self.enc.H[-1]
+    be.gemm(embed, self.dz_obs, Gobs[D:], ta=True, beta=1.0)
+    Ggru = gm.G('rssm/gru_out/kernel')
+    be.gemm(self.m_deter, self.dz_gru, Ggru[:D], ta=True, beta=1.0)
+    be.gemm(self.x_in, self.dz_gru, Ggru[D:], ta=True, beta=1.0)
+    Gin = gm.G('rssm/img_in/kernel')
+    be.gemm(self.m_stoch, self.dz_in, Gin[:SC], ta=True, beta=1.0)
+    be.gemm(self.m_act, self.dz_in, Gin[SC:], ta=True, beta=1.0)
+    # initial_deter = tanh(v)
+    be.tanh_bwd(self.d_initdeter, self.init_deter,
+                gm.G('rssm/initial_deter').view(1, D), True)
+    # encoder
+    be.gemm(self.dz_obs, Wobs[D:], self.d_embed, tb=True)
+    self.enc.bwd(self.d_embed, 0, N, [(self.obs, 0)], [], True)
+
+  def opt_step(self, group, ci):
+    s, be, g = self.spec, self.be, self.groups[group]
+    if self.allreduce and self.world > 1:
+      self.allreduce(g.g)
+    be.sumsq(g.g, g.sumsq)
+    be.adam(g.p, g.g, g.m, g.v, g.n_decay, s.lr, s.beta1, s.beta2, s.adam_eps,
+            s.wd, s.clip, 1.0, g.sumsq, self.counters, ci)
+
+  # ==========================================================================
+  # 2. imagination rollout (A/agent.py:234-261)
+  # ==========================================================================
+  def _actor_fwd(self, t):
+    s, be, ga = self.spec, self.be, self.groups['actor']
+    N = self.N
+    r0, r1 = t * N, (t + 1) * N
+    h = self.actor.fwd([(self.tfeat[t], 0)], r0, r1)
+    self._out_fwd(ga, 'actor/dist_out/out', h, self.a_mraw[r0:r1])
+    self._out_fwd(ga, 'actor/dist_out/std', h, self.a_sraw[r0:r1])
+    be.actor_sample(self.a_mraw[r0:r1], self.a_sraw[r0:r1], self.eps_act[t],
+                    s.actor_minstd, s.actor_maxstd, self.taction[t],
+                    self.tmean[t], self.tstd[t])
+
+  def imagine(self):
+    s, be, gm = self.spec, self.be, self.groups['model']
+    N, H = self.N, self.H
+    D, U, SC, A = s.deter, s.units, s.sc, s.act_dim
+    tf = self.tfeat
+    be.copy_(tf[0], self.feat)
+    be.copy_(self.tlogit[0], self.post_logit)
+    Win = gm.P('rssm/img_in/kernel')
+    Wgru = gm.P('rssm/gru_out/kernel')
+    self._actor_fwd(0)
+    for t in range(H):
+      be.gemm(tf[t][:, D:], Win[:SC], self.i_zin[t])
+      be.gemm(self.taction[t], Win[SC:], self.i_zin[t], beta=1.0)
+      be.ln_fwd(self.i_zin[t], gm.P('rssm/img_in/norm/scale'),
+                gm.P('rssm/img_in/norm/bias'), self.i_xin[t], self.i_stin[t], 1)
+      be.gemm(tf[t][:, :D], Wgru[:D], self.i_zgru[t])
+      be.gemm(self.i_xin[t], Wgru[D:], self.i_zgru[t], beta=1.0)
+      be.ln_fwd(self.i_zgru[t], gm.P('rssm/gru_out/norm/scale'),
+                gm.P('rssm/gru_out/norm/bias'), self.i_ygru[t], self.i_stgru[t], 0)
+      be.gru_fwd(self.i_ygru[t], tf[t][:, :D], tf[t + 1][:, :D])
+      self._prior_stats_fwd(self.i_prior, t * N, (t + 1) * N, tf[t + 1][:, :D],
+                            self.i_zs, self.g_img[t], self.tlogit[t + 1],
+                            tf[t + 1][:, D:], None, 0)
+      self._actor_fwd(t + 1)
+
+  # ==========================================================================
+  # 3. trajectory heads, lambda-return, critic update (A/agent.py:398-454)
+  # ==========================================================================
+  def _traj_head(self, trunk, group, prefix, out, r0, r1):
+    flat = self.tfeat.view(-1, self.spec.feat)
+    h = trunk.fwd([(flat[r0:r1], 0)], r0, r1, group)
+    self._out_fwd(group, f'{prefix}/dist_out/out', h, out.view(-1, 1)[r0:r1])
+
+  def traj_values(self, slow_only=False):
+    s, be = self.spec, self.be
+    N, H, T = self.N, self.H, self.H + 1
+    gm, gs = self.groups['model'], self.groups['slow_critic']
+    if not slow_only:
+      self._traj_head(self.t_reward, gm, 'reward', self.rho, N, T * N)
+      self._traj_head(self.t_cont, gm, 'cont', self.kraw, N, T * N)
+    self._traj_head(self.t_slow, gs, 'slow_critic', self.vraw, 0, T * N)
+    be.lambda_fwd(self.rho, self.vraw, self.kraw, self.cont0, s.discount, s.lam,
+                  self.r_reward, self.r_value, self.r_cont, self.r_weight, self.r_ret)
+
+  def critic_update(self):
+    s, be, gc = self.spec, self.be, self.groups['critic']
+    N, H = self.N, self.H
+    M = H * N
+    flat = self.tfeat.view(-1, s.feat)[:M]
+    h = self.t_critic.fwd([(flat, 0)], 0, M)
+    self._out_fwd(gc, 'critic/dist_out/out', h, self.vpred)
+    coef = 1.0 / (M * self.world)
+    be.head_loss(1, self.vpred, self.r_ret.view(M, 1), self.r_weight.view(-1)[:M],
+                 coef, self.closs_row, self.d_vpred)
+    be.fill_(gc.g, 0.0)
+    dH = self.tmp(0, M, s.head_units)
+    self._out_bwd(gc, 'critic/dist_out/out', h, self.d_vpred, dH, True)
+    self.t_critic.bwd(dH, 0, M, [(flat, 0)], [], True)
+    # metrics before the update changes anything
+    self._stat(self.r_reward, 'imag_reward')
+    be.symexp(self.vpred, self.vsym)
+    self._stat(self.vsym, 'imag_critic')
+    self._stat(self.r_ret, 'imag_return')
+    self._stat(self.closs_row, 'closs')
+    self.opt_step('critic', C_CRITIC)
+    be.slow_sync(gc.p, self.groups['slow_critic'].p, self.counters, C_SLOW, s.slow_every)
+
+  # ==========================================================================
+  # 4. actor update (A/agent.py:326-381), gradients through the dynamics
+  # ==========================================================================
+  def actor_update(self):
+    s, be = self.spec, self.be
+    gm, ga, gs = self.groups['model'], self.groups['actor'], self.groups['slow_critic']
+    N, H, T = self.N, self.H, self.H + 1
+    D, U, SC, A = s.deter, s.units, s.sc, s.act_dim
+    M = H * N
+    hu = s.head_units
+    # score with the (possibly refreshed) slow critic
+    self.traj_values(slow_only=True)
+    be.sub(self.score, self.r_ret, self.r_value[:H])
+    self._stat(self.score, 'score')
+    # Normalize EMAs: retnorm/scorenorm are impl 'off' (state only), advnorm used
+    for i, (src, key, decay) in enumerate((
+        (self.score, 'score_ctrl', s.advnorm_decay), (self.r_ret, 'ret_ctrl', 0.999),
+        (self.score, 'score_ctrl', 0.99))):
+      row = self.mstat[self.midx[key]]
+      be.stats(src, row)
+      if self.allreduce and self.world > 1:
+        self.allreduce(row)
+      be.normalize_update(self.norm_state[i], row, decay, s.advnorm_max,
+                          self.adv if i == 0 else self.scratch2)
+    # entropy controller (A/agent.py:361-371, A/tfutils.py:464-474)
+    be.actor_ent(self.tstd.view(-1, A)[:M], s.actor_minstd, s.actor_maxstd, self.ent)
+    be.colsum(self.ent, self.ent_sum)
+    if self.allreduce and self.world > 1:
+      self.allreduce(self.ent_sum)
+    be.autoadapt(self.actent_scale, self.ent_sum, float(M * self.world), s.actent_target,
+                 s.actent_min, s.actent_max, s.ctrl_vel, s.ctrl_thres, True)
+    self._stat(self.ent, 'ent')
+    be.actor_loss(self.r_ret, self.r_value, self.adv, self.ent, self.actent_scale,
+                  self.r_weight, self.aloss_row)
+    self._stat(self.aloss_row, 'aloss')
+
+    coef = 1.0 / (M * self.world)
+    be.lambda_bwd(self.rho, self.vraw, self.r_value, self.r_cont, self.r_weight,
+                  self.r_ret, self.adv, coef, s.discount, s.lam,
+                  self.d_rho, self.d_vraw, self.d_kraw)
+    # heads: input grads only (world model and slow critic are constants here)
+    dtf = self.dtfeat.view(-1, s.feat)
+    flat = self.tfeat.view(-1, s.feat)
+    for trunk, g, prefix, dOut, r0, beta in (
+        (self.t_slow, gs, 'slow_critic', self.d_vraw, 0, 0.0),
+        (self.t_reward, gm, 'reward', self.d_rho, N, 1.0),
+        (self.t_cont, gm, 'cont', self.d_kraw, N, 1.0)):
+      n = T * N - r0
+      dH = self.tmp(0, n, hu)
+      self._out_bwd(g, f'{prefix}/dist_out/out', trunk.H[-1][r0:], dOut.view(-1, 1)[r0:], dH, False)
+      trunk.bwd(dH, r0, T * N, [(flat[r0:], 0)], [(dtf[r0:], 0, beta)], False, g)
+
+    # reverse through the rollout: t = H .. 1
+    Win = gm.P('rssm/img_in/kernel')
+    Wgru = gm.P('rssm/gru_out/kernel')
+    for t in range(H, 0, -1):
+      k = t - 1
+      dzs = self.tmp(2, N, SC)
+      be.stats_bwd(self.dtfeat[t][:, D:], None, self.tlogit[t], dzs, s.stoch,
+                   s.classes, s.rssm_unimix)
+      dH = self.tmp(0, N, U)
+      self._out_bwd(gm, 'rssm/img_stats', self.i_prior.H[-1][k * N:(k + 1) * N], dzs, dH, False)
+      self._prior_trunk_bwd(self.i_prior, k * N, (k + 1) * N, self.tfeat[t][:, :D], dH,
+                            self.dtfeat[t][:, :D], 1.0, False)
+      dy = self.tmp(0, N, 3 * D)
+      dzg = self.tmp(1, N, 3 * D)
+      be.gru_bwd(self.dtfeat[t][:, :D], self.i_ygru[k], self.tfeat[k][:, :D], dy,
+                 self.dtfeat[k][:, :D], True)
+      be.ln_bwd(dy, self.i_zgru[k], self.i_stgru[k], gm.P('rssm/gru_out/norm/scale'),
+                gm.P('rssm/gru_out/norm/bias'), dzg, None, None, 0)
+      if k > 0:
+        be.gemm(dzg, Wgru[:D], self.dtfeat[k][:, :D], tb=True, beta=1.0)
+      dx = self.tmp(0, N, U)
+      be.gemm(dzg, Wgru[D:], dx, tb=True)
+      dzi = self.tmp(2, N, U)
+      be.ln_bwd(dx, self.i_zin[k], self.i_stin[k], gm.P('rssm/img_in/norm/scale'),
+                gm.P('rssm/img_in/norm/bias'), dzi, None, None, 1)
+      if k > 0:
+        be.gemm(dzi, Win[:SC], self.dtfeat[k][:, D:], tb=True, beta=1.0)
+      be.gemm(dzi, Win[SC:], self.da[k * N:(k + 1) * N], tb=True)
+
+    # actor network backward over all t < H at once
+    be.actor_bwd(self.da, self.eps_act.view(-1, A)[:M], self.tmean.view(-1, A)[:M],
+                 self.tstd.view(-1, A)[:M], self.r_weight.view(-1)[:M],
+                 self.actent_scale, coef, s.actor_minstd, s.actor_maxstd,
+                 self.d_mraw, self.d_sraw)
+    be.fill_(ga.g, 0.0)
+    h = self.actor.H[-1][:M]
+    dH = self.tmp(0, M, hu)
+    be.gemm(h, self.d_mraw, ga.G('actor/dist_out/out/kernel'), ta=True, beta=1.0)
+    be.colsum(self.d_mraw, ga.G('actor/dist_out/out/bias'), acc=True)
+    be.gemm(h, self.d_sraw, ga.G('actor/dist_out/std/kernel'), ta=True, beta=1.0)
+    be.colsum(self.d_sraw, ga.G('actor/dist_out/std/bias'), acc=True)
+    be.gemm(self.d_mraw, ga.P('actor/dist_out/out/kernel'), dH, tb=True)
+    be.gemm(self.d_sraw, ga.P('actor/dist_out/std/kernel'), dH, tb=True, beta=1.0)
+    self.actor.bwd(dH, 0, M, [(flat[:M], 0)], [], True)
+    self.opt_step('actor', C_ACTOR)
+
+  # ==========================================================================
+  # the whole step
+  # ==========================================================================
+  def launch_step(self, draw=True):
+    """Everything between 'inputs are on the device' and 'metrics are on the
+    device'.  Pure launch sequence: safe to capture into a CUDA graph."""
+    if draw:
+      self.draw_noise()
+    self.wm_forward()
+    self.wm_losses()
+    self.wm_backward()
+    self.opt_step('model', C_MODEL)
+    # carried train state = post[:, -1] (A/agent.py:211)
+    s, B, L = self.spec, self.B, self.L
+    r = slice((L - 1) * B, L * B)
+    self.be.copy_(self.prev_deter, self.feat[r, :s.deter])
+    self.be.copy_(self.prev_stoch, self.feat[r, s.deter:])
+    self.be.copy_(self.cont0.view(-1, 1), self.cont)
+    self.imagine()
+    self.traj_values()
+    self.critic_update()
+    self.actor_update()
+
+  # -- host side of the metrics --------------------------------------------
+  def read_metrics(self) -> Dict[str, float]:
+    s = self.spec
+    ms = self.mstat.detach().cpu().numpy()
+    cnt = self.counters.detach().cpu().numpy()
+    wm = float(self.wmkl_scale.detach().cpu().numpy()[0])
+    ae = self.actent_scale.detach().cpu().numpy().astype(np.float64)
+    w = self.world
+    sq = {g: float(self.groups[g].sumsq.detach().cpu().numpy()[0])
+          for g in ('model', 'critic', 'actor')}
+    row = lambda k: ms[self.midx[k]]
+    mean = lambda k: row(k)[0] / row(k)[6]
+    std = lambda k: math.sqrt(max(row(k)[1] / row(k)[6] - mean(k) ** 2, 0.0))
+    m = {}
+    m.update(wmkl_mean=mean('kl'), wmkl_std=std('kl'), wmkl_scale_mean=wm,
+             wmkl_scale_std=0.0, kl_loss_mean=wm * mean('kl'), kl_loss_std=wm * std('kl'))
+    for k in s.obs_dims:
+      m[f'{k}_loss_mean'], m[f'{k}_loss_std'] = mean(f'loss_{k}'), std(f'loss_{k}')
+    for k in ('reward', 'cont'):
+      m[f'{k}_loss_mean'], m[f'{k}_loss_std'] = mean(f'{k}_loss'), std(f'{k}_loss')
+      b = row(f'bal_{k}')
+      div = lambda a, c: a / c if c > 0 else float('nan')
+      n = b[0] + b[1]
+      m.update({f'{k}_pos_loss': div(b[2], b[0]), f'{k}_neg_loss': div(b[3], b[1]),
+                f'{k}_pos_acc': div(b[4], b[0]), f'{k}_neg_acc': div(b[5], b[1]),
+                f'{k}_rate': b[0] / n, f'{k}_avg': b[6] / n, f'{k}_pred': b[7] / n})
+    m.update(prior_ent_mean=mean('ent_prior'), post_ent_mean=mean('ent_post'),
+             prior_ent_min=row('ent_prior')[2], post_ent_min=row('ent_post')[2],
+             model_loss_mean=mean('total_loss'), model_loss_std=std('total_loss'),
+             model_loss=mean('total_loss'),
+             model_grad_norm=math.sqrt(sq['model']) / w, model_grad_steps=int(cnt[C_MODEL]),
+             extr_critic_loss=mean('closs'),
+             extr_critic_grad_norm=math.sqrt(sq['critic']) / w,
+             extr_critic_grad_steps=int(cnt[C_CRITIC]),
+             extr_imag_reward_mean=mean('imag_reward'), extr_imag_reward_std=std('imag_reward'),
+             extr_imag_critic_mean=mean('imag_critic'), extr_imag_critic_std=std('imag_critic'),
+             extr_imag_return_mean=mean('imag_return'), extr_imag_return_std=std('imag_return'),
+             extr_score_mean=mean('score'), extr_score_std=std('score'),
+             extr_score_mag=row('score')[4] / row('score')[6], extr_score_max=row('score')[5],
+             actent_mean=mean('ent'), actent_std=std('ent'),
+             actent_scale_mean=float(ae.mean()), actent_scale_std=float(ae.std()),
+             actor_loss=mean('aloss'),
+             actor_grad_norm=math.sqrt(sq['actor']) / w, actor_grad_steps=int(cnt[C_ACTOR]))
+    return m

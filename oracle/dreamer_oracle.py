@@ -733,6 +733,6 @@ class Learner:
           post=post, prior={k: v.detach() for k, v in aux['prior'].items()},
           embed=aux['embed'].detach(), kl=aux['kl'].detach(),
           traj={k: v.detach() for k, v in traj.items()},
-          target=target, score=score.detach())
+          target=target, ret=ret.detach(), score=score.detach())
       return {}, new_state, mets, aux_all
     return {}, new_state, mets

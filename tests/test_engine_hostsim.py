@@ -1,0 +1,69 @@
+"""Host logic check (no GPU): the product's orchestration (engine.py, hand-written
+backward) running on the torch-CPU primitive simulator must reproduce the
+oracle's autograd train step."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dreamer_oracle as O
+from daydreamer_b200 import engine as E
+from tests import util
+from tests.hostsim import HostSim
+
+
+def rel(a, b):
+  a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+  return np.abs(a - b).max() / (np.abs(b).max() + 1e-12)
+
+
+@pytest.mark.parametrize('B,L,steps', [(3, 5, 1), (2, 6, 3)])
+def test_train_step_matches_oracle(B, L, steps):
+  torch.manual_seed(0)
+  ospec = O.tiny_spec()
+  spec = util.to_engine_spec(ospec)
+  params = O.init_params(ospec, seed=1)
+  # make LN params / biases non-trivial so every gradient path is exercised
+  rng = np.random.default_rng(5)
+  for k, v in params.items():
+    if not k.endswith('/kernel'):
+      params[k] = (v + 0.1 * rng.standard_normal(v.shape)).astype(np.float32)
+  ol = O.Learner(ospec, params)
+  eng = E.Engine(spec, HostSim(), B, L)
+  eng.load_params(params)
+  ostate = None
+  estate = None
+  for it in range(steps):
+    batch = util.make_batch(ospec, B, L, seed=10 + it)
+    noise = util.make_noise(ospec, B, L, seed=20 + it)
+    _, ostate, omets, aux = ol.train_step(batch, noise, ostate, keep=True)
+    util.load_batch(eng, spec, batch, noise, estate)
+    eng.launch_step(draw=False)
+    estate = {'deter': eng.prev_deter.numpy().copy(), 'stoch': eng.prev_stoch.numpy().copy()}
+    # posterior indices bit-exact, features close
+    post_stoch = util.tm(aux['post']['stoch'].numpy().reshape(B, L, -1))
+    assert np.array_equal(eng.feat[:, spec.deter:].numpy(), post_stoch)
+    assert rel(eng.feat[:, :spec.deter].numpy(), util.tm(aux['post']['deter'].numpy())) < 1e-5
+    # gradients of all three groups
+    for group in ('model', 'critic', 'actor'):
+      eg = eng.get_grads(group)
+      og = aux[f'{group}_grads']
+      for k in og:
+        assert rel(eg[k], og[k].numpy()) < 2e-4, (it, group, k, rel(eg[k], og[k].numpy()))
+    # trajectory
+    traj = aux['traj']
+    tstoch = util.ref_rows_to_tm(traj['stoch'].numpy().reshape(spec.horizon + 1, B * L, -1), B, L)
+    assert np.array_equal(eng.tfeat[:, :, spec.deter:].numpy(), tstoch)
+    assert rel(eng.r_ret.numpy(), util.ref_rows_to_tm(aux['ret'].numpy()[..., None], B, L)[..., 0]) < 1e-4
+    # updated parameters
+    ep = eng.get_params()
+    for k, v in ol.params.items():
+      assert rel(ep[k], v.numpy()) < 1e-5, (it, k)
+    # metrics
+    em = eng.read_metrics()
+    for k, v in omets.items():
+      assert k in em, k
+      if np.isnan(v):
+        assert np.isnan(em[k]), k
+      else:
+        assert abs(em[k] - v) <= 2e-4 * max(1.0, abs(v)), (it, k, em[k], v)
+    assert set(em) == set(omets)
