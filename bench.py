@@ -1,0 +1,367 @@
+"""Headline benchmark: imagined latent-steps/sec (B x L x H per Agent.train call /
+step time) on the a1 proprio config (deter=units=512, stoch 32x32, L=64, H=15,
+B=16 sequences per GPU, synthetic replay), BASELINE.json configs[1].
+
+  python bench.py --gpus N --steps K --warmup W            # this framework
+  python bench.py --impl reference --gpus N --steps K ...  # reference CPU path
+
+Under torchrun (N>1) every rank drives one GPU on its own shard of B=16
+sequences (weak scaling); gradients are all-reduced over NCCL.  `value` times
+the device-resident step (inputs already in HBM, CUDA-graph replay, CUDA
+events); `e2e` times Agent.train(host numpy batch) including the pinned H2D
+copy of the batch and the D2H read of the metrics.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+import numpy as np
+
+B_PER_GPU, L, H = 16, 64, 15
+WORKLOAD = 'a1 proprio RSSM deter=512 stoch=32x32 batch=16/GPU seq=64 H=15, synthetic replay'
+METRIC = 'imagined latent-steps/sec (BxLxH)'
+UNIT = 'latent-steps/s'
+
+
+def synthetic_batch(B, seed):
+  """SURVEY.md 8(d) cfg2 synthetic replay (the unused `image` key is omitted
+  from both arms)."""
+  rng = np.random.default_rng(seed)
+  first = np.zeros((B, L), bool)
+  first[:, 0] = True
+  term = rng.uniform(size=(B, L)) < 0.01
+  return {
+      'vector': rng.standard_normal((B, L, 16)).astype(np.float32),
+      'action': rng.uniform(-1, 1, (B, L, 12)).astype(np.float32),
+      'reward': (0.1 * rng.standard_normal((B, L))).astype(np.float32),
+      'is_first': first, 'is_terminal': term, 'is_last': term.copy(),
+  }
+
+
+class Space:
+  def __init__(self, shape, dtype=np.float32, discrete=False):
+    self.shape, self.dtype, self.discrete = tuple(shape), np.dtype(dtype), discrete
+
+
+def spaces():
+  obs = {'vector': Space((16,)), 'reward': Space(()), 'is_first': Space((), bool),
+         'is_last': Space((), bool), 'is_terminal': Space((), bool)}
+  return obs, {'action': Space((12,)), 'reset': Space((), bool, True)}
+
+
+def load_peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    p = json.load(open(path))
+    return {'hbm_gbs': p['hbm_gbs'], 'tflops': p.get('bf16_tflops_sustained', p['bf16_tflops']),
+            'source': 'MEASURED_PEAKS.json (sustained bf16, copy HBM)'}
+  return {'hbm_gbs': 6650.0, 'tflops': 1590.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons DURING the timed region."""
+  QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+           'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+           'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index=0):
+    self.index, self.proc, self.lines = index, None, []
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.QUERY}',
+           '--format=csv,noheader,nounits', '-lms', '100'],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if not self.proc:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for line in self.lines:
+      parts = [p.strip() for p in line.split(',')]
+      if len(parts) < 6:
+        continue
+      try:
+        sm.append(float(parts[0]))
+        mx.append(float(parts[1]))
+      except ValueError:
+        continue
+      for n, v in zip(names, parts[2:6]):
+        if v.lower().startswith('active'):
+          reasons.add(n)
+    return {'sm_mhz': float(np.median(sm)) if sm else None,
+            'sm_max_mhz': float(np.max(mx)) if mx else None,
+            'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------
+# reference arm: the reference learner's CPU path (oracle port, all host cores)
+# ----------------------------------------------------------------------------
+
+def run_reference(args, rank, world):
+  if rank != 0:
+    return
+  import torch
+  from oracle import dreamer_oracle as O
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  spec = O.a1_spec()
+  learner = O.Learner(spec)
+
+  def noise_for(B, seed):
+    rng = np.random.default_rng(seed)
+    gum = lambda *s: (-np.log(-np.log(rng.uniform(1e-6, 1 - 1e-6, s)))).astype(np.float32)
+    return {'obs_post': gum(L, B, 32, 32), 'img': gum(H, B * L, 32, 32),
+            'act': rng.standard_normal((H + 1, B * L, 12)).astype(np.float32)}
+
+  # bounded sample: shrink the number of sequences so the whole run takes minutes
+  budget = 150.0
+  B = B_PER_GPU
+  t0 = time.perf_counter()
+  learner.train_step(synthetic_batch(B, 0), noise_for(B, 0))
+  t1 = time.perf_counter() - t0
+  total = args.steps + args.warmup
+  if t1 * total > budget:
+    B = max(1, int(B * budget / (t1 * total)))
+  for i in range(args.warmup):
+    learner.train_step(synthetic_batch(B, i), noise_for(B, i))
+  t0 = time.perf_counter()
+  for i in range(args.steps):
+    learner.train_step(synthetic_batch(B, 100 + i), noise_for(B, 100 + i))
+  dt = (time.perf_counter() - t0) / args.steps
+  value = B * L * H / dt
+  sample = f'{B} of 16 sequences x L=64 x H=15 per step, {args.steps} steps, eager PyTorch-CPU fp32'
+  print(json.dumps({
+      'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+      'data': 'synthetic', 'config': {'workload': WORKLOAD, 'sample_sequences': B},
+      'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                       'sample': sample,
+                       'note': 'reference restated (PyTorch-CPU oracle), not TF2: tensorflow is '
+                               'not installable in this image'},
+      'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+  }))
+
+
+# ----------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------
+
+class GemmOnly:
+  """Backend view that forwards only dd_gemm launches (and counts their flops);
+  used to time the dominant kernel over exactly the launches of one step."""
+
+  def __init__(self, be):
+    self._be, self.flops, self.calls = be, 0.0, 0
+
+  def __getattr__(self, name):
+    attr = getattr(self._be, name)
+    if name in ('zeros', 'upload', 'sync', 'device', 'stream', 'lib', 'launch_count'):
+      return attr
+    if name == 'gemm':
+      def gemm(A, B, C, ta=False, tb=False, beta=0.0, bias=None):
+        K = A.shape[0] if ta else A.shape[1]
+        self.flops += 2.0 * C.shape[0] * C.shape[1] * K
+        self.calls += 1
+        return attr(A, B, C, ta=ta, tb=tb, beta=beta, bias=bias)
+      return gemm
+    return (lambda *a, **k: None) if callable(attr) else attr
+
+
+def run_ours(args, rank, world, local_rank):
+  import torch
+  import torch.distributed as dist
+  torch.cuda.set_device(local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
+  from daydreamer_b200.agent import Agent
+  from daydreamer_b200.config import make_config
+
+  cfg = make_config('a1', **{'rssm.deter': 512, 'rssm.units': 512, 'batch_size': B_PER_GPU * world,
+                            'replay_chunk': L, 'imag_horizon': H})
+  obs_space, act_space = spaces()
+  agent = Agent(obs_space, act_space, None, cfg)
+  be = agent.be
+  batches = [synthetic_batch(B_PER_GPU, 1000 * rank + i) for i in range(4)]
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # ---- e2e: the public API with host batches --------------------------------
+  state = None
+  for i in range(max(args.warmup, 3)):
+    _, state, mets = agent.train(batches[i % 4], state)
+  eng = agent._main
+  barrier()
+  t0 = time.perf_counter()
+  for i in range(args.steps):
+    _, state, mets = agent.train(batches[i % 4], state)
+  torch.cuda.synchronize()
+  e2e_dt = torch.tensor([(time.perf_counter() - t0) / args.steps], device='cuda')
+  if world > 1:
+    dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+  e2e_dt = float(e2e_dt)
+  h2d = sum(v.numel() * 4 for v in eng.h_stage.values()) + eng.first0.numel() * 4
+  d2h = (eng.mstat.numel() * 8 + eng.counters.numel() * 8 + 4 + eng.actent_scale.numel() * 4
+         + 3 * 8)
+
+  # ---- device-resident step: graph replay timed with CUDA events -----------
+  graph = agent._graphs[(id(eng), 'train')]
+  for _ in range(max(args.warmup, 3)):
+    graph.replay()
+  clocks = ClockSampler(local_rank)
+  barrier()
+  clocks.start()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ev0.record()
+  for _ in range(args.steps):
+    graph.replay()
+  ev1.record()
+  torch.cuda.synchronize()
+  clock_info = clocks.stop()
+  dt = torch.tensor([ev0.elapsed_time(ev1) / 1e3 / args.steps], device='cuda')
+  if world > 1:
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+  dt = float(dt)
+  barrier()
+
+  # launches per step (counted while re-issuing the launch sequence eagerly once)
+  n0 = be.launch_count()
+  agent._unstage(eng)
+  eng.launch_step()
+  torch.cuda.synchronize()
+  launches_per_step = be.launch_count() - n0
+
+  # ---- dominant kernel (fp32 GEMM) over exactly one step's launches --------
+  roofline = None
+  if rank == 0:
+    real = eng.be
+    probe = GemmOnly(real)
+    eng.be = probe
+    try:
+      if world > 1:
+        saved, eng.allreduce = eng.allreduce, None
+      g2 = torch.cuda.CUDAGraph()
+      torch.cuda.synchronize()
+      with torch.cuda.graph(g2):
+        eng.launch_step()
+      for _ in range(3):
+        g2.replay()
+      torch.cuda.synchronize()
+      ev0.record()
+      reps = 5
+      for _ in range(reps):
+        g2.replay()
+      ev1.record()
+      torch.cuda.synchronize()
+      gemm_s = ev0.elapsed_time(ev1) / 1e3 / reps
+    finally:
+      eng.be = real
+      if world > 1:
+        eng.allreduce = saved
+    peaks = load_peaks()
+    tf = probe.flops / gemm_s / 1e12
+    scan_bytes = 222.4e6        # fused observe+imagine scan, a1, per GPU
+    roofline = {
+        'kernel': 'dd::gemm_kernel (fp32 SIMT)', 'bound': 'tensor', 'achieved': tf,
+        'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': tf / peaks['tflops'],
+        'traffic': None, 'peak_source': peaks['source'],
+        'launches_per_step': probe.calls, 'avg_launch_us': gemm_s / probe.calls * 1e6,
+        'flops_per_step': probe.flops, 'share_of_step': gemm_s / dt,
+        'step_hbm': {'algorithmic_bytes': scan_bytes,
+                     'achieved_gbs': scan_bytes / dt / 1e9,
+                     'frac_of_hbm_peak': scan_bytes / dt / 1e9 / peaks['hbm_gbs']},
+    }
+
+  # ---- CPU baseline on the box's host cores (rank 0, N=1 only) -------------
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu:
+    from oracle import dreamer_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    learner = O.Learner(O.a1_spec())
+    rng = np.random.default_rng(0)
+    gum = lambda *s: (-np.log(-np.log(rng.uniform(1e-6, 1 - 1e-6, s)))).astype(np.float32)
+    noise = {'obs_post': gum(L, B_PER_GPU, 32, 32), 'img': gum(H, B_PER_GPU * L, 32, 32),
+             'act': rng.standard_normal((H + 1, B_PER_GPU * L, 12)).astype(np.float32)}
+    learner.train_step(batches[0], noise)
+    t0 = time.perf_counter()
+    n_cpu = 3
+    for i in range(n_cpu):
+      learner.train_step(batches[i % 4], noise)
+    cdt = (time.perf_counter() - t0) / n_cpu
+    cpu = {'value': B_PER_GPU * L * H / cdt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+           'sample': f'{n_cpu} full train steps (B=16, L=64, H=15) after 1 warm-up, '
+                     'eager PyTorch-CPU fp32 oracle',
+           'ms_per_step': cdt * 1e3}
+
+  if rank == 0:
+    units = B_PER_GPU * world * L * H
+    out = {
+        'metric': METRIC, 'value': units / dt, 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'global_batch': B_PER_GPU * world, 'seq_len': L,
+                   'horizon': H, 'parallelism': f'dp{world}',
+                   'l2': 'per-step working set (~2 GB of saved activations) exceeds the 126 MB L2; '
+                         'no explicit flush'},
+        'clocks': clock_info,
+        'e2e': {'value': units / e2e_dt, 'unit': UNIT, 'ms_per_step': e2e_dt * 1e3,
+                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': launches_per_step * args.steps,
+        'launches_per_step': launches_per_step,
+        'roofline': roofline, 'cpu_baseline': cpu,
+        'last_metrics': {k: mets[k] for k in ('model_loss', 'actor_loss', 'extr_critic_loss')},
+    }
+    print(json.dumps(out))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=5)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+  args = ap.parse_args()
+  rank = int(os.environ.get('RANK', 0))
+  world = int(os.environ.get('WORLD_SIZE', 1))
+  local_rank = int(os.environ.get('LOCAL_RANK', 0))
+  if args.impl == 'reference':
+    run_reference(args, rank, world)
+  else:
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+  main()

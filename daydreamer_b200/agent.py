@@ -1,0 +1,340 @@
+"""`embodied.Agent` surface of the B200-native DreamerV2+ learner.
+
+Drop-in for the reference's agent (embodied/agents/dreamerv2plus/agent.py:15-139
+behind tfagent.py:22-134): same constructor, `configs`, `dataset`, `train`,
+`report`, `policy`, `save`, `load`; numpy in, numpy / python scalars out; methods
+are plain instance attributes so `embodied.Timer.wrap` can re-bind them
+(embodied/core/timer.py:28-31).  The work happens in engine.Engine on
+hand-written sm_100a kernels; this file is host plumbing only (config ->
+Spec, pinned staging, CUDA-graph capture/replay, metric read-back).
+"""
+import re
+import threading
+import queue as queuelib
+
+import numpy as np
+import torch
+
+from . import configs as _configs
+from . import engine as _engine
+from .backend import CudaBackend
+
+
+def _get(cfg, path):
+  node = cfg
+  for part in path.split('.'):
+    node = node[part] if isinstance(node, dict) or hasattr(node, '__getitem__') else getattr(node, part)
+  return node
+
+
+def _space_shape(space):
+  return tuple(getattr(space, 'shape', space))
+
+
+def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
+  """Resolve an embodied.Config (or nested dict) + spaces into engine.Spec,
+  rejecting loudly every setting whose kernels are not built."""
+  g = lambda p: _get(config, p)
+  act = act_space['action'] if isinstance(act_space, dict) else act_space
+  if getattr(act, 'discrete', False):
+    raise NotImplementedError('discrete (one-hot, reinforce) actor is not built yet')
+  if g('task_behavior') != 'Greedy' or g('expl_behavior') != 'None':
+    raise NotImplementedError('only task_behavior=Greedy, expl_behavior=None are built')
+  if g('critic_type') != 'vfunction':
+    raise NotImplementedError('only critic_type=vfunction is built')
+  checks = {
+      'rssm.act': 'elu', 'rssm.norm': 'layer', 'rssm.initial': 'learned2',
+      'rssm.post_layers': 1, 'rssm.gru_layers': 1, 'encoder.act': 'elu',
+      'encoder.norm': 'layer', 'reward_head.dist': 'symlog', 'cont_head.dist': 'binary',
+      'critic.dist': 'symlog', 'actor_dist_cont': 'normal', 'actor_grad_cont': 'backprop',
+      'actor_return': 'gve', 'critic_return': 'gve', 'slow_target': True,
+      'slow_target_fraction': 1.0, 'advnorm.impl': 'mean_std', 'retnorm.impl': 'off',
+      'scorenorm.impl': 'off', 'wmkl.impl': 'mult', 'actent.impl': 'mult',
+      'transform_rewards': 'off', 'train_wm': True, 'actent_norm': True,
+  }
+  for key, want in checks.items():
+    if g(key) != want:
+      raise NotImplementedError(f'config {key}={g(key)!r} is not built (only {want!r})')
+  if not g('rssm.classes'):
+    raise NotImplementedError('continuous (Gaussian) latents are not built')
+  shapes = {k: _space_shape(v) for k, v in obs_space.items() if not k.startswith('log_')}
+
+  def vec_keys(pattern, excluded, ranks):
+    return {k: int(np.prod(s)) for k, s in shapes.items()
+            if k not in excluded and re.match(pattern, k) and len(s) in ranks}
+
+  def cnn_keys(pattern, excluded):
+    return [k for k, s in shapes.items()
+            if k not in excluded and re.match(pattern, k) and len(s) == 3]
+
+  enc_ex = ('is_first', 'is_last')
+  dec_ex = ('is_first', 'is_last', 'is_terminal', 'reward')
+  if cnn_keys(g('encoder.cnn_keys'), enc_ex) or cnn_keys(g('decoder.cnn_keys'), dec_ex):
+    raise NotImplementedError('image (CNN) encoder/decoder keys are not built yet: '
+                              'use proprio configs such as a1 / dmc_proprio')
+  enc = vec_keys(g('encoder.mlp_keys'), enc_ex, (0, 1))
+  dec = vec_keys(g('decoder.mlp_keys'), dec_ex, (1,))
+  if list(enc) != list(dec) or not enc:
+    raise NotImplementedError(f'encoder keys {list(enc)} must equal decoder keys {list(dec)}')
+  heads = [g(f'{h}.layers') for h in ('reward_head', 'cont_head', 'actor', 'critic')]
+  units = [g(f'{h}.units') for h in ('reward_head', 'cont_head', 'actor', 'critic')]
+  heads.append(g('decoder.mlp_layers'))
+  units.append(g('decoder.mlp_units'))
+  if len(set(heads)) != 1 or len(set(units)) != 1:
+    raise NotImplementedError('heads must share layers/units')
+  opts = [tuple(g(f'{o}.{k}') for k in ('lr', 'eps', 'clip', 'wd', 'warmup'))
+          for o in ('model_opt', 'actor_opt', 'critic_opt')]
+  if len(set(opts)) != 1 or opts[0][4]:
+    raise NotImplementedError('optimizers must share lr/eps/clip/wd and warmup=0')
+  return _engine.Spec(
+      obs_dims=enc, act_dim=int(np.prod(_space_shape(act))), discrete=False,
+      deter=int(g('rssm.deter')), units=int(g('rssm.units')), stoch=int(g('rssm.stoch')),
+      classes=int(g('rssm.classes')), prior_layers=int(g('rssm.prior_layers')),
+      rssm_unimix=float(g('rssm.unimix')), enc_layers=int(g('encoder.mlp_layers')),
+      enc_units=int(g('encoder.mlp_units')), head_layers=int(heads[0]),
+      head_units=int(units[0]), horizon=int(g('imag_horizon')), discount=float(g('discount')),
+      lam=float(g('return_lambda')), kl_balance=float(g('wmkl_balance')),
+      wmkl_target=float(g('wmkl.target')), wmkl_min=float(g('wmkl.min')),
+      wmkl_max=float(g('wmkl.max')), actent_target=float(g('actent.target')),
+      actent_min=float(g('actent.min')), actent_max=float(g('actent.max')),
+      ctrl_vel=float(g('wmkl.vel')), actor_minstd=float(g('actor.minstd')),
+      actor_maxstd=float(g('actor.maxstd')), actor_unimix=float(g('actor.unimix')),
+      lr=float(opts[0][0]), adam_eps=float(opts[0][1]), clip=float(opts[0][2]),
+      wd=float(opts[0][3]), slow_every=int(g('slow_target_update')),
+      advnorm_decay=float(g('advnorm.decay')), advnorm_max=float(g('advnorm.max')))
+
+
+class Batcher:
+  """zip() over `batch_size` replay generators with worker threads: the role of
+  embodied.Prefetch (embodied/core/prefetch.py:6-67) in Agent.dataset()."""
+
+  def __init__(self, generator, batch_size, workers=8, prefetch=4):
+    self._queues = [queuelib.Queue(prefetch) for _ in range(batch_size)]
+    self._running = True
+    for w in range(min(workers, batch_size)):
+      qs = self._queues[w::workers]
+      threading.Thread(target=self._fill, args=(generator, qs), daemon=True).start()
+
+  def _fill(self, generator, queues):
+    try:
+      its = [generator() for _ in queues]
+      while self._running:
+        for it, q in zip(its, queues):
+          q.put(next(it))
+    except Exception as e:      # surface worker errors to the consumer
+      queues[0].put(e)
+      raise
+
+  def __iter__(self):
+    return self
+
+  def __next__(self):
+    elems = [q.get() for q in self._queues]
+    for e in elems:
+      if isinstance(e, Exception):
+        raise e
+    return {k: np.stack([e[k] for e in elems], 0) for k in elems[0]}
+
+
+class Agent:
+
+  configs = _configs.CONFIGS
+
+  def __init__(self, obs_space, act_space, step, config, seed=None):
+    self.config = config
+    self.obs_space = obs_space
+    self.act_space = act_space['action'] if isinstance(act_space, dict) else act_space
+    self.step = step
+    self.spec = spec_from_config(config, obs_space, act_space)
+    self.be = CudaBackend()                     # raises without GPU / .so
+    self.seed = int(_get(config, 'seed')) if seed is None else int(seed)
+    self.world, self.rank, self._allreduce = 1, 0, None
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+      self.world = torch.distributed.get_world_size()
+      self.rank = torch.distributed.get_rank()
+      if self.world > 1:
+        self._allreduce = lambda t: torch.distributed.all_reduce(t)
+    self._engines = {}
+    self._main = None
+    self._policies = {}
+    self._graphs = {}
+    self._calls = {}
+    self.use_graph = True
+    self._init_params = _engine.init_params(self.spec, seed=self.seed + 1)
+    self.expl_noise = float(_get(config, 'expl_noise'))
+    self.eval_noise = float(_get(config, 'eval_noise'))
+
+  # -- engines ----------------------------------------------------------------
+  def _engine_for(self, B, L):
+    key = (B, L)
+    if key not in self._engines:
+      # every rank draws different noise but starts from identical weights
+      eng = _engine.Engine(self.spec, self.be, B, L, seed=self.seed * 1000003 + self.rank,
+                           world=self.world, allreduce=self._allreduce, share=self._main)
+      if self._main is None:
+        eng.load_params(self._init_params)
+        self._main = eng
+      self._engines[key] = eng
+      eng.h_stage = {
+          k: torch.zeros(B, L, d, pin_memory=True)
+          for k, d in (('obs', self.spec.obs_total), ('action', self.spec.act_dim),
+                       ('first', 1), ('reward', 1), ('cont', 1))}
+      eng.d_stage = {k: torch.zeros_like(v, device=self.be.device) for k, v in eng.h_stage.items()}
+    return self._engines[key]
+
+  def _main_engine(self):
+    if self._main is None:
+      B = int(_get(self.config, 'batch_size'))
+      L = int(_get(self.config, 'replay_chunk'))
+      self._engine_for(max(B // self.world, 1), L)
+    return self._main
+
+  def _stage(self, eng, data, state):
+    """numpy batch [B, L, ...] -> pinned host -> device -> time-major buffers."""
+    s = self.spec
+    B, L = eng.B, eng.L
+    h = eng.h_stage
+    off = 0
+    for k, d in s.obs_dims.items():
+      h['obs'][:, :, off:off + d] = torch.from_numpy(
+          np.asarray(data[k], np.float32).reshape(B, L, d))
+      off += d
+    h['action'].copy_(torch.from_numpy(np.asarray(data['action'], np.float32).reshape(B, L, -1)))
+    first = np.asarray(data['is_first'], np.float32).reshape(B, L, 1)
+    h['first'].copy_(torch.from_numpy(first))
+    h['reward'].copy_(torch.from_numpy(np.asarray(data['reward'], np.float32).reshape(B, L, 1)))
+    h['cont'].copy_(torch.from_numpy(
+        1.0 - np.asarray(data['is_terminal'], np.float32).reshape(B, L, 1)))
+    for k in h:
+      eng.d_stage[k].copy_(h[k], non_blocking=True)
+    if state is None:
+      eng.first0.fill_(1.0)
+    else:
+      eng.first0.copy_(torch.from_numpy(first[:, 0, 0].copy()), non_blocking=True)
+      if state['deter'].data_ptr() != eng.prev_deter.data_ptr():
+        eng.prev_deter.copy_(torch.as_tensor(state['deter']).to(self.be.device))
+        eng.prev_stoch.copy_(torch.as_tensor(state['stoch']).to(self.be.device).reshape(B, -1))
+
+  @staticmethod
+  def _unstage(eng):
+    be, d = eng.be, eng.d_stage
+    be.transpose01(d['obs'], eng.obs)
+    be.transpose01(d['action'], eng.action)
+    be.transpose01(d['first'], eng.first)
+    be.transpose01(d['reward'], eng.reward)
+    be.transpose01(d['cont'], eng.cont)
+
+  def _run(self, eng, name, fn):
+    """Eager on the first call of a launch sequence, CUDA-graph replay after."""
+    key = (id(eng), name)
+    n = self._calls.get(key, 0)
+    self._calls[key] = n + 1
+    if not self.use_graph or n == 0:
+      fn()
+      return
+    if key not in self._graphs:
+      torch.cuda.synchronize()
+      graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(graph):
+        fn()
+      self._graphs[key] = graph
+    self._graphs[key].replay()
+
+  # -- embodied.Agent surface -------------------------------------------------
+  def dataset(self, generator):
+    return Batcher(generator, int(_get(self.config, 'batch_size')))
+
+  def train(self, data, state=None):
+    B, L = np.asarray(data['is_first']).shape[:2]
+    eng = self._engine_for(B, L)
+    self._stage(eng, data, state)
+
+    def launch():
+      self._unstage(eng)
+      eng.launch_step()
+    self._run(eng, 'train', launch)
+    metrics = eng.read_metrics()
+    if not np.isfinite(metrics['model_loss']):
+      raise FloatingPointError('model_loss is not finite')       # A/tfutils.py:207
+    outs = {}
+    state = {'deter': eng.prev_deter, 'stoch': eng.prev_stoch}
+    return outs, state, metrics
+
+  def report(self, data):
+    B, L = np.asarray(data['is_first']).shape[:2]
+    eng = self._engine_for(B, L)
+    self._stage(eng, data, None)
+
+    def launch():
+      self._unstage(eng)
+      eng.launch_report()
+    self._run(eng, 'report', launch)
+    full = eng.read_metrics(report=True)
+    return {k: np.float32(v) for k, v in full.items()}
+
+  def policy(self, obs, state=None, mode='train'):
+    obs = {k: v for k, v in obs.items() if not k.startswith('log_')}
+    P = len(np.asarray(obs['is_first']))
+    main = self._main_engine()
+    if P not in self._policies:
+      self._policies[P] = _engine.PolicyEngine(main, P)
+    pol = self._policies[P]
+    s = self.spec
+    vec = np.concatenate(
+        [np.asarray(obs[k], np.float32).reshape(P, -1) for k in s.obs_dims], -1)
+    pol.obs.copy_(torch.from_numpy(vec))
+    first = np.asarray(obs['is_first'], np.float32).reshape(P)
+    if state is None:
+      first = np.ones(P, np.float32)
+      pol.prev_action.zero_()
+    else:
+      pol.prev_action.copy_(torch.from_numpy(np.asarray(state['action'], np.float32)))
+      if state['deter'].data_ptr() != pol.prev_deter.data_ptr():
+        pol.prev_deter.copy_(state['deter'])
+        pol.prev_stoch.copy_(state['stoch'])
+    pol.first.copy_(torch.from_numpy(first))
+    self._run(pol, 'policy', pol.launch)
+    noise = self.expl_noise
+    if mode == 'eval':
+      action = pol.mean.cpu().numpy()
+      noise = self.eval_noise
+    else:
+      action = pol.action.cpu().numpy()
+    if noise:                                                     # A/tfutils.py:85-93
+      action = np.clip(action + noise * np.random.standard_normal(action.shape), -1, 1)
+    action = action.astype(np.float32).reshape((P,) + tuple(self.act_space.shape))
+    state = {'deter': pol.prev_deter, 'stoch': pol.prev_stoch, 'action': action}
+    return {'action': action}, state
+
+  # -- checkpointing (embodied/core/checkpoint.py:20-24,41-60) ----------------
+  def save(self):
+    eng = self._main_engine()
+    self.be.sync()
+    data = {f'param/{k}': v for k, v in eng.get_params().items()}
+    for gname in ('model', 'actor', 'critic'):
+      g = eng.groups[gname]
+      for n, _ in g.order:
+        data[f'adam_m/{n}'] = g.view(g.m, n).cpu().numpy().copy()
+        data[f'adam_v/{n}'] = g.view(g.v, n).cpu().numpy().copy()
+    data['ctrl/counters'] = eng.counters.cpu().numpy().copy()
+    data['ctrl/wmkl_scale'] = eng.wmkl_scale.cpu().numpy().copy()
+    data['ctrl/actent_scale'] = eng.actent_scale.cpu().numpy().copy()
+    data['ctrl/norm_state'] = eng.norm_state.cpu().numpy().copy()
+    count = int(sum(v.size for k, v in data.items() if k.startswith('param/')))
+    print(f'Saving agent with {len(data)} tensors and {count} parameters.')
+    return data
+
+  def load(self, data):
+    eng = self._main_engine()
+    eng.load_params({k[len('param/'):]: v for k, v in data.items() if k.startswith('param/')})
+    dev = self.be.device
+    for gname in ('model', 'actor', 'critic'):
+      g = eng.groups[gname]
+      for n, _ in g.order:
+        g.view(g.m, n).copy_(torch.as_tensor(data[f'adam_m/{n}']).to(dev))
+        g.view(g.v, n).copy_(torch.as_tensor(data[f'adam_v/{n}']).to(dev))
+    eng.counters.copy_(torch.as_tensor(data['ctrl/counters']).to(dev))
+    eng.wmkl_scale.copy_(torch.as_tensor(data['ctrl/wmkl_scale']).to(dev))
+    eng.actent_scale.copy_(torch.as_tensor(data['ctrl/actent_scale']).to(dev))
+    eng.norm_state.copy_(torch.as_tensor(data['ctrl/norm_state']).to(dev))
+    self.be.sync()

@@ -1,0 +1,208 @@
+// fp32 GEMM for the learner's Linear layers and their gradients.
+//
+//   C[M,N] = op(A) op(B) (+ bias[N]) + beta*C          (beta in {0, 1})
+//
+// Replaces `x @ kernel (+ bias)` of Linear (reference nets.py:566-579) and the
+// matmul gradients TF autodiff derives from it (dX = dY W^T, dW = X^T dY).
+//
+// Why SIMT fp32 and not tcgen05 here: the parity bar is 1e-4 relative to the
+// reference's fp32 CPU path *through 64 recurrent steps with Gumbel-argmax
+// draws* (a flipped categorical index changes the whole trajectory), so operand
+// rounding to bf16/tf32 is not admissible on this path; see DESIGN.md
+// ("precision") for the 3xTF32 tcgen05 plan that keeps fp32 accuracy.
+//
+// Tiling: BMxBN output tile per CTA, BK-deep smem stages (double buffered,
+// register prefetch of the next stage), TMxTN register micro-tile per thread
+// laid out in 4-wide groups so smem reads are conflict-free LDS.128.
+// Three tile shapes: 128x128 (big batched layers), 64x64 (M~1024 rollout
+// layers: 128+ CTAs), 16x64 (the M=B observe-scan steps).  Weight-gradient
+// calls (beta=1) may split K across gridDim.z and reduce with atomics so that
+// a 512x512 output with K=16384 still fills the 148 SMs.
+#include "dd_common.cuh"
+
+namespace dd {
+
+template <int BM, int BN, int BK, int TM, int TN, bool TA, bool TB>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+            float* __restrict__ C, int ldc, int M, int N, int K, float beta,
+            const float* __restrict__ bias, int klen, int atomic) {
+  constexpr int TX = BN / TN, TY = BM / TM, NT = TX * TY;
+  constexpr int VM = TM < 4 ? TM : 4, GM = TM / VM;
+  constexpr int VN = TN < 4 ? TN : 4, GN = TN / VN;
+  constexpr int PAD = 4;
+  constexpr int LA = (BM * BK) / NT, LB = (BK * BN) / NT;
+  static_assert((BM * BK) % NT == 0 && (BK * BN) % NT == 0, "tile/threads");
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * klen;
+  const int kend = min(K, kbeg + klen);
+  const int ntiles = (kend - kbeg + BK - 1) / BK;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float ra[LA], rb[LB];
+
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int e = tid + i * NT;
+      int m, k;
+      if (TA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < kend)
+        v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      ra[i] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int e = tid + i * NT;
+      int n, k;
+      if (TB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < kend)
+        v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+      rb[i] = v;
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < LA; ++i) {
+      const int e = tid + i * NT;
+      int m, k;
+      if (TA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
+      As[buf][k][m] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < LB; ++i) {
+      const int e = tid + i * NT;
+      int n, k;
+      if (TB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
+      Bs[buf][k][n] = rb[i];
+    }
+  };
+
+  if (ntiles > 0) {
+    gload(kbeg);
+    sstore(0);
+  }
+  __syncthreads();
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) gload(kbeg + (t + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int g = 0; g < GM; ++g) {
+        const float* p = &As[buf][k][g * (BM / GM) + ty * VM];
+        if (VM == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(p);
+          a[g * VM + 0] = v.x; a[g * VM + 1] = v.y; a[g * VM + 2] = v.z; a[g * VM + 3] = v.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < VM; ++i) a[g * VM + i] = p[i];
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < GN; ++g) {
+        const float* p = &Bs[buf][k][g * (BN / GN) + tx * VN];
+        if (VN == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(p);
+          b[g * VN + 0] = v.x; b[g * VN + 1] = v.y; b[g * VN + 2] = v.z; b[g * VN + 3] = v.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < VN; ++j) b[g * VN + j] = p[j];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (t + 1 < ntiles) sstore(buf ^ 1);
+    __syncthreads();
+  }
+
+  const bool lead = (blockIdx.z == 0);
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + (i / VM) * (BM / GM) + ty * VM + (i % VM);
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + (j / VN) * (BN / GN) + tx * VN + (j % VN);
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias != nullptr && lead) v += bias[n];
+      float* c = &C[(size_t)m * ldc + n];
+      if (atomic) {
+        atomicAdd(c, v);
+      } else {
+        *c = (beta != 0.f) ? v + beta * (*c) : v;
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int BK, int TM, int TN>
+static int launch(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
+                  int ldc, int M, int N, int K, float beta, const float* bias, int splits,
+                  cudaStream_t st) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
+  int klen = (K + splits - 1) / splits;
+  klen = (klen + BK - 1) / BK * BK;
+  if (klen < BK) klen = BK;
+  const int atomic = splits > 1 ? 1 : 0;
+#define DD_GO(TA_, TB_)                                                                   \
+  gemm_kernel<BM, BN, BK, TM, TN, TA_, TB_><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, \
+                                                                K, beta, bias, klen, atomic)
+  if (!ta && !tb) DD_GO(false, false);
+  else if (ta && !tb) DD_GO(true, false);
+  else if (!ta && tb) DD_GO(false, true);
+  else DD_GO(true, true);
+#undef DD_GO
+  return launched("dd_gemm");
+}
+
+}  // namespace dd
+
+extern "C" int dd_gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
+                       int ldc, int M, int N, int K, float beta, const float* bias,
+                       dd_stream_t stream) {
+  using namespace dd;
+  if (M <= 0 || N <= 0) return 0;
+  if (K < 0 || (beta != 0.f && beta != 1.f)) return fail("dd_gemm", "bad K or beta");
+  cudaStream_t st = S(stream);
+  const int kNumSm = 148;
+  auto ctas = [&](int bm, int bn) { return ((M + bm - 1) / bm) * ((N + bn - 1) / bn); };
+  auto pick_splits = [&](int c, int bk) {
+    if (beta != 1.f || bias != nullptr || c >= kNumSm) return 1;
+    int s = (2 * kNumSm + c - 1) / c;
+    const int maxs = K / (bk * 8) > 1 ? K / (bk * 8) : 1;
+    if (s > maxs) s = maxs;
+    if (s > 64) s = 64;
+    return s < 1 ? 1 : s;
+  };
+  if (M <= 16) {
+    return launch<16, 64, 16, 1, 4>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias,
+                                    pick_splits(ctas(16, 64), 16), st);
+  }
+  if (ctas(128, 128) >= 2 * kNumSm) {
+    return launch<128, 128, 16, 8, 8>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias, 1, st);
+  }
+  return launch<64, 64, 16, 4, 4>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias,
+                                  pick_splits(ctas(64, 64), 16), st);
+}

@@ -1,0 +1,522 @@
+// Row-wise fused operators of the RSSM cell: LayerNorm(+elu) forward/backward,
+// GRU gates, the categorical latent (unimix softmax, Gumbel-argmax draw,
+// straight-through backward), KL balance, and the is_first masking of the
+// observe scan.  Reference: embodied/agents/dreamerv2plus/nets.py:99-183,
+// :585-602; tfutils.py:359-387.  All HBM-bound: one pass over the row, fp32.
+#include "dd_common.cuh"
+
+namespace dd {
+
+// ---------------------------------------------------------------------------
+// LayerNorm + optional elu.  One CTA per row; the row is staged in shared
+// memory so the mean / centred variance / normalise passes touch HBM once.
+// ---------------------------------------------------------------------------
+__global__ void ln_fwd_kernel(const float* __restrict__ Z, int ldz,
+                              const float* __restrict__ scale,
+                              const float* __restrict__ bias, float* __restrict__ H, int ldh,
+                              float* __restrict__ stats, int M, int N, int act) {
+  extern __shared__ float row[];
+  __shared__ float red[33];
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    const float* z = Z + (size_t)m * ldz;
+    float s = 0.f;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      const float v = z[j];
+      row[j] = v;
+      s += v;
+    }
+    const float mean = block_sum(s, red) / N;
+    float q = 0.f;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      const float d = row[j] - mean;
+      q += d * d;
+    }
+    const float var = block_sum(q, red) / N;
+    const float rstd = rsqrtf(var + DD_LN_EPS);
+    float* h = H + (size_t)m * ldh;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      float y = (row[j] - mean) * rstd * scale[j] + bias[j];
+      if (act) y = y > 0.f ? y : expm1f(y);
+      h[j] = y;
+    }
+    if (threadIdx.x == 0) {
+      stats[2 * m] = mean;
+      stats[2 * m + 1] = rstd;
+    }
+    __syncthreads();
+  }
+}
+
+// Backward.  Each CTA walks a strided set of rows, keeps the per-column
+// dscale/dbias partial sums in registers and issues one atomicAdd per column at
+// the end (M/gridDim-fold fewer atomics than per-row).
+template <int PER, int BLK>
+__global__ void __launch_bounds__(BLK) ln_bwd_kernel(const float* __restrict__ dH, int lddh,
+                              const float* __restrict__ Z, int ldz,
+                              const float* __restrict__ stats,
+                              const float* __restrict__ scale,
+                              const float* __restrict__ bias, float* __restrict__ dZ,
+                              int lddz, float* __restrict__ dscale,
+                              float* __restrict__ dbias, int M, int N, int act) {
+  __shared__ float red[33];
+  float gs[PER], gb[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) gs[i] = gb[i] = 0.f;
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    const float mean = stats[2 * m], rstd = stats[2 * m + 1];
+    const float* z = Z + (size_t)m * ldz;
+    const float* dh = dH + (size_t)m * lddh;
+    float xh[PER], dx[PER];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int j = threadIdx.x + i * blockDim.x;
+      xh[i] = 0.f;
+      dx[i] = 0.f;
+      if (j < N) {
+        const float x = (z[j] - mean) * rstd;
+        const float sc = scale[j];
+        float dy = dh[j];
+        if (act) {
+          const float y = x * sc + bias[j];
+          if (y <= 0.f) dy *= expf(y);
+        }
+        gs[i] += dy * x;
+        gb[i] += dy;
+        xh[i] = x;
+        dx[i] = dy * sc;
+        s1 += dx[i];
+        s2 += dx[i] * x;
+      }
+    }
+    const float m1 = block_sum(s1, red) / N;
+    const float m2 = block_sum(s2, red) / N;
+    float* dz = dZ + (size_t)m * lddz;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int j = threadIdx.x + i * blockDim.x;
+      if (j < N) dz[j] = rstd * (dx[i] - m1 - xh[i] * m2);
+    }
+  }
+  if (dscale != nullptr) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int j = threadIdx.x + i * blockDim.x;
+      if (j < N) {
+        atomicAdd(&dscale[j], gs[i]);
+        atomicAdd(&dbias[j], gb[i]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// GRU gates (nets.py:155-160)
+// ---------------------------------------------------------------------------
+__global__ void gru_fwd_kernel(const float* __restrict__ Y, int ldy,
+                               const float* __restrict__ prev, int ldp,
+                               float* __restrict__ out, int ldo, int M, int D) {
+  const int64_t n = (int64_t)M * D;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int m = e / D, j = e % D;
+    const float* y = Y + (size_t)m * ldy;
+    const float r = sigmoidf_(y[j]);
+    const float c = tanhf(r * y[D + j]);
+    const float u = sigmoidf_(y[2 * D + j] - 1.f);
+    out[(size_t)m * ldo + j] = u * c + (1.f - u) * prev[(size_t)m * ldp + j];
+  }
+}
+
+__global__ void gru_bwd_kernel(const float* __restrict__ dOut, int lddo,
+                               const float* __restrict__ Y, int ldy,
+                               const float* __restrict__ prev, int ldp,
+                               float* __restrict__ dY, int lddy, float* __restrict__ dPrev,
+                               int lddp, int M, int D, int acc) {
+  const int64_t n = (int64_t)M * D;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int m = e / D, j = e % D;
+    const float* y = Y + (size_t)m * ldy;
+    const float yc = y[D + j];
+    const float r = sigmoidf_(y[j]);
+    const float c = tanhf(r * yc);
+    const float u = sigmoidf_(y[2 * D + j] - 1.f);
+    const float p = prev[(size_t)m * ldp + j];
+    const float g = dOut[(size_t)m * lddo + j];
+    const float dpre = g * u * (1.f - c * c);
+    float* dy = dY + (size_t)m * lddy;
+    dy[j] = dpre * yc * r * (1.f - r);
+    dy[D + j] = dpre * r;
+    dy[2 * D + j] = g * (c - p) * u * (1.f - u);
+    float* dp = &dPrev[(size_t)m * lddp + j];
+    const float v = g * (1.f - u);
+    *dp = acc ? *dp + v : v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Categorical latent.  One warp per (row, group); C <= 64 classes.
+// ---------------------------------------------------------------------------
+__global__ void stats_fwd_kernel(const float* __restrict__ Z, int ldz,
+                                 const float* __restrict__ G, int ldg,
+                                 float* __restrict__ logit, int ldl,
+                                 float* __restrict__ stoch, int lds,
+                                 int32_t* __restrict__ idx, int M, int S, int C, float mix,
+                                 int mode) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int64_t ngroups = (int64_t)M * S;
+  for (int64_t gidx = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); gidx < ngroups;
+       gidx += (int64_t)gridDim.x * wpb) {
+    const int m = gidx / S, s = gidx % S;
+    const float* z = Z + (size_t)m * ldz + s * C;
+    const int c0 = lane, c1 = lane + 32;
+    const float z0 = c0 < C ? z[c0] : -INFINITY;
+    const float z1 = c1 < C ? z[c1] : -INFINITY;
+    const float mx = warp_max(fmaxf(z0, z1));
+    const float e0 = c0 < C ? expf(z0 - mx) : 0.f;
+    const float e1 = c1 < C ? expf(z1 - mx) : 0.f;
+    const float inv = 1.f / warp_sum(e0 + e1);
+    const float u = mix / C;
+    const float l0 = logf((1.f - mix) * e0 * inv + u);
+    const float l1 = logf((1.f - mix) * e1 * inv + u);
+    float* lg = logit + (size_t)m * ldl + s * C;
+    if (c0 < C) lg[c0] = l0;
+    if (c1 < C) lg[c1] = l1;
+    if (mode == 2) continue;
+    float k0 = l0, k1 = l1;
+    if (mode == 0) {
+      const float* g = G + (size_t)m * ldg + s * C;
+      if (c0 < C) k0 += g[c0];
+      if (c1 < C) k1 += g[c1];
+    }
+    // argmax with first-index tie break (torch.argmax / tf.argmax semantics)
+    float bv = c0 < C ? k0 : -INFINITY;
+    int bi = c0 < C ? c0 : 0x7fffffff;
+    if (c1 < C && k1 > bv) { bv = k1; bi = c1; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    float* st = stoch + (size_t)m * lds + s * C;
+    if (c0 < C) st[c0] = (c0 == bi) ? 1.f : 0.f;
+    if (c1 < C) st[c1] = (c1 == bi) ? 1.f : 0.f;
+    if (idx != nullptr && lane == 0) idx[(size_t)m * S + s] = bi;
+  }
+}
+
+__global__ void stats_bwd_kernel(const float* __restrict__ dStoch, int ldds,
+                                 const float* __restrict__ dLogit, int lddl,
+                                 const float* __restrict__ logit, int ldl,
+                                 float* __restrict__ dZ, int lddz, int M, int S, int C,
+                                 float mix) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int64_t ngroups = (int64_t)M * S;
+  const float u = mix / C;
+  for (int64_t gidx = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); gidx < ngroups;
+       gidx += (int64_t)gridDim.x * wpb) {
+    const int m = gidx / S, s = gidx % S;
+    const float* lg = logit + (size_t)m * ldl + s * C;
+    float q[2], dl[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = lane + 32 * i;
+      q[i] = c < C ? expf(lg[c]) : 0.f;
+      dl[i] = 0.f;
+    }
+    if (dStoch != nullptr) {
+      const float* ds = dStoch + (size_t)m * ldds + s * C;
+      float d[2], dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = lane + 32 * i;
+        d[i] = c < C ? ds[c] : 0.f;
+        dot += q[i] * d[i];
+      }
+      dot = warp_sum(dot);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) dl[i] = q[i] * (d[i] - dot);
+    }
+    if (dLogit != nullptr) {
+      const float* d = dLogit + (size_t)m * lddl + s * C;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) dl[i] += d[c];
+      }
+    }
+    float p[2], dp[2], dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = lane + 32 * i;
+      p[i] = c < C ? (q[i] - u) / (1.f - mix) : 0.f;
+      dp[i] = c < C ? (1.f - mix) * dl[i] / q[i] : 0.f;
+      dot += p[i] * dp[i];
+    }
+    dot = warp_sum(dot);
+    float* dz = dZ + (size_t)m * lddz + s * C;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) dz[c] = p[i] * (dp[i] - dot);
+    }
+  }
+}
+
+// log_softmax of one group held two-per-lane
+__device__ __forceinline__ void group_lsm(const float* x, int C, int lane, float out[2]) {
+  float v[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < C ? x[c] : -INFINITY;
+  }
+  const float mx = warp_max(fmaxf(v[0], v[1]));
+  float e = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) e += (lane + 32 * i) < C ? expf(v[i] - mx) : 0.f;
+  const float lse = mx + logf(warp_sum(e));
+#pragma unroll
+  for (int i = 0; i < 2; ++i) out[i] = v[i] - lse;
+}
+
+// One CTA per row: warps stride over the S groups, then a block reduction.
+__global__ void kl_fwd_kernel(const float* __restrict__ post, int ldp,
+                              const float* __restrict__ prior, int ldq, int M, int S, int C,
+                              float* __restrict__ kl_row, float* __restrict__ ent_post,
+                              float* __restrict__ ent_prior) {
+  __shared__ float red[33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    float kl = 0.f, ea = 0.f, eb = 0.f;
+    for (int s = warp; s < S; s += nw) {
+      float a[2], b[2];
+      group_lsm(post + (size_t)m * ldp + s * C, C, lane, a);
+      group_lsm(prior + (size_t)m * ldq + s * C, C, lane, b);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (lane + 32 * i < C) {
+          const float pa = expf(a[i]), pb = expf(b[i]);
+          kl += pa * (a[i] - b[i]);
+          ea -= pa * a[i];
+          eb -= pb * b[i];
+        }
+      }
+    }
+    kl = block_sum(kl, red);
+    ea = block_sum(ea, red);
+    eb = block_sum(eb, red);
+    if (threadIdx.x == 0) {
+      kl_row[m] = kl;
+      ent_post[m] = ea;
+      ent_prior[m] = eb;
+    }
+  }
+}
+
+__global__ void kl_bwd_kernel(const float* __restrict__ post, int ldp,
+                              const float* __restrict__ prior, int ldq, int M, int S, int C,
+                              float bal, float coef, const float* __restrict__ scale,
+                              float* __restrict__ dpost, int lddp, float* __restrict__ dprior,
+                              int lddq) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int64_t ngroups = (int64_t)M * S;
+  const float k = coef * scale[0];
+  for (int64_t gidx = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); gidx < ngroups;
+       gidx += (int64_t)gridDim.x * wpb) {
+    const int m = gidx / S, s = gidx % S;
+    float a[2], b[2], pa[2], pb[2];
+    group_lsm(post + (size_t)m * ldp + s * C, C, lane, a);
+    group_lsm(prior + (size_t)m * ldq + s * C, C, lane, b);
+    float kl = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool ok = lane + 32 * i < C;
+      pa[i] = ok ? expf(a[i]) : 0.f;
+      pb[i] = ok ? expf(b[i]) : 0.f;
+      if (ok) kl += pa[i] * (a[i] - b[i]);
+    }
+    kl = warp_sum(kl);
+    float* dp = dpost + (size_t)m * lddp + s * C;
+    float* dq = dprior + (size_t)m * lddq + s * C;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        dp[c] = k * (1.f - bal) * pa[i] * ((a[i] - b[i]) - kl);
+        dq[c] = k * bal * (pb[i] - pa[i]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// is_first masking of the scan carry (nets.py:100-107)
+// ---------------------------------------------------------------------------
+__global__ void mask_fwd_kernel(const float* __restrict__ pd, int ldpd,
+                                const float* __restrict__ ps, int ldps,
+                                const float* __restrict__ act, int lda,
+                                const float* __restrict__ first,
+                                const float* __restrict__ init_d,
+                                const float* __restrict__ init_s, float* __restrict__ od,
+                                int ldod, float* __restrict__ os, int ldos,
+                                float* __restrict__ oa, int ldoa, int M, int D, int SC, int A) {
+  const int W = D + SC + A;
+  const int64_t n = (int64_t)M * W;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+       e += (int64_t)gridDim.x * blockDim.x) {
+    const int m = e / W;
+    int j = e % W;
+    const float f = first[m], k = 1.f - f;
+    if (j < D) {
+      od[(size_t)m * ldod + j] = pd[(size_t)m * ldpd + j] * k + init_d[j] * f;
+    } else if ((j -= D) < SC) {
+      os[(size_t)m * ldos + j] = ps[(size_t)m * ldps + j] * k + init_s[j] * f;
+    } else {
+      j -= SC;
+      oa[(size_t)m * ldoa + j] = act[(size_t)m * lda + j] * k;
+    }
+  }
+}
+
+__global__ void mask_bwd_kernel(const float* __restrict__ dd_, int lddd,
+                                const float* __restrict__ ds, int ldds,
+                                const float* __restrict__ first, float* __restrict__ dpd,
+                                int lddpd, float* __restrict__ dps, int lddps,
+                                float* __restrict__ dinit, int M, int D, int SC) {
+  const int W = D + SC;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < W; j += gridDim.x * blockDim.x) {
+    if (j < D) {
+      float acc = 0.f;
+      for (int m = 0; m < M; ++m) {
+        const float f = first[m];
+        const float g = dd_[(size_t)m * lddd + j];
+        acc += g * f;
+        if (dpd != nullptr) dpd[(size_t)m * lddpd + j] += g * (1.f - f);
+      }
+      dinit[j] += acc;
+    } else if (dps != nullptr) {
+      const int c = j - D;
+      for (int m = 0; m < M; ++m)
+        dps[(size_t)m * lddps + c] += ds[(size_t)m * ldds + c] * (1.f - first[m]);
+    }
+  }
+}
+
+}  // namespace dd
+
+using namespace dd;
+
+extern "C" int dd_ln_fwd(const float* Z, int ldz, const float* scale, const float* bias, float* H,
+                         int ldh, float* stats, int M, int N, int act, dd_stream_t stream) {
+  if (M <= 0) return 0;
+  if (N > 12000) return fail("dd_ln_fwd", "row too wide for shared-memory staging");
+  const int block = N >= 2048 ? 512 : (N >= 256 ? 128 : 64);
+  ln_fwd_kernel<<<min(M, 148 * 32), block, N * sizeof(float), S(stream)>>>(
+      Z, ldz, scale, bias, H, ldh, stats, M, N, act);
+  return launched("dd_ln_fwd");
+}
+
+extern "C" int dd_ln_bwd(const float* dH, int lddh, const float* Z, int ldz, const float* stats,
+                         const float* scale, const float* bias, float* dZ, int lddz, float* dscale,
+                         float* dbias, int M, int N, int act, dd_stream_t stream) {
+  if (M <= 0) return 0;
+  const int grid = min(M, 148 * 8);
+#define DD_LNB(PER, BLK)                                                                      \
+  ln_bwd_kernel<PER, BLK><<<grid, BLK, 0, S(stream)>>>(dH, lddh, Z, ldz, stats, scale, bias, dZ, \
+                                                  lddz, dscale, dbias, M, N, act)
+  if (N <= 128) DD_LNB(1, 128);
+  else if (N <= 512) DD_LNB(4, 128);
+  else if (N <= 2048) DD_LNB(8, 256);
+  else if (N <= 8192) DD_LNB(8, 1024);
+  else return fail("dd_ln_bwd", "N > 8192 unsupported");
+#undef DD_LNB
+  return launched("dd_ln_bwd");
+}
+
+extern "C" int dd_gru_fwd(const float* Y, int ldy, const float* prev, int ldp, float* out, int ldo,
+                          int M, int D, dd_stream_t stream) {
+  if (M <= 0) return 0;
+  gru_fwd_kernel<<<grid_for((int64_t)M * D, 256), 256, 0, S(stream)>>>(Y, ldy, prev, ldp, out,
+                                                                       ldo, M, D);
+  return launched("dd_gru_fwd");
+}
+
+extern "C" int dd_gru_bwd(const float* dOut, int lddo, const float* Y, int ldy, const float* prev,
+                          int ldp, float* dY, int lddy, float* dPrev, int lddp, int M, int D,
+                          int acc_prev, dd_stream_t stream) {
+  if (M <= 0) return 0;
+  gru_bwd_kernel<<<grid_for((int64_t)M * D, 256), 256, 0, S(stream)>>>(
+      dOut, lddo, Y, ldy, prev, ldp, dY, lddy, dPrev, lddp, M, D, acc_prev);
+  return launched("dd_gru_bwd");
+}
+
+extern "C" int dd_stats_fwd(const float* Z, int ldz, const float* G, int ldg, float* logit,
+                            int ldl, float* stoch, int lds, int32_t* idx, int M, int S_, int C,
+                            float mix, int mode, dd_stream_t stream) {
+  if (M <= 0) return 0;
+  if (C > 64) return fail("dd_stats_fwd", "classes > 64 unsupported");
+  if (mode == 0 && G == nullptr) return fail("dd_stats_fwd", "mode 0 needs noise");
+  if (mode != 2 && stoch == nullptr) return fail("dd_stats_fwd", "stoch output missing");
+  const int64_t groups = (int64_t)M * S_;
+  stats_fwd_kernel<<<grid_for(groups, 8), 256, 0, S(stream)>>>(Z, ldz, G, ldg, logit, ldl, stoch,
+                                                               lds, idx, M, S_, C, mix, mode);
+  return launched("dd_stats_fwd");
+}
+
+extern "C" int dd_stats_bwd(const float* dStoch, int ldds, const float* dLogit, int lddl,
+                            const float* logit, int ldl, float* dZ, int lddz, int M, int S_, int C,
+                            float mix, dd_stream_t stream) {
+  if (M <= 0) return 0;
+  if (C > 64) return fail("dd_stats_bwd", "classes > 64 unsupported");
+  const int64_t groups = (int64_t)M * S_;
+  stats_bwd_kernel<<<grid_for(groups, 8), 256, 0, S(stream)>>>(dStoch, ldds, dLogit, lddl, logit,
+                                                               ldl, dZ, lddz, M, S_, C, mix);
+  return launched("dd_stats_bwd");
+}
+
+extern "C" int dd_kl_fwd(const float* post, int ldp, const float* prior, int ldq, int M, int S_,
+                         int C, float* kl_row, float* ent_post, float* ent_prior,
+                         dd_stream_t stream) {
+  if (M <= 0) return 0;
+  if (C > 64) return fail("dd_kl_fwd", "classes > 64 unsupported");
+  kl_fwd_kernel<<<min(M, 148 * 16), 256, 0, S(stream)>>>(post, ldp, prior, ldq, M, S_, C, kl_row,
+                                                         ent_post, ent_prior);
+  return launched("dd_kl_fwd");
+}
+
+extern "C" int dd_kl_bwd(const float* post, int ldp, const float* prior, int ldq, int M, int S_,
+                         int C, float bal, float coef, const float* scale, float* dpost, int lddp,
+                         float* dprior, int lddq, dd_stream_t stream) {
+  if (M <= 0) return 0;
+  if (C > 64) return fail("dd_kl_bwd", "classes > 64 unsupported");
+  const int64_t groups = (int64_t)M * S_;
+  kl_bwd_kernel<<<grid_for(groups, 8), 256, 0, S(stream)>>>(post, ldp, prior, ldq, M, S_, C, bal,
+                                                            coef, scale, dpost, lddp, dprior, lddq);
+  return launched("dd_kl_bwd");
+}
+
+extern "C" int dd_mask_fwd(const float* pd, int ldpd, const float* ps, int ldps, const float* act,
+                           int lda, const float* first, const float* init_d, const float* init_s,
+                           float* od, int ldod, float* os, int ldos, float* oa, int ldoa, int M,
+                           int D, int SC, int A, dd_stream_t stream) {
+  if (M <= 0) return 0;
+  mask_fwd_kernel<<<grid_for((int64_t)M * (D + SC + A), 256), 256, 0, S(stream)>>>(
+      pd, ldpd, ps, ldps, act, lda, first, init_d, init_s, od, ldod, os, ldos, oa, ldoa, M, D, SC,
+      A);
+  return launched("dd_mask_fwd");
+}
+
+extern "C" int dd_mask_bwd(const float* dd_, int lddd, const float* ds, int ldds,
+                           const float* first, float* dpd, int lddpd, float* dps, int lddps,
+                           float* dinit, int M, int D, int SC, dd_stream_t stream) {
+  if (M <= 0) return 0;
+  mask_bwd_kernel<<<grid_for(D + SC, 128), 128, 0, S(stream)>>>(dd_, lddd, ds, ldds, first, dpd,
+                                                                lddpd, dps, lddps, dinit, M, D, SC);
+  return launched("dd_mask_bwd");
+}

@@ -271,7 +271,7 @@ STREAM_OBS, STREAM_IMG, STREAM_ACT = 1, 2, 3
 class Engine:
 
   def __init__(self, spec: Spec, be, B: int, L: int, seed: int = 0,
-               world: int = 1, allreduce=None):
+               world: int = 1, allreduce=None, share: 'Engine' = None):
     assert not spec.discrete, 'discrete (one-hot) actor is not built yet'
     self.spec, self.be = spec, be
     self.B, self.L, self.N, self.H = B, L, B * L, spec.horizon
@@ -282,20 +282,25 @@ class Engine:
     D, U, SC, A, E = s.deter, s.units, s.sc, s.act_dim, s.enc_units
     z = be.zeros
     shapes = param_shapes(spec)
-    self.groups = {
-        g: ParamGroup(be, [(n, sh) for n, sh in shapes.items() if n.startswith(pre)],
-                      opt=(g != 'slow_critic'))
-        for g, pre in GROUP_PREFIXES.items()}
+    if share is not None:
+      # a second shape (e.g. report() on another batch) on the same learner state
+      self.groups = share.groups
+      self.counters, self.wmkl_scale = share.counters, share.wmkl_scale
+      self.actent_scale, self.norm_state = share.actent_scale, share.norm_state
+    else:
+      self.groups = {
+          g: ParamGroup(be, [(n, sh) for n, sh in shapes.items() if n.startswith(pre)],
+                        opt=(g != 'slow_critic'))
+          for g, pre in GROUP_PREFIXES.items()}
+      # controllers / counters (device-resident so the step is one static graph)
+      self.counters = z(8, dtype=torch.int64)
+      self.wmkl_scale = z(1)
+      self.actent_scale = z(A)
+      self.norm_state = z(3, 3, dtype=torch.float64)     # adv / ret / score
+      self.reset_state()
     gm = self.groups['model']
-
-    # controllers / counters (device-resident so the step is one static graph)
-    self.counters = z(8, dtype=torch.int64)
-    self.wmkl_scale = z(1)
-    self.actent_scale = z(A)
-    self.norm_state = z(3, 3, dtype=torch.float64)     # adv / ret / score
     self.adv = z(2)                                    # (mean, scale) transform
     self.scratch2 = z(2)
-    self.reset_state()
 
     # inputs (time-major)
     self.obs = z(N, s.obs_total)
@@ -418,8 +423,8 @@ class Engine:
     self.mnames = [
         'kl', 'ent_post', 'ent_prior', 'reward_loss', 'cont_loss', 'total_loss',
         *[f'loss_{k}' for k in s.obs_dims], 'bal_reward', 'bal_cont',
-        'imag_reward', 'imag_critic', 'imag_return', 'closs', 'score', 'ret_ctrl',
-        'score_ctrl', 'ent', 'aloss']
+        'imag_reward', 'imag_critic', 'imag_return', 'closs', 'score', 'adv_ctrl',
+        'ret_ctrl', 'score_ctrl', 'ent', 'aloss']
     self.mstat = z(len(self.mnames), 8, dtype=torch.float64)
     self.midx = {k: i for i, k in enumerate(self.mnames)}
 
@@ -585,17 +590,18 @@ class Engine:
   # ==========================================================================
   # 1b. world model: losses, backward, optimizer
   # ==========================================================================
-  def wm_losses(self):
+  def wm_losses(self, update=True):
     s, be = self.spec, self.be
     N = self.N
     coef = 1.0 / (N * self.world)
     be.kl_fwd(self.post_logit, self.prior_logit, s.stoch, s.classes, s.kl_balance,
               self.kl_row, self.ent_post, self.ent_prior)
-    be.colsum(self.kl_row.view(N, 1), self.kl_sum)
-    if self.allreduce and self.world > 1:
-      self.allreduce(self.kl_sum)
-    be.autoadapt(self.wmkl_scale, self.kl_sum, float(N * self.world), s.wmkl_target,
-                 s.wmkl_min, s.wmkl_max, s.ctrl_vel, s.ctrl_thres, False)
+    if update:      # AutoAdapt.update precedes the use of the scale (A/tfutils.py:441)
+      be.colsum(self.kl_row.view(N, 1), self.kl_sum)
+      if self.allreduce and self.world > 1:
+        self.allreduce(self.kl_sum)
+      be.autoadapt(self.wmkl_scale, self.kl_sum, float(N * self.world), s.wmkl_target,
+                   s.wmkl_min, s.wmkl_max, s.ctrl_vel, s.ctrl_thres, False)
     off = 0
     tot = self.loss_rows['total']
     be.fill_(tot, 0.0)
@@ -813,7 +819,7 @@ class Engine:
     self._stat(self.score, 'score')
     # Normalize EMAs: retnorm/scorenorm are impl 'off' (state only), advnorm used
     for i, (src, key, decay) in enumerate((
-        (self.score, 'score_ctrl', s.advnorm_decay), (self.r_ret, 'ret_ctrl', 0.999),
+        (self.score, 'adv_ctrl', s.advnorm_decay), (self.r_ret, 'ret_ctrl', 0.999),
         (self.score, 'score_ctrl', 0.99))):
       row = self.mstat[self.midx[key]]
       be.stats(src, row)
@@ -903,6 +909,7 @@ class Engine:
     device'.  Pure launch sequence: safe to capture into a CUDA graph."""
     if draw:
       self.draw_noise()
+    self.be.stats_init(self.mstat)
     self.wm_forward()
     self.wm_losses()
     self.wm_backward()
@@ -918,8 +925,17 @@ class Engine:
     self.critic_update()
     self.actor_update()
 
+  def launch_report(self, draw=True):
+    """WorldModel.report's scalar part (A/agent.py:266-268): the loss metrics of
+    a batch without touching parameters, controllers or the carried state."""
+    if draw:
+      self.draw_noise()
+    self.be.stats_init(self.mstat)
+    self.wm_forward()
+    self.wm_losses(update=False)
+
   # -- host side of the metrics --------------------------------------------
-  def read_metrics(self) -> Dict[str, float]:
+  def read_metrics(self, report=False) -> Dict[str, float]:
     s = self.spec
     ms = self.mstat.detach().cpu().numpy()
     cnt = self.counters.detach().cpu().numpy()
@@ -946,8 +962,10 @@ class Engine:
                 f'{k}_rate': b[0] / n, f'{k}_avg': b[6] / n, f'{k}_pred': b[7] / n})
     m.update(prior_ent_mean=mean('ent_prior'), post_ent_mean=mean('ent_post'),
              prior_ent_min=row('ent_prior')[2], post_ent_min=row('ent_post')[2],
-             model_loss_mean=mean('total_loss'), model_loss_std=std('total_loss'),
-             model_loss=mean('total_loss'),
+             model_loss_mean=mean('total_loss'), model_loss_std=std('total_loss'))
+    if report:
+      return m
+    m.update(model_loss=mean('total_loss'),
              model_grad_norm=math.sqrt(sq['model']) / w, model_grad_steps=int(cnt[C_MODEL]),
              extr_critic_loss=mean('closs'),
              extr_critic_grad_norm=math.sqrt(sq['critic']) / w,
@@ -962,3 +980,81 @@ class Engine:
              actor_loss=mean('aloss'),
              actor_grad_norm=math.sqrt(sq['actor']) / w, actor_grad_steps=int(cnt[C_ACTOR]))
     return m
+
+
+# ----------------------------------------------------------------------------
+# Acting path: one obs_step + actor per call (A/agent.py:42-65)
+# ----------------------------------------------------------------------------
+
+STREAM_POL_OBS, STREAM_POL_ACT, C_POLICY = 4, 5, 5
+
+
+class PolicyEngine:
+  """`Agent.policy`: encoder -> one RSSM.obs_step -> actor, for P parallel
+  environments, on the learner's live parameters (shares `eng.groups`)."""
+
+  def __init__(self, eng: Engine, P: int):
+    self.eng, self.be, self.spec, self.P = eng, eng.be, eng.spec, P
+    s, z = eng.spec, eng.be.zeros
+    D, U, SC, A, E = s.deter, s.units, s.sc, s.act_dim, s.enc_units
+    gm, ga = eng.groups['model'], eng.groups['actor']
+    self.obs = z(P, s.obs_total)
+    self.first = z(P)
+    self.prev_action = z(P, A)
+    self.prev_deter = z(P, D)
+    self.prev_stoch = z(P, SC)
+    self.enc = Trunk(eng, gm, 'enc', s.enc_layers, E, P)
+    self.init_deter = z(1, D)
+    self.init_trunk = Trunk(eng, gm, 'rssm/initp', s.prior_layers, U, 1)
+    self.init_zs, self.init_logit, self.init_stoch = z(1, SC), z(1, SC), z(1, SC)
+    self.m_deter, self.m_stoch, self.m_act = z(P, D), z(P, SC), z(P, A)
+    self.z_in, self.x_in, self.st_in = z(P, U), z(P, U), z(P, 2)
+    self.z_gru, self.y_gru, self.st_gru = z(P, 3 * D), z(P, 3 * D), z(P, 2)
+    self.feat = z(P, D + SC)
+    self.z_obs, self.h_obs, self.st_obs = z(P, U), z(P, U), z(P, 2)
+    self.zs, self.logit = z(P, SC), z(P, SC)
+    self.g, self.eps = z(P, SC), z(P, A)
+    self.actor = Trunk(eng, ga, 'actor', s.head_layers, s.head_units, P)
+    self.mraw, self.sraw = z(P, A), z(P, A)
+    self.action, self.mean, self.std = z(P, A), z(P, A), z(P, A)
+
+  def launch(self):
+    eng, be, s = self.eng, self.be, self.spec
+    gm, ga = eng.groups['model'], eng.groups['actor']
+    D, SC = s.deter, s.sc
+    P = self.P
+    be.fill_gumbel(self.g, eng.seed, STREAM_POL_OBS, eng.counters, C_POLICY)
+    be.fill_normal(self.eps, eng.seed, STREAM_POL_ACT, eng.counters, C_POLICY)
+    be.counter_inc(eng.counters, C_POLICY)
+    embed = self.enc.fwd([(self.obs, 0)], 0, P)
+    be.tanh_fwd(gm.P('rssm/initial_deter').view(1, D), self.init_deter)
+    eng._prior_stats_fwd(self.init_trunk, 0, 1, self.init_deter, self.init_zs, None,
+                         self.init_logit, self.init_stoch, None, 1)
+    be.mask_fwd(self.prev_deter, self.prev_stoch, self.prev_action, self.first,
+                self.init_deter[0], self.init_stoch[0], self.m_deter, self.m_stoch, self.m_act)
+    Win, Wgru, Wobs = (gm.P('rssm/img_in/kernel'), gm.P('rssm/gru_out/kernel'),
+                       gm.P('rssm/obs_out/kernel'))
+    be.gemm(self.m_stoch, Win[:SC], self.z_in)
+    be.gemm(self.m_act, Win[SC:], self.z_in, beta=1.0)
+    be.ln_fwd(self.z_in, gm.P('rssm/img_in/norm/scale'), gm.P('rssm/img_in/norm/bias'),
+              self.x_in, self.st_in, 1)
+    be.gemm(self.m_deter, Wgru[:D], self.z_gru)
+    be.gemm(self.x_in, Wgru[D:], self.z_gru, beta=1.0)
+    be.ln_fwd(self.z_gru, gm.P('rssm/gru_out/norm/scale'), gm.P('rssm/gru_out/norm/bias'),
+              self.y_gru, self.st_gru, 0)
+    be.gru_fwd(self.y_gru, self.m_deter, self.feat[:, :D])
+    be.gemm(self.feat[:, :D], Wobs[:D], self.z_obs)
+    be.gemm(embed, Wobs[D:], self.z_obs, beta=1.0)
+    be.ln_fwd(self.z_obs, gm.P('rssm/obs_out/norm/scale'), gm.P('rssm/obs_out/norm/bias'),
+              self.h_obs, self.st_obs, 1)
+    eng._out_fwd(gm, 'rssm/obs_stats', self.h_obs, self.zs)
+    be.stats_fwd(self.zs, self.g, self.logit, self.feat[:, D:], None, s.stoch, s.classes,
+                 s.rssm_unimix, 0)
+    h = self.actor.fwd([(self.feat, 0)], 0, P)
+    eng._out_fwd(ga, 'actor/dist_out/out', h, self.mraw)
+    eng._out_fwd(ga, 'actor/dist_out/std', h, self.sraw)
+    be.actor_sample(self.mraw, self.sraw, self.eps, s.actor_minstd, s.actor_maxstd,
+                    self.action, self.mean, self.std)
+    # carry: latent and the action just taken
+    be.copy_(self.prev_deter, self.feat[:, :D])
+    be.copy_(self.prev_stoch, self.feat[:, D:])

@@ -1,0 +1,191 @@
+/* dd_kernels.h -- C-ABI of the B200 (sm_100a) kernel library behind the
+ * DreamerV2+ learner hot path.
+ *
+ * The reference (danijar/daydreamer) has no FFI on this path: its learner calls
+ * TensorFlow ops from Python (embodied/agents/dreamerv2plus/{agent,nets,tfutils}.py).
+ * This ABI is therefore the seam a maintainer would bind with ctypes from the
+ * reference-side Python; every entry point names the
+ * reference code whose arithmetic it replaces.  A/ = embodied/agents/dreamerv2plus.
+ *
+ * Conventions
+ *   - every pointer is a caller-owned DEVICE pointer (fp32 unless stated);
+ *     matrices are row-major with an explicit row stride `ld*` in elements;
+ *   - no allocation, no host synchronisation, no global state: each call only
+ *     enqueues kernels on `stream` (cudaStream_t passed as void*), so a whole
+ *     train step can be captured into one CUDA graph;
+ *   - return value 0 = enqueued, negative = rejected argument / launch error,
+ *     message via dd_last_error() (thread-local).
+ */
+#ifndef DD_KERNELS_H_
+#define DD_KERNELS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dd_stream_t;
+
+int dd_version(void);
+const char* dd_last_error(void);
+/* number of kernel launches enqueued by this library since process start */
+int64_t dd_launch_count(void);
+
+/* ---- dense ------------------------------------------------------------ */
+/* C[M,N] = op(A) op(B) (+ bias[N]) + beta*C ; op = transpose when t*=1.
+ * Replaces `x @ kernel (+ bias)` of Linear (A/nets.py:566-579) and the
+ * matmul gradients TF derives for it.  beta must be 0 or 1. */
+int dd_gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb,
+            float* C, int ldc, int M, int N, int K, float beta,
+            const float* bias, dd_stream_t stream);
+
+/* LayerNorm(eps 1e-3, population variance) + optional elu (A/nets.py:585-602,
+ * :580-581).  stats[M,2] = (mean, rstd).  act: 0 none, 1 elu. */
+int dd_ln_fwd(const float* Z, int ldz, const float* scale, const float* bias,
+              float* H, int ldh, float* stats, int M, int N, int act,
+              dd_stream_t stream);
+/* dZ from dH; dscale/dbias (+=) may be NULL to skip parameter gradients. */
+int dd_ln_bwd(const float* dH, int lddh, const float* Z, int ldz,
+              const float* stats, const float* scale, const float* bias,
+              float* dZ, int lddz, float* dscale, float* dbias, int M, int N,
+              int act, dd_stream_t stream);
+
+/* GRU gates on the post-LayerNorm 3D vector (A/nets.py:155-160):
+ * r=sig(y_r); c=tanh(r*y_c); u=sig(y_u-1); out=u*c+(1-u)*prev. */
+int dd_gru_fwd(const float* Y, int ldy, const float* prev, int ldp, float* out,
+               int ldo, int M, int D, dd_stream_t stream);
+int dd_gru_bwd(const float* dOut, int lddo, const float* Y, int ldy,
+               const float* prev, int ldp, float* dY, int lddy, float* dPrev,
+               int lddp, int M, int D, int acc_prev, dd_stream_t stream);
+
+/* ---- categorical latent ------------------------------------------------ */
+/* unimix logits log((1-mix) softmax(z) + mix/C) (A/nets.py:162-171) and the
+ * OneHotDist draw idx = argmax(logit + G) (A/tfutils.py:368-382).
+ * mode 0: sample with Gumbel noise G; 1: argmax (dist.mode, A/nets.py:147);
+ * 2: logits only.  idx (int32 [M,S]) may be NULL. */
+int dd_stats_fwd(const float* Z, int ldz, const float* G, int ldg, float* logit,
+                 int ldl, float* stoch, int lds, int32_t* idx, int M, int S,
+                 int C, float mix, int mode, dd_stream_t stream);
+/* straight-through gradient (dStoch, wrt probs) + direct logit gradient
+ * (dLogit), either may be NULL, pulled back to the raw linear output. */
+int dd_stats_bwd(const float* dStoch, int ldds, const float* dLogit, int lddl,
+                 const float* logit, int ldl, float* dZ, int lddz, int M, int S,
+                 int C, float mix, dd_stream_t stream);
+/* KL(post||prior) summed over S groups + entropies (A/nets.py:178-183,
+ * A/agent.py:198-201). */
+int dd_kl_fwd(const float* post, int ldp, const float* prior, int ldq, int M,
+              int S, int C, float* kl_row, float* ent_post, float* ent_prior,
+              dd_stream_t stream);
+/* gradients of coef*scale[0]*(bal*KL(sg(post)||prior)+(1-bal)*KL(post||sg(prior))) */
+int dd_kl_bwd(const float* post, int ldp, const float* prior, int ldq, int M,
+              int S, int C, float bal, float coef, const float* scale,
+              float* dpost, int lddp, float* dprior, int lddq,
+              dd_stream_t stream);
+
+/* ---- observe-scan masking (A/nets.py:100-107) ------------------------ */
+int dd_mask_fwd(const float* pd, int ldpd, const float* ps, int ldps,
+                const float* act, int lda, const float* first,
+                const float* init_d, const float* init_s, float* od, int ldod,
+                float* os, int ldos, float* oa, int ldoa, int M, int D, int SC,
+                int A, dd_stream_t stream);
+/* dpd/dps (+=) may be NULL (first step of a chunk); dinit[D] += sum_m dd*first */
+int dd_mask_bwd(const float* dd, int lddd, const float* ds, int ldds,
+                const float* first, float* dpd, int lddpd, float* dps,
+                int lddps, float* dinit, int M, int D, int SC,
+                dd_stream_t stream);
+
+/* ---- 2-D elementwise helpers ------------------------------------------ */
+int dd_add(float* dst, int ldd, const float* src, int lds, int rows, int cols,
+           dd_stream_t stream);                       /* dst += src */
+int dd_copy(float* dst, int ldd, const float* src, int lds, int rows, int cols,
+            dd_stream_t stream);
+int dd_fill(float* dst, int ldd, int rows, int cols, float value,
+            dd_stream_t stream);
+int dd_fill_f64(double* dst, int64_t n, double value, dd_stream_t stream);
+int dd_axpy(float* dst, int ldd, const float* src, int lds, int rows, int cols,
+            const float* scale, dd_stream_t stream);  /* dst += scale[0]*src */
+int dd_sub(float* dst, const float* a, const float* b, int64_t n,
+           dd_stream_t stream);
+int dd_symexp(const float* src, float* dst, int64_t n, dd_stream_t stream);
+int dd_transpose01(const float* src, float* dst, int A, int B, int F,
+                   dd_stream_t stream);               /* [A,B,F] -> [B,A,F] */
+int dd_colsum(const float* X, int ldx, int M, int N, float* out, int acc,
+              dd_stream_t stream);
+int dd_tanh_fwd(const float* x, float* y, int64_t n, dd_stream_t stream);
+int dd_tanh_bwd(const float* dy, const float* y, float* dx, int64_t n, int acc,
+                dd_stream_t stream);
+
+/* ---- losses ------------------------------------------------------------ */
+/* kind 0: MSEDist sum (A/tfutils.py:320-329); 1: SymlogDist (:347-356);
+ * 2: -Bernoulli(logits).log_prob (A/nets.py:469-471).  weight[M] may be NULL.
+ * loss_row[m] = w*loss ; dpred = coef*w*dloss/dpred. */
+int dd_head_loss(int kind, const float* pred, int ldp, const float* target,
+                 int ldt, const float* weight, float coef, float* loss_row,
+                 float* dpred, int lddp, int M, int dim, dd_stream_t stream);
+/* balance_stats sums (A/tfutils.py:395-411); out f64[8]. */
+int dd_balance(int kind, const float* pred, const float* loss_row,
+               const float* target, float thres, int M, double* out,
+               dd_stream_t stream);
+
+/* ---- imagination / actor-critic ---------------------------------------- */
+/* mean=tanh(m), std=(hi-lo)sigmoid(s)+lo, a=mean+std*eps (A/nets.py:461-468). */
+int dd_actor_sample(const float* mraw, const float* sraw, const float* eps,
+                    float lo, float hi, float* action, float* mean, float* std,
+                    int64_t n, dd_stream_t stream);
+/* normalised Normal entropy per action dim (A/agent.py:361-367). */
+int dd_actor_ent(const float* std, float lo, float hi, float* ent, int64_t n,
+                 dd_stream_t stream);
+/* per-row actor loss (A/agent.py:351-381, 'backprop'); adv = (mean, scale). */
+int dd_actor_loss(const float* ret, const float* value, const float* adv,
+                  const float* ent, const float* scale, const float* weight,
+                  float* out, int64_t M, int A, dd_stream_t stream);
+int dd_actor_bwd(const float* dA, const float* eps, const float* mean,
+                 const float* std, const float* weight, const float* scale,
+                 float coef, float lo, float hi, float* dmraw, float* dsraw,
+                 int64_t M, int A, dd_stream_t stream);
+/* lambda-return 'gve' + cont/weight (A/agent.py:256-259, :422-442). */
+int dd_lambda_fwd(const float* rho, const float* vraw, const float* kraw,
+                  const float* cont0, float gamma, float lam, float* reward,
+                  float* value, float* cont, float* weight, float* ret, int H,
+                  int N, dd_stream_t stream);
+int dd_lambda_bwd(const float* rho, const float* vraw, const float* value,
+                  const float* cont, const float* weight, const float* ret,
+                  const float* adv, float coef, float gamma, float lam,
+                  float* drho, float* dvraw, float* dkraw, int H, int N,
+                  dd_stream_t stream);
+
+/* ---- reductions, controllers, optimizer ------------------------------- */
+/* rows of 8 doubles: [sum, sumsq, min, max, abssum, absmax, n, 0] */
+int dd_stats_init(double* rows, int nrows, dd_stream_t stream);
+int dd_stats(const float* X, int ldx, int rows, int cols, double* out,
+             dd_stream_t stream);                    /* accumulates into out */
+/* AutoAdapt 'mult' (A/tfutils.py:460-474); avg = sums[k]/denom. */
+int dd_autoadapt(float* scale, const float* sums, int k, float denom,
+                 float target, float lo, float hi, float vel, float thres,
+                 int inverse, dd_stream_t stream);
+/* Normalize.update + transform constants (A/tfutils.py:502-517), float64. */
+int dd_normalize_update(double* state, const double* st, double decay,
+                        double maxv, float* out, dd_stream_t stream);
+int dd_sumsq(const float* g, int64_t n, double* out, dd_stream_t stream);
+/* counters[ci]+=1; clip by global norm; weight decay on [0,n_decay); Adam
+ * (A/tfutils.py:243-302). */
+int dd_adam(float* p, const float* g, float* m, float* v, int64_t n,
+            int64_t n_decay, float lr, double b1, double b2, float eps, float wd,
+            float clip, float gscale, const double* sumsq, int64_t* counters,
+            int ci, dd_stream_t stream);
+/* VFunction.update_slow hard copy (A/agent.py:444-454). */
+int dd_slow_sync(const float* src, float* dst, int64_t n, int64_t* counters,
+                 int ci, int every, dd_stream_t stream);
+int dd_counter_inc(int64_t* counters, int ci, dd_stream_t stream);
+
+/* ---- noise (Philox4x32-10; stream layout in oracle/philox.py) --------- */
+int dd_fill_gumbel(float* buf, int64_t n, uint64_t seed, uint32_t stream_id,
+                   const int64_t* counters, int ci, dd_stream_t stream);
+int dd_fill_normal(float* buf, int64_t n, uint64_t seed, uint32_t stream_id,
+                   const int64_t* counters, int ci, dd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DD_KERNELS_H_ */

@@ -280,13 +280,21 @@ class HostSim:
     dkraw[0] = 0.0
 
   # -- reductions / controllers --------------------------------------------
+  def stats_init(self, rows):
+    rows.copy_(torch.tensor([0.0, 0.0, float('inf'), float('-inf'), 0.0, 0.0, 0.0, 0.0],
+                            dtype=torch.float64).expand_as(rows))
+
   def stats(self, X, out):
-    """out f64[8] = [sum, sumsq, min, max, abssum, absmax, n, 0]."""
+    """Accumulates into out f64[8] = [sum, sumsq, min, max, abssum, absmax, n, 0]
+    (rows start from stats_init)."""
     x = X.double().reshape(-1)
-    out.copy_(torch.stack([
-        x.sum(), (x * x).sum(), x.min(), x.max(), x.abs().sum(), x.abs().max(),
-        torch.tensor(float(x.numel()), dtype=torch.float64),
-        torch.tensor(0.0, dtype=torch.float64)]))
+    out[0] += x.sum()
+    out[1] += (x * x).sum()
+    out[2] = torch.minimum(out[2], x.min())
+    out[3] = torch.maximum(out[3], x.max())
+    out[4] += x.abs().sum()
+    out[5] = torch.maximum(out[5], x.abs().max())
+    out[6] += float(x.numel())
 
   def autoadapt(self, scale, sums, denom, target, lo, hi, vel, thres, inverse):
     avg = sums / denom

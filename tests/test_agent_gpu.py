@@ -1,0 +1,141 @@
+"""-m gpu: the embodied.Agent surface (train/report/policy/save/load) on the
+CUDA path, CUDA-graph replay vs eager launches, in-kernel Philox noise, and
+size-independent properties at the full a1 size."""
+import numpy as np
+import pytest
+import torch
+
+from daydreamer_b200.config import make_config
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+class Space:
+  def __init__(self, shape, dtype=np.float32, discrete=False):
+    self.shape, self.dtype, self.discrete = tuple(shape), np.dtype(dtype), discrete
+
+
+def spaces(obs_dim=16, act_dim=12):
+  obs = {'vector': Space((obs_dim,)), 'image': Space((64, 64, 3), np.uint8),
+         'reward': Space(()), 'is_first': Space((), bool), 'is_last': Space((), bool),
+         'is_terminal': Space((), bool)}
+  return obs, {'action': Space((act_dim,)), 'reset': Space((), bool, True)}
+
+
+def small_config(**kw):
+  base = {'rssm.deter': 64, 'rssm.units': 64, 'rssm.stoch': 8, 'rssm.classes': 8,
+          r'.*\.layers': 2, r'.*\.units': 64, 'encoder.mlp_layers': 2, 'encoder.mlp_units': 64,
+          'decoder.mlp_layers': 2, 'decoder.mlp_units': 64, 'imag_horizon': 4,
+          'batch_size': 4, 'replay_chunk': 8}
+  base.update(kw)
+  return make_config('a1', **base)
+
+
+class FakeSpec:
+  def __init__(self, obs_dim, act_dim):
+    self.obs_dims, self.act_dim = {'vector': obs_dim}, act_dim
+
+
+def test_graph_replay_equals_eager():
+  from daydreamer_b200.agent import Agent
+  obs, act = spaces()
+  cfg = small_config()
+  a1 = Agent(obs, act, None, cfg)
+  a2 = Agent(obs, act, None, cfg)
+  a2.use_graph = False
+  s1 = s2 = None
+  for it in range(4):
+    batch = util.make_batch(FakeSpec(16, 12), 4, 8, seed=it)
+    _, s1, m1 = a1.train(batch, s1)
+    _, s2, m2 = a2.train(batch, s2)
+    assert set(m1) == set(m2)
+    for k in m1:
+      if np.isnan(m1[k]):
+        assert np.isnan(m2[k])
+      else:
+        assert abs(m1[k] - m2[k]) <= 1e-4 * max(1.0, abs(m2[k])), (it, k, m1[k], m2[k])
+  assert m1['model_grad_steps'] == 4 and m1['actor_grad_steps'] == 4
+
+
+def test_surface_policy_report_save_load():
+  from daydreamer_b200.agent import Agent
+  obs, act = spaces()
+  cfg = small_config()
+  agent = Agent(obs, act, None, cfg)
+  batch = util.make_batch(FakeSpec(16, 12), 4, 8, seed=0)
+  state = None
+  for _ in range(3):
+    outs, state, mets = agent.train(batch, state)
+  assert outs == {}
+  assert all(np.isscalar(v) or np.ndim(v) == 0 for v in mets.values())
+  rep = agent.report(batch)
+  assert 'model_loss_mean' in rep and np.isfinite(rep['model_loss_mean'])
+  # report must not advance the optimizer
+  _, _, mets2 = agent.train(batch, state)
+  assert mets2['model_grad_steps'] == 4
+  # policy: 2 envs, three steps, all modes
+  ob = {'vector': np.random.randn(2, 16).astype(np.float32),
+        'image': np.zeros((2, 64, 64, 3), np.uint8), 'reward': np.zeros(2, np.float32),
+        'is_first': np.array([True, True]), 'is_last': np.zeros(2, bool),
+        'is_terminal': np.zeros(2, bool)}
+  pst = None
+  for mode in ('train', 'explore', 'eval'):
+    out, pst = agent.policy(ob, pst, mode)
+    assert out['action'].shape == (2, 12) and out['action'].dtype == np.float32
+    assert np.isfinite(out['action']).all()
+    ob['is_first'] = np.array([False, False])
+  # eval mode is the distribution mean: |a| <= 1 (tanh)
+  assert np.abs(out['action']).max() <= 1.0
+  # checkpoint round trip through a fresh agent
+  data = agent.save()
+  import pickle
+  data = pickle.loads(pickle.dumps(data))
+  other = Agent(obs, act, None, cfg, seed=99)
+  other.load(data)
+  p1, p2 = agent._main.get_params(), other._main.get_params()
+  for k in p1:
+    assert np.array_equal(p1[k], p2[k]), k
+  assert np.array_equal(agent._main.counters.cpu().numpy(), other._main.counters.cpu().numpy())
+
+
+def test_rejects_unbuilt_configs_loudly():
+  from daydreamer_b200.agent import Agent
+  obs, act = spaces()
+  with pytest.raises(NotImplementedError):
+    Agent(obs, act, None, make_config('a1', critic_type='qfunction'))
+  with pytest.raises(NotImplementedError):
+    Agent(obs, act, None, make_config('xarm'))          # image keys
+
+
+def test_a1_full_size_properties():
+  """Size-independent properties at B=16, L=64, H=15 (BASELINE.json configs[1])."""
+  from daydreamer_b200.agent import Agent
+  obs, act = spaces()
+  cfg = make_config('a1', **{'rssm.deter': 512, 'rssm.units': 512, 'batch_size': 16,
+                            'replay_chunk': 64})
+  agent = Agent(obs, act, None, cfg)
+  B, L, H = 16, 64, 15
+  state = None
+  losses = []
+  batch = util.make_batch(FakeSpec(16, 12), B, L, seed=0)
+  for it in range(6):
+    _, state, m = agent.train(batch, state if it else None)
+    assert all(np.isfinite(v) or np.isnan(v) for v in m.values())
+    losses.append(m['model_loss'])
+  assert losses[-1] < losses[0], losses          # same batch: the model fits it
+  eng = agent._main
+  S, C, D = 32, 32, 512
+  st = eng.tfeat[:, :, D:].reshape(H + 1, B * L, S, C)
+  assert torch.all(st.sum(-1) == 1.0) and torch.all((st == 0) | (st == 1))   # one-hot
+  lg = eng.tlogit[1:].reshape(H, B * L, S, C)
+  assert torch.allclose(torch.logsumexp(lg, -1), torch.zeros_like(lg[..., 0]), atol=1e-4)
+  w, c = eng.r_weight, eng.r_cont
+  assert torch.allclose(w[0], c[0])
+  assert torch.allclose(w[1:], w[:-1] * c[1:] * 0.995, rtol=1e-5, atol=1e-7)
+  # lambda-return recursion holds on the device buffers
+  R, V, r = eng.r_ret, eng.r_value, eng.r_reward
+  d = 0.995 * c[1:]
+  nxt = torch.cat([R[1:], V[H:]], 0)
+  assert torch.allclose(R, r + d * (0.05 * V[1:] + 0.95 * nxt), rtol=1e-4, atol=1e-5)
+  assert int(eng.counters[0]) == 6 and int(eng.counters[4]) == 6

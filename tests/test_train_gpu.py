@@ -1,0 +1,104 @@
+"""-m gpu: the whole train step on the CUDA kernels (through the C-ABI) against
+the CPU oracle on identical seeded replay batches and identical injected noise.
+
+Tolerance (BASELINE.json north_star): 1e-4 relative fp32 on values; categorical
+indices bit-exact.  Gradients are compared per tensor relative to the tensor's
+max magnitude."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dreamer_oracle as O
+from daydreamer_b200 import engine as E
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+  a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+  return np.abs(a - b).max() / (np.abs(b).max() + 1e-12)
+
+
+def perturbed_params(ospec, seed=1):
+  params = O.init_params(ospec, seed=seed)
+  rng = np.random.default_rng(5)
+  for k, v in params.items():
+    if not k.endswith('/kernel'):
+      params[k] = (v + 0.1 * rng.standard_normal(v.shape)).astype(np.float32)
+  return params
+
+
+def run_pair(ospec, B, L, steps, grad_tol, par_tol=2e-5, met_tol=3e-4):
+  from daydreamer_b200.backend import CudaBackend
+  spec = util.to_engine_spec(ospec)
+  params = perturbed_params(ospec)
+  ol = O.Learner(ospec, params)
+  eng = E.Engine(spec, CudaBackend(), B, L)
+  eng.load_params(params)
+  ostate = estate = None
+  D = spec.deter
+  for it in range(steps):
+    batch = util.make_batch(ospec, B, L, seed=10 + it)
+    noise = util.make_noise(ospec, B, L, seed=20 + it)
+    _, ostate, omets, aux = ol.train_step(batch, noise, ostate, keep=True)
+    util.load_batch(eng, spec, batch, noise, estate)
+    eng.launch_step(draw=False)
+    eng.be.sync()
+    estate = {'deter': eng.prev_deter.cpu().numpy().copy(),
+              'stoch': eng.prev_stoch.cpu().numpy().copy()}
+    feat = eng.feat.cpu().numpy()
+    post_stoch = util.tm(aux['post']['stoch'].numpy().reshape(B, L, -1))
+    assert np.array_equal(feat[:, D:], post_stoch), 'posterior indices differ'
+    assert rel(feat[:, :D], util.tm(aux['post']['deter'].numpy())) < 1e-4
+    assert rel(eng.post_logit.cpu().numpy(),
+               util.tm(aux['post']['logit'].numpy().reshape(B, L, -1))) < 1e-4
+    assert rel(eng.prior_logit.cpu().numpy(),
+               util.tm(aux['prior']['logit'].numpy().reshape(B, L, -1))) < 1e-4
+    traj = aux['traj']
+    H1 = spec.horizon + 1
+    tf = eng.tfeat.cpu().numpy()
+    tstoch = util.ref_rows_to_tm(traj['stoch'].numpy().reshape(H1, B * L, -1), B, L)
+    assert np.array_equal(tf[:, :, D:], tstoch), 'imagined indices differ'
+    assert rel(tf[:, :, :D], util.ref_rows_to_tm(traj['deter'].numpy(), B, L)) < 1e-4
+    assert rel(eng.taction.cpu().numpy(), util.ref_rows_to_tm(traj['action'].numpy(), B, L)) < 1e-4
+    assert rel(eng.r_weight.cpu().numpy(),
+               util.ref_rows_to_tm(traj['weight'].numpy()[..., None], B, L)[..., 0]) < 1e-4
+    assert rel(eng.r_ret.cpu().numpy(),
+               util.ref_rows_to_tm(aux['ret'].numpy()[..., None], B, L)[..., 0]) < 2e-4
+    for group in ('model', 'critic', 'actor'):
+      eg = eng.get_grads(group)
+      for k, v in aux[f'{group}_grads'].items():
+        assert rel(eg[k], v.numpy()) < grad_tol, (it, group, k, rel(eg[k], v.numpy()))
+    ep = eng.get_params()
+    for k, v in ol.params.items():
+      assert rel(ep[k], v.numpy()) < par_tol, (it, k, rel(ep[k], v.numpy()))
+    em = eng.read_metrics()
+    assert set(em) == set(omets)
+    for k, v in omets.items():
+      if np.isnan(v):
+        assert np.isnan(em[k]), k
+      else:
+        assert abs(em[k] - v) <= met_tol * max(1.0, abs(v)), (it, k, em[k], v)
+  return eng
+
+
+def test_tiny_matches_oracle():
+  run_pair(O.tiny_spec(), 3, 5, 3, grad_tol=3e-4)
+
+
+def test_ragged_classes_matches_oracle():
+  # 48 classes exercises the two-elements-per-lane path of the categorical kernels
+  spec = O.tiny_spec(stoch=3, classes=48, deter=40, units=36, head_units=24, act_dim=2)
+  run_pair(spec, 2, 4, 2, grad_tol=3e-4)
+
+
+def test_medium_matches_oracle():
+  spec = O.Spec(obs_dims={'vector': 16}, act_dim=12, deter=128, units=128, stoch=16, classes=16,
+                enc_layers=2, enc_units=64, head_layers=2, head_units=128, horizon=5)
+  run_pair(spec, 8, 16, 2, grad_tol=1e-3)
+
+
+def test_a1_full_size_one_step_matches_oracle():
+  """BASELINE.json configs[1]: deter=units=512, 32x32 latent, B=16 L=64 H=15."""
+  run_pair(O.a1_spec(), 16, 64, 1, grad_tol=3e-3, met_tol=1e-3)
