@@ -25,6 +25,8 @@ _U32 = ctypes.c_uint32
 # name -> argtypes (all return int); mirrors include/dd_kernels.h one to one
 SIGNATURES = {
     'dd_gemm': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _F, _P, _P],
+    'dd_set_gemm_tc': [_I],
+    'dd_set_gemm_tc_debug': [_I],
     'dd_ln_fwd': [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _P],
     'dd_ln_bwd': [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P],
     'dd_gru_fwd': [_P, _I, _P, _I, _P, _I, _I, _I, _P],
@@ -128,6 +130,9 @@ class CudaBackend:
   def _ck(self, rc):
     if rc != 0:
       raise RuntimeError(self.lib.dd_last_error().decode())
+
+  def set_gemm_tc(self, on):
+    return self.lib.dd_set_gemm_tc(int(on))
 
   def launch_count(self):
     return int(self.lib.dd_launch_count())

@@ -18,6 +18,8 @@
 // layers: 128+ CTAs), 16x64 (the M=B observe-scan steps).  Weight-gradient
 // calls (beta=1) may split K across gridDim.z and reduce with atomics so that
 // a 512x512 output with K=16384 still fills the 148 SMs.
+#include <stdlib.h>
+
 #include "dd_common.cuh"
 
 namespace dd {
@@ -177,7 +179,28 @@ static int launch(const float* A, int lda, int ta, const float* B, int ldb, int 
   return launched("dd_gemm");
 }
 
+int gemm_skinny_try(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
+                    int ldc, int M, int N, int K, float beta, const float* bias,
+                    cudaStream_t st);
+int gemm_tc_try(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C, int ldc,
+                int M, int N, int K, float beta, const float* bias, cudaStream_t st);
+
+static int g_tc_on = -1;
+static bool tc_enabled() {
+  if (g_tc_on < 0) {
+    const char* e = getenv("DD_GEMM_TC");
+    g_tc_on = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return g_tc_on == 1;
+}
+
 }  // namespace dd
+
+extern "C" int dd_set_gemm_tc(int on) {
+  const int prev = dd::tc_enabled() ? 1 : 0;
+  dd::g_tc_on = on ? 1 : 0;
+  return prev;
+}
 
 extern "C" int dd_gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
                        int ldc, int M, int N, int K, float beta, const float* bias,
@@ -186,6 +209,18 @@ extern "C" int dd_gemm(const float* A, int lda, int ta, const float* B, int ldb,
   if (M <= 0 || N <= 0) return 0;
   if (K < 0 || (beta != 0.f && beta != 1.f)) return fail("dd_gemm", "bad K or beta");
   cudaStream_t st = S(stream);
+  {
+    const int r = gemm_skinny_try(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias, st);
+    if (r != 0) return r > 0 ? 0 : r;
+  }
+  if (tc_enabled()) {
+    // bias vectors are read as float4 by the tensor-core epilogue
+    const bool bias_ok = bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
+    if (bias_ok) {
+      const int r = gemm_tc_try(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias, st);
+      if (r != 0) return r > 0 ? 0 : r;
+    }
+  }
   const int kNumSm = 148;
   auto ctas = [&](int bm, int bn) { return ((M + bm - 1) / bm) * ((N + bn - 1) / bn); };
   auto pick_splits = [&](int c, int bk) {

@@ -40,6 +40,12 @@ int dd_gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb,
             float* C, int ldc, int M, int N, int K, float beta,
             const float* bias, dd_stream_t stream);
 
+/* 1 (default): eligible shapes run on the tcgen05 3xTF32 kernel; 0: always the
+ * fp32 SIMT kernel.  Returns the previous setting.  (env DD_GEMM_TC=0 too.) */
+int dd_set_gemm_tc(int on);
+/* profiling aid: bit 0 = skip operand loads, bit 1 = skip MMA issue (garbage results) */
+int dd_set_gemm_tc_debug(int bits);
+
 /* LayerNorm(eps 1e-3, population variance) + optional elu (A/nets.py:585-602,
  * :580-581).  stats[M,2] = (mean, rstd).  act: 0 none, 1 elu. */
 int dd_ln_fwd(const float* Z, int ldz, const float* scale, const float* bias,

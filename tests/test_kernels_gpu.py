@@ -285,3 +285,70 @@ def test_noise_matches_numpy_philox(backends):
     cu.sync()
     np.testing.assert_allclose(g.cpu().numpy(), philox.gumbel(n, 1234567890123, 2, 7), rtol=2e-5, atol=2e-6)
     np.testing.assert_allclose(z.cpu().numpy(), philox.normal(n, 1234567890123, 3, 7), rtol=2e-4, atol=2e-5)
+
+
+TC_SHAPES = [(1024, 512, 512), (1024, 1536, 1024), (16384, 512, 1536), (200, 96, 64),
+             (129, 36, 40), (1024, 512, 1036), (4096, 256, 12 * 4)]
+
+
+@pytest.mark.parametrize('M,N,K', TC_SHAPES)
+@pytest.mark.parametrize('ta,tb', [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_tcgen05_3xtf32(backends, M, N, K, ta, tb):
+  """The tensor-core kernel must stay at fp32-class accuracy (3xTF32 split)."""
+  hs, cu = backends
+  A = rnd(*((K, M) if ta else (M, K)), seed=1)
+  B = rnd(*((N, K) if tb else (K, N)), seed=2)
+  C0 = rnd(M, N, seed=3)
+  bias = rnd(N, seed=4)
+  ref = (A.t() if ta else A).double() @ (B.t() if tb else B).double()
+  scale = float(ref.abs().max())
+  dA, dB, dbias = A.cuda(), B.cuda(), bias.cuda()
+  outs = {}
+  for on in (1, 0):
+    cu.set_gemm_tc(on)
+    before = cu.launch_count()
+    c = C0.cuda()
+    cu.gemm(dA, dB, c, ta=ta, tb=tb, beta=0.0, bias=dbias)
+    c0 = c.clone()
+    cu.gemm(dA, dB, c, ta=ta, tb=tb, beta=1.0)
+    cu.sync()
+    outs[on] = (c0.cpu().double(), c.cpu().double())
+  cu.set_gemm_tc(1)
+  # fp32 SIMT rounds per FMA; the tensor core truncates once per K=8 accumulate,
+  # so its error grows ~linearly in K/8 ulps (measured 4e-6 at K=512)
+  tol = {0: 4e-6 * max(1.0, K / 4096), 1: 1.2e-5 * max(1.0, K / 1024)}
+  for on, (c0, c1) in outs.items():
+    e0 = float((c0 - (ref + bias.double())).abs().max()) / scale
+    e1 = float((c1 - (2 * ref + bias.double())).abs().max()) / scale
+    assert e0 < tol[on] and e1 < 2 * tol[on], (on, e0, e1)
+  # tensor-core result vs SIMT result, elementwise
+  assert float((outs[1][0] - outs[0][0]).abs().max()) / scale < tol[1]
+
+
+def test_gemm_tcgen05_splitk_wgrad(backends):
+  hs, cu = backends
+  X, dY = rnd(16384, 512, seed=1), rnd(16384, 512, seed=2, scale=0.1)
+  ref = X.double().t() @ dY.double()
+  G = torch.zeros(512, 512).cuda()
+  cu.set_gemm_tc(1)
+  cu.gemm(X.cuda(), dY.cuda(), G, ta=True, beta=1.0)
+  cu.sync()
+  assert float((G.cpu().double() - ref).abs().max()) / float(ref.abs().max()) < 5e-5
+
+
+@pytest.mark.parametrize('M,N,K', [(16, 512, 1036), (16, 1536, 512), (16, 1024, 512), (32, 512, 1536),
+                                   (9, 100, 300), (16, 40, 64), (24, 2304, 2048)])
+@pytest.mark.parametrize('tb', [False, True])
+def test_gemm_skinny(backends, M, N, K, tb):
+  """The observe-scan (M = sequences per GPU) GEMM path, strided views included."""
+  def case(be, T):
+    A = T(rnd(M, K + 8, seed=1))[:, 4:4 + K]
+    B = T(rnd(*((N, K) if tb else (K, N)), seed=2))
+    C = T(rnd(M, N + 4, seed=3))
+    bias = T(rnd(N, seed=4))
+    c = C[:, :N]
+    be.gemm(A, B, c, tb=tb, beta=0.0, bias=bias)
+    c1 = c.clone()
+    be.gemm(A, B, c, tb=tb, beta=1.0)
+    return {'c0': c1, 'c1': c.clone(), 'pad': C[:, N:].clone()}
+  both(backends, case, rtol=1e-4, atol=2e-5 * np.sqrt(K))
