@@ -252,7 +252,7 @@ def run_ours(args, rank, world, local_rank):
          + 3 * 8)
 
   # ---- device-resident step: graph replay timed with CUDA events -----------
-  graph = agent._graphs[(id(eng), 'train')]
+  graph = agent._graphs[(id(eng), 'train')]     # steady-state step (no slow-target refresh)
   for _ in range(max(args.warmup, 3)):
     graph.replay()
   clocks = ClockSampler(local_rank)

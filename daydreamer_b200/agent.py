@@ -159,6 +159,7 @@ class Agent:
     self._policies = {}
     self._graphs = {}
     self._calls = {}
+    self._slow_updates = -1           # host mirror of the device slow-target counter
     self.use_graph = True
     self._init_params = _engine.init_params(self.spec, seed=self.seed + 1)
     self.expl_noise = float(_get(config, 'expl_noise'))
@@ -249,10 +250,14 @@ class Agent:
     eng = self._engine_for(B, L)
     self._stage(eng, data, state)
 
+    refresh = eng.slow_refresh_due(self._slow_updates)
+    self._slow_updates = (0 if refresh else self._slow_updates) + 1
+
     def launch():
       self._unstage(eng)
-      eng.launch_step()
-    self._run(eng, 'train', launch)
+      eng.launch_step(slow_refreshed=refresh)
+    # two launch sequences (with / without the slow-critic re-evaluation), each its own graph
+    self._run(eng, 'train_refresh' if refresh else 'train', launch)
     metrics = eng.read_metrics()
     if not np.isfinite(metrics['model_loss']):
       raise FloatingPointError('model_loss is not finite')       # A/tfutils.py:207
@@ -337,4 +342,5 @@ class Agent:
     eng.wmkl_scale.copy_(torch.as_tensor(data['ctrl/wmkl_scale']).to(dev))
     eng.actent_scale.copy_(torch.as_tensor(data['ctrl/actent_scale']).to(dev))
     eng.norm_state.copy_(torch.as_tensor(data['ctrl/norm_state']).to(dev))
+    self._slow_updates = int(data['ctrl/counters'][_engine.C_SLOW])
     self.be.sync()

@@ -69,6 +69,17 @@ SIGNATURES = {
 }
 
 
+class DdObserveFwd(ctypes.Structure):
+  """Mirror of `struct DdObserveFwd` in include/dd_kernels.h."""
+  _PTRS = ('action', 'first', 'first0', 'prev_deter', 'prev_stoch', 'init_deter', 'init_stoch',
+           'g_obs', 'Win', 'ln_in_s', 'ln_in_b', 'Wgru', 'ln_gru_s', 'ln_gru_b', 'Wobs',
+           'ln_obs_s', 'ln_obs_b', 'Wst', 'bst', 'm_deter', 'm_stoch', 'm_act', 'z_in', 'x_in',
+           'st_in', 'z_gru', 'y_gru', 'st_gru', 'feat', 'z_obs', 'h_obs', 'st_obs', 'post_logit',
+           'post_idx', 'partial', 'barrier', 'timing')
+  _fields_ = ([(n, ctypes.c_int) for n in ('B', 'L', 'D', 'U', 'S', 'C', 'A')] +
+              [('mix', ctypes.c_float)] + [(n, ctypes.c_void_p) for n in _PTRS])
+
+
 def load_library(path=LIB_PATH):
   """dlopen the kernel library and type every entry point.  Raises if absent."""
   path = pathlib.Path(path)
@@ -81,6 +92,10 @@ def load_library(path=LIB_PATH):
     fn = getattr(lib, name)
     fn.argtypes = argtypes
     fn.restype = ctypes.c_int
+  lib.dd_observe_fwd_grid.argtypes = [ctypes.POINTER(DdObserveFwd)]
+  lib.dd_observe_fwd_grid.restype = ctypes.c_int
+  lib.dd_observe_fwd.argtypes = [ctypes.POINTER(DdObserveFwd), _P]
+  lib.dd_observe_fwd.restype = ctypes.c_int
   lib.dd_version.restype = ctypes.c_int
   lib.dd_last_error.restype = ctypes.c_char_p
   lib.dd_launch_count.restype = ctypes.c_int64
@@ -216,6 +231,27 @@ class CudaBackend:
     pdq, _, _, lddq = _mat(dprior)
     self._ck(self.lib.dd_kl_bwd(pp, ldp, pq, ldq, M, S, C, float(bal), float(coef),
                                 scale.data_ptr(), pdp, lddp, pdq, lddq, self.stream))
+
+  # -- fused observe scan -------------------------------------------------------
+  def _observe_params(self, dims, mix, tensors):
+    p = DdObserveFwd()
+    for k, v in dims.items():
+      setattr(p, k, int(v))
+    p.mix = float(mix)
+    for name in DdObserveFwd._PTRS:
+      t = tensors.get(name)
+      if t is None:
+        continue                      # optional pointer (timing)
+      assert t.is_contiguous(), name
+      setattr(p, name, t.data_ptr())
+    return p
+
+  def observe_fwd_grid(self, dims, mix, tensors):
+    return int(self.lib.dd_observe_fwd_grid(ctypes.byref(self._observe_params(dims, mix, tensors))))
+
+  def observe_fwd(self, dims, mix, tensors):
+    p = self._observe_params(dims, mix, tensors)
+    self._ck(self.lib.dd_observe_fwd(ctypes.byref(p), self.stream))
 
   # -- observe masking --------------------------------------------------------
   def mask_fwd(self, pd, ps, act, first, init_d, init_s, od, os_, oa):

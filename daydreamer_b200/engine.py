@@ -369,6 +369,10 @@ class Engine:
     self.dz_in = z(N, U)
     self.d_embed = z(N, E)
     self.d_initdeter = z(1, D)
+    # fused observe scan (persistent cooperative kernel) workspace
+    self.fused_scan = True
+    self.scan_partial = z(148 * 16 * 2)
+    self.scan_barrier = z(4, dtype=torch.int32)
 
     # -- imagination buffers ------------------------------------------------
     ga, gc, gs = self.groups['actor'], self.groups['critic'], self.groups['slow_critic']
@@ -547,8 +551,57 @@ class Engine:
     self._prior_stats_fwd(self.init_trunk, 0, 1, self.init_deter, self.init_zs,
                           None, self.init_logit, self.init_stoch, None, 1)
 
+    if not self._observe_fused():
+      self._observe_steps()
+
+    # prior logits for every step at once (the prior draw is unused by observe)
+    self._prior_stats_fwd(self.prior, 0, N, feat[:, :D], self.zs_tmp, None,
+                          self.prior_logit, None, None, 2)
+
+    # heads on the posterior features (A/agent.py:170-176)
+    xs = [(feat, 0)]
+    self._out_fwd(gm, 'dec/dist_out/out', self.heads['dec'].fwd(xs, 0, N), self.out_dec)
+    self._out_fwd(gm, 'reward/dist_out/out', self.heads['reward'].fwd(xs, 0, N), self.out_rew)
+    self._out_fwd(gm, 'cont/dist_out/out', self.heads['cont'].fwd(xs, 0, N), self.out_con)
+
+  def _observe_fused(self):
+    """All L obs_steps in one persistent cooperative kernel (csrc/dd_scan.cu) when
+    the backend has it and the shape is eligible; False -> per-step launches."""
+    be, s, gm = self.be, self.spec, self.groups['model']
+    if not (self.fused_scan and hasattr(be, 'observe_fwd')):
+      return False
+    P = gm.P
+    dims = dict(B=self.B, L=self.L, D=s.deter, U=s.units, S=s.stoch, C=s.classes, A=s.act_dim)
+    tensors = dict(
+        action=self.action, first=self.first, first0=self.first0, prev_deter=self.prev_deter,
+        prev_stoch=self.prev_stoch, init_deter=self.init_deter, init_stoch=self.init_stoch,
+        g_obs=self.g_obs, Win=P('rssm/img_in/kernel'), ln_in_s=P('rssm/img_in/norm/scale'),
+        ln_in_b=P('rssm/img_in/norm/bias'), Wgru=P('rssm/gru_out/kernel'),
+        ln_gru_s=P('rssm/gru_out/norm/scale'), ln_gru_b=P('rssm/gru_out/norm/bias'),
+        Wobs=P('rssm/obs_out/kernel'), ln_obs_s=P('rssm/obs_out/norm/scale'),
+        ln_obs_b=P('rssm/obs_out/norm/bias'), Wst=P('rssm/obs_stats/kernel'),
+        bst=P('rssm/obs_stats/bias'), m_deter=self.m_deter, m_stoch=self.m_stoch,
+        m_act=self.m_act, z_in=self.z_in, x_in=self.x_in, st_in=self.st_in, z_gru=self.z_gru,
+        y_gru=self.y_gru, st_gru=self.st_gru, feat=self.feat, z_obs=self.z_obs,
+        h_obs=self.h_obs, st_obs=self.st_obs, post_logit=self.post_logit,
+        post_idx=self.post_idx, partial=self.scan_partial, barrier=self.scan_barrier,
+        timing=getattr(self, 'scan_timing', None))
+    if not hasattr(self, '_scan_ok'):
+      self._scan_ok = be.observe_fwd_grid(dims, s.rssm_unimix, tensors) > 0
+    if not self._scan_ok:
+      return False
+    be.observe_fwd(dims, s.rssm_unimix, tensors)
+    return True
+
+  def _observe_steps(self):
+    """The scan as ~12 launches per step (also the reference semantics of the fused kernel)."""
+    s, be, gm = self.spec, self.be, self.groups['model']
+    B, L = self.B, self.L
+    D, SC = s.deter, s.sc
+    feat = self.feat
     Win = gm.P('rssm/img_in/kernel')
     Wgru = gm.P('rssm/gru_out/kernel')
+    Wobs = gm.P('rssm/obs_out/kernel')
     for t in range(L):
       r = slice(t * B, (t + 1) * B)
       if t == 0:
@@ -576,16 +629,6 @@ class Engine:
       self._out_fwd(gm, 'rssm/obs_stats', self.h_obs[r], self.zs_tmp[r])
       be.stats_fwd(self.zs_tmp[r], self.g_obs[t], self.post_logit[r], feat[r, D:],
                    self.post_idx[r], s.stoch, s.classes, s.rssm_unimix, 0)
-
-    # prior logits for every step at once (the prior draw is unused by observe)
-    self._prior_stats_fwd(self.prior, 0, N, feat[:, :D], self.zs_tmp, None,
-                          self.prior_logit, None, None, 2)
-
-    # heads on the posterior features (A/agent.py:170-176)
-    xs = [(feat, 0)]
-    self._out_fwd(gm, 'dec/dist_out/out', self.heads['dec'].fwd(xs, 0, N), self.out_dec)
-    self._out_fwd(gm, 'reward/dist_out/out', self.heads['reward'].fwd(xs, 0, N), self.out_rew)
-    self._out_fwd(gm, 'cont/dist_out/out', self.heads['cont'].fwd(xs, 0, N), self.out_con)
 
   # ==========================================================================
   # 1b. world model: losses, backward, optimizer
@@ -806,15 +849,17 @@ class Engine:
   # ==========================================================================
   # 4. actor update (A/agent.py:326-381), gradients through the dynamics
   # ==========================================================================
-  def actor_update(self):
+  def actor_update(self, slow_refreshed=True):
     s, be = self.spec, self.be
     gm, ga, gs = self.groups['model'], self.groups['actor'], self.groups['slow_critic']
     N, H, T = self.N, self.H, self.H + 1
     D, U, SC, A = s.deter, s.units, s.sc, s.act_dim
     M = H * N
     hu = s.head_units
-    # score with the (possibly refreshed) slow critic
-    self.traj_values(slow_only=True)
+    # score with the slow critic: its values are unchanged since traj_values() unless
+    # update_slow just copied the critic into it (first step and every slow_every-th)
+    if slow_refreshed:
+      self.traj_values(slow_only=True)
     be.sub(self.score, self.r_ret, self.r_value[:H])
     self._stat(self.score, 'score')
     # Normalize EMAs: retnorm/scorenorm are impl 'off' (state only), advnorm used
@@ -904,9 +949,16 @@ class Engine:
   # ==========================================================================
   # the whole step
   # ==========================================================================
-  def launch_step(self, draw=True):
+  def slow_refresh_due(self, updates):
+    """Host mirror of VFunction.update_slow (A/agent.py:444-454): given the value of
+    the `updates` counter BEFORE this step, does this step hard-copy the critic?"""
+    return updates == -1 or updates >= self.spec.slow_every
+
+  def launch_step(self, draw=True, slow_refreshed=True):
     """Everything between 'inputs are on the device' and 'metrics are on the
-    device'.  Pure launch sequence: safe to capture into a CUDA graph."""
+    device'.  Pure launch sequence: safe to capture into a CUDA graph.
+    slow_refreshed=False (only valid when slow_refresh_due() is False for this
+    step) skips re-evaluating the slow critic after the critic update."""
     if draw:
       self.draw_noise()
     self.be.stats_init(self.mstat)
@@ -923,7 +975,7 @@ class Engine:
     self.imagine()
     self.traj_values()
     self.critic_update()
-    self.actor_update()
+    self.actor_update(slow_refreshed)
 
   def launch_report(self, draw=True):
     """WorldModel.report's scalar part (A/agent.py:266-268): the loss metrics of
@@ -941,7 +993,6 @@ class Engine:
     cnt = self.counters.detach().cpu().numpy()
     wm = float(self.wmkl_scale.detach().cpu().numpy()[0])
     ae = self.actent_scale.detach().cpu().numpy().astype(np.float64)
-    w = self.world
     sq = {g: float(self.groups[g].sumsq.detach().cpu().numpy()[0])
           for g in ('model', 'critic', 'actor')}
     row = lambda k: ms[self.midx[k]]
@@ -966,9 +1017,9 @@ class Engine:
     if report:
       return m
     m.update(model_loss=mean('total_loss'),
-             model_grad_norm=math.sqrt(sq['model']) / w, model_grad_steps=int(cnt[C_MODEL]),
+             model_grad_norm=math.sqrt(sq['model']), model_grad_steps=int(cnt[C_MODEL]),
              extr_critic_loss=mean('closs'),
-             extr_critic_grad_norm=math.sqrt(sq['critic']) / w,
+             extr_critic_grad_norm=math.sqrt(sq['critic']),
              extr_critic_grad_steps=int(cnt[C_CRITIC]),
              extr_imag_reward_mean=mean('imag_reward'), extr_imag_reward_std=std('imag_reward'),
              extr_imag_critic_mean=mean('imag_critic'), extr_imag_critic_std=std('imag_critic'),
@@ -978,7 +1029,7 @@ class Engine:
              actent_mean=mean('ent'), actent_std=std('ent'),
              actent_scale_mean=float(ae.mean()), actent_scale_std=float(ae.std()),
              actor_loss=mean('aloss'),
-             actor_grad_norm=math.sqrt(sq['actor']) / w, actor_grad_steps=int(cnt[C_ACTOR]))
+             actor_grad_norm=math.sqrt(sq['actor']), actor_grad_steps=int(cnt[C_ACTOR]))
     return m
 
 

@@ -89,6 +89,32 @@ int dd_kl_bwd(const float* post, int ldp, const float* prior, int ldq, int M,
               float* dpost, int lddp, float* dprior, int lddq,
               dd_stream_t stream);
 
+/* ---- fused observe scan (forward) ---------------------------------------- */
+/* RSSM.observe (A/nets.py:66-76): all L obs_steps (A/nets.py:99-117) in ONE
+ * persistent cooperative kernel.  Time-major buffers, row = t*B + b.
+ * z_obs must be pre-filled with embed @ obs_out.kernel[D:] (the batched part).
+ * Semantics per step are exactly dd_mask_fwd -> dd_gemm/dd_ln_fwd (img_in) ->
+ * dd_gemm/dd_ln_fwd/dd_gru_fwd (GRU) -> dd_gemm/dd_ln_fwd (obs_out) ->
+ * dd_gemm + dd_stats_fwd mode 0 (obs_stats). */
+typedef struct DdObserveFwd {
+  int B, L, D, U, S, C, A;
+  float mix;
+  const float *action, *first, *first0, *prev_deter, *prev_stoch;
+  const float *init_deter, *init_stoch, *g_obs;
+  const float *Win, *ln_in_s, *ln_in_b, *Wgru, *ln_gru_s, *ln_gru_b;
+  const float *Wobs, *ln_obs_s, *ln_obs_b, *Wst, *bst;
+  float *m_deter, *m_stoch, *m_act, *z_in, *x_in, *st_in, *z_gru, *y_gru, *st_gru;
+  float *feat, *z_obs, *h_obs, *st_obs, *post_logit;
+  int32_t* post_idx;
+  float* partial;          /* workspace: 148 * 16 * 2 floats */
+  unsigned int* barrier;   /* workspace: 1 counter */
+  long long* timing;       /* optional: 10 per-phase SM-clock totals of CTA 0, or NULL */
+} DdObserveFwd;
+/* CTAs the fused scan would use, or 0 when the shape is not eligible
+ * (B > 16, weights do not fit the shared-memory slices, ...). */
+int dd_observe_fwd_grid(const DdObserveFwd* p);
+int dd_observe_fwd(const DdObserveFwd* p, dd_stream_t stream);
+
 /* ---- observe-scan masking (A/nets.py:100-107) ------------------------ */
 int dd_mask_fwd(const float* pd, int ldpd, const float* ps, int ldps,
                 const float* act, int lda, const float* first,

@@ -37,7 +37,8 @@ def test_train_step_matches_oracle(B, L, steps):
     noise = util.make_noise(ospec, B, L, seed=20 + it)
     _, ostate, omets, aux = ol.train_step(batch, noise, ostate, keep=True)
     util.load_batch(eng, spec, batch, noise, estate)
-    eng.launch_step(draw=False)
+    # steps after the first do not refresh the slow critic -> exercise the skip path
+    eng.launch_step(draw=False, slow_refreshed=eng.slow_refresh_due(int(eng.counters[E.C_SLOW])))
     estate = {'deter': eng.prev_deter.numpy().copy(), 'stoch': eng.prev_stoch.numpy().copy()}
     # posterior indices bit-exact, features close
     post_stoch = util.tm(aux['post']['stoch'].numpy().reshape(B, L, -1))

@@ -53,7 +53,7 @@ def run_pair(ospec, B, L, steps, grad_tol, met_tol=3e-4):
     noise = util.make_noise(ospec, B, L, seed=20 + it)
     _, ostate, omets, aux = ol.train_step(batch, noise, ostate, keep=True)
     util.load_batch(eng, spec, batch, noise, estate)
-    eng.launch_step(draw=False)
+    eng.launch_step(draw=False, slow_refreshed=eng.slow_refresh_due(int(eng.counters[E.C_SLOW])))
     eng.be.sync()
     estate = {'deter': eng.prev_deter.cpu().numpy().copy(),
               'stoch': eng.prev_stoch.cpu().numpy().copy()}
@@ -112,3 +112,53 @@ def test_medium_matches_oracle():
 def test_a1_full_size_one_step_matches_oracle():
   """BASELINE.json configs[1]: deter=units=512, 32x32 latent, B=16 L=64 H=15."""
   run_pair(O.a1_spec(), 16, 64, 1, grad_tol=3e-3, met_tol=1e-3)
+
+
+@pytest.mark.parametrize('name', ['tiny', 'ragged', 'medium', 'a1'])
+def test_fused_observe_scan_equals_per_step_launches(name):
+  """The persistent cooperative observe kernel (csrc/dd_scan.cu) against the same
+  scan issued as per-step launches: identical indices, values to fp32 rounding."""
+  from daydreamer_b200.backend import CudaBackend
+  ospec, B, L = {
+      'tiny': (O.tiny_spec(), 3, 5),
+      'ragged': (O.tiny_spec(stoch=3, classes=48, deter=40, units=36, head_units=24, act_dim=2), 2, 4),
+      'medium': (O.Spec(obs_dims={'vector': 16}, act_dim=12, deter=128, units=128, stoch=16, classes=16,
+                        enc_layers=2, enc_units=64, head_layers=2, head_units=128, horizon=5), 8, 16),
+      'a1': (O.a1_spec(), 16, 64)}[name]
+  spec = util.to_engine_spec(ospec)
+  params = perturbed_params(ospec)
+  be = CudaBackend()
+  engs = []
+  for fused in (True, False):
+    eng = E.Engine(spec, be, B, L)
+    eng.fused_scan = fused
+    eng.load_params(params)
+    batch = util.make_batch(ospec, B, L, seed=3)
+    noise = util.make_noise(ospec, B, L, seed=4)
+    util.load_batch(eng, spec, batch, noise, None)
+    eng.be.stats_init(eng.mstat)
+    eng.wm_forward()
+    be.sync()
+    # second chunk with a carried state and a mid-chunk episode boundary
+    state = {'deter': eng.feat[(L - 1) * B:, :spec.deter].cpu().numpy().copy(),
+             'stoch': eng.feat[(L - 1) * B:, spec.deter:].cpu().numpy().copy()}
+    first = {k: getattr(eng, k).clone() for k in ('feat', 'post_logit', 'z_gru', 'y_gru', 'x_in', 'h_obs')}
+    batch2 = util.make_batch(ospec, B, L, seed=5)
+    batch2['is_first'][:, 0] = False
+    batch2['is_first'][0, 0] = True
+    util.load_batch(eng, spec, batch2, util.make_noise(ospec, B, L, seed=6), state)
+    eng.wm_forward()
+    be.sync()
+    engs.append((eng, first))
+  (f, f1), (u, u1) = engs
+  assert f._scan_ok, 'fused scan was not eligible for this shape'
+  D = spec.deter
+  for a, b in ((f1, u1), (None, None)):
+    get = (lambda e, k, a=a, b=b: (a if e is f else b)[k]) if a is not None else (lambda e, k: getattr(e, k))
+    assert torch.equal(get(f, 'feat')[:, D:], get(u, 'feat')[:, D:]), 'indices differ'
+    for k in ('feat', 'post_logit', 'z_gru', 'y_gru', 'x_in', 'h_obs'):
+      x, y = get(f, k).cpu().numpy(), get(u, k).cpu().numpy()
+      assert rel(x, y) < 2e-5, (k, rel(x, y))
+  for k in ('m_deter', 'm_stoch', 'm_act', 'z_in', 'st_in', 'st_gru', 'z_obs', 'st_obs', 'prior_logit'):
+    assert rel(getattr(f, k).cpu().numpy(), getattr(u, k).cpu().numpy()) < 2e-5, k
+  assert torch.equal(f.post_idx, u.post_idx)
