@@ -27,6 +27,7 @@ SIGNATURES = {
     'dd_gemm': [_P, _I, _I, _P, _I, _I, _P, _I, _I, _I, _I, _F, _P, _P],
     'dd_set_gemm_tc': [_I],
     'dd_set_gemm_tc_debug': [_I],
+    'dd_set_gemm_tc_persistent': [_I],
     'dd_ln_fwd': [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _P],
     'dd_ln_bwd': [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P],
     'dd_gru_fwd': [_P, _I, _P, _I, _P, _I, _I, _I, _P],

@@ -26,6 +26,7 @@
 
 namespace dd {
 int g_tc_debug = 0;
+int g_tc_persistent = 1;
 namespace tc {
 
 constexpr int BM = 128;
@@ -60,6 +61,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // Round-to-nearest (ties away) to tf32 with two ALU ops.  cvt.rna.tf32.f32 gives
 // the same value but issues on the 16/clk/SM conversion pipe, which made the
 // loaders -- not the tensor core -- the bottleneck (profiles/r01_tc_dissect.txt).
+// (r01 experiment: electing one lane per warp for the mbarrier wait/arrive made every
+// shape 10-20% SLOWER than letting all threads arrive; kept for reference, unused.)
+__device__ __forceinline__ void warp_mbar_wait(uint32_t bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void warp_mbar_arrive(uint32_t bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
 __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
@@ -241,15 +253,24 @@ gemm_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
       mbar_wait(empty0 + 8 * s, ph ^ 1);
       char* st = smem + s * STAGE_BYTES;
       if (!(dbg & 1)) {
-        tile_split_store<BM, A_MN>(ra, st, st + A_BYTES, gtid);
-        tile_split_store<BN, B_MN>(rb, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, gtid);
+        if (!(dbg & 8)) {
+          tile_split_store<BM, A_MN>(ra, st, st + A_BYTES, gtid);
+          tile_split_store<BN, B_MN>(rb, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, gtid);
+        } else {                                       // dbg 8: consume the loads, skip the stores
+          float acc = 0.f;
+#pragma unroll
+          for (int i = 0; i < TileMap<BM, A_MN>::PER; ++i) acc += ra[i].x + ra[i].w;
+#pragma unroll
+          for (int i = 0; i < TileMap<BN, B_MN>::PER; ++i) acc += rb[i].x + rb[i].w;
+          if (acc == 1.2345e-30f) *reinterpret_cast<float*>(st) = acc;
+        }
       }
-      if (kb + 2 < nkb && !(dbg & 1)) {
+      if (kb + 2 < nkb && !(dbg & 1) && !(dbg & 16)) {  // dbg 16: no global loads after the first
         const int k1 = kbeg + (kb + 2) * BK;
         tile_gload<BM, A_MN>(A, lda, m0, M, k1, kend, gtid, ra);
         tile_gload<BN, B_MN>(B, ldb, n0, N, k1, kend, gtid, rb);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (!(dbg & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // dbg 4
       mbar_arrive(full0 + 8 * s);
     }
     // ===== epilogue: TMEM -> registers -> global =============================
@@ -367,6 +388,241 @@ gemm_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
   }
 }
 
+// ---------------------------------------------------------------------------
+// Persistent variant for GEMMs with more output tiles than SMs (the M ~ 16K head
+// and trajectory layers).  r01 measurement (profiles/r01_tc_gemm_dissect.txt):
+// ~10 us of every one-tile CTA is fixed cost (launch, TMEM alloc, barrier setup
+// and an epilogue nothing overlaps).  Here one CTA per SM walks a static tile
+// schedule; the TMEM accumulator is double buffered (2 x (main + cross) = 4*BN
+// = 512 columns) and 4 dedicated epilogue warps drain tile i while the loaders
+// and the MMA warp already work on tile i+1.
+//   warps 0-7 loaders (two alternating groups), warps 8-11 epilogue (TMEM lane
+//   quadrant = warp % 4), warp 12 TMEM alloc + MMA issue.
+// ---------------------------------------------------------------------------
+constexpr int P_THREADS = 13 * 32;
+
+template <int BN, int STAGES, bool TA, bool TB>
+__global__ void __launch_bounds__(P_THREADS, 1)
+gemm_tc_persistent_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                          float* __restrict__ C, int ldc, int M, int N, int K, float beta,
+                          const float* __restrict__ bias) {
+  constexpr bool A_MN = TA, B_MN = !TB;
+  constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  extern __shared__ __align__(1024) char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BM - 1) / BM;
+  const int ntiles = tiles_m * tiles_n;
+  const int nkb = (K + BK - 1) / BK;
+
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+  const uint32_t acc_full0 = smem_u32(bars + 2 * STAGES), acc_empty0 = smem_u32(bars + 2 * STAGES + 2);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, GROUP_THREADS);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full0 + 8 * b, 1);
+      mbar_init(acc_empty0 + 8 * b, 4);            // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)(4 * BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < LOADER_WARPS) {
+    // ===== loaders: global k-block index `it` runs across tiles ==================
+    const int grp = warp / GROUP_WARPS, gtid = tid % GROUP_THREADS;
+    const int my_tiles = ntiles > (int)blockIdx.x ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const long total = (long)my_tiles * nkb;
+    float4 ra[TileMap<BM, A_MN>::PER], rb[TileMap<BN, B_MN>::PER];
+    auto coords = [&](long it, int& m0, int& n0, int& k0) {
+      const int ti = (int)(it / nkb);
+      const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+      m0 = (tile / tiles_n) * BM;
+      n0 = (tile % tiles_n) * BN;
+      k0 = (int)(it % nkb) * BK;
+    };
+    if (grp < total) {
+      int m0, n0, k0;
+      coords(grp, m0, n0, k0);
+      tile_gload<BM, A_MN>(A, lda, m0, M, k0, K, gtid, ra);
+      tile_gload<BN, B_MN>(B, ldb, n0, N, k0, K, gtid, rb);
+    }
+    for (long it = grp; it < total; it += 2) {
+      const int s = (int)(it % STAGES);
+      const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+      mbar_wait(empty0 + 8 * s, ph ^ 1);
+      char* st = smem + s * STAGE_BYTES;
+      tile_split_store<BM, A_MN>(ra, st, st + A_BYTES, gtid);
+      tile_split_store<BN, B_MN>(rb, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, gtid);
+      if (it + 2 < total) {
+        int m0, n0, k0;
+        coords(it + 2, m0, n0, k0);
+        tile_gload<BM, A_MN>(A, lda, m0, M, k0, K, gtid, ra);
+        tile_gload<BN, B_MN>(B, ldb, n0, N, k0, K, gtid, rb);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(full0 + 8 * s);
+    }
+  } else if (warp < 12) {
+    // ===== epilogue warps: drain accumulator buffer (ti & 1) =========================
+    const int quad = warp & 3;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      const uint32_t ph = (uint32_t)((ti >> 1) & 1);
+      mbar_wait(acc_full0 + 8 * buf, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int m = m0 + quad * 32 + lane;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t v[32], w[32];
+        const uint32_t ta0 = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                             (uint32_t)(buf * 2 * BN + ch * 32);
+        tmem_ld32(ta0, v);
+        tmem_ld32(ta0 + BN, w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        const int nb = n0 + ch * 32;
+        const bool vec = (ldc & 3) == 0 && nb + 32 <= N &&
+                         (reinterpret_cast<uintptr_t>(C) & 15) == 0;
+        if (m < M && vec) {
+          float4* crow4 = reinterpret_cast<float4*>(C + (size_t)m * ldc + nb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 x = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            if (bias != nullptr) {
+              const float4 b = *reinterpret_cast<const float4*>(bias + nb + 4 * j);
+              x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+            }
+            if (beta != 0.f) {
+              const float4 c = crow4[j];
+              x.x += beta * c.x; x.y += beta * c.y; x.z += beta * c.z; x.w += beta * c.w;
+            }
+            crow4[j] = x;
+          }
+        } else if (m < M) {
+          float* crow = C + (size_t)m * ldc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            if (n < N) {
+              float x = __uint_as_float(v[j]);
+              if (bias != nullptr) x += bias[n];
+              crow[n] = (beta != 0.f) ? x + beta * crow[n] : x;
+            }
+          }
+        }
+      }
+      // this buffer may be overwritten by the MMAs of tile ti + 2
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
+    }
+  } else {
+    // ===== MMA issuer ==================================================================
+    constexpr uint32_t IDESC = make_idesc(A_MN ? 1 : 0, B_MN ? 1 : 0, BN);
+    constexpr uint32_t A_LBO = A_MN ? 512 : (BM / 8) * 128;
+    constexpr uint32_t B_LBO = B_MN ? 512 : (BN / 8) * 128;
+    constexpr uint32_t A_SBO = A_MN ? (BM / 32) * 512 : 128;
+    constexpr uint32_t B_SBO = B_MN ? (BN / 32) * 512 : 128;
+    constexpr uint32_t A_STEP = A_MN ? 2 * A_SBO : 2 * A_LBO;
+    constexpr uint32_t B_STEP = B_MN ? 2 * B_SBO : 2 * B_LBO;
+    constexpr uint32_t A_LT = A_MN ? 1u : 0u, B_LT = B_MN ? 1u : 0u;
+    long it = 0;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ti) {
+      const int buf = ti & 1;
+      const uint32_t aph = (uint32_t)((ti >> 1) & 1);
+      mbar_wait(acc_empty0 + 8 * buf, aph ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + (uint32_t)(buf * 2 * BN);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = (int)(it % STAGES);
+        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+        mbar_wait(full0 + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
+          const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            const uint64_t dah = make_desc(a_hi + ks * A_STEP, A_LBO, A_SBO, A_LT);
+            const uint64_t dal = make_desc(a_lo + ks * A_STEP, A_LBO, A_SBO, A_LT);
+            const uint64_t dbh = make_desc(b_hi + ks * B_STEP, B_LBO, B_SBO, B_LT);
+            const uint64_t dbl = make_desc(b_lo + ks * B_STEP, B_LBO, B_SBO, B_LT);
+            mma_tf32(tacc + BN, dal, dbh, IDESC, (kb | ks) != 0);
+            mma_tf32(tacc + BN, dah, dbl, IDESC, 1u);
+            mma_tf32(tacc, dah, dbh, IDESC, (kb | ks) != 0);
+          }
+          asm volatile(
+              "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                  empty0 + 8 * s)
+              : "memory");
+          if (kb == nkb - 1)
+            asm volatile(
+                "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                    acc_full0 + 8 * buf)
+                : "memory");
+        }
+        __syncwarp();
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 12) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(4 * BN))
+                 : "memory");
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_persistent(const float* A, int lda, int ta, const float* B, int ldb, int tb,
+                             float* C, int ldc, int M, int N, int K, float beta, const float* bias,
+                             cudaStream_t st) {
+  constexpr int STAGE_BYTES = 2 * BM * BK * 4 + 2 * BN * BK * 4;
+  constexpr int SMEM = STAGES * STAGE_BYTES + (2 * STAGES + 4) * 8 + 16;
+  const int ntiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = ntiles < 148 ? ntiles : 148;
+#define DD_TCP(TA_, TB_)                                                                       \
+  do {                                                                                         \
+    static bool attr_set = false;                                                              \
+    auto kern = gemm_tc_persistent_kernel<BN, STAGES, TA_, TB_>;                               \
+    if (!attr_set) {                                                                           \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);           \
+      attr_set = true;                                                                         \
+    }                                                                                          \
+    kern<<<grid, P_THREADS, SMEM, st>>>(A, lda, B, ldb, C, ldc, M, N, K, beta, bias);          \
+  } while (0)
+  if (!ta && !tb) DD_TCP(false, false);
+  else if (ta && !tb) DD_TCP(true, false);
+  else if (!ta && tb) DD_TCP(false, true);
+  else DD_TCP(true, true);
+#undef DD_TCP
+  return launched("dd_gemm_tc_persistent");
+}
+
 template <int BN, int STAGES>
 static int launch(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
                   int ldc, int M, int N, int K, float beta, const float* bias, int splits,
@@ -419,7 +675,9 @@ int gemm_tc_try(const float* A, int lda, int ta, const float* B, int ldb, int tb
     return s > 32 ? 32 : (s < 1 ? 1 : s);
   };
   int rc;
-  if (tiles128 >= kNumSm / 2) {
+  if (tiles128 > kNumSm + kNumSm / 2 && g_tc_persistent && K >= tc::BK) {
+    rc = tc::launch_persistent<128, 3>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias, st);
+  } else if (tiles128 >= kNumSm / 2) {
     rc = tc::launch<128, 3>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias,
                             pick_splits(tiles128), st);
   } else {
@@ -430,6 +688,12 @@ int gemm_tc_try(const float* A, int lda, int ta, const float* B, int ldb, int tb
 }
 
 }  // namespace dd
+
+extern "C" int dd_set_gemm_tc_persistent(int on) {
+  const int prev = dd::g_tc_persistent;
+  dd::g_tc_persistent = on ? 1 : 0;
+  return prev;
+}
 
 extern "C" int dd_set_gemm_tc_debug(int bits) {
   const int prev = dd::g_tc_debug;

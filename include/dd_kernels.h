@@ -43,6 +43,9 @@ int dd_gemm(const float* A, int lda, int ta, const float* B, int ldb, int tb,
 /* 1 (default): eligible shapes run on the tcgen05 3xTF32 kernel; 0: always the
  * fp32 SIMT kernel.  Returns the previous setting.  (env DD_GEMM_TC=0 too.) */
 int dd_set_gemm_tc(int on);
+/* 1 (default): GEMMs with more 128x128 tiles than ~1.5x the SM count use the persistent
+ * tensor-core kernel (double-buffered TMEM, overlapped epilogue).  Returns previous. */
+int dd_set_gemm_tc_persistent(int on);
 /* profiling aid: bit 0 = skip operand loads, bit 1 = skip MMA issue (garbage results) */
 int dd_set_gemm_tc_debug(int bits);
 
