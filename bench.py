@@ -212,12 +212,22 @@ class GemmOnly:
     return (lambda *a, **k: None) if callable(attr) else attr
 
 
+def note(msg):
+  if os.environ.get('DD_BENCH_VERBOSE'):
+    print(f'[bench rank {os.environ.get("RANK", 0)} +{time.perf_counter() - T0:.1f}s] {msg}',
+          file=sys.stderr, flush=True)
+
+
+T0 = time.perf_counter()
+
+
 def run_ours(args, rank, world, local_rank):
   import torch
   import torch.distributed as dist
   torch.cuda.set_device(local_rank)
   if world > 1:
     dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
+    note('process group up')
   from daydreamer_b200.agent import Agent
   from daydreamer_b200.config import make_config
 
@@ -239,6 +249,7 @@ def run_ours(args, rank, world, local_rank):
   for i in range(max(args.warmup, 3)):
     _, state, mets = agent.train(batches[i % 4], state)
   eng = agent._main
+  note('e2e warm-up done (eager + graph capture)')
   barrier()
   t0 = time.perf_counter()
   for i in range(args.steps):
@@ -248,21 +259,29 @@ def run_ours(args, rank, world, local_rank):
   if world > 1:
     dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
   e2e_dt = float(e2e_dt)
+  note('e2e timed')
   h2d = sum(v.numel() * 4 for v in eng.h_stage.values()) + eng.first0.numel() * 4
   d2h = (eng.mstat.numel() * 8 + eng.counters.numel() * 8 + 4 + eng.actent_scale.numel() * 4
          + 3 * 8)
 
   # ---- device-resident step: graph replay timed with CUDA events -----------
-  graph = agent._graphs[(id(eng), 'train')]     # steady-state step (no slow-target refresh)
+  segs = agent._graphs[(id(eng), 'train')]      # steady-state step (no slow-target refresh)
+
+  def replay():                                 # graph segments + eager NCCL all-reduces (N > 1)
+    for kind, item in segs:
+      if kind == 'graph':
+        item.replay()
+      else:
+        agent._allreduce(item)
   for _ in range(max(args.warmup, 3)):
-    graph.replay()
+    replay()
   clocks = ClockSampler(local_rank)
   barrier()
   clocks.start()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   ev0.record()
   for _ in range(args.steps):
-    graph.replay()
+    replay()
   ev1.record()
   torch.cuda.synchronize()
   clock_info = clocks.stop()
@@ -270,6 +289,7 @@ def run_ours(args, rank, world, local_rank):
   if world > 1:
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
   dt = float(dt)
+  note('device-resident timed')
   barrier()
 
   # launches per step (counted while re-issuing the launch sequence eagerly once)

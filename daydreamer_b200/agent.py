@@ -226,7 +226,10 @@ class Agent:
     be.transpose01(d['cont'], eng.cont)
 
   def _run(self, eng, name, fn):
-    """Eager on the first call of a launch sequence, CUDA-graph replay after."""
+    """Eager on the first call of a launch sequence, CUDA-graph replay after.  With a
+    collective hook installed (data parallel) the sequence is captured as graph
+    SEGMENTS split at every all-reduce and the collectives run eagerly between the
+    segment replays: NCCL never executes inside a captured graph."""
     key = (id(eng), name)
     n = self._calls.get(key, 0)
     self._calls[key] = n + 1
@@ -234,12 +237,49 @@ class Agent:
       fn()
       return
     if key not in self._graphs:
-      torch.cuda.synchronize()
-      graph = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(graph):
+      self._graphs[key] = self._capture(eng, fn)
+    for kind, item in self._graphs[key]:
+      if kind == 'graph':
+        item.replay()
+      else:
+        self._allreduce(item)
+
+  def _capture(self, eng, fn):
+    main = getattr(eng, 'eng', eng)            # PolicyEngine shares the learner's hooks
+    be = self.be
+    segs, cur = [], {}
+    side = torch.cuda.Stream(device=be.device)
+
+    def begin():
+      cur['g'] = torch.cuda.CUDAGraph()
+      cur['n0'] = be.launch_count()
+      cur['g'].capture_begin(capture_error_mode='thread_local')
+
+    def end():
+      cur['g'].capture_end()
+      if be.launch_count() > cur['n0']:
+        segs.append(('graph', cur['g']))
+
+    def hook(t):
+      end()
+      segs.append(('allreduce', t))
+      begin()
+
+    saved = main.allreduce
+    if saved is not None:
+      main.allreduce = hook
+    torch.cuda.synchronize()
+    side.wait_stream(torch.cuda.current_stream())
+    try:
+      with torch.cuda.stream(side):
+        begin()
         fn()
-      self._graphs[key] = graph
-    self._graphs[key].replay()
+        end()
+    finally:
+      main.allreduce = saved
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    return segs
 
   # -- embodied.Agent surface -------------------------------------------------
   def dataset(self, generator):

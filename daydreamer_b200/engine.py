@@ -641,7 +641,7 @@ class Engine:
               self.kl_row, self.ent_post, self.ent_prior)
     if update:      # AutoAdapt.update precedes the use of the scale (A/tfutils.py:441)
       be.colsum(self.kl_row.view(N, 1), self.kl_sum)
-      if self.allreduce and self.world > 1:
+      if self.allreduce is not None:
         self.allreduce(self.kl_sum)
       be.autoadapt(self.wmkl_scale, self.kl_sum, float(N * self.world), s.wmkl_target,
                    s.wmkl_min, s.wmkl_max, s.ctrl_vel, s.ctrl_thres, False)
@@ -759,7 +759,7 @@ class Engine:
 
   def opt_step(self, group, ci):
     s, be, g = self.spec, self.be, self.groups[group]
-    if self.allreduce and self.world > 1:
+    if self.allreduce is not None:
       self.allreduce(g.g)
     be.sumsq(g.g, g.sumsq)
     be.adam(g.p, g.g, g.m, g.v, g.n_decay, s.lr, s.beta1, s.beta2, s.adam_eps,
@@ -868,14 +868,14 @@ class Engine:
         (self.score, 'score_ctrl', 0.99))):
       row = self.mstat[self.midx[key]]
       be.stats(src, row)
-      if self.allreduce and self.world > 1:
+      if self.allreduce is not None:
         self.allreduce(row)
       be.normalize_update(self.norm_state[i], row, decay, s.advnorm_max,
                           self.adv if i == 0 else self.scratch2)
     # entropy controller (A/agent.py:361-371, A/tfutils.py:464-474)
     be.actor_ent(self.tstd.view(-1, A)[:M], s.actor_minstd, s.actor_maxstd, self.ent)
     be.colsum(self.ent, self.ent_sum)
-    if self.allreduce and self.world > 1:
+    if self.allreduce is not None:
       self.allreduce(self.ent_sum)
     be.autoadapt(self.actent_scale, self.ent_sum, float(M * self.world), s.actent_target,
                  s.actent_min, s.actent_max, s.ctrl_vel, s.ctrl_thres, True)

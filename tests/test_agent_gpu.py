@@ -139,3 +139,32 @@ def test_a1_full_size_properties():
   nxt = torch.cat([R[1:], V[H:]], 0)
   assert torch.allclose(R, r + d * (0.05 * V[1:] + 0.95 * nxt), rtol=1e-4, atol=1e-5)
   assert int(eng.counters[0]) == 6 and int(eng.counters[4]) == 6
+
+
+def test_segmented_graph_capture_around_collectives():
+  """Data-parallel launch path on one GPU: with a collective hook installed the step is
+  captured as graph segments split at every all-reduce (NCCL never runs inside a graph);
+  with an identity collective the results must equal the single-graph agent."""
+  from daydreamer_b200.agent import Agent
+  obs, act = spaces()
+  cfg = small_config()
+  a1 = Agent(obs, act, None, cfg)
+  a2 = Agent(obs, act, None, cfg)
+  calls = []
+  a2._allreduce = lambda t: calls.append(t.numel())
+  s1 = s2 = None
+  for it in range(5):
+    batch = util.make_batch(FakeSpec(16, 12), 4, 8, seed=it)
+    if it == 0:
+      _, s2, m2 = a2.train(batch, s2)
+      a2._main.allreduce = a2._allreduce        # install the hook once the engine exists
+    else:
+      _, s2, m2 = a2.train(batch, s2)
+    _, s1, m1 = a1.train(batch, s1)
+    for k in m1:
+      if not np.isnan(m1[k]):
+        assert abs(m1[k] - m2[k]) <= 1e-4 * max(1.0, abs(m1[k])), (it, k, m1[k], m2[k])
+  segs = a2._graphs[(id(a2._main), 'train')]
+  kinds = [k for k, _ in segs]
+  assert kinds.count('allreduce') == 8 and kinds.count('graph') >= 8, kinds
+  assert len(calls) == 8 * 5                     # 5 steps x 8 collectives (eager, capture replay, replays)
