@@ -36,8 +36,7 @@ def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
   rejecting loudly every setting whose kernels are not built."""
   g = lambda p: _get(config, p)
   act = act_space['action'] if isinstance(act_space, dict) else act_space
-  if getattr(act, 'discrete', False):
-    raise NotImplementedError('discrete (one-hot, reinforce) actor is not built yet')
+  discrete = bool(getattr(act, 'discrete', False))
   if g('task_behavior') != 'Greedy' or g('expl_behavior') != 'None':
     raise NotImplementedError('only task_behavior=Greedy, expl_behavior=None are built')
   if g('critic_type') != 'vfunction':
@@ -47,6 +46,7 @@ def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
       'rssm.post_layers': 1, 'rssm.gru_layers': 1, 'encoder.act': 'elu',
       'encoder.norm': 'layer', 'reward_head.dist': 'symlog', 'cont_head.dist': 'binary',
       'critic.dist': 'symlog', 'actor_dist_cont': 'normal', 'actor_grad_cont': 'backprop',
+      'actor_dist_disc': 'onehot', 'actor_grad_disc': 'reinforce',
       'actor_return': 'gve', 'critic_return': 'gve', 'slow_target': True,
       'slow_target_fraction': 1.0, 'advnorm.impl': 'mean_std', 'retnorm.impl': 'off',
       'scorenorm.impl': 'off', 'wmkl.impl': 'mult', 'actent.impl': 'mult',
@@ -87,7 +87,7 @@ def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
   if len(set(opts)) != 1 or opts[0][4]:
     raise NotImplementedError('optimizers must share lr/eps/clip/wd and warmup=0')
   return _engine.Spec(
-      obs_dims=enc, act_dim=int(np.prod(_space_shape(act))), discrete=False,
+      obs_dims=enc, act_dim=int(np.prod(_space_shape(act))), discrete=discrete,
       deter=int(g('rssm.deter')), units=int(g('rssm.units')), stoch=int(g('rssm.stoch')),
       classes=int(g('rssm.classes')), prior_layers=int(g('rssm.prior_layers')),
       rssm_unimix=float(g('rssm.unimix')), enc_layers=int(g('encoder.mlp_layers')),
@@ -345,7 +345,11 @@ class Agent:
       noise = self.eval_noise
     else:
       action = pol.action.cpu().numpy()
-    if noise:                                                     # A/tfutils.py:85-93
+    if noise and self.spec.discrete:                              # A/tfutils.py:85-93
+      probs = noise / action.shape[-1] + (1 - noise) * action
+      draw = (probs.cumsum(-1) > np.random.uniform(size=action.shape[:-1] + (1,))).argmax(-1)
+      action = np.eye(action.shape[-1], dtype=np.float32)[draw]
+    elif noise:
       action = np.clip(action + noise * np.random.standard_normal(action.shape), -1, 1)
     action = action.astype(np.float32).reshape((P,) + tuple(self.act_space.shape))
     state = {'deter': pol.prev_deter, 'stoch': pol.prev_stoch, 'action': action}

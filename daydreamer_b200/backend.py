@@ -55,6 +55,8 @@ SIGNATURES = {
     'dd_actor_ent': [_P, _F, _F, _P, _L, _P],
     'dd_actor_loss': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
     'dd_actor_bwd': [_P, _P, _P, _P, _P, _P, _F, _F, _F, _P, _P, _L, _I, _P],
+    'dd_actor_disc_ent': [_P, _P, _L, _I, _P],
+    'dd_actor_disc_loss': [_P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _L, _I, _P],
     'dd_lambda_fwd': [_P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _I, _I, _P],
     'dd_lambda_bwd': [_P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _P, _P, _P, _I, _I, _P],
     'dd_stats_init': [_P, _I, _P],
@@ -363,6 +365,18 @@ class CudaBackend:
                                    _flat(weight)[0], scale.data_ptr(), float(coef), float(lo),
                                    float(hi), _flat(dmraw)[0], _flat(dsraw)[0], M, A,
                                    self.stream))
+
+  def actor_disc_ent(self, logit, ent):
+    M, A = logit.shape
+    self._ck(self.lib.dd_actor_disc_ent(_flat(logit)[0], _flat(ent)[0], M, A, self.stream))
+
+  def actor_disc_loss(self, logit, action, ret, value, adv, ent, scale, weight, coef,
+                      loss_row, dlogit):
+    M, A = logit.shape
+    self._ck(self.lib.dd_actor_disc_loss(
+        _flat(logit)[0], _flat(action)[0], _flat(ret)[0], _flat(value)[0], adv.data_ptr(),
+        _flat(ent)[0], scale.data_ptr(), _flat(weight)[0], float(coef), loss_row.data_ptr(),
+        _flat(dlogit)[0], M, A, self.stream))
 
   def lambda_fwd(self, rho, vraw, kraw, cont0, gamma, lam, reward, value, cont, weight, ret):
     H, N = rho.shape[0] - 1, rho.shape[1]

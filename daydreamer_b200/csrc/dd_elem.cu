@@ -280,6 +280,74 @@ __global__ void lambda_bwd_kernel(const float* __restrict__ rho, const float* __
   }
 }
 
+// ---------------------------------------------------------------------------
+// Discrete actor ('onehot' head with 'reinforce' gradient, nets.py:480-491,
+// agent.py:351-381).  One warp per row, A <= 64 classes.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void row_log_softmax(const float* lg, int A, int lane, float a[2]) {
+  const float l0 = lane < A ? lg[lane] : -INFINITY;
+  const float l1 = lane + 32 < A ? lg[lane + 32] : -INFINITY;
+  const float mx = warp_max(fmaxf(l0, l1));
+  const float se = warp_sum((lane < A ? expf(l0 - mx) : 0.f) + (lane + 32 < A ? expf(l1 - mx) : 0.f));
+  const float lse = mx + logf(se);
+  a[0] = l0 - lse;
+  a[1] = l1 - lse;
+}
+
+__global__ void actor_disc_ent_kernel(const float* __restrict__ logit, float* __restrict__ ent,
+                                      int64_t M, int A) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const float inv = 1.f / logf((float)A);
+  for (int64_t m = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); m < M;
+       m += (int64_t)gridDim.x * wpb) {
+    float a[2];
+    row_log_softmax(logit + m * A, A, lane, a);
+    float h = 0.f;
+    if (lane < A) h -= expf(a[0]) * a[0];
+    if (lane + 32 < A) h -= expf(a[1]) * a[1];
+    h = warp_sum(h);
+    if (lane == 0) ent[m] = h * inv;
+  }
+}
+
+__global__ void actor_disc_loss_kernel(const float* __restrict__ logit,
+                                       const float* __restrict__ action,
+                                       const float* __restrict__ ret,
+                                       const float* __restrict__ value,
+                                       const float* __restrict__ adv,
+                                       const float* __restrict__ ent,
+                                       const float* __restrict__ scale,
+                                       const float* __restrict__ weight, float coef,
+                                       float* __restrict__ loss_row, float* __restrict__ dlogit,
+                                       int64_t M, int A) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const float lnA = logf((float)A);
+  const float mean = adv[0], sc = adv[1], es = scale[0];
+  for (int64_t m = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); m < M;
+       m += (int64_t)gridDim.x * wpb) {
+    float a[2];
+    row_log_softmax(logit + m * A, A, lane, a);
+    const float* act = action + m * A;
+    const float x0 = lane < A ? act[lane] : 0.f;
+    const float x1 = lane + 32 < A ? act[lane + 32] : 0.f;
+    const float q0 = lane < A ? expf(a[0]) : 0.f;
+    const float q1 = lane + 32 < A ? expf(a[1]) : 0.f;
+    float logp = (lane < A ? x0 * a[0] : 0.f) + (lane + 32 < A ? x1 * a[1] : 0.f);
+    float h = -((lane < A ? q0 * a[0] : 0.f) + (lane + 32 < A ? q1 * a[1] : 0.f));
+    float xs = x0 + x1;
+    logp = warp_sum(logp);
+    h = warp_sum(h);
+    xs = warp_sum(xs);
+    const float score = (ret[m] - value[m] - mean) * sc;
+    const float w = weight[m];
+    if (lane == 0) loss_row[m] = (-logp * score - es * ent[m]) * w;
+    const float k = coef * w;
+    float* dl = dlogit + m * A;
+    if (lane < A) dl[lane] = k * (score * (q0 * xs - x0) + es / lnA * q0 * (a[0] + h));
+    if (lane + 32 < A) dl[lane + 32] = k * (score * (q1 * xs - x1) + es / lnA * q1 * (a[1] + h));
+  }
+}
+
 }  // namespace dd
 
 using namespace dd;
@@ -417,6 +485,26 @@ extern "C" int dd_actor_bwd(const float* dA, const float* eps, const float* mean
   DD_EW(actor_bwd_kernel, M * A, dA, eps, mean, std, weight, scale, coef, lo, hi, dmraw, dsraw, M,
         A);
   return launched("dd_actor_bwd");
+}
+
+extern "C" int dd_actor_disc_ent(const float* logit, float* ent, int64_t M, int A,
+                                 dd_stream_t stream) {
+  if (M <= 0) return 0;
+  if (A > 64 || A < 2) return fail("dd_actor_disc_ent", "needs 2 <= classes <= 64");
+  actor_disc_ent_kernel<<<grid_for(M, 8), 256, 0, S(stream)>>>(logit, ent, M, A);
+  return launched("dd_actor_disc_ent");
+}
+
+extern "C" int dd_actor_disc_loss(const float* logit, const float* action, const float* ret,
+                                  const float* value, const float* adv, const float* ent,
+                                  const float* scale, const float* weight, float coef,
+                                  float* loss_row, float* dlogit, int64_t M, int A,
+                                  dd_stream_t stream) {
+  if (M <= 0) return 0;
+  if (A > 64 || A < 2) return fail("dd_actor_disc_loss", "needs 2 <= classes <= 64");
+  actor_disc_loss_kernel<<<grid_for(M, 8), 256, 0, S(stream)>>>(
+      logit, action, ret, value, adv, ent, scale, weight, coef, loss_row, dlogit, M, A);
+  return launched("dd_actor_disc_loss");
 }
 
 extern "C" int dd_lambda_fwd(const float* rho, const float* vraw, const float* kraw,

@@ -272,7 +272,6 @@ class Engine:
 
   def __init__(self, spec: Spec, be, B: int, L: int, seed: int = 0,
                world: int = 1, allreduce=None, share: 'Engine' = None):
-    assert not spec.discrete, 'discrete (one-hot) actor is not built yet'
     self.spec, self.be = spec, be
     self.B, self.L, self.N, self.H = B, L, B * L, spec.horizon
     self.seed = seed
@@ -295,7 +294,7 @@ class Engine:
       # controllers / counters (device-resident so the step is one static graph)
       self.counters = z(8, dtype=torch.int64)
       self.wmkl_scale = z(1)
-      self.actent_scale = z(A)
+      self.actent_scale = z(1 if spec.discrete else A)   # A/agent.py:305-307
       self.norm_state = z(3, 3, dtype=torch.float64)     # adv / ret / score
       self.reset_state()
     gm = self.groups['model']
@@ -382,6 +381,7 @@ class Engine:
     self.taction = z(T, N, A)
     self.tmean = z(T, N, A)
     self.tstd = z(T, N, A)
+    self.talogit = z(T, N, A) if s.discrete else None     # unimixed action logits
     self.a_mraw = z(T * N, A)
     self.a_sraw = z(T * N, A)
     self.actor = Trunk(self, ga, 'actor', s.head_layers, s.head_units, T * N)
@@ -412,8 +412,8 @@ class Engine:
     self.closs_row = z(H * N)
     self.score = z(H, N)
     self.vsym = z(H * N, 1)
-    self.ent = z(H * N, A)
-    self.ent_sum = z(A)
+    self.ent = z(H * N, 1 if s.discrete else A)
+    self.ent_sum = z(1 if s.discrete else A)
     self.aloss_row = z(H * N)
     self.d_rho = z(T, N)
     self.d_vraw = z(T, N)
@@ -529,7 +529,10 @@ class Engine:
     be = self.be
     be.fill_gumbel(self.g_obs, self.seed, STREAM_OBS, self.counters, C_RNG)
     be.fill_gumbel(self.g_img, self.seed, STREAM_IMG, self.counters, C_RNG)
-    be.fill_normal(self.eps_act, self.seed, STREAM_ACT, self.counters, C_RNG)
+    if self.spec.discrete:       # Gumbel-max draw of the one-hot action
+      be.fill_gumbel(self.eps_act, self.seed, STREAM_ACT, self.counters, C_RNG)
+    else:
+      be.fill_normal(self.eps_act, self.seed, STREAM_ACT, self.counters, C_RNG)
     be.counter_inc(self.counters, C_RNG)
 
   # ==========================================================================
@@ -774,6 +777,10 @@ class Engine:
     r0, r1 = t * N, (t + 1) * N
     h = self.actor.fwd([(self.tfeat[t], 0)], r0, r1)
     self._out_fwd(ga, 'actor/dist_out/out', h, self.a_mraw[r0:r1])
+    if s.discrete:       # OneHotDist over unimix logits, straight-through sample (A/nets.py:480-491)
+      be.stats_fwd(self.a_mraw[r0:r1], self.eps_act[t], self.talogit[t], self.taction[t],
+                   None, 1, s.act_dim, s.actor_unimix, 0)
+      return
     self._out_fwd(ga, 'actor/dist_out/std', h, self.a_sraw[r0:r1])
     be.actor_sample(self.a_mraw[r0:r1], self.a_sraw[r0:r1], self.eps_act[t],
                     s.actor_minstd, s.actor_maxstd, self.taction[t],
@@ -872,6 +879,8 @@ class Engine:
         self.allreduce(row)
       be.normalize_update(self.norm_state[i], row, decay, s.advnorm_max,
                           self.adv if i == 0 else self.scratch2)
+    if s.discrete:
+      return self._actor_update_reinforce()
     # entropy controller (A/agent.py:361-371, A/tfutils.py:464-474)
     be.actor_ent(self.tstd.view(-1, A)[:M], s.actor_minstd, s.actor_maxstd, self.ent)
     be.colsum(self.ent, self.ent_sum)
@@ -943,6 +952,34 @@ class Engine:
     be.colsum(self.d_sraw, ga.G('actor/dist_out/std/bias'), acc=True)
     be.gemm(self.d_mraw, ga.P('actor/dist_out/out/kernel'), dH, tb=True)
     be.gemm(self.d_sraw, ga.P('actor/dist_out/std/kernel'), dH, tb=True, beta=1.0)
+    self.actor.bwd(dH, 0, M, [(flat[:M], 0)], [], True)
+    self.opt_step('actor', C_ACTOR)
+
+  def _actor_update_reinforce(self):
+    """Discrete actions: loss = -log pi(a) sg(score) - scale*ent (A/agent.py:357-358,
+    :372-379); the score is a constant, so nothing flows back through the rollout."""
+    s, be, ga = self.spec, self.be, self.groups['actor']
+    N, H, A = self.N, self.H, s.act_dim
+    M = H * N
+    logit = self.talogit.view(-1, A)[:M]
+    be.actor_disc_ent(logit, self.ent)
+    be.colsum(self.ent, self.ent_sum)
+    if self.allreduce is not None:
+      self.allreduce(self.ent_sum)
+    be.autoadapt(self.actent_scale, self.ent_sum, float(M * self.world), s.actent_target,
+                 s.actent_min, s.actent_max, s.ctrl_vel, s.ctrl_thres, True)
+    self._stat(self.ent, 'ent')
+    coef = 1.0 / (M * self.world)
+    dlogit = self.da                       # [M, A] scratch
+    be.actor_disc_loss(logit, self.taction.view(-1, A)[:M], self.r_ret, self.r_value, self.adv,
+                       self.ent, self.actent_scale, self.r_weight, coef, self.aloss_row, dlogit)
+    self._stat(self.aloss_row, 'aloss')
+    be.stats_bwd(None, dlogit, logit, self.d_mraw, 1, A, s.actor_unimix)
+    be.fill_(ga.g, 0.0)
+    h = self.actor.H[-1][:M]
+    dH = self.tmp(0, M, s.head_units)
+    self._out_bwd(ga, 'actor/dist_out/out', h, self.d_mraw, dH, True)
+    flat = self.tfeat.view(-1, s.feat)
     self.actor.bwd(dH, 0, M, [(flat[:M], 0)], [], True)
     self.opt_step('actor', C_ACTOR)
 
@@ -1075,7 +1112,10 @@ class PolicyEngine:
     D, SC = s.deter, s.sc
     P = self.P
     be.fill_gumbel(self.g, eng.seed, STREAM_POL_OBS, eng.counters, C_POLICY)
-    be.fill_normal(self.eps, eng.seed, STREAM_POL_ACT, eng.counters, C_POLICY)
+    if s.discrete:
+      be.fill_gumbel(self.eps, eng.seed, STREAM_POL_ACT, eng.counters, C_POLICY)
+    else:
+      be.fill_normal(self.eps, eng.seed, STREAM_POL_ACT, eng.counters, C_POLICY)
     be.counter_inc(eng.counters, C_POLICY)
     embed = self.enc.fwd([(self.obs, 0)], 0, P)
     be.tanh_fwd(gm.P('rssm/initial_deter').view(1, D), self.init_deter)
@@ -1103,9 +1143,15 @@ class PolicyEngine:
                  s.rssm_unimix, 0)
     h = self.actor.fwd([(self.feat, 0)], 0, P)
     eng._out_fwd(ga, 'actor/dist_out/out', h, self.mraw)
-    eng._out_fwd(ga, 'actor/dist_out/std', h, self.sraw)
-    be.actor_sample(self.mraw, self.sraw, self.eps, s.actor_minstd, s.actor_maxstd,
-                    self.action, self.mean, self.std)
+    if s.discrete:      # `action` = sample, `mean` = mode (A/agent.py:52-60)
+      be.stats_fwd(self.mraw, self.eps, self.std, self.action, None, 1, s.act_dim,
+                   s.actor_unimix, 0)
+      be.stats_fwd(self.mraw, None, self.std, self.mean, None, 1, s.act_dim,
+                   s.actor_unimix, 1)
+    else:
+      eng._out_fwd(ga, 'actor/dist_out/std', h, self.sraw)
+      be.actor_sample(self.mraw, self.sraw, self.eps, s.actor_minstd, s.actor_maxstd,
+                      self.action, self.mean, self.std)
     # carry: latent and the action just taken
     be.copy_(self.prev_deter, self.feat[:, :D])
     be.copy_(self.prev_stoch, self.feat[:, D:])

@@ -179,6 +179,17 @@ int dd_actor_bwd(const float* dA, const float* eps, const float* mean,
                  const float* std, const float* weight, const float* scale,
                  float coef, float lo, float hi, float* dmraw, float* dsraw,
                  int64_t M, int A, dd_stream_t stream);
+/* discrete 'onehot' actor with the 'reinforce' gradient (A/nets.py:480-491,
+ * A/agent.py:357-358,372-379): ent[m] = H(softmax(logit))/ln(A);
+ * loss_row = (-logp(action)*score - scale*ent)*w, score = (ret-value-adv[0])*adv[1];
+ * dlogit = coef * d loss_row / d logit (score and w are constants). */
+int dd_actor_disc_ent(const float* logit, float* ent, int64_t M, int A,
+                      dd_stream_t stream);
+int dd_actor_disc_loss(const float* logit, const float* action, const float* ret,
+                       const float* value, const float* adv, const float* ent,
+                       const float* scale, const float* weight, float coef,
+                       float* loss_row, float* dlogit, int64_t M, int A,
+                       dd_stream_t stream);
 /* lambda-return 'gve' + cont/weight (A/agent.py:256-259, :422-442). */
 int dd_lambda_fwd(const float* rho, const float* vraw, const float* kraw,
                   const float* cont0, float gamma, float lam, float* reward,

@@ -237,6 +237,25 @@ class HostSim:
     sg = (std - lo) / (hi - lo)
     dsraw.copy_(dstd * (hi - lo) * sg * (1.0 - sg))
 
+  def actor_disc_ent(self, logit, ent):
+    a = torch.log_softmax(logit, -1)
+    ent.reshape(-1).copy_(-(torch.exp(a) * a).sum(-1) / math.log(logit.shape[-1]))
+
+  def actor_disc_loss(self, logit, action, ret, value, adv, ent, scale, weight, coef,
+                      loss_row, dlogit):
+    """'reinforce' actor loss rows and their gradient wrt the (unimixed) logits."""
+    M, A = logit.shape
+    a = torch.log_softmax(logit, -1)
+    q = torch.exp(a)
+    score = ((ret.reshape(-1)[:M] - value.reshape(-1)[:M] - adv[0]) * adv[1])[:, None]
+    w = weight.reshape(-1)[:M, None]
+    e = ent.reshape(-1)[:M, None]
+    logp = (action * a).sum(-1, keepdim=True)
+    h = -(q * a).sum(-1, keepdim=True)
+    loss_row.copy_(((-logp * score - scale.reshape(-1)[0] * e) * w)[:, 0])
+    dlogit.copy_(coef * w * (score * (q * action.sum(-1, keepdim=True) - action)
+                             + scale.reshape(-1)[0] / math.log(A) * q * (a + h)))
+
   def lambda_fwd(self, rho, vraw, kraw, cont0, gamma, lam,
                  reward, value, cont, weight, ret):
     """rho/vraw/kraw [H+1,N] raw head outputs (row 0 of rho/kraw unused)."""

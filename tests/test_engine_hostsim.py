@@ -16,10 +16,13 @@ def rel(a, b):
   return np.abs(a - b).max() / (np.abs(b).max() + 1e-12)
 
 
-@pytest.mark.parametrize('B,L,steps', [(3, 5, 1), (2, 6, 3)])
-def test_train_step_matches_oracle(B, L, steps):
+@pytest.mark.parametrize('B,L,steps,kw', [
+    (3, 5, 1, {}), (2, 6, 3, {}),
+    (3, 5, 2, dict(discrete=True, act_dim=5, actent_target=0.4)),   # xarm/ur5-style one-hot actor
+])
+def test_train_step_matches_oracle(B, L, steps, kw):
   torch.manual_seed(0)
-  ospec = O.tiny_spec()
+  ospec = O.tiny_spec(**kw)
   spec = util.to_engine_spec(ospec)
   params = O.init_params(ospec, seed=1)
   # make LN params / biases non-trivial so every gradient path is exercised

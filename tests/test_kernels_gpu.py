@@ -239,6 +239,28 @@ def test_actor_and_lambda(backends):
   both(backends, case, rtol=2e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize('H,N,A', [(3, 50, 6), (15, 1024, 6), (2, 9, 40)])
+def test_actor_discrete(backends, H, N, A):
+  def case(be, T):
+    M = H * N
+    raw = T(rnd(M, A, seed=1))
+    G = T(rnd(M, A, seed=2))
+    logit, action = T(torch.zeros(M, A)), T(torch.zeros(M, A))
+    be.stats_fwd(raw, G, logit, action, None, 1, A, 0.1, 0)
+    ent = T(torch.zeros(M, 1))
+    be.actor_disc_ent(logit, ent)
+    ret, value = T(rnd(H, N, seed=3)), T(rnd(H + 1, N, seed=4))
+    weight = T(torch.rand(H + 1, N, generator=torch.Generator().manual_seed(5)))
+    adv, scale = T(torch.tensor([0.1, 1.7])), T(torch.tensor([0.3]))
+    loss, dlogit = T(torch.zeros(M)), T(torch.zeros(M, A))
+    be.actor_disc_loss(logit, action, ret, value, adv, ent, scale, weight, 1.0 / M, loss, dlogit)
+    draw = T(torch.zeros(M, A))
+    be.stats_bwd(None, dlogit, logit, draw, 1, A, 0.1)
+    return {'logit': logit, 'action': action, 'ent': ent, 'loss': loss, 'dlogit': dlogit,
+            'draw': draw}
+  both(backends, case, rtol=1e-4, atol=1e-6, exact=('action',))
+
+
 def test_controllers_and_adam(backends):
   def case(be, T):
     rows = T(torch.zeros(3, 8, dtype=torch.float64))

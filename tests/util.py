@@ -18,6 +18,8 @@ def make_batch(spec, B, L, seed=0, term=0.05, mid_first=True):
   b = {k: rng.standard_normal((B, L, d)).astype(np.float32)
        for k, d in spec.obs_dims.items()}
   b['action'] = rng.uniform(-1, 1, (B, L, spec.act_dim)).astype(np.float32)
+  if spec.discrete:            # one-hot actions (embodied OneHotAction wrapper)
+    b['action'] = np.eye(spec.act_dim, dtype=np.float32)[rng.integers(0, spec.act_dim, (B, L))]
   b['reward'] = (0.1 * rng.standard_normal((B, L))).astype(np.float32)
   f = np.zeros((B, L), bool)
   f[:, 0] = True
@@ -35,7 +37,8 @@ def make_noise(spec, B, L, seed=2):
   gum = lambda *s: (-np.log(-np.log(rng.uniform(1e-6, 1 - 1e-6, s)))).astype(np.float32)
   return {'obs_post': gum(L, B, spec.stoch, spec.classes),
           'img': gum(spec.horizon, N, spec.stoch, spec.classes),
-          'act': rng.standard_normal((spec.horizon + 1, N, spec.act_dim)).astype(np.float32)}
+          'act': (gum(spec.horizon + 1, N, spec.act_dim) if spec.discrete else
+                  rng.standard_normal((spec.horizon + 1, N, spec.act_dim)).astype(np.float32))}
 
 
 def tm(x):
