@@ -49,6 +49,11 @@ SIGNATURES = {
     'dd_colsum': [_P, _I, _I, _I, _P, _I, _P],
     'dd_tanh_fwd': [_P, _P, _L, _P],
     'dd_tanh_bwd': [_P, _P, _P, _L, _I, _P],
+    'dd_im2col': [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    'dd_col2im': [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    'dd_image_stage': [_P, _I, _I, _I, _I, _P, _I, _I, _F, _P],
+    'dd_image_loss': [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P],
+    'dd_sigmoid': [_P, _P, _L, _P],
     'dd_head_loss': [_I, _P, _I, _P, _I, _P, _F, _P, _P, _I, _I, _I, _P],
     'dd_balance': [_I, _P, _P, _P, _F, _I, _P, _P],
     'dd_actor_sample': [_P, _P, _P, _F, _F, _P, _P, _P, _L, _P],
@@ -328,6 +333,42 @@ class CudaBackend:
   def tanh_bwd(self, dy, y, dx, acc=True):
     p, n = _flat(dy)
     self._ck(self.lib.dd_tanh_bwd(p, _flat(y)[0], _flat(dx)[0], n, int(acc), self.stream))
+
+  # -- image path --------------------------------------------------------------
+  def im2col(self, X, k, stride, col):
+    N, H, W, C = X.shape
+    assert X.is_contiguous() and col.is_contiguous()
+    Ho, Wo = (H - k) // stride + 1, (W - k) // stride + 1
+    assert col.numel() == N * Ho * Wo * k * k * C, (X.shape, col.shape)
+    self._ck(self.lib.dd_im2col(X.data_ptr(), N, H, W, C, k, stride, col.data_ptr(), self.stream))
+
+  def col2im(self, col, k, stride, bias, X):
+    N, H, W, C = X.shape
+    assert X.is_contiguous() and col.is_contiguous()
+    Ho, Wo = (H - k) // stride + 1, (W - k) // stride + 1
+    assert col.numel() == N * Ho * Wo * k * k * C, (X.shape, col.shape)
+    self._ck(self.lib.dd_col2im(col.data_ptr(), N, H, W, C, k, stride, _ptr(bias), X.data_ptr(),
+                                self.stream))
+
+  def image_stage(self, src, dst, c0, scale):
+    B, L = src.shape[:2]
+    Ck = src.shape[-1]
+    P = src.numel() // (B * L * Ck)
+    assert src.dtype == torch.uint8 and src.is_contiguous() and dst.is_contiguous()
+    assert dst.numel() == B * L * P * dst.shape[-1]
+    self._ck(self.lib.dd_image_stage(src.data_ptr(), B, L, P, Ck, dst.data_ptr(), dst.shape[-1],
+                                     int(c0), float(scale), self.stream))
+
+  def image_loss(self, Z, target, c0, c1, coef, loss_row, dZ):
+    M, Ctot = Z.shape[0], Z.shape[-1]
+    P = Z.numel() // (M * Ctot)
+    assert Z.is_contiguous() and target.is_contiguous() and dZ.is_contiguous()
+    self._ck(self.lib.dd_image_loss(Z.data_ptr(), target.data_ptr(), M, P, Ctot, int(c0), int(c1),
+                                    float(coef), loss_row.data_ptr(), dZ.data_ptr(), self.stream))
+
+  def sigmoid(self, x, y):
+    p, n = _flat(x)
+    self._ck(self.lib.dd_sigmoid(p, _flat(y)[0], n, self.stream))
 
   # -- losses -----------------------------------------------------------------
   def head_loss(self, kind, pred, target, weight, coef, loss_row, dpred):

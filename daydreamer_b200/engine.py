@@ -74,10 +74,71 @@ class Spec:
   slow_every: int = 100
   advnorm_decay: float = 0.99
   advnorm_max: float = 1e8
+  # image keys -> (H, W, C), channel-concatenated for the CNN (A/nets.py:218-222)
+  cnn_keys: Dict[str, Tuple[int, int, int]] = dataclasses.field(default_factory=dict)
+  cnn_depth: int = 64
+  enc_kernels: Tuple[int, ...] = (4, 4, 4, 4)
+  dec_kernels: Tuple[int, ...] = (5, 5, 6, 6)
 
   @property
   def sc(self):
     return self.stoch * self.classes
+
+  @property
+  def img_shape(self):
+    if not self.cnn_keys:
+      return None
+    shapes = [tuple(v) for v in self.cnn_keys.values()]
+    if any(x[:2] != shapes[0][:2] for x in shapes):
+      raise ValueError(f'image keys must share height/width: {shapes}')
+    return shapes[0][:2] + (sum(x[2] for x in shapes),)
+
+  @property
+  def enc_conv_shapes(self):
+    """[(Hin, Win, Cin, k, Hout, Wout, Cout)] per layer of ImageEncoderSimple: stride 2,
+    VALID, depth doubling (A/nets.py:298-305)."""
+    out = []
+    if not self.cnn_keys:
+      return out
+    h, w, c = self.img_shape
+    depth = self.cnn_depth
+    for k in self.enc_kernels:
+      ho, wo = (h - k) // 2 + 1, (w - k) // 2 + 1
+      if ho < 1 or wo < 1:
+        raise ValueError(f'image {self.img_shape} too small for encoder kernels {self.enc_kernels}')
+      out.append((h, w, c, k, ho, wo, depth))
+      h, w, c, depth = ho, wo, depth, depth * 2
+    return out
+
+  @property
+  def dec_conv_shapes(self):
+    """Same tuples for ImageDecoderSimple: transposed convs, stride 2, VALID, out =
+    2 in + k - 2, from a 1x1 map of the features (A/nets.py:316-327, :529-533)."""
+    out = []
+    if not self.cnn_keys:
+      return out
+    h, w, c = 1, 1, self.feat
+    depth = self.cnn_depth * 2 ** (len(self.dec_kernels) - 2)
+    for i, k in enumerate(self.dec_kernels):
+      last = i == len(self.dec_kernels) - 1
+      co = self.img_shape[2] if last else depth
+      ho, wo = h * 2 + k - 2, w * 2 + k - 2
+      out.append((h, w, c, k, ho, wo, co))
+      h, w, c, depth = ho, wo, co, depth // 2
+    if (h, w, c) != tuple(self.img_shape):       # the reference asserts this (A/nets.py:326)
+      raise ValueError(f'decoder kernels {self.dec_kernels} produce {(h, w, c)}, '
+                       f'not the image shape {self.img_shape}')
+    return out
+
+  @property
+  def cnn_out(self):
+    sh = self.enc_conv_shapes
+    return sh[-1][4] * sh[-1][5] * sh[-1][6] if sh else 0
+
+  @property
+  def embed(self):
+    """Encoder output width: [cnn features | mlp features] (A/nets.py:220-231)."""
+    return self.cnn_out + (self.enc_units if self.obs_dims else 0)
 
   @property
   def feat(self):
@@ -107,17 +168,32 @@ def param_shapes(spec: Spec) -> Dict[str, Tuple[int, ...]]:
       dense(f'{prefix}/dense{i}', fin if i == 0 else units, units)
 
   D, U, SC, A = spec.deter, spec.units, spec.sc, spec.act_dim
-  mlp('enc', spec.obs_total, spec.enc_layers, spec.enc_units)
+  for i, (_, _, ci, k, _, _, co) in enumerate(spec.enc_conv_shapes):
+    s[f'enc/conv{i}/kernel'] = (k, k, ci, co)                 # HWIO (A/nets.py:541)
+    s[f'enc/conv{i}/bias'] = (co,)
+    s[f'enc/conv{i}/norm/scale'] = (co,)
+    s[f'enc/conv{i}/norm/bias'] = (co,)
+  if spec.obs_dims:
+    mlp('enc', spec.obs_total, spec.enc_layers, spec.enc_units)
   dense('rssm/img_in', SC + A, U)
   dense('rssm/gru_out', D + U, 3 * D)
   for i in range(spec.prior_layers):
     dense(f'rssm/img_out_{i}', D if i == 0 else U, U)
   out('rssm/img_stats', U, SC)
-  dense('rssm/obs_out', D + spec.enc_units, U)
+  dense('rssm/obs_out', D + spec.embed, U)
   out('rssm/obs_stats', U, SC)
   s['rssm/initial_deter'] = (D,)
-  mlp('dec', spec.feat, spec.head_layers, spec.head_units)
-  out('dec/dist_out/out', spec.head_units, spec.obs_total)
+  dshapes = spec.dec_conv_shapes
+  for i, (_, _, ci, k, _, _, co) in enumerate(dshapes):
+    name = 'dec/conv_out' if i == len(dshapes) - 1 else f'dec/conv{i}'
+    s[f'{name}/kernel'] = (k, k, co, ci)                      # [k,k,out,in] (A/nets.py:523)
+    s[f'{name}/bias'] = (co,)
+    if i < len(dshapes) - 1:
+      s[f'{name}/norm/scale'] = (co,)
+      s[f'{name}/norm/bias'] = (co,)
+  if spec.obs_dims:
+    mlp('dec', spec.feat, spec.head_layers, spec.head_units)
+    out('dec/dist_out/out', spec.head_units, spec.obs_total)
   for name in ('reward', 'cont'):
     mlp(name, spec.feat, spec.head_layers, spec.head_units)
     out(f'{name}/dist_out/out', spec.head_units, 1)
@@ -146,7 +222,13 @@ def init_params(spec: Spec, seed=1) -> Dict[str, np.ndarray]:
   rng = np.random.default_rng(seed)
   out = {}
   for name, shape in param_shapes(spec).items():
-    if name.endswith('/kernel'):
+    if name.endswith('/kernel') and len(shape) == 4:
+      # Conv2D U(+-sqrt(3/mean(in,out))) (A/nets.py:542-543); transposed
+      # U(+-sqrt(3/(k*k*mean(out,in)))) (A/nets.py:524-525)
+      spatial = shape[0] * shape[1] if name.startswith('dec/') else 1
+      limit = math.sqrt(3.0 / (spatial * (shape[2] + shape[3]) / 2.0))
+      out[name] = rng.uniform(-limit, limit, shape).astype(np.float32)
+    elif name.endswith('/kernel'):
       outscale = 0.1 if name.endswith('dist_out/out/kernel') else 1.0
       limit = math.sqrt(3.0 * outscale / ((shape[0] + shape[1]) / 2.0))
       out[name] = rng.uniform(-limit, limit, shape).astype(np.float32)
@@ -261,6 +343,123 @@ class Trunk:
 
 
 # ----------------------------------------------------------------------------
+# Image encoder / decoder (conv as im2col | col2im around the dense GEMM)
+# ----------------------------------------------------------------------------
+
+class ConvEncoder:
+  """ImageEncoderSimple (A/nets.py:291-305): per layer conv(k, stride 2, VALID) +
+  bias -> LayerNorm over channels -> elu, on `rows` NHWC images.  Keeps the
+  im2col matrix, pre-norm Z, output H and LN stats of every layer for backward."""
+
+  def __init__(self, eng, group, rows, train=True):
+    be, s = eng.be, eng.spec
+    self.eng, self.group, self.rows = eng, group, rows
+    self.shapes = s.enc_conv_shapes
+    z = be.zeros
+    self.col = [z(rows * ho * wo, k * k * ci) for (_, _, ci, k, ho, wo, _) in self.shapes]
+    self.Z = [z(rows * ho * wo, co) for (_, _, _, _, ho, wo, co) in self.shapes]
+    self.H = [z(rows, ho, wo, co) for (_, _, _, _, ho, wo, co) in self.shapes]
+    self.st = [z(rows * ho * wo, 2) for (_, _, _, _, ho, wo, _) in self.shapes]
+    if train:
+      self.dZ = [z(rows * ho * wo, co) for (_, _, _, _, ho, wo, co) in self.shapes]
+      self.dH = [z(rows, ho, wo, co) for (_, _, _, _, ho, wo, co) in self.shapes[:-1]]
+      self.dcol = z(max([c.numel() for c in self.col[1:]] + [1]))
+
+  def _names(self, i):
+    b = f'enc/conv{i}'
+    return f'{b}/kernel', f'{b}/bias', f'{b}/norm/scale', f'{b}/norm/bias'
+
+  def fwd(self, img):
+    be, g = self.eng.be, self.group
+    x = img
+    for i, (_, _, ci, k, ho, wo, co) in enumerate(self.shapes):
+      kn, bn, sn, nbn = self._names(i)
+      be.im2col(x, k, 2, self.col[i])
+      be.gemm(self.col[i], g.P(kn).view(k * k * ci, co), self.Z[i], bias=g.P(bn))
+      be.ln_fwd(self.Z[i], g.P(sn), g.P(nbn), self.H[i].view(-1, co), self.st[i], 1)
+      x = self.H[i]
+    return self.H[-1].view(self.rows, -1)
+
+  def bwd(self, dOut):
+    """dOut [rows, cnn_out]: grad wrt the flattened output.  Accumulates parameter grads."""
+    be, g = self.eng.be, self.group
+    dH = dOut.view(-1, self.shapes[-1][6])
+    for i in reversed(range(len(self.shapes))):
+      _, _, ci, k, ho, wo, co = self.shapes[i]
+      kn, bn, sn, nbn = self._names(i)
+      W = g.P(kn).view(k * k * ci, co)
+      dZ = self.dZ[i]
+      be.ln_bwd(dH, self.Z[i], self.st[i], g.P(sn), g.P(nbn), dZ, g.G(sn), g.G(nbn), 1)
+      be.colsum(dZ, g.G(bn), acc=True)
+      be.gemm(self.col[i], dZ, g.G(kn).view(k * k * ci, co), ta=True, beta=1.0)
+      if i > 0:
+        dcol = self.dcol[:self.col[i].numel()].view(self.col[i].shape)
+        be.gemm(dZ, W, dcol, tb=True)
+        be.col2im(dcol, k, 2, None, self.dH[i - 1])
+        dH = self.dH[i - 1].view(-1, ci)
+
+
+class ConvDecoder:
+  """ImageDecoderSimple (A/nets.py:308-327): features as a 1x1 map -> transposed
+  convs (stride 2, VALID) with LayerNorm+elu, last layer plain; returns the
+  PRE-sigmoid image (the sigmoid lives in the loss / report kernels)."""
+
+  def __init__(self, eng, group, rows, train=True):
+    be, s = eng.be, eng.spec
+    self.eng, self.group, self.rows = eng, group, rows
+    self.shapes = s.dec_conv_shapes
+    z = be.zeros
+    self.Z = [z(rows, ho, wo, co) for (_, _, _, _, ho, wo, co) in self.shapes]
+    self.H = [z(rows, ho, wo, co) for (_, _, _, _, ho, wo, co) in self.shapes[:-1]]
+    self.st = [z(rows * ho * wo, 2) for (_, _, _, _, ho, wo, _) in self.shapes[:-1]]
+    self.ycol = z(max(rows * hi * wi * k * k * co for (hi, wi, _, k, _, _, co) in self.shapes))
+    if train:
+      self.dZ = [z(rows, ho, wo, co) for (_, _, _, _, ho, wo, co) in self.shapes[:-1]]
+      self.dH = [z(rows, ho, wo, co) for (_, _, _, _, ho, wo, co) in self.shapes[:-1]]
+
+  def _names(self, i):
+    b = 'dec/conv_out' if i == len(self.shapes) - 1 else f'dec/conv{i}'
+    return f'{b}/kernel', f'{b}/bias', f'{b}/norm/scale', f'{b}/norm/bias'
+
+  def fwd(self, feat):
+    be, g = self.eng.be, self.group
+    x = feat
+    last = len(self.shapes) - 1
+    for i, (hi, wi, ci, k, ho, wo, co) in enumerate(self.shapes):
+      kn, bn, sn, nbn = self._names(i)
+      ycol = self.ycol[:self.rows * hi * wi * k * k * co].view(self.rows * hi * wi, k * k * co)
+      be.gemm(x, g.P(kn).view(k * k * co, ci), ycol, tb=True)
+      be.col2im(ycol, k, 2, g.P(bn), self.Z[i])
+      if i < last:
+        be.ln_fwd(self.Z[i].view(-1, co), g.P(sn), g.P(nbn), self.H[i].view(-1, co),
+                  self.st[i], 1)
+        x = self.H[i].view(-1, co)
+    return self.Z[-1]
+
+  def bwd(self, dZ, feat, dfeat, beta):
+    """dZ: grad wrt the pre-sigmoid image; dfeat (+)= grad wrt the features."""
+    be, g = self.eng.be, self.group
+    for i in reversed(range(len(self.shapes))):
+      hi, wi, ci, k, ho, wo, co = self.shapes[i]
+      kn, bn, sn, nbn = self._names(i)
+      W = g.P(kn).view(k * k * co, ci)
+      be.colsum(dZ.view(-1, co), g.G(bn), acc=True)
+      dycol = self.ycol[:self.rows * hi * wi * k * k * co].view(self.rows * hi * wi, k * k * co)
+      be.im2col(dZ, k, 2, dycol)
+      x = feat if i == 0 else self.H[i - 1].view(-1, ci)
+      be.gemm(dycol, x, g.G(kn).view(k * k * co, ci), ta=True, beta=1.0)
+      if i == 0:
+        be.gemm(dycol, W, dfeat, beta=beta)
+      else:
+        psn, pnbn = self._names(i - 1)[2:]
+        dH = self.dH[i - 1].view(-1, ci)
+        be.gemm(dycol, W, dH)
+        be.ln_bwd(dH, self.Z[i - 1].view(-1, ci), self.st[i - 1], g.P(psn), g.P(pnbn),
+                  self.dZ[i - 1].view(-1, ci), g.G(psn), g.G(pnbn), 1)
+        dZ = self.dZ[i - 1]
+
+
+# ----------------------------------------------------------------------------
 # Engine
 # ----------------------------------------------------------------------------
 
@@ -303,6 +502,7 @@ class Engine:
 
     # inputs (time-major)
     self.obs = z(N, s.obs_total)
+    self.img = z(N, *s.img_shape) if s.cnn_keys else None     # f32 in [0,1], channel-concat
     self.action = z(N, A)
     self.first = z(N)
     self.reward = z(N, 1)
@@ -322,7 +522,11 @@ class Engine:
     self._tmp = [z(R * wide) for _ in range(3)]
 
     # -- world model buffers -------------------------------------------------
-    self.enc = Trunk(self, gm, 'enc', s.enc_layers, E, N)
+    self.enc = Trunk(self, gm, 'enc', s.enc_layers, E, N) if s.obs_dims else None
+    self.enc_cnn = ConvEncoder(self, gm, N) if s.cnn_keys else None
+    self.dec_cnn = ConvDecoder(self, gm, N) if s.cnn_keys else None
+    self.d_img = z(N, *s.img_shape) if s.cnn_keys else None
+    self.d_cnn = z(N, s.cnn_out) if s.cnn_keys else None
     self.init_deter = z(1, D)
     self.init_trunk = Trunk(self, gm, 'rssm/initp', s.prior_layers, U, 1)
     self.init_zs = z(1, SC)
@@ -347,7 +551,7 @@ class Engine:
     self.prior = Trunk(self, gm, 'rssm/priorp', s.prior_layers, U, N)
     self.prior_logit = z(N, SC)
     self.heads = {k: Trunk(self, gm, k, s.head_layers, s.head_units, N)
-                  for k in ('dec', 'reward', 'cont')}
+                  for k in (('dec',) if s.obs_dims else ()) + ('reward', 'cont')}
     self.out_dec = z(N, s.obs_total)
     self.out_rew = z(N, 1)
     self.out_con = z(N, 1)
@@ -357,7 +561,8 @@ class Engine:
     self.kl_row = z(N)
     self.ent_post = z(N)
     self.ent_prior = z(N)
-    self.loss_rows = {k: z(N) for k in list(s.obs_dims) + ['reward', 'cont', 'total']}
+    self.loss_rows = {k: z(N) for k in list(s.cnn_keys) + list(s.obs_dims) +
+                      ['reward', 'cont', 'total']}
     self.kl_sum = z(1)
     self.dfeat = z(N, D + SC)
     self.dpost_logit = z(N, SC)
@@ -426,7 +631,7 @@ class Engine:
     # metrics: rows of 8 doubles written by `stats`/`balance`
     self.mnames = [
         'kl', 'ent_post', 'ent_prior', 'reward_loss', 'cont_loss', 'total_loss',
-        *[f'loss_{k}' for k in s.obs_dims], 'bal_reward', 'bal_cont',
+        *[f'loss_{k}' for k in list(s.cnn_keys) + list(s.obs_dims)], 'bal_reward', 'bal_cont',
         'imag_reward', 'imag_critic', 'imag_return', 'closs', 'score', 'adv_ctrl',
         'ret_ctrl', 'score_ctrl', 'ent', 'aloss']
     self.mstat = z(len(self.mnames), 8, dtype=torch.float64)
@@ -544,10 +749,18 @@ class Engine:
     D, U, SC, A, E = s.deter, s.units, s.sc, s.act_dim, s.enc_units
     feat = self.feat
 
-    embed = self.enc.fwd([(self.obs, 0)], 0, N)
-    # embed part of obs_out's pre-activation, all steps at once
+    # MultiEncoder: [cnn features | mlp features] (A/nets.py:212-232); their part of
+    # obs_out's pre-activation is one GEMM per encoder output over all steps at once
     Wobs = gm.P('rssm/obs_out/kernel')
-    be.gemm(embed, Wobs[D:], self.z_obs)
+    self.embed_parts = []
+    if s.cnn_keys:
+      self.embed_parts.append(self.enc_cnn.fwd(self.img))
+    if s.obs_dims:
+      self.embed_parts.append(self.enc.fwd([(self.obs, 0)], 0, N))
+    off, beta = D, 0.0
+    for part in self.embed_parts:
+      be.gemm(part, Wobs[off:off + part.shape[1]], self.z_obs, beta=beta)
+      off, beta = off + part.shape[1], 1.0
 
     # learned initial state (A/nets.py:54-62): deter0 = tanh(v), stoch0 = mode
     be.tanh_fwd(gm.P('rssm/initial_deter').view(1, D), self.init_deter)
@@ -563,7 +776,10 @@ class Engine:
 
     # heads on the posterior features (A/agent.py:170-176)
     xs = [(feat, 0)]
-    self._out_fwd(gm, 'dec/dist_out/out', self.heads['dec'].fwd(xs, 0, N), self.out_dec)
+    if s.cnn_keys:
+      self.dec_cnn.fwd(feat)
+    if s.obs_dims:
+      self._out_fwd(gm, 'dec/dist_out/out', self.heads['dec'].fwd(xs, 0, N), self.out_dec)
     self._out_fwd(gm, 'reward/dist_out/out', self.heads['reward'].fwd(xs, 0, N), self.out_rew)
     self._out_fwd(gm, 'cont/dist_out/out', self.heads['cont'].fwd(xs, 0, N), self.out_con)
 
@@ -648,9 +864,15 @@ class Engine:
         self.allreduce(self.kl_sum)
       be.autoadapt(self.wmkl_scale, self.kl_sum, float(N * self.world), s.wmkl_target,
                    s.wmkl_min, s.wmkl_max, s.ctrl_vel, s.ctrl_thres, False)
-    off = 0
     tot = self.loss_rows['total']
     be.fill_(tot, 0.0)
+    off = 0
+    for k, shp in s.cnn_keys.items():       # MSEDist(sigmoid(out), 3, 'sum')
+      be.image_loss(self.dec_cnn.Z[-1], self.img, off, off + shp[2], coef, self.loss_rows[k],
+                    self.d_img)
+      be.add_(tot, self.loss_rows[k])
+      off += shp[2]
+    off = 0
     for k, d in s.obs_dims.items():
       be.head_loss(0, self.out_dec[:, off:off + d], self.obs[:, off:off + d], None,
                    coef, self.loss_rows[k], self.d_dec[:, off:off + d])
@@ -670,7 +892,7 @@ class Engine:
     self._stat(self.loss_rows['reward'], 'reward_loss')
     self._stat(self.loss_rows['cont'], 'cont_loss')
     self._stat(tot, 'total_loss')
-    for k in s.obs_dims:
+    for k in list(s.cnn_keys) + list(s.obs_dims):
       self._stat(self.loss_rows[k], f'loss_{k}')
     be.balance(1, self.out_rew, self.loss_rows['reward'], self.reward, 0.1,
                self.mstat[self.midx['bal_reward']])
@@ -688,7 +910,12 @@ class Engine:
 
     # heads -> dfeat
     beta = 0.0
+    if s.cnn_keys:
+      self.dec_cnn.bwd(self.d_img, feat, dfeat, beta)
+      beta = 1.0
     for name, dOut in (('dec', self.d_dec), ('reward', self.d_rew), ('cont', self.d_con)):
+      if name not in self.heads:
+        continue
       tr = self.heads[name]
       dH = self.tmp(0, N, hu)
       self._out_bwd(gm, f'{name}/dist_out/out', tr.H[-1], dOut, dH, True)
@@ -745,8 +972,10 @@ class Engine:
     be.colsum(self.dzs, gm.G('rssm/obs_stats/bias'), acc=True)
     Gobs = gm.G('rssm/obs_out/kernel')
     be.gemm(feat[:, :D], self.dz_obs, Gobs[:D], ta=True, beta=1.0)
-    embed = self.enc.H[-1]
-    be.gemm(embed, self.dz_obs, Gobs[D:], ta=True, beta=1.0)
+    off = D
+    for part in self.embed_parts:
+      be.gemm(part, self.dz_obs, Gobs[off:off + part.shape[1]], ta=True, beta=1.0)
+      off += part.shape[1]
     Ggru = gm.G('rssm/gru_out/kernel')
     be.gemm(self.m_deter, self.dz_gru, Ggru[:D], ta=True, beta=1.0)
     be.gemm(self.x_in, self.dz_gru, Ggru[D:], ta=True, beta=1.0)
@@ -756,9 +985,15 @@ class Engine:
     # initial_deter = tanh(v)
     be.tanh_bwd(self.d_initdeter, self.init_deter,
                 gm.G('rssm/initial_deter').view(1, D), True)
-    # encoder
-    be.gemm(self.dz_obs, Wobs[D:], self.d_embed, tb=True)
-    self.enc.bwd(self.d_embed, 0, N, [(self.obs, 0)], [], True)
+    # encoders
+    off = D
+    if s.cnn_keys:
+      be.gemm(self.dz_obs, Wobs[off:off + s.cnn_out], self.d_cnn, tb=True)
+      self.enc_cnn.bwd(self.d_cnn)
+      off += s.cnn_out
+    if s.obs_dims:
+      be.gemm(self.dz_obs, Wobs[off:], self.d_embed, tb=True)
+      self.enc.bwd(self.d_embed, 0, N, [(self.obs, 0)], [], True)
 
   def opt_step(self, group, ci):
     s, be, g = self.spec, self.be, self.groups[group]
@@ -1038,7 +1273,7 @@ class Engine:
     m = {}
     m.update(wmkl_mean=mean('kl'), wmkl_std=std('kl'), wmkl_scale_mean=wm,
              wmkl_scale_std=0.0, kl_loss_mean=wm * mean('kl'), kl_loss_std=wm * std('kl'))
-    for k in s.obs_dims:
+    for k in list(s.cnn_keys) + list(s.obs_dims):
       m[f'{k}_loss_mean'], m[f'{k}_loss_std'] = mean(f'loss_{k}'), std(f'loss_{k}')
     for k in ('reward', 'cont'):
       m[f'{k}_loss_mean'], m[f'{k}_loss_std'] = mean(f'{k}_loss'), std(f'{k}_loss')

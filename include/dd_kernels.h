@@ -151,6 +151,25 @@ int dd_tanh_fwd(const float* x, float* y, int64_t n, dd_stream_t stream);
 int dd_tanh_bwd(const float* dy, const float* y, float* dx, int64_t n, int acc,
                 dd_stream_t stream);
 
+/* ---- image path: convolutions as (im2col | col2im) + dd_gemm ---------------
+ * NHWC; col[(n,ho,wo),(kh,kw,c)], ho=(H-k)/stride+1 (VALID).  im2col serves the
+ * conv forward (A/nets.py:541-547) and the conv-transpose backward; col2im (+bias)
+ * the conv backward and the conv-transpose forward (A/nets.py:523-539). */
+int dd_im2col(const float* X, int N, int H, int W, int C, int k, int stride,
+              float* col, dd_stream_t stream);
+int dd_col2im(const float* col, int N, int H, int W, int C, int k, int stride,
+              const float* bias, float* X, dd_stream_t stream);
+/* replay uint8 [B,L,P,Ck] -> f32 time-major [L*B,P,Ctot] at channel c0, times
+ * scale (1/255; A/agent.py:128-129) -- channel concat of A/nets.py:218. */
+int dd_image_stage(const uint8_t* src, int B, int L, int P, int Ck, float* dst,
+                   int Ctot, int c0, float scale, dd_stream_t stream);
+/* MSEDist(sigmoid(Z), 3, 'sum') on channels [c0,c1) (A/nets.py:283-288,325):
+ * loss_row[m] = sum (sigmoid(z)-t)^2 ; dZ = coef * dloss/dz on those channels. */
+int dd_image_loss(const float* Z, const float* target, int M, int P, int Ctot,
+                  int c0, int c1, float coef, float* loss_row, float* dZ,
+                  dd_stream_t stream);
+int dd_sigmoid(const float* x, float* y, int64_t n, dd_stream_t stream);
+
 /* ---- losses ------------------------------------------------------------ */
 /* kind 0: MSEDist sum (A/tfutils.py:320-329); 1: SymlogDist (:347-356);
  * 2: -Bernoulli(logits).log_prob (A/nets.py:469-471).  weight[M] may be NULL.

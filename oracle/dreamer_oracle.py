@@ -78,10 +78,67 @@ class Spec:
   slow_every: int = 100
   advnorm_decay: float = 0.99
   advnorm_max: float = 1e8
+  # image keys -> (H, W, C); channel-concatenated for the CNN (A/nets.py:218-222)
+  cnn_keys: Dict[str, Tuple[int, int, int]] = dataclasses.field(default_factory=dict)
+  cnn_depth: int = 64                         # A/configs.yaml:54-55
+  enc_kernels: Tuple[int, ...] = (4, 4, 4, 4)
+  dec_kernels: Tuple[int, ...] = (5, 5, 6, 6)
 
   @property
   def sc(self):
     return self.stoch * self.classes
+
+  @property
+  def img_shape(self):
+    """(H, W, sum of channels) of the merged image, or None without cnn keys."""
+    if not self.cnn_keys:
+      return None
+    shapes = [tuple(v) for v in self.cnn_keys.values()]
+    assert all(x[:2] == shapes[0][:2] for x in shapes), shapes
+    return shapes[0][:2] + (sum(x[2] for x in shapes),)
+
+  @property
+  def enc_conv_shapes(self):
+    """[(Hin, Win, Cin, k, Hout, Wout, Cout)] of ImageEncoderSimple: stride 2,
+    VALID, depth doubling (A/nets.py:298-305)."""
+    out = []
+    if not self.cnn_keys:
+      return out
+    h, w, c = self.img_shape
+    depth = self.cnn_depth
+    for k in self.enc_kernels:
+      ho, wo = (h - k) // 2 + 1, (w - k) // 2 + 1
+      out.append((h, w, c, k, ho, wo, depth))
+      h, w, c, depth = ho, wo, depth, depth * 2
+    return out
+
+  @property
+  def dec_conv_shapes(self):
+    """Same tuples for ImageDecoderSimple: transposed, stride 2, VALID, out =
+    in*2 + k - 2, starting from a 1x1 map of the features (A/nets.py:316-327,529-533)."""
+    out = []
+    if not self.cnn_keys:
+      return out
+    h, w, c = 1, 1, self.feat
+    depth = self.cnn_depth * 2 ** (len(self.dec_kernels) - 2)
+    for i, k in enumerate(self.dec_kernels):
+      last = i == len(self.dec_kernels) - 1
+      co = self.img_shape[2] if last else depth
+      ho, wo = h * 2 + k - 2, w * 2 + k - 2
+      out.append((h, w, c, k, ho, wo, co))
+      h, w, c, depth = ho, wo, co, depth // 2
+    assert (h, w, c) == tuple(self.img_shape), ((h, w, c), self.img_shape)
+    return out
+
+  @property
+  def cnn_out(self):
+    sh = self.enc_conv_shapes
+    return sh[-1][4] * sh[-1][5] * sh[-1][6] if sh else 0
+
+  @property
+  def embed(self):
+    """Encoder output width: [cnn features, mlp features] (A/nets.py:220-231)."""
+    return self.cnn_out + (self.enc_units if self.obs_dims else 0)
 
   @property
   def feat(self):
@@ -134,17 +191,32 @@ def param_shapes(spec: Spec) -> Dict[str, Tuple[int, ...]]:
       dense(f'{prefix}/dense{i}', fin if i == 0 else units, units)
 
   D, U, SC, A = spec.deter, spec.units, spec.sc, spec.act_dim
-  mlp('enc', spec.obs_total, spec.enc_layers, spec.enc_units)
+  for i, (_, _, ci, k, _, _, co) in enumerate(spec.enc_conv_shapes):
+    s[f'enc/conv{i}/kernel'] = (k, k, ci, co)                 # HWIO, A/nets.py:541
+    s[f'enc/conv{i}/bias'] = (co,)
+    s[f'enc/conv{i}/norm/scale'] = (co,)
+    s[f'enc/conv{i}/norm/bias'] = (co,)
+  if spec.obs_dims:
+    mlp('enc', spec.obs_total, spec.enc_layers, spec.enc_units)
   dense('rssm/img_in', SC + A, U)
   dense('rssm/gru_out', D + U, 3 * D)
   for i in range(spec.prior_layers):
     dense(f'rssm/img_out_{i}', D if i == 0 else U, U)
   out('rssm/img_stats', U, SC)
-  dense('rssm/obs_out', D + spec.enc_units, U)
+  dense('rssm/obs_out', D + spec.embed, U)
   out('rssm/obs_stats', U, SC)
   s['rssm/initial_deter'] = (D,)
-  mlp('dec', spec.feat, spec.head_layers, spec.head_units)
-  out('dec/dist_out/out', spec.head_units, spec.obs_total)
+  dshapes = spec.dec_conv_shapes
+  for i, (_, _, ci, k, _, _, co) in enumerate(dshapes):
+    name = 'dec/conv_out' if i == len(dshapes) - 1 else f'dec/conv{i}'
+    s[f'{name}/kernel'] = (k, k, co, ci)                      # [k,k,out,in], A/nets.py:523
+    s[f'{name}/bias'] = (co,)
+    if i < len(dshapes) - 1:
+      s[f'{name}/norm/scale'] = (co,)
+      s[f'{name}/norm/bias'] = (co,)
+  if spec.obs_dims:
+    mlp('dec', spec.feat, spec.head_layers, spec.head_units)
+    out('dec/dist_out/out', spec.head_units, spec.obs_total)
   for name in ('reward', 'cont'):
     mlp(name, spec.feat, spec.head_layers, spec.head_units)
     out(f'{name}/dist_out/out', spec.head_units, 1)
@@ -176,7 +248,13 @@ def init_params(spec: Spec, seed=1) -> Dict[str, np.ndarray]:
   rng = np.random.default_rng(seed)
   out = {}
   for name, shape in param_shapes(spec).items():
-    if name.endswith('/kernel'):
+    if name.endswith('/kernel') and len(shape) == 4:
+      # Conv2D: U(+-sqrt(3/mean(in,out))) (A/nets.py:542-543); transposed:
+      # U(+-sqrt(3/(k*k*mean(out,in)))) (A/nets.py:524-525)
+      spatial = shape[0] * shape[1] if name.startswith('dec/') else 1
+      limit = math.sqrt(3.0 / (spatial * (shape[2] + shape[3]) / 2.0))
+      out[name] = rng.uniform(-limit, limit, shape).astype(np.float32)
+    elif name.endswith('/kernel'):
       # DistLayer 'out' has outscale 0.1, 'std' 1.0 (A/nets.py:448-454);
       # rssm stats layers use plain Linear (outscale 1.0, A/nets.py:164).
       outscale = 0.1 if name.endswith('dist_out/out/kernel') else 1.0
@@ -365,10 +443,52 @@ def head(feat, p, prefix, spec: Spec, out='out'):
   return linear_bias(x, p, f'{prefix}/dist_out/{out}')
 
 
+def conv_layer(x, p, name, transp=False, norm=True):
+  """Conv2D(stride 2, VALID) + bias [+ LayerNorm over channels + elu] on NHWC
+  (A/nets.py:495-554).  Forward kernel HWIO; transposed kernel [k,k,out,in] with
+  tf.nn.conv2d_transpose semantics: out[ho,wo,co] = sum x[hi,wi,ci] K[ho-2hi, wo-2wi, co, ci]."""
+  w = p[f'{name}/kernel']
+  x = x.permute(0, 3, 1, 2)
+  if transp:
+    x = F.conv_transpose2d(x, w.permute(3, 2, 0, 1), stride=2)
+  else:
+    x = F.conv2d(x, w.permute(3, 2, 0, 1), stride=2)
+  x = x.permute(0, 2, 3, 1) + p[f'{name}/bias']
+  if norm:
+    x = F.elu(layer_norm(x, p[f'{name}/norm/scale'], p[f'{name}/norm/bias']))
+  return x
+
+
+def image_encoder(x, p, spec: Spec):
+  """ImageEncoderSimple (A/nets.py:291-305): x [M,H,W,C] -> [M, cnn_out] (h,w,c order)."""
+  for i in range(len(spec.enc_kernels)):
+    x = conv_layer(x, p, f'enc/conv{i}')
+  return x.reshape(x.shape[0], -1)
+
+
+def image_decoder(feat, p, spec: Spec):
+  """ImageDecoderSimple (A/nets.py:308-327): feat [M,F] -> sigmoid image [M,H,W,C]."""
+  x = feat.reshape(feat.shape[0], 1, 1, feat.shape[-1])
+  n = len(spec.dec_kernels)
+  for i in range(n - 1):
+    x = conv_layer(x, p, f'dec/conv{i}', transp=True)
+  x = conv_layer(x, p, 'dec/conv_out', transp=True, norm=False)
+  return torch.sigmoid(x)
+
+
 def encoder(data, p, spec: Spec):
-  x = torch.cat([data[k].reshape(data[k].shape[:2] + (-1,))
-                 for k in spec.obs_dims], -1)
-  return mlp_trunk(x, p, 'enc', spec.enc_layers)
+  """MultiEncoder (A/nets.py:212-232): [cnn(channel-concat images), mlp(concat vectors)]."""
+  outs = []
+  lead = data['is_first'].shape if 'is_first' in data else None
+  if spec.cnn_keys:
+    img = torch.cat([data[k] for k in spec.cnn_keys], -1)
+    lead = img.shape[:-3]
+    outs.append(image_encoder(img.reshape((-1,) + img.shape[-3:]), p, spec).reshape(lead + (-1,)))
+  if spec.obs_dims:
+    x = torch.cat([data[k].reshape(data[k].shape[:2] + (-1,))
+                   for k in spec.obs_dims], -1)
+    outs.append(mlp_trunk(x, p, 'enc', spec.enc_layers))
+  return torch.cat(outs, -1)
 
 
 def actor_dist(feat, p, spec: Spec):
@@ -517,8 +637,13 @@ class Learner:
   @staticmethod
   def preprocess(batch):
     """A/agent.py:123-139 (reward transform 'off')."""
-    data = {k: torch.as_tensor(np.asarray(v)).float() for k, v in batch.items()
-            if not k.startswith('log_') and k != 'key'}
+    data = {}
+    for k, v in batch.items():
+      if k.startswith('log_') or k == 'key':
+        continue
+      v = np.asarray(v)
+      t = torch.as_tensor(v).float()
+      data[k] = t / 255.0 if (v.ndim > 3 and v.dtype == np.uint8) else t
     data['cont'] = 1.0 - data['is_terminal']
     return data
 
@@ -531,9 +656,14 @@ class Learner:
     post, prior = observe(
         embed, data['action'], data['is_first'], state, p, spec, g_post)
     feat = feat_of(post, spec)
-    target = torch.cat([data[k].reshape(data[k].shape[:2] + (-1,))
-                        for k in spec.obs_dims], -1)
-    dec = head(feat, p, 'dec', spec)
+    dec = recon = None
+    if spec.obs_dims:
+      target = torch.cat([data[k].reshape(data[k].shape[:2] + (-1,))
+                          for k in spec.obs_dims], -1)
+      dec = head(feat, p, 'dec', spec)
+    if spec.cnn_keys:
+      recon = image_decoder(feat.reshape(-1, spec.feat), p, spec)
+      recon = recon.reshape(feat.shape[:2] + recon.shape[1:])
     rew = head(feat, p, 'reward', spec)[..., 0]
     con = head(feat, p, 'cont', spec)[..., 0]
     losses = {}
@@ -546,6 +676,11 @@ class Learner:
     losses['kl'] = scale * kl
     mets.update(wmkl_mean=kl.mean(), wmkl_std=_std(kl),
                 wmkl_scale_mean=scale.mean(), wmkl_scale_std=scale.std(unbiased=False) if scale.dim() else torch.zeros(()))
+    off = 0
+    for k, shp in spec.cnn_keys.items():       # MSEDist(mean, 3, 'sum'), A/nets.py:283-288
+      c = shp[2]
+      losses[k] = ((recon[..., off:off + c] - data[k]) ** 2).sum((-1, -2, -3))
+      off += c
     off = 0
     for k, d in spec.obs_dims.items():
       losses[k] = ((dec[..., off:off + d] - target[..., off:off + d]) ** 2).sum(-1)
@@ -566,7 +701,7 @@ class Learner:
     mets.update({f'reward_{k}': v for k, v in st.items()})
     st = balance_stats(torch.sigmoid(con), losses['cont'], data['cont'], 0.5)
     mets.update({f'cont_{k}': v for k, v in st.items()})
-    aux = {'embed': embed, 'post': post, 'prior': prior, 'dec': dec,
+    aux = {'embed': embed, 'post': post, 'prior': prior, 'dec': dec, 'recon': recon,
            'reward': rew, 'cont': con, 'kl': kl, 'losses': losses}
     return model_loss.mean(), aux, mets
 

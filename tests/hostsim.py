@@ -182,6 +182,45 @@ class HostSim:
     g = dy * (1.0 - y * y)
     dx.copy_(dx + g if acc else g)
 
+  # -- image path --------------------------------------------------------------
+  def im2col(self, X, k, stride, col):
+    N, H, W, C = X.shape
+    Ho, Wo = (H - k) // stride + 1, (W - k) // stride + 1
+    c = col.view(N, Ho, Wo, k, k, C)
+    for kh in range(k):
+      for kw in range(k):
+        c[:, :, :, kh, kw, :] = X[:, kh:kh + stride * (Ho - 1) + 1:stride,
+                                  kw:kw + stride * (Wo - 1) + 1:stride, :]
+
+  def col2im(self, col, k, stride, bias, X):
+    N, H, W, C = X.shape
+    Ho, Wo = (H - k) // stride + 1, (W - k) // stride + 1
+    c = col.view(N, Ho, Wo, k, k, C)
+    X.zero_()
+    if bias is not None:
+      X += bias
+    for kh in range(k):
+      for kw in range(k):
+        X[:, kh:kh + stride * (Ho - 1) + 1:stride,
+          kw:kw + stride * (Wo - 1) + 1:stride, :] += c[:, :, :, kh, kw, :]
+
+  def image_stage(self, src, dst, c0, scale):
+    B, L = src.shape[:2]
+    Ck = src.shape[-1]
+    v = src.reshape(B, L, -1, Ck).transpose(0, 1).float() * scale
+    dst.view(L * B, -1, dst.shape[-1])[:, :, c0:c0 + Ck] = v.reshape(L * B, -1, Ck)
+
+  def image_loss(self, Z, target, c0, c1, coef, loss_row, dZ):
+    M = Z.shape[0]
+    z = Z.reshape(M, -1, Z.shape[-1])[:, :, c0:c1]
+    t = target.reshape(M, -1, Z.shape[-1])[:, :, c0:c1]
+    sg = torch.sigmoid(z)
+    loss_row.copy_(((sg - t) ** 2).sum((-1, -2)))
+    dZ.view(M, -1, Z.shape[-1])[:, :, c0:c1] = coef * 2.0 * (sg - t) * sg * (1.0 - sg)
+
+  def sigmoid(self, x, y):
+    y.copy_(torch.sigmoid(x))
+
   # -- losses -----------------------------------------------------------------
   def head_loss(self, kind, pred, target, weight, coef, loss_row, dpred):
     """kind 0: sum_d (p-t)^2; 1: (p-symlog(t))^2 summed; 2: softplus(p)-t*p.

@@ -19,6 +19,12 @@ def rel(a, b):
 @pytest.mark.parametrize('B,L,steps,kw', [
     (3, 5, 1, {}), (2, 6, 3, {}),
     (3, 5, 2, dict(discrete=True, act_dim=5, actent_target=0.4)),   # xarm/ur5-style one-hot actor
+    # image + depth CNN encoder/decoder next to the proprio MLP (xarm-style), one-hot actor
+    (2, 4, 2, dict(discrete=True, act_dim=5, cnn_keys={'image': (18, 18, 3), 'depth': (18, 18, 1)},
+                   cnn_depth=4, enc_kernels=(4, 4), dec_kernels=(3, 4, 4))),
+    # image only, continuous actions
+    (2, 3, 1, dict(obs_dims={}, cnn_keys={'image': (10, 10, 3)}, cnn_depth=4, enc_kernels=(4, 4),
+                   dec_kernels=(4, 4))),
 ])
 def test_train_step_matches_oracle(B, L, steps, kw):
   torch.manual_seed(0)

@@ -261,6 +261,44 @@ def test_actor_discrete(backends, H, N, A):
   both(backends, case, rtol=1e-4, atol=1e-6, exact=('action',))
 
 
+@pytest.mark.parametrize('N,H,W,C,k', [(3, 18, 18, 4, 4), (2, 31, 31, 64, 4), (5, 10, 10, 3, 4),
+                                       (2, 13, 13, 8, 5), (3, 30, 30, 8, 6), (2, 64, 64, 3, 6),
+                                       (4, 5, 5, 16, 5), (7, 3, 3, 8, 3)])
+def test_im2col_col2im(backends, N, H, W, C, k):
+  def case(be, T):
+    Ho = (H - k) // 2 + 1
+    X = T(rnd(N, H, W, C, seed=1))
+    col = T(torch.zeros(N * Ho * Ho, k * k * C))
+    be.im2col(X, k, 2, col)
+    col2 = T(rnd(N * Ho * Ho, k * k * C, seed=2))
+    bias = T(rnd(C, seed=3))
+    Y, Y0 = T(rnd(N, H, W, C, seed=4)), T(rnd(N, H, W, C, seed=5))
+    be.col2im(col2, k, 2, bias, Y)
+    be.col2im(col2, k, 2, None, Y0)
+    return {'col': col, 'Y': Y, 'Y0': Y0}
+  both(backends, case, rtol=1e-5, atol=1e-5, exact=('col',))
+
+
+def test_image_stage_and_loss(backends):
+  def case(be, T):
+    B, L, H, W = 3, 4, 10, 10
+    g = torch.Generator().manual_seed(0)
+    rgb = torch.randint(0, 256, (B, L, H, W, 3), generator=g, dtype=torch.uint8)
+    dep = torch.randint(0, 256, (B, L, H, W, 1), generator=g, dtype=torch.uint8)
+    img = T(torch.zeros(L * B, H, W, 4))
+    be.image_stage(T(rgb), img, 0, 1.0 / 255.0)
+    be.image_stage(T(dep), img, 3, 1.0 / 255.0)
+    Z = T(rnd(L * B, H, W, 4, seed=1))
+    l0, l1 = T(torch.zeros(L * B)), T(torch.zeros(L * B))
+    dZ = T(torch.zeros(L * B, H, W, 4))
+    be.image_loss(Z, img, 0, 3, 0.01, l0, dZ)
+    be.image_loss(Z, img, 3, 4, 0.01, l1, dZ)
+    sg = T(torch.zeros(L * B, H, W, 4))
+    be.sigmoid(Z, sg)
+    return {'img': img, 'l0': l0, 'l1': l1, 'dZ': dZ, 'sg': sg}
+  both(backends, case, rtol=2e-5, atol=1e-6)
+
+
 def test_controllers_and_adam(backends):
   def case(be, T):
     rows = T(torch.zeros(3, 8, dtype=torch.float64))

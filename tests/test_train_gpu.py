@@ -109,6 +109,28 @@ def test_medium_matches_oracle():
   run_pair(spec, 8, 16, 2, grad_tol=1e-3)
 
 
+def test_discrete_actor_matches_oracle():
+  # one-hot actions + 'reinforce' actor gradient (xarm / ur5 action space)
+  run_pair(O.tiny_spec(discrete=True, act_dim=6, actent_target=0.4), 3, 5, 3, grad_tol=3e-4)
+
+
+def test_image_keys_tiny_matches_oracle():
+  # image + depth through the conv encoder / transposed-conv decoder next to the proprio MLP
+  spec = O.tiny_spec(discrete=True, act_dim=5, cnn_keys={'image': (18, 18, 3), 'depth': (18, 18, 1)},
+                     cnn_depth=4, enc_kernels=(4, 4), dec_kernels=(3, 4, 4))
+  run_pair(spec, 2, 4, 2, grad_tol=5e-4)
+
+
+def test_image_64x64_reference_geometry_matches_oracle():
+  """The reference's image geometry (A/configs.yaml:54-55): 64x64x3, encoder kernels
+  4,4,4,4 (64->31->14->6->2), decoder 5,5,6,6 (1->5->13->30->64); reduced depth."""
+  spec = O.Spec(obs_dims={'joint_positions': 6, 'gripper_pos': 1}, cnn_keys={'image': (64, 64, 3)},
+                cnn_depth=8, act_dim=6, discrete=True, deter=64, units=64, stoch=8, classes=8,
+                enc_layers=2, enc_units=32, head_layers=2, head_units=64, horizon=3,
+                actent_target=0.4)
+  run_pair(spec, 2, 4, 1, grad_tol=1e-3)
+
+
 def test_a1_full_size_one_step_matches_oracle():
   """BASELINE.json configs[1]: deter=units=512, 32x32 latent, B=16 L=64 H=15."""
   run_pair(O.a1_spec(), 16, 64, 1, grad_tol=3e-3, met_tol=1e-3)

@@ -17,6 +17,8 @@ def make_batch(spec, B, L, seed=0, term=0.05, mid_first=True):
   rng = np.random.default_rng(seed)
   b = {k: rng.standard_normal((B, L, d)).astype(np.float32)
        for k, d in spec.obs_dims.items()}
+  for k, shp in spec.cnn_keys.items():
+    b[k] = rng.integers(0, 256, (B, L) + tuple(shp)).astype(np.uint8)
   b['action'] = rng.uniform(-1, 1, (B, L, spec.act_dim)).astype(np.float32)
   if spec.discrete:            # one-hot actions (embodied OneHotAction wrapper)
     b['action'] = np.eye(spec.act_dim, dtype=np.float32)[rng.integers(0, spec.act_dim, (B, L))]
@@ -61,9 +63,14 @@ def load_batch(eng, spec, batch, noise=None, state=None):
   B, L = eng.B, eng.L
   dev = eng.obs.device
   put = lambda dst, arr: dst.copy_(torch.as_tensor(np.ascontiguousarray(arr, np.float32)).to(dev).reshape(dst.shape))
-  obs = np.concatenate([np.asarray(batch[k], np.float32).reshape(B, L, -1)
-                        for k in spec.obs_dims], -1)
-  put(eng.obs, tm(obs))
+  if spec.obs_dims:
+    obs = np.concatenate([np.asarray(batch[k], np.float32).reshape(B, L, -1)
+                          for k in spec.obs_dims], -1)
+    put(eng.obs, tm(obs))
+  if spec.cnn_keys:
+    img = np.concatenate([np.asarray(batch[k], np.float32) / np.float32(255.0)
+                          for k in spec.cnn_keys], -1)
+    put(eng.img, tm(img))
   put(eng.action, tm(batch['action']))
   put(eng.first, tm(batch['is_first'].astype(np.float32)))
   put(eng.reward, tm(batch['reward']))
