@@ -64,17 +64,27 @@ def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
             if k not in excluded and re.match(pattern, k) and len(s) in ranks}
 
   def cnn_keys(pattern, excluded):
-    return [k for k, s in shapes.items()
-            if k not in excluded and re.match(pattern, k) and len(s) == 3]
+    return {k: tuple(int(d) for d in s) for k, s in shapes.items()
+            if k not in excluded and re.match(pattern, k) and len(s) == 3}
 
   enc_ex = ('is_first', 'is_last')
   dec_ex = ('is_first', 'is_last', 'is_terminal', 'reward')
-  if cnn_keys(g('encoder.cnn_keys'), enc_ex) or cnn_keys(g('decoder.cnn_keys'), dec_ex):
-    raise NotImplementedError('image (CNN) encoder/decoder keys are not built yet: '
-                              'use proprio configs such as a1 / dmc_proprio')
+  enc_cnn = cnn_keys(g('encoder.cnn_keys'), enc_ex)
+  dec_cnn = cnn_keys(g('decoder.cnn_keys'), dec_ex)
+  if enc_cnn != dec_cnn:
+    raise NotImplementedError(f'encoder image keys {list(enc_cnn)} must equal decoder image '
+                              f'keys {list(dec_cnn)}')
+  if enc_cnn:
+    for part in ('encoder', 'decoder'):
+      if g(f'{part}.cnn') != 'simple':
+        raise NotImplementedError(f'{part}.cnn={g(f"{part}.cnn")!r} is not built (only simple)')
+    if g('decoder.image_dist') != 'mse':
+      raise NotImplementedError('decoder.image_dist must be mse')
+    if int(g('encoder.cnn_depth')) != int(g('decoder.cnn_depth')):
+      raise NotImplementedError('encoder.cnn_depth must equal decoder.cnn_depth')
   enc = vec_keys(g('encoder.mlp_keys'), enc_ex, (0, 1))
   dec = vec_keys(g('decoder.mlp_keys'), dec_ex, (1,))
-  if list(enc) != list(dec) or not enc:
+  if list(enc) != list(dec) or not (enc or enc_cnn):
     raise NotImplementedError(f'encoder keys {list(enc)} must equal decoder keys {list(dec)}')
   heads = [g(f'{h}.layers') for h in ('reward_head', 'cont_head', 'actor', 'critic')]
   units = [g(f'{h}.units') for h in ('reward_head', 'cont_head', 'actor', 'critic')]
@@ -101,7 +111,10 @@ def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
       actor_maxstd=float(g('actor.maxstd')), actor_unimix=float(g('actor.unimix')),
       lr=float(opts[0][0]), adam_eps=float(opts[0][1]), clip=float(opts[0][2]),
       wd=float(opts[0][3]), slow_every=int(g('slow_target_update')),
-      advnorm_decay=float(g('advnorm.decay')), advnorm_max=float(g('advnorm.max')))
+      advnorm_decay=float(g('advnorm.decay')), advnorm_max=float(g('advnorm.max')),
+      cnn_keys=enc_cnn, cnn_depth=int(g('encoder.cnn_depth')),
+      enc_kernels=tuple(int(k) for k in g('encoder.cnn_kernels')),
+      dec_kernels=tuple(int(k) for k in g('decoder.cnn_kernels')))
 
 
 class Batcher:
@@ -180,6 +193,9 @@ class Agent:
           k: torch.zeros(B, L, d, pin_memory=True)
           for k, d in (('obs', self.spec.obs_total), ('action', self.spec.act_dim),
                        ('first', 1), ('reward', 1), ('cont', 1))}
+      # images travel as uint8 and are scaled / channel-concatenated on the device
+      for k, shp in self.spec.cnn_keys.items():
+        eng.h_stage[f'img/{k}'] = torch.zeros(B, L, *shp, dtype=torch.uint8, pin_memory=True)
       eng.d_stage = {k: torch.zeros_like(v, device=self.be.device) for k, v in eng.h_stage.items()}
     return self._engines[key]
 
@@ -200,6 +216,11 @@ class Agent:
       h['obs'][:, :, off:off + d] = torch.from_numpy(
           np.asarray(data[k], np.float32).reshape(B, L, d))
       off += d
+    for k, shp in s.cnn_keys.items():
+      arr = np.asarray(data[k])
+      if arr.dtype != np.uint8:
+        raise TypeError(f'image key {k!r} must be uint8 (got {arr.dtype}); A/agent.py:128')
+      h[f'img/{k}'].copy_(torch.from_numpy(arr.reshape((B, L) + tuple(shp))))
     h['action'].copy_(torch.from_numpy(np.asarray(data['action'], np.float32).reshape(B, L, -1)))
     first = np.asarray(data['is_first'], np.float32).reshape(B, L, 1)
     h['first'].copy_(torch.from_numpy(first))
@@ -219,7 +240,12 @@ class Agent:
   @staticmethod
   def _unstage(eng):
     be, d = eng.be, eng.d_stage
-    be.transpose01(d['obs'], eng.obs)
+    if eng.spec.obs_dims:
+      be.transpose01(d['obs'], eng.obs)
+    c0 = 0
+    for k, shp in eng.spec.cnn_keys.items():
+      be.image_stage(d[f'img/{k}'], eng.img, c0, 1.0 / 255.0)
+      c0 += shp[2]
     be.transpose01(d['action'], eng.action)
     be.transpose01(d['first'], eng.first)
     be.transpose01(d['reward'], eng.reward)
@@ -325,9 +351,13 @@ class Agent:
       self._policies[P] = _engine.PolicyEngine(main, P)
     pol = self._policies[P]
     s = self.spec
-    vec = np.concatenate(
-        [np.asarray(obs[k], np.float32).reshape(P, -1) for k in s.obs_dims], -1)
-    pol.obs.copy_(torch.from_numpy(vec))
+    if s.obs_dims:
+      vec = np.concatenate(
+          [np.asarray(obs[k], np.float32).reshape(P, -1) for k in s.obs_dims], -1)
+      pol.obs.copy_(torch.from_numpy(vec))
+    for k, shp in s.cnn_keys.items():
+      pol.img_u8[k].copy_(torch.from_numpy(
+          np.asarray(obs[k], np.uint8).reshape((P, 1) + tuple(shp))))
     first = np.asarray(obs['is_first'], np.float32).reshape(P)
     if state is None:
       first = np.ones(P, np.float32)

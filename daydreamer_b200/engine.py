@@ -1322,11 +1322,14 @@ class PolicyEngine:
     D, U, SC, A, E = s.deter, s.units, s.sc, s.act_dim, s.enc_units
     gm, ga = eng.groups['model'], eng.groups['actor']
     self.obs = z(P, s.obs_total)
+    self.img = z(P, *s.img_shape) if s.cnn_keys else None
+    self.img_u8 = {k: z(P, 1, *shp, dtype=torch.uint8) for k, shp in s.cnn_keys.items()}
     self.first = z(P)
     self.prev_action = z(P, A)
     self.prev_deter = z(P, D)
     self.prev_stoch = z(P, SC)
-    self.enc = Trunk(eng, gm, 'enc', s.enc_layers, E, P)
+    self.enc = Trunk(eng, gm, 'enc', s.enc_layers, E, P) if s.obs_dims else None
+    self.enc_cnn = ConvEncoder(eng, gm, P, train=False) if s.cnn_keys else None
     self.init_deter = z(1, D)
     self.init_trunk = Trunk(eng, gm, 'rssm/initp', s.prior_layers, U, 1)
     self.init_zs, self.init_logit, self.init_stoch = z(1, SC), z(1, SC), z(1, SC)
@@ -1352,7 +1355,15 @@ class PolicyEngine:
     else:
       be.fill_normal(self.eps, eng.seed, STREAM_POL_ACT, eng.counters, C_POLICY)
     be.counter_inc(eng.counters, C_POLICY)
-    embed = self.enc.fwd([(self.obs, 0)], 0, P)
+    parts = []
+    c0 = 0
+    for k, shp in s.cnn_keys.items():          # uint8 -> [0,1], channel concat
+      be.image_stage(self.img_u8[k], self.img, c0, 1.0 / 255.0)
+      c0 += shp[2]
+    if s.cnn_keys:
+      parts.append(self.enc_cnn.fwd(self.img))
+    if s.obs_dims:
+      parts.append(self.enc.fwd([(self.obs, 0)], 0, P))
     be.tanh_fwd(gm.P('rssm/initial_deter').view(1, D), self.init_deter)
     eng._prior_stats_fwd(self.init_trunk, 0, 1, self.init_deter, self.init_zs, None,
                          self.init_logit, self.init_stoch, None, 1)
@@ -1370,7 +1381,10 @@ class PolicyEngine:
               self.y_gru, self.st_gru, 0)
     be.gru_fwd(self.y_gru, self.m_deter, self.feat[:, :D])
     be.gemm(self.feat[:, :D], Wobs[:D], self.z_obs)
-    be.gemm(embed, Wobs[D:], self.z_obs, beta=1.0)
+    off = D
+    for part in parts:
+      be.gemm(part, Wobs[off:off + part.shape[1]], self.z_obs, beta=1.0)
+      off += part.shape[1]
     be.ln_fwd(self.z_obs, gm.P('rssm/obs_out/norm/scale'), gm.P('rssm/obs_out/norm/bias'),
               self.h_obs, self.st_obs, 1)
     eng._out_fwd(gm, 'rssm/obs_stats', self.h_obs, self.zs)

@@ -168,3 +168,72 @@ def test_segmented_graph_capture_around_collectives():
   kinds = [k for k, _ in segs]
   assert kinds.count('allreduce') == 8 and kinds.count('graph') >= 8, kinds
   assert len(calls) == 8 * 5                     # 5 steps x 8 collectives (eager, capture replay, replays)
+
+
+def xarm_like_spaces(act_dim=6):
+  """xarm_dummy observation / action spaces (E/envs/robot_interface.py:395-410, :604-608)."""
+  obs = {'image': Space((64, 64, 3), np.uint8), 'depth': Space((64, 64, 1), np.uint8),
+         'cartesian_position': Space((6,)), 'joint_positions': Space((7,)),
+         'gripper_pos': Space((1,)), 'gripper_side': Space((3,)), 'grasped_side': Space((3,)),
+         'reward': Space(()), 'is_first': Space((), bool), 'is_last': Space((), bool),
+         'is_terminal': Space((), bool)}
+  return obs, {'action': Space((act_dim,), np.float32, True), 'reset': Space((), bool, True)}
+
+
+def xarm_like_batch(B, L, A, seed):
+  rng = np.random.default_rng(seed)
+  f = np.zeros((B, L), bool)
+  f[:, 0] = True
+  b = {'image': rng.integers(0, 256, (B, L, 64, 64, 3)).astype(np.uint8),
+       'depth': rng.integers(0, 256, (B, L, 64, 64, 1)).astype(np.uint8),
+       'action': np.eye(A, dtype=np.float32)[rng.integers(0, A, (B, L))],
+       'reward': rng.standard_normal((B, L)).astype(np.float32), 'is_first': f,
+       'is_terminal': rng.uniform(size=(B, L)) < 0.05}
+  for k, d in (('cartesian_position', 6), ('joint_positions', 7), ('gripper_pos', 1),
+               ('gripper_side', 3), ('grasped_side', 3)):
+    b[k] = rng.standard_normal((B, L, d)).astype(np.float32)
+  b['is_last'] = b['is_terminal'].copy()
+  return b
+
+
+def test_xarm_image_config_surface():
+  """BASELINE.json configs[0] shape (xarm: image+depth CNN, proprio MLP, 6-way one-hot
+  actions, reinforce actor) through the Agent surface: graph replay == eager, losses
+  finite and decreasing on a repeated batch, policy returns one-hot actions."""
+  from daydreamer_b200.agent import Agent
+  obs, act = xarm_like_spaces()
+  cfg = make_config('xarm', **{
+      'rssm.deter': 64, 'rssm.units': 64, 'rssm.stoch': 8, 'rssm.classes': 8,
+      r'.*\.layers': 2, r'.*\.units': 64, 'encoder.mlp_layers': 2, 'encoder.mlp_units': 64,
+      'decoder.mlp_layers': 2, 'decoder.mlp_units': 64, r'.*\.cnn_depth': 8, 'imag_horizon': 3,
+      'batch_size': 2, 'replay_chunk': 4})
+  a1 = Agent(obs, act, None, cfg)
+  a2 = Agent(obs, act, None, cfg)
+  a2.use_graph = False
+  assert a1.spec.discrete and list(a1.spec.cnn_keys) == ['image', 'depth']
+  assert a1.spec.obs_total == 20 and a1.spec.embed == 2 * 2 * 64 + 64
+  s1 = s2 = None
+  first = None
+  for it in range(4):
+    batch = xarm_like_batch(2, 4, 6, seed=0)
+    _, s1, m1 = a1.train(batch, s1)
+    _, s2, m2 = a2.train(batch, s2)
+    s1 = s2 = None
+    for k in m1:
+      if np.isnan(m1[k]):
+        assert np.isnan(m2[k]), k
+      else:
+        assert abs(m1[k] - m2[k]) <= 2e-4 * max(1.0, abs(m2[k])), (it, k, m1[k], m2[k])
+    first = first or m1
+  for k in ('image_loss_mean', 'depth_loss_mean', 'model_loss'):
+    assert np.isfinite(m1[k]) and m1[k] < first[k], (k, first[k], m1[k])
+  rep = a1.report(batch)
+  assert np.isfinite(rep['image_loss_mean'])
+  ob = {k: v[:, 0] for k, v in xarm_like_batch(3, 1, 6, seed=5).items() if k != 'action'}
+  state = None
+  for mode in ('train', 'eval', 'explore'):
+    if mode == 'explore':
+      continue
+    out, state = a1.policy(ob, state, mode=mode)
+    a = out['action']
+    assert a.shape == (3, 6) and np.all(a.sum(-1) == 1.0) and set(np.unique(a)) <= {0.0, 1.0}

@@ -149,3 +149,64 @@ def test_train_step_is_deterministic_and_learns():
     _, _, ma = a.train_step(batch, noise)
   assert ma['model_loss'] < first
   assert ma['model_grad_steps'] == 32 and ma['actor_grad_steps'] == 32
+
+
+def test_conv_layers_match_the_tf_definition():
+  """conv_layer vs naive loops over the TensorFlow definitions (tf.nn.conv2d VALID stride 2
+  on HWIO kernels; tf.nn.conv2d_transpose = scatter of x[hi,wi,ci]*K[kh,kw,co,ci] at
+  (2hi+kh, 2wi+kw), output size 2*in + k - 2; A/nets.py:523-547)."""
+  rng = np.random.default_rng(0)
+  x = rng.standard_normal((2, 9, 9, 3)).astype(np.float32)
+  K = rng.standard_normal((4, 4, 3, 5)).astype(np.float32)
+  b = rng.standard_normal(5).astype(np.float32)
+  p = {'c/kernel': torch.tensor(K), 'c/bias': torch.tensor(b)}
+  got = O.conv_layer(torch.tensor(x), p, 'c', norm=False).numpy()
+  ho = (9 - 4) // 2 + 1
+  want = np.zeros((2, ho, ho, 5), np.float64)
+  for i in range(ho):
+    for j in range(ho):
+      patch = x[:, 2 * i:2 * i + 4, 2 * j:2 * j + 4, :].astype(np.float64)
+      want[:, i, j, :] = np.einsum('nhwc,hwco->no', patch, K.astype(np.float64)) + b
+  assert got.shape == want.shape and np.abs(got - want).max() < 1e-4
+  # transposed
+  x = rng.standard_normal((2, 3, 3, 4)).astype(np.float32)
+  K = rng.standard_normal((5, 5, 6, 4)).astype(np.float32)       # [k, k, out, in]
+  b = rng.standard_normal(6).astype(np.float32)
+  p = {'t/kernel': torch.tensor(K), 't/bias': torch.tensor(b)}
+  got = O.conv_layer(torch.tensor(x), p, 't', transp=True, norm=False).numpy()
+  ho = 3 * 2 + 5 - 2
+  want = np.zeros((2, ho, ho, 6), np.float64) + b
+  for hi in range(3):
+    for wi in range(3):
+      contrib = np.einsum('nc,hwoc->nhwo', x[:, hi, wi, :].astype(np.float64), K.astype(np.float64))
+      want[:, 2 * hi:2 * hi + 5, 2 * wi:2 * wi + 5, :] += contrib
+  assert got.shape == want.shape and np.abs(got - want).max() < 1e-4
+
+
+def test_image_geometry_and_loss():
+  """Reference geometry (A/configs.yaml:54-55): 64 -> 31 -> 14 -> 6 -> 2 and 1 -> 5 -> 13 ->
+  30 -> 64; embed = cnn(2*2*8*depth) + mlp; image loss = sum over H,W,C of (sigmoid - x/255)^2."""
+  spec = O.Spec(obs_dims={'v': 19}, cnn_keys={'image': (64, 64, 3)}, discrete=True, act_dim=6)
+  assert [s[4] for s in spec.enc_conv_shapes] == [31, 14, 6, 2]
+  assert [s[6] for s in spec.enc_conv_shapes] == [64, 128, 256, 512]
+  assert [s[4] for s in spec.dec_conv_shapes] == [5, 13, 30, 64]
+  assert [s[6] for s in spec.dec_conv_shapes] == [256, 128, 64, 3]
+  assert spec.cnn_out == 2048 and spec.embed == 2560            # SURVEY.md 8(a) a2
+  shapes = O.param_shapes(spec)
+  assert shapes['rssm/obs_out/kernel'] == (512 + 2560, 512)
+  assert shapes['dec/conv0/kernel'] == (5, 5, 256, 1536)
+  small = O.tiny_spec(obs_dims={}, cnn_keys={'image': (10, 10, 3)}, cnn_depth=4,
+                      enc_kernels=(4, 4), dec_kernels=(4, 4))
+  p = {k: torch.tensor(v) for k, v in O.init_params(small, 3).items()}
+  for k in p:
+    if k.startswith('dec/conv'):
+      p[k] = torch.zeros_like(p[k])          # decoder outputs sigmoid(0) = 0.5 everywhere
+  learner = O.Learner(small, {k: v.numpy() for k, v in p.items()})
+  B, L = 2, 3
+  from tests import util
+  batch = util.make_batch(small, B, L, seed=0)
+  batch['image'][:] = 255
+  data = learner.preprocess(batch)
+  g = torch.zeros(L, B, small.stoch, small.classes)
+  _, aux, mets = learner.wm_loss(learner.params, data, None, g, training=False)
+  assert abs(float(mets['image_loss_mean']) - 10 * 10 * 3 * 0.25) < 1e-3
