@@ -260,7 +260,7 @@ def run_ours(args, rank, world, local_rank):
     dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
   e2e_dt = float(e2e_dt)
   note('e2e timed')
-  h2d = sum(v.numel() * 4 for v in eng.h_stage.values()) + eng.first0.numel() * 4
+  h2d = sum(v.numel() * v.element_size() for v in eng.h_stage.values()) + eng.first0.numel() * 4
   d2h = (eng.mstat.numel() * 8 + eng.counters.numel() * 8 + 4 + eng.actent_scale.numel() * 4
          + 3 * 8)
 
@@ -374,6 +374,7 @@ def run_ours(args, rank, world, local_rank):
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'global_batch': B_PER_GPU * world, 'seq_len': L,
                    'horizon': H, 'parallelism': f'dp{world}',
+                   'pdl': bool(int(os.environ.get('DD_PDL', '0') or 0)),
                    'l2': 'per-step working set (~2 GB of saved activations) exceeds the 126 MB L2; '
                          'no explicit flush'},
         'clocks': clock_info,

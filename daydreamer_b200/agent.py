@@ -328,8 +328,25 @@ class Agent:
     if not np.isfinite(metrics['model_loss']):
       raise FloatingPointError('model_loss is not finite')       # A/tfutils.py:207
     outs = {}
+    if 'key' in data:                    # prioritized replay hook (A/agent.py:90-92)
+      outs = {'key': data['key'], 'priority': self._criterion(eng, data)}
     state = {'deter': eng.prev_deter, 'stoch': eng.prev_stoch}
     return outs, state, metrics
+
+  def _criterion(self, eng, data):
+    """`criteria[config.priority]` of the reference: a data key or a `<head>_loss`
+    of the world model, as a [B, L] array."""
+    name = str(_get(self.config, 'priority'))
+    if name in data:
+      return np.asarray(data[name])
+    rows = {f'{k}_loss': v for k, v in eng.loss_rows.items() if k != 'total'}
+    rows['kl_loss'] = eng.kl_row
+    if name not in rows:
+      raise KeyError(f'priority={name!r} is neither a batch key nor one of {sorted(rows)}')
+    tm = rows[name].detach().cpu().numpy().reshape(eng.L, eng.B)
+    if name == 'kl_loss':
+      tm = tm * float(eng.wmkl_scale.cpu().numpy()[0])
+    return np.ascontiguousarray(tm.T)
 
   def report(self, data):
     B, L = np.asarray(data['is_first']).shape[:2]

@@ -7,6 +7,7 @@ enqueues hand-written CUDA kernels through the C-ABI on torch's current stream
 (so a torch.cuda.graph capture records them).
 """
 import ctypes
+import os
 import pathlib
 
 import numpy as np
@@ -28,6 +29,7 @@ SIGNATURES = {
     'dd_set_gemm_tc': [_I],
     'dd_set_gemm_tc_debug': [_I],
     'dd_set_gemm_tc_persistent': [_I],
+    'dd_set_pdl': [_I],
     'dd_ln_fwd': [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _P],
     'dd_ln_bwd': [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P],
     'dd_gru_fwd': [_P, _I, _P, _I, _P, _I, _I, _I, _P],
@@ -144,6 +146,11 @@ class CudaBackend:
     self.device = torch.device(device if device is not None else
                                f'cuda:{torch.cuda.current_device()}')
     torch.cuda.set_device(self.device)
+    if os.environ.get('DD_PDL', '') != '':
+      self.lib.dd_set_pdl(int(os.environ['DD_PDL']))
+
+  def set_pdl(self, on):
+    return self.lib.dd_set_pdl(int(on))
 
   # -- plumbing ---------------------------------------------------------------
   @property

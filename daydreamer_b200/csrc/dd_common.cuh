@@ -34,6 +34,35 @@ inline int launched(const char* what, int n = 1) {
 
 inline cudaStream_t S(dd_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch (dd_set_pdl).  Every kernel starts with
+// pdl_prologue(): it lets the next kernel of the stream be scheduled as soon as all
+// CTAs of this one are resident, then blocks until the previous kernel has
+// completed and its memory is visible -- so the data dependence between
+// consecutive launches is unchanged and only launch / CTA-scheduling latency
+// overlaps.  Without the launch attribute both instructions are no-ops.
+extern int g_pdl;
+
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
   int64_t g = (n + block - 1) / block;
   if (g < 1) g = 1;

@@ -16,6 +16,7 @@ namespace dd {
 template <int VEC>
 __global__ void im2col_kernel(const float* __restrict__ X, int N, int H, int W, int C, int k,
                               int s, int Ho, int Wo, float* __restrict__ col) {
+  pdl_prologue();
   const int Cv = C / VEC;
   const int64_t rowlen = (int64_t)k * k * Cv;
   const int64_t total = (int64_t)N * Ho * Wo * rowlen;
@@ -44,6 +45,7 @@ template <int VEC>
 __global__ void col2im_kernel(const float* __restrict__ col, int N, int H, int W, int C, int k,
                               int s, int Ho, int Wo, const float* __restrict__ bias,
                               float* __restrict__ X) {
+  pdl_prologue();
   const int Cv = C / VEC;
   const int64_t total = (int64_t)N * H * W * Cv;
   const int64_t rowlen = (int64_t)k * k * C;
@@ -81,6 +83,7 @@ __global__ void col2im_kernel(const float* __restrict__ col, int N, int H, int W
 // src u8 [B, L, P, Ck] (replay layout) -> dst f32 [L*B, P, Ctot] at channel c0, scaled.
 __global__ void image_stage_kernel(const uint8_t* __restrict__ src, int B, int L, int P, int Ck,
                                    float* __restrict__ dst, int Ctot, int c0, float scale) {
+  pdl_prologue();
   const int64_t per = (int64_t)P * Ck;
   const int64_t total = (int64_t)B * L * per;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
@@ -99,6 +102,7 @@ __global__ void image_stage_kernel(const uint8_t* __restrict__ src, int B, int L
 __global__ void image_loss_kernel(const float* __restrict__ Z, const float* __restrict__ T, int M,
                                   int P, int Ctot, int c0, int c1, float coef,
                                   float* __restrict__ loss_row, float* __restrict__ dZ) {
+  pdl_prologue();
   __shared__ float red[33];
   const int cw = c1 - c0;
   const int64_t n = (int64_t)P * cw;
@@ -118,6 +122,7 @@ __global__ void image_loss_kernel(const float* __restrict__ Z, const float* __re
 }
 
 __global__ void sigmoid_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  pdl_prologue();
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x)
     y[e] = sigmoidf_(x[e]);
@@ -142,8 +147,8 @@ extern "C" int dd_im2col(const float* X, int N, int H, int W, int C, int k, int 
   const bool v4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(col)) & 15) == 0;
   const int64_t total = (int64_t)N * Ho * Wo * k * k * (v4 ? C / 4 : C);
   const int grid = grid_for(total, 256, 148 * 32);
-  if (v4) im2col_kernel<4><<<grid, 256, 0, S(stream)>>>(X, N, H, W, C, k, stride, Ho, Wo, col);
-  else im2col_kernel<1><<<grid, 256, 0, S(stream)>>>(X, N, H, W, C, k, stride, Ho, Wo, col);
+  if (v4) launch_k(im2col_kernel<4>, grid, 256, 0, S(stream), X, N, H, W, C, k, stride, Ho, Wo, col);
+  else launch_k(im2col_kernel<1>, grid, 256, 0, S(stream), X, N, H, W, C, k, stride, Ho, Wo, col);
   return launched("dd_im2col");
 }
 
@@ -155,8 +160,8 @@ extern "C" int dd_col2im(const float* col, int N, int H, int W, int C, int k, in
   const bool v4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(col)) & 15) == 0;
   const int64_t total = (int64_t)N * H * W * (v4 ? C / 4 : C);
   const int grid = grid_for(total, 256, 148 * 32);
-  if (v4) col2im_kernel<4><<<grid, 256, 0, S(stream)>>>(col, N, H, W, C, k, stride, Ho, Wo, bias, X);
-  else col2im_kernel<1><<<grid, 256, 0, S(stream)>>>(col, N, H, W, C, k, stride, Ho, Wo, bias, X);
+  if (v4) launch_k(col2im_kernel<4>, grid, 256, 0, S(stream), col, N, H, W, C, k, stride, Ho, Wo, bias, X);
+  else launch_k(col2im_kernel<1>, grid, 256, 0, S(stream), col, N, H, W, C, k, stride, Ho, Wo, bias, X);
   return launched("dd_col2im");
 }
 
@@ -165,7 +170,7 @@ extern "C" int dd_image_stage(const uint8_t* src, int B, int L, int P, int Ck, f
   if (c0 < 0 || c0 + Ck > Ctot) return fail("dd_image_stage", "channel range outside the image");
   const int64_t total = (int64_t)B * L * P * Ck;
   if (total <= 0) return 0;
-  image_stage_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, S(stream)>>>(src, B, L, P, Ck, dst,
+  launch_k(image_stage_kernel, grid_for(total, 256, 148 * 32), 256, 0, S(stream), src, B, L, P, Ck, dst,
                                                                             Ctot, c0, scale);
   return launched("dd_image_stage");
 }
@@ -174,13 +179,13 @@ extern "C" int dd_image_loss(const float* Z, const float* target, int M, int P, 
                              int c1, float coef, float* loss_row, float* dZ, dd_stream_t stream) {
   if (c0 < 0 || c1 > Ctot || c1 <= c0) return fail("dd_image_loss", "bad channel range");
   if (M <= 0) return 0;
-  image_loss_kernel<<<M < 148 * 8 ? M : 148 * 8, 256, 0, S(stream)>>>(Z, target, M, P, Ctot, c0, c1,
+  launch_k(image_loss_kernel, M < 148 * 8 ? M : 148 * 8, 256, 0, S(stream), Z, target, M, P, Ctot, c0, c1,
                                                                       coef, loss_row, dZ);
   return launched("dd_image_loss");
 }
 
 extern "C" int dd_sigmoid(const float* x, float* y, int64_t n, dd_stream_t stream) {
   if (n <= 0) return 0;
-  sigmoid_kernel<<<grid_for(n, 256, 148 * 32), 256, 0, S(stream)>>>(x, y, n);
+  launch_k(sigmoid_kernel, grid_for(n, 256, 148 * 32), 256, 0, S(stream), x, y, n);
   return launched("dd_sigmoid");
 }

@@ -9,9 +9,11 @@ namespace dd {
 
 thread_local char g_err[256] = "";
 std::atomic<int64_t> g_launches{0};
+int g_pdl = 0;
 
 // ---- moments of a strided 2-D view, accumulated into 8 doubles ------------
 __global__ void stats_init_kernel(double* rows, int nrows) {
+  pdl_prologue();
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < nrows; r += gridDim.x * blockDim.x) {
     double* o = rows + 8 * r;
     o[0] = 0.0; o[1] = 0.0; o[2] = INFINITY; o[3] = -INFINITY;
@@ -21,6 +23,7 @@ __global__ void stats_init_kernel(double* rows, int nrows) {
 
 __global__ void stats_kernel(const float* __restrict__ X, int ldx, int rows, int cols,
                              double* __restrict__ out) {
+  pdl_prologue();
   __shared__ double sh[6][32];
   const int64_t n = (int64_t)rows * cols;
   double s = 0.0, q = 0.0, a = 0.0;
@@ -70,6 +73,7 @@ __global__ void stats_kernel(const float* __restrict__ X, int ldx, int rows, int
 __global__ void autoadapt_kernel(float* scale, const float* sums, int k, float denom,
                                  float target, float lo, float hi, float vel, float thres,
                                  int inverse) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= k) return;
   const float avg = sums[i] / denom;
@@ -85,6 +89,7 @@ __global__ void autoadapt_kernel(float* scale, const float* sums, int k, float d
 // ---- Normalize (tfutils.py:502-517), float64 like the reference --------------
 __global__ void normalize_update_kernel(double* state, const double* st, double decay,
                                         double maxv, float* out) {
+  pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double n = st[6];
   state[2] += 1.0;
@@ -99,6 +104,7 @@ __global__ void normalize_update_kernel(double* state, const double* st, double 
 
 // ---- optimizer ------------------------------------------------------------------
 __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+  pdl_prologue();
   __shared__ double sh[32];
   double s = 0.0;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
@@ -118,6 +124,7 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t n, double* __r
 }
 
 __global__ void counter_inc_kernel(int64_t* counters, int ci) {
+  pdl_prologue();
   if (threadIdx.x == 0 && blockIdx.x == 0) counters[ci] += 1;
 }
 
@@ -126,6 +133,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                             int64_t n_decay, float lr, double b1d, double b2d, float eps, float wd,
                             float clip, float gscale, const double* __restrict__ sumsq,
                             const int64_t* __restrict__ counters, int ci) {
+  pdl_prologue();
   const double t = (double)counters[ci];
   const float b1 = (float)b1d, b2 = (float)b2d;
   const float norm = (float)(sqrt(sumsq[0]) * (double)gscale);
@@ -150,6 +158,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
 __global__ void slow_copy_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                  int64_t n, const int64_t* __restrict__ counters, int ci,
                                  int every) {
+  pdl_prologue();
   const int64_t u = counters[ci];
   if (!(u == -1 || u >= every)) return;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
@@ -158,6 +167,7 @@ __global__ void slow_copy_kernel(const float* __restrict__ src, float* __restric
 }
 
 __global__ void slow_counter_kernel(int64_t* counters, int ci, int every) {
+  pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int64_t u = counters[ci];
   if (u == -1 || u >= every) u = 0;
@@ -171,10 +181,15 @@ using namespace dd;
 extern "C" int dd_version(void) { return 100; }
 extern "C" const char* dd_last_error(void) { return g_err; }
 extern "C" int64_t dd_launch_count(void) { return g_launches.load(); }
+extern "C" int dd_set_pdl(int on) {
+  const int prev = g_pdl;
+  g_pdl = on ? 1 : 0;
+  return prev;
+}
 
 extern "C" int dd_stats_init(double* rows, int nrows, dd_stream_t stream) {
   if (nrows <= 0) return 0;
-  stats_init_kernel<<<grid_for(nrows, 64), 64, 0, S(stream)>>>(rows, nrows);
+  launch_k(stats_init_kernel, grid_for(nrows, 64), 64, 0, S(stream), rows, nrows);
   return launched("dd_stats_init");
 }
 
@@ -182,7 +197,7 @@ extern "C" int dd_stats(const float* X, int ldx, int rows, int cols, double* out
                         dd_stream_t stream) {
   const int64_t n = (int64_t)rows * cols;
   if (n <= 0) return 0;
-  stats_kernel<<<grid_for(n, 256 * 8, 64), 256, 0, S(stream)>>>(X, ldx, rows, cols, out);
+  launch_k(stats_kernel, grid_for(n, 256 * 8, 64), 256, 0, S(stream), X, ldx, rows, cols, out);
   return launched("dd_stats");
 }
 
@@ -190,26 +205,26 @@ extern "C" int dd_autoadapt(float* scale, const float* sums, int k, float denom,
                             float lo, float hi, float vel, float thres, int inverse,
                             dd_stream_t stream) {
   if (k <= 0) return 0;
-  autoadapt_kernel<<<grid_for(k, 64), 64, 0, S(stream)>>>(scale, sums, k, denom, target, lo, hi,
+  launch_k(autoadapt_kernel, grid_for(k, 64), 64, 0, S(stream), scale, sums, k, denom, target, lo, hi,
                                                           vel, thres, inverse);
   return launched("dd_autoadapt");
 }
 
 extern "C" int dd_normalize_update(double* state, const double* st, double decay, double maxv,
                                    float* out, dd_stream_t stream) {
-  normalize_update_kernel<<<1, 32, 0, S(stream)>>>(state, st, decay, maxv, out);
+  launch_k(normalize_update_kernel, 1, 32, 0, S(stream), state, st, decay, maxv, out);
   return launched("dd_normalize_update");
 }
 
 extern "C" int dd_sumsq(const float* g, int64_t n, double* out, dd_stream_t stream) {
   if (dd_fill_f64(out, 1, 0.0, stream) != 0) return -1;
   if (n <= 0) return 0;
-  sumsq_kernel<<<grid_for(n, 256 * 8, 296), 256, 0, S(stream)>>>(g, n, out);
+  launch_k(sumsq_kernel, grid_for(n, 256 * 8, 296), 256, 0, S(stream), g, n, out);
   return launched("dd_sumsq");
 }
 
 extern "C" int dd_counter_inc(int64_t* counters, int ci, dd_stream_t stream) {
-  counter_inc_kernel<<<1, 32, 0, S(stream)>>>(counters, ci);
+  launch_k(counter_inc_kernel, 1, 32, 0, S(stream), counters, ci);
   return launched("dd_counter_inc");
 }
 
@@ -218,8 +233,8 @@ extern "C" int dd_adam(float* p, const float* g, float* m, float* v, int64_t n, 
                        float gscale, const double* sumsq, int64_t* counters, int ci,
                        dd_stream_t stream) {
   if (n <= 0) return 0;
-  counter_inc_kernel<<<1, 32, 0, S(stream)>>>(counters, ci);
-  adam_kernel<<<grid_for(n, 256 * 4), 256, 0, S(stream)>>>(p, g, m, v, n, n_decay, lr, b1, b2, eps,
+  launch_k(counter_inc_kernel, 1, 32, 0, S(stream), counters, ci);
+  launch_k(adam_kernel, grid_for(n, 256 * 4), 256, 0, S(stream), p, g, m, v, n, n_decay, lr, b1, b2, eps,
                                                           wd, clip, gscale, sumsq, counters, ci);
   return launched("dd_adam", 2);
 }
@@ -227,7 +242,7 @@ extern "C" int dd_adam(float* p, const float* g, float* m, float* v, int64_t n, 
 extern "C" int dd_slow_sync(const float* src, float* dst, int64_t n, int64_t* counters, int ci,
                             int every, dd_stream_t stream) {
   if (n <= 0) return 0;
-  slow_copy_kernel<<<grid_for(n, 256 * 4), 256, 0, S(stream)>>>(src, dst, n, counters, ci, every);
-  slow_counter_kernel<<<1, 32, 0, S(stream)>>>(counters, ci, every);
+  launch_k(slow_copy_kernel, grid_for(n, 256 * 4), 256, 0, S(stream), src, dst, n, counters, ci, every);
+  launch_k(slow_counter_kernel, 1, 32, 0, S(stream), counters, ci, every);
   return launched("dd_slow_sync", 2);
 }

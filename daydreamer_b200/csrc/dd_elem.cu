@@ -12,6 +12,7 @@ namespace dd {
        e += (int64_t)gridDim.x * blockDim.x)
 
 __global__ void add_kernel(float* dst, int ldd, const float* src, int lds, int rows, int cols) {
+  pdl_prologue();
   const int64_t n = (int64_t)rows * cols;
   DD_GRID_STRIDE(e, n) {
     const int r = e / cols, c = e % cols;
@@ -20,6 +21,7 @@ __global__ void add_kernel(float* dst, int ldd, const float* src, int lds, int r
 }
 
 __global__ void copy_kernel(float* dst, int ldd, const float* src, int lds, int rows, int cols) {
+  pdl_prologue();
   const int64_t n = (int64_t)rows * cols;
   DD_GRID_STRIDE(e, n) {
     const int r = e / cols, c = e % cols;
@@ -28,6 +30,7 @@ __global__ void copy_kernel(float* dst, int ldd, const float* src, int lds, int 
 }
 
 __global__ void fill_kernel(float* dst, int ldd, int rows, int cols, float v) {
+  pdl_prologue();
   const int64_t n = (int64_t)rows * cols;
   DD_GRID_STRIDE(e, n) {
     const int r = e / cols, c = e % cols;
@@ -36,11 +39,13 @@ __global__ void fill_kernel(float* dst, int ldd, int rows, int cols, float v) {
 }
 
 __global__ void fill_f64_kernel(double* dst, int64_t n, double v) {
+  pdl_prologue();
   DD_GRID_STRIDE(e, n) dst[e] = v;
 }
 
 __global__ void axpy_kernel(float* dst, int ldd, const float* src, int lds, int rows, int cols,
                             const float* scale) {
+  pdl_prologue();
   const int64_t n = (int64_t)rows * cols;
   const float a = scale[0];
   DD_GRID_STRIDE(e, n) {
@@ -50,14 +55,17 @@ __global__ void axpy_kernel(float* dst, int ldd, const float* src, int lds, int 
 }
 
 __global__ void sub_kernel(float* dst, const float* a, const float* b, int64_t n) {
+  pdl_prologue();
   DD_GRID_STRIDE(e, n) dst[e] = a[e] - b[e];
 }
 
 __global__ void symexp_kernel(const float* src, float* dst, int64_t n) {
+  pdl_prologue();
   DD_GRID_STRIDE(e, n) dst[e] = symexpf_(src[e]);
 }
 
 __global__ void transpose01_kernel(const float* src, float* dst, int A, int B, int F) {
+  pdl_prologue();
   const int64_t n = (int64_t)A * B * F;
   DD_GRID_STRIDE(e, n) {
     const int f = e % F;
@@ -70,6 +78,7 @@ __global__ void transpose01_kernel(const float* src, float* dst, int A, int B, i
 // Column sums: block = 32 columns x 8 row-lanes, rows strided over gridDim.y.
 __global__ void colsum_kernel(const float* __restrict__ X, int ldx, int M, int N,
                               float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float part[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
@@ -88,10 +97,12 @@ __global__ void colsum_kernel(const float* __restrict__ X, int ldx, int M, int N
 }
 
 __global__ void tanh_fwd_kernel(const float* x, float* y, int64_t n) {
+  pdl_prologue();
   DD_GRID_STRIDE(e, n) y[e] = tanhf(x[e]);
 }
 
 __global__ void tanh_bwd_kernel(const float* dy, const float* y, float* dx, int64_t n, int acc) {
+  pdl_prologue();
   DD_GRID_STRIDE(e, n) {
     const float g = dy[e] * (1.f - y[e] * y[e]);
     dx[e] = acc ? dx[e] + g : g;
@@ -106,6 +117,7 @@ __global__ void head_loss_kernel(int kind, const float* __restrict__ pred, int l
                                  const float* __restrict__ weight, float coef,
                                  float* __restrict__ loss_row, float* __restrict__ dpred,
                                  int lddp, int M, int dim) {
+  pdl_prologue();
   DD_GRID_STRIDE(m, M) {
     const float w = weight != nullptr ? weight[m] : 1.f;
     float loss = 0.f;
@@ -138,6 +150,7 @@ __global__ void balance_kernel(int kind, const float* __restrict__ pred,
                                const float* __restrict__ loss_row,
                                const float* __restrict__ target, float thres, int M,
                                double* __restrict__ out) {
+  pdl_prologue();
   __shared__ double sh[8][32];
   double v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
@@ -169,6 +182,7 @@ __global__ void balance_kernel(int kind, const float* __restrict__ pred,
 __global__ void actor_sample_kernel(const float* mraw, const float* sraw, const float* eps,
                                     float lo, float hi, float* action, float* mean, float* std,
                                     int64_t n) {
+  pdl_prologue();
   DD_GRID_STRIDE(e, n) {
     const float mu = tanhf(mraw[e]);
     const float sd = (hi - lo) * sigmoidf_(sraw[e]) + lo;
@@ -179,6 +193,7 @@ __global__ void actor_sample_kernel(const float* mraw, const float* sraw, const 
 }
 
 __global__ void actor_ent_kernel(const float* std, float lo, float hi, float* ent, int64_t n) {
+  pdl_prologue();
   const float inv = 1.f / (logf(hi) - logf(lo));
   const float llo = logf(lo);
   DD_GRID_STRIDE(e, n) ent[e] = (logf(std[e]) - llo) * inv;
@@ -187,6 +202,7 @@ __global__ void actor_ent_kernel(const float* std, float lo, float hi, float* en
 __global__ void actor_loss_kernel(const float* ret, const float* value, const float* adv,
                                   const float* ent, const float* scale, const float* weight,
                                   float* out, int64_t M, int A) {
+  pdl_prologue();
   const float mean = adv[0], sc = adv[1];
   DD_GRID_STRIDE(m, M) {
     const float score = (ret[m] - value[m] - mean) * sc;
@@ -200,6 +216,7 @@ __global__ void actor_bwd_kernel(const float* dA, const float* eps, const float*
                                  const float* std, const float* weight, const float* scale,
                                  float coef, float lo, float hi, float* dmraw, float* dsraw,
                                  int64_t M, int A) {
+  pdl_prologue();
   const float inv = 1.f / (logf(hi) - logf(lo));
   const int64_t n = M * A;
   DD_GRID_STRIDE(e, n) {
@@ -223,6 +240,7 @@ __global__ void lambda_fwd_kernel(const float* __restrict__ rho, const float* __
                                   float* __restrict__ reward, float* __restrict__ value,
                                   float* __restrict__ cont, float* __restrict__ weight,
                                   float* __restrict__ ret, int H, int N) {
+  pdl_prologue();
   DD_GRID_STRIDE(n, N) {
     float w = 1.f / gamma;
     for (int t = 0; t <= H; ++t) {
@@ -252,6 +270,7 @@ __global__ void lambda_bwd_kernel(const float* __restrict__ rho, const float* __
                                   float coef, float gamma, float lam, float* __restrict__ drho,
                                   float* __restrict__ dvraw, float* __restrict__ dkraw, int H,
                                   int N) {
+  pdl_prologue();
   const float sc = adv[1];
   DD_GRID_STRIDE(n, N) {
     float g = 0.f;
@@ -296,6 +315,7 @@ __device__ __forceinline__ void row_log_softmax(const float* lg, int A, int lane
 
 __global__ void actor_disc_ent_kernel(const float* __restrict__ logit, float* __restrict__ ent,
                                       int64_t M, int A) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const float inv = 1.f / logf((float)A);
   for (int64_t m = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); m < M;
@@ -320,6 +340,7 @@ __global__ void actor_disc_loss_kernel(const float* __restrict__ logit,
                                        const float* __restrict__ weight, float coef,
                                        float* __restrict__ loss_row, float* __restrict__ dlogit,
                                        int64_t M, int A) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const float lnA = logf((float)A);
   const float mean = adv[0], sc = adv[1], es = scale[0];
@@ -353,7 +374,7 @@ __global__ void actor_disc_loss_kernel(const float* __restrict__ logit,
 using namespace dd;
 
 #define DD_EW(kernel, n, ...)                                                     \
-  kernel<<<grid_for((n), 256), 256, 0, S(stream)>>>(__VA_ARGS__)
+  launch_k(kernel, grid_for((n), 256), 256, 0, S(stream), __VA_ARGS__)
 
 extern "C" int dd_add(float* dst, int ldd, const float* src, int lds, int rows, int cols,
                       dd_stream_t stream) {
@@ -413,14 +434,14 @@ extern "C" int dd_colsum(const float* X, int ldx, int M, int N, float* out, int 
   if (N <= 0) return 0;
   int nl = 0;
   if (!acc) {
-    fill_kernel<<<grid_for(N, 256), 256, 0, S(stream)>>>(out, N, 1, N, 0.f);
+    launch_k(fill_kernel, grid_for(N, 256), 256, 0, S(stream), out, N, 1, N, 0.f);
     ++nl;
   }
   if (M > 0) {
     int gy = (M + 63) / 64;
     if (gy > 296) gy = 296;
     dim3 grid((N + 31) / 32, gy), block(32, 8);
-    colsum_kernel<<<grid, block, 0, S(stream)>>>(X, ldx, M, N, out);
+    launch_k(colsum_kernel, grid, block, 0, S(stream), X, ldx, M, N, out);
     ++nl;
   }
   return launched("dd_colsum", nl);
@@ -444,14 +465,14 @@ extern "C" int dd_head_loss(int kind, const float* pred, int ldp, const float* t
                             int lddp, int M, int dim, dd_stream_t stream) {
   if (M <= 0) return 0;
   if (kind < 0 || kind > 2) return fail("dd_head_loss", "kind must be 0, 1 or 2");
-  head_loss_kernel<<<grid_for(M, 128), 128, 0, S(stream)>>>(kind, pred, ldp, target, ldt, weight,
+  launch_k(head_loss_kernel, grid_for(M, 128), 128, 0, S(stream), kind, pred, ldp, target, ldt, weight,
                                                             coef, loss_row, dpred, lddp, M, dim);
   return launched("dd_head_loss");
 }
 
 extern "C" int dd_balance(int kind, const float* pred, const float* loss_row, const float* target,
                           float thres, int M, double* out, dd_stream_t stream) {
-  balance_kernel<<<1, 256, 0, S(stream)>>>(kind, pred, loss_row, target, thres, M, out);
+  launch_k(balance_kernel, 1, 256, 0, S(stream), kind, pred, loss_row, target, thres, M, out);
   return launched("dd_balance");
 }
 
@@ -491,7 +512,7 @@ extern "C" int dd_actor_disc_ent(const float* logit, float* ent, int64_t M, int 
                                  dd_stream_t stream) {
   if (M <= 0) return 0;
   if (A > 64 || A < 2) return fail("dd_actor_disc_ent", "needs 2 <= classes <= 64");
-  actor_disc_ent_kernel<<<grid_for(M, 8), 256, 0, S(stream)>>>(logit, ent, M, A);
+  launch_k(actor_disc_ent_kernel, grid_for(M, 8), 256, 0, S(stream), logit, ent, M, A);
   return launched("dd_actor_disc_ent");
 }
 
@@ -502,7 +523,7 @@ extern "C" int dd_actor_disc_loss(const float* logit, const float* action, const
                                   dd_stream_t stream) {
   if (M <= 0) return 0;
   if (A > 64 || A < 2) return fail("dd_actor_disc_loss", "needs 2 <= classes <= 64");
-  actor_disc_loss_kernel<<<grid_for(M, 8), 256, 0, S(stream)>>>(
+  launch_k(actor_disc_loss_kernel, grid_for(M, 8), 256, 0, S(stream), 
       logit, action, ret, value, adv, ent, scale, weight, coef, loss_row, dlogit, M, A);
   return launched("dd_actor_disc_loss");
 }
@@ -512,7 +533,7 @@ extern "C" int dd_lambda_fwd(const float* rho, const float* vraw, const float* k
                              float* value, float* cont, float* weight, float* ret, int H, int N,
                              dd_stream_t stream) {
   if (N <= 0) return 0;
-  lambda_fwd_kernel<<<grid_for(N, 64), 64, 0, S(stream)>>>(rho, vraw, kraw, cont0, gamma, lam,
+  launch_k(lambda_fwd_kernel, grid_for(N, 64), 64, 0, S(stream), rho, vraw, kraw, cont0, gamma, lam,
                                                            reward, value, cont, weight, ret, H, N);
   return launched("dd_lambda_fwd");
 }
@@ -522,7 +543,7 @@ extern "C" int dd_lambda_bwd(const float* rho, const float* vraw, const float* v
                              const float* adv, float coef, float gamma, float lam, float* drho,
                              float* dvraw, float* dkraw, int H, int N, dd_stream_t stream) {
   if (N <= 0) return 0;
-  lambda_bwd_kernel<<<grid_for(N, 64), 64, 0, S(stream)>>>(rho, vraw, value, cont, weight, ret,
+  launch_k(lambda_bwd_kernel, grid_for(N, 64), 64, 0, S(stream), rho, vraw, value, cont, weight, ret,
                                                            adv, coef, gamma, lam, drho, dvraw,
                                                            dkraw, H, N);
   return launched("dd_lambda_bwd");

@@ -29,6 +29,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 gemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
             float* __restrict__ C, int ldc, int M, int N, int K, float beta,
             const float* __restrict__ bias, int klen, int atomic) {
+  pdl_prologue();
   constexpr int TX = BN / TN, TY = BM / TM, NT = TX * TY;
   constexpr int VM = TM < 4 ? TM : 4, GM = TM / VM;
   constexpr int VN = TN < 4 ? TN : 4, GN = TN / VN;
@@ -169,7 +170,7 @@ static int launch(const float* A, int lda, int ta, const float* B, int ldb, int 
   if (klen < BK) klen = BK;
   const int atomic = splits > 1 ? 1 : 0;
 #define DD_GO(TA_, TB_)                                                                   \
-  gemm_kernel<BM, BN, BK, TM, TN, TA_, TB_><<<grid, NT, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, \
+  launch_k(gemm_kernel<BM, BN, BK, TM, TN, TA_, TB_>, grid, NT, 0, st, A, lda, B, ldb, C, ldc, M, N, \
                                                                 K, beta, bias, klen, atomic)
   if (!ta && !tb) DD_GO(false, false);
   else if (ta && !tb) DD_GO(true, false);

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256)
 skinny_nn_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                  float* __restrict__ C, int ldc, int M, int N, int K, int KC, float beta,
                  const float* __restrict__ bias) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sk_smem[];
   float (*As)[MT + 4] = reinterpret_cast<float (*)[MT + 4]>(sk_smem);       // [KC][MT+4]
   float (*red)[MT][16] = reinterpret_cast<float (*)[MT][16]>(sk_smem);      // [8][MT][16]
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(256)
 skinny_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                  float* __restrict__ C, int ldc, int M, int N, int K, int KC, float beta,
                  const float* __restrict__ bias) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sk_smem[];                          // [MT][KC + 4]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = blockIdx.x * 8 + warp;
@@ -184,14 +186,14 @@ int gemm_skinny_try(const float* A, int lda, int ta, const float* B, int ldb, in
     const int red_bytes = 8 * MT * 16 * 4;
     const int smem = max(KC * per_k, red_bytes);
     const int grid = (N + 15) / 16;
-    if (MT == 16) skinny_nn_kernel<16><<<grid, 256, smem, st>>>(A, lda, B, ldb, C, ldc, M, N, K, KC, beta, bias);
-    else skinny_nn_kernel<32><<<grid, 256, smem, st>>>(A, lda, B, ldb, C, ldc, M, N, K, KC, beta, bias);
+    if (MT == 16) launch_k(skinny_nn_kernel<16>, grid, 256, smem, st, A, lda, B, ldb, C, ldc, M, N, K, KC, beta, bias);
+    else launch_k(skinny_nn_kernel<32>, grid, 256, smem, st, A, lda, B, ldb, C, ldc, M, N, K, KC, beta, bias);
   } else {
     int KC = min((K + 3) / 4 * 4, (SK_SMEM_MAX / (MT * 4) - 4) / 128 * 128);
     const int smem = MT * (KC + 4) * 4;
     const int grid = (N + 7) / 8;
-    if (MT == 16) skinny_nt_kernel<16><<<grid, 256, smem, st>>>(A, lda, B, ldb, C, ldc, M, N, K, KC, beta, bias);
-    else skinny_nt_kernel<32><<<grid, 256, smem, st>>>(A, lda, B, ldb, C, ldc, M, N, K, KC, beta, bias);
+    if (MT == 16) launch_k(skinny_nt_kernel<16>, grid, 256, smem, st, A, lda, B, ldb, C, ldc, M, N, K, KC, beta, bias);
+    else launch_k(skinny_nt_kernel<32>, grid, 256, smem, st, A, lda, B, ldb, C, ldc, M, N, K, KC, beta, bias);
   }
   return launched("dd_gemm_skinny") == 0 ? 1 : -1;
 }

@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                float* __restrict__ C, int ldc, int M, int N, int K, float beta,
                const float* __restrict__ bias, int klen, int atomic, int dbg) {
+  pdl_prologue();
   // dbg (profiling only): bit 0 skips the loader's global loads / smem stores,
   // bit 1 skips the MMA issue; results are garbage, timing isolates each side.
   // A operand: TA ? MN-major ([K, M] in memory) : K-major.  B operand (n, k):
@@ -406,6 +407,7 @@ __global__ void __launch_bounds__(P_THREADS, 1)
 gemm_tc_persistent_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                           float* __restrict__ C, int ldc, int M, int N, int K, float beta,
                           const float* __restrict__ bias) {
+  pdl_prologue();
   constexpr bool A_MN = TA, B_MN = !TB;
   constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -613,7 +615,7 @@ static int launch_persistent(const float* A, int lda, int ta, const float* B, in
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);           \
       attr_set = true;                                                                         \
     }                                                                                          \
-    kern<<<grid, P_THREADS, SMEM, st>>>(A, lda, B, ldb, C, ldc, M, N, K, beta, bias);          \
+    launch_k(kern, grid, P_THREADS, SMEM, st, A, lda, B, ldb, C, ldc, M, N, K, beta, bias);          \
   } while (0)
   if (!ta && !tb) DD_TCP(false, false);
   else if (ta && !tb) DD_TCP(true, false);
@@ -641,7 +643,7 @@ static int launch(const float* A, int lda, int ta, const float* B, int ldb, int 
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);           \
       attr_set = true;                                                                         \
     }                                                                                          \
-    kern<<<grid, THREADS, SMEM, st>>>(A, lda, B, ldb, C, ldc, M, N, K, beta, bias, klen, atomic, \
+    launch_k(kern, grid, THREADS, SMEM, st, A, lda, B, ldb, C, ldc, M, N, K, beta, bias, klen, atomic, \
                                       g_tc_debug);                                             \
   } while (0)
   if (!ta && !tb) DD_TC(false, false);
@@ -668,14 +670,20 @@ int gemm_tc_try(const float* A, int lda, int ta, const float* B, int ldb, int tb
   const int tiles128 = ((M + 127) / 128) * ((N + 127) / 128);
   const int tiles64 = ((M + 127) / 128) * ((N + 63) / 64);
   auto pick_splits = [&](int ctas) {
-    if (beta != 1.f || bias != nullptr || ctas >= kNumSm) return 1;
+    if (beta != 1.f || bias != nullptr) return 1;
+    // very long reductions (conv weight gradients: K = images x pixels) are cut into
+    // <= 16K-long pieces so the truncating TMEM accumulation stays at fp32-level error
+    const int by_k = K > 32768 ? (K + 16383) / 16384 : 1;
+    if (ctas >= kNumSm) return by_k > 256 ? 256 : by_k;
     int s = (kNumSm + ctas - 1) / ctas;
     const int maxs = K / (tc::BK * 4) > 1 ? K / (tc::BK * 4) : 1;
     if (s > maxs) s = maxs;
-    return s > 32 ? 32 : (s < 1 ? 1 : s);
+    s = s > 32 ? 32 : (s < 1 ? 1 : s);
+    return s > by_k ? s : (by_k > 256 ? 256 : by_k);
   };
   int rc;
-  if (tiles128 > kNumSm + kNumSm / 2 && g_tc_persistent && K >= tc::BK) {
+  if (tiles128 > kNumSm + kNumSm / 2 && g_tc_persistent && K >= tc::BK &&
+      pick_splits(tiles128) == 1) {
     rc = tc::launch_persistent<128, 3>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias, st);
   } else if (tiles128 >= kNumSm / 2) {
     rc = tc::launch<128, 3>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias,

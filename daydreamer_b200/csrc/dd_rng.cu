@@ -31,6 +31,7 @@ __device__ __forceinline__ float u01(uint32_t x) {
 __global__ void fill_noise_kernel(float* __restrict__ buf, int64_t n, uint64_t seed,
                                   uint32_t stream_id, const int64_t* __restrict__ counters,
                                   int ci, int normal) {
+  pdl_prologue();
   const uint32_t step = (uint32_t)(counters[ci] & 0xffffffffll);
   const int64_t nb = (n + 3) / 4;
   for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < nb;
@@ -61,7 +62,7 @@ using namespace dd;
 extern "C" int dd_fill_gumbel(float* buf, int64_t n, uint64_t seed, uint32_t stream_id,
                               const int64_t* counters, int ci, dd_stream_t stream) {
   if (n <= 0) return 0;
-  fill_noise_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, S(stream)>>>(buf, n, seed, stream_id,
+  launch_k(fill_noise_kernel, grid_for((n + 3) / 4, 256), 256, 0, S(stream), buf, n, seed, stream_id,
                                                                        counters, ci, 0);
   return launched("dd_fill_gumbel");
 }
@@ -69,7 +70,7 @@ extern "C" int dd_fill_gumbel(float* buf, int64_t n, uint64_t seed, uint32_t str
 extern "C" int dd_fill_normal(float* buf, int64_t n, uint64_t seed, uint32_t stream_id,
                               const int64_t* counters, int ci, dd_stream_t stream) {
   if (n <= 0) return 0;
-  fill_noise_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, S(stream)>>>(buf, n, seed, stream_id,
+  launch_k(fill_noise_kernel, grid_for((n + 3) / 4, 256), 256, 0, S(stream), buf, n, seed, stream_id,
                                                                        counters, ci, 1);
   return launched("dd_fill_normal");
 }

@@ -15,6 +15,7 @@ __global__ void ln_fwd_kernel(const float* __restrict__ Z, int ldz,
                               const float* __restrict__ scale,
                               const float* __restrict__ bias, float* __restrict__ H, int ldh,
                               float* __restrict__ stats, int M, int N, int act) {
+  pdl_prologue();
   extern __shared__ float row[];
   __shared__ float red[33];
   for (int m = blockIdx.x; m < M; m += gridDim.x) {
@@ -58,6 +59,7 @@ __global__ void __launch_bounds__(BLK) ln_bwd_kernel(const float* __restrict__ d
                               const float* __restrict__ bias, float* __restrict__ dZ,
                               int lddz, float* __restrict__ dscale,
                               float* __restrict__ dbias, int M, int N, int act) {
+  pdl_prologue();
   __shared__ float red[33];
   float gs[PER], gb[PER];
 #pragma unroll
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(BLK) ln_bwd_kernel(const float* __restrict__ d
 __global__ void gru_fwd_kernel(const float* __restrict__ Y, int ldy,
                                const float* __restrict__ prev, int ldp,
                                float* __restrict__ out, int ldo, int M, int D) {
+  pdl_prologue();
   const int64_t n = (int64_t)M * D;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x) {
@@ -133,6 +136,7 @@ __global__ void gru_bwd_kernel(const float* __restrict__ dOut, int lddo,
                                const float* __restrict__ prev, int ldp,
                                float* __restrict__ dY, int lddy, float* __restrict__ dPrev,
                                int lddp, int M, int D, int acc) {
+  pdl_prologue();
   const int64_t n = (int64_t)M * D;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
        e += (int64_t)gridDim.x * blockDim.x) {
@@ -164,6 +168,7 @@ __global__ void stats_fwd_kernel(const float* __restrict__ Z, int ldz,
                                  float* __restrict__ stoch, int lds,
                                  int32_t* __restrict__ idx, int M, int S, int C, float mix,
                                  int mode) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int64_t ngroups = (int64_t)M * S;
@@ -213,6 +218,7 @@ __global__ void stats_bwd_kernel(const float* __restrict__ dStoch, int ldds,
                                  const float* __restrict__ logit, int ldl,
                                  float* __restrict__ dZ, int lddz, int M, int S, int C,
                                  float mix) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int64_t ngroups = (int64_t)M * S;
@@ -289,6 +295,7 @@ __global__ void kl_fwd_kernel(const float* __restrict__ post, int ldp,
                               const float* __restrict__ prior, int ldq, int M, int S, int C,
                               float* __restrict__ kl_row, float* __restrict__ ent_post,
                               float* __restrict__ ent_prior) {
+  pdl_prologue();
   __shared__ float red[33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int m = blockIdx.x; m < M; m += gridDim.x) {
@@ -323,6 +330,7 @@ __global__ void kl_bwd_kernel(const float* __restrict__ post, int ldp,
                               float bal, float coef, const float* __restrict__ scale,
                               float* __restrict__ dpost, int lddp, float* __restrict__ dprior,
                               int lddq) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int64_t ngroups = (int64_t)M * S;
@@ -366,6 +374,7 @@ __global__ void mask_fwd_kernel(const float* __restrict__ pd, int ldpd,
                                 const float* __restrict__ init_s, float* __restrict__ od,
                                 int ldod, float* __restrict__ os, int ldos,
                                 float* __restrict__ oa, int ldoa, int M, int D, int SC, int A) {
+  pdl_prologue();
   const int W = D + SC + A;
   const int64_t n = (int64_t)M * W;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
@@ -389,6 +398,7 @@ __global__ void mask_bwd_kernel(const float* __restrict__ dd_, int lddd,
                                 const float* __restrict__ first, float* __restrict__ dpd,
                                 int lddpd, float* __restrict__ dps, int lddps,
                                 float* __restrict__ dinit, int M, int D, int SC) {
+  pdl_prologue();
   const int W = D + SC;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < W; j += gridDim.x * blockDim.x) {
     if (j < D) {
@@ -417,7 +427,7 @@ extern "C" int dd_ln_fwd(const float* Z, int ldz, const float* scale, const floa
   if (M <= 0) return 0;
   if (N > 12000) return fail("dd_ln_fwd", "row too wide for shared-memory staging");
   const int block = N >= 2048 ? 512 : (N >= 256 ? 128 : 64);
-  ln_fwd_kernel<<<min(M, 148 * 32), block, N * sizeof(float), S(stream)>>>(
+  launch_k(ln_fwd_kernel, min(M, 148 * 32), block, N * sizeof(float), S(stream), 
       Z, ldz, scale, bias, H, ldh, stats, M, N, act);
   return launched("dd_ln_fwd");
 }
@@ -428,7 +438,7 @@ extern "C" int dd_ln_bwd(const float* dH, int lddh, const float* Z, int ldz, con
   if (M <= 0) return 0;
   const int grid = min(M, 148 * 8);
 #define DD_LNB(PER, BLK)                                                                      \
-  ln_bwd_kernel<PER, BLK><<<grid, BLK, 0, S(stream)>>>(dH, lddh, Z, ldz, stats, scale, bias, dZ, \
+  launch_k(ln_bwd_kernel<PER, BLK>, grid, BLK, 0, S(stream), dH, lddh, Z, ldz, stats, scale, bias, dZ, \
                                                   lddz, dscale, dbias, M, N, act)
   if (N <= 128) DD_LNB(1, 128);
   else if (N <= 512) DD_LNB(4, 128);
@@ -442,7 +452,7 @@ extern "C" int dd_ln_bwd(const float* dH, int lddh, const float* Z, int ldz, con
 extern "C" int dd_gru_fwd(const float* Y, int ldy, const float* prev, int ldp, float* out, int ldo,
                           int M, int D, dd_stream_t stream) {
   if (M <= 0) return 0;
-  gru_fwd_kernel<<<grid_for((int64_t)M * D, 256), 256, 0, S(stream)>>>(Y, ldy, prev, ldp, out,
+  launch_k(gru_fwd_kernel, grid_for((int64_t)M * D, 256), 256, 0, S(stream), Y, ldy, prev, ldp, out,
                                                                        ldo, M, D);
   return launched("dd_gru_fwd");
 }
@@ -451,7 +461,7 @@ extern "C" int dd_gru_bwd(const float* dOut, int lddo, const float* Y, int ldy, 
                           int ldp, float* dY, int lddy, float* dPrev, int lddp, int M, int D,
                           int acc_prev, dd_stream_t stream) {
   if (M <= 0) return 0;
-  gru_bwd_kernel<<<grid_for((int64_t)M * D, 256), 256, 0, S(stream)>>>(
+  launch_k(gru_bwd_kernel, grid_for((int64_t)M * D, 256), 256, 0, S(stream), 
       dOut, lddo, Y, ldy, prev, ldp, dY, lddy, dPrev, lddp, M, D, acc_prev);
   return launched("dd_gru_bwd");
 }
@@ -464,7 +474,7 @@ extern "C" int dd_stats_fwd(const float* Z, int ldz, const float* G, int ldg, fl
   if (mode == 0 && G == nullptr) return fail("dd_stats_fwd", "mode 0 needs noise");
   if (mode != 2 && stoch == nullptr) return fail("dd_stats_fwd", "stoch output missing");
   const int64_t groups = (int64_t)M * S_;
-  stats_fwd_kernel<<<grid_for(groups, 8), 256, 0, S(stream)>>>(Z, ldz, G, ldg, logit, ldl, stoch,
+  launch_k(stats_fwd_kernel, grid_for(groups, 8), 256, 0, S(stream), Z, ldz, G, ldg, logit, ldl, stoch,
                                                                lds, idx, M, S_, C, mix, mode);
   return launched("dd_stats_fwd");
 }
@@ -475,7 +485,7 @@ extern "C" int dd_stats_bwd(const float* dStoch, int ldds, const float* dLogit, 
   if (M <= 0) return 0;
   if (C > 64) return fail("dd_stats_bwd", "classes > 64 unsupported");
   const int64_t groups = (int64_t)M * S_;
-  stats_bwd_kernel<<<grid_for(groups, 8), 256, 0, S(stream)>>>(dStoch, ldds, dLogit, lddl, logit,
+  launch_k(stats_bwd_kernel, grid_for(groups, 8), 256, 0, S(stream), dStoch, ldds, dLogit, lddl, logit,
                                                                ldl, dZ, lddz, M, S_, C, mix);
   return launched("dd_stats_bwd");
 }
@@ -485,7 +495,7 @@ extern "C" int dd_kl_fwd(const float* post, int ldp, const float* prior, int ldq
                          dd_stream_t stream) {
   if (M <= 0) return 0;
   if (C > 64) return fail("dd_kl_fwd", "classes > 64 unsupported");
-  kl_fwd_kernel<<<min(M, 148 * 16), 256, 0, S(stream)>>>(post, ldp, prior, ldq, M, S_, C, kl_row,
+  launch_k(kl_fwd_kernel, min(M, 148 * 16), 256, 0, S(stream), post, ldp, prior, ldq, M, S_, C, kl_row,
                                                          ent_post, ent_prior);
   return launched("dd_kl_fwd");
 }
@@ -496,7 +506,7 @@ extern "C" int dd_kl_bwd(const float* post, int ldp, const float* prior, int ldq
   if (M <= 0) return 0;
   if (C > 64) return fail("dd_kl_bwd", "classes > 64 unsupported");
   const int64_t groups = (int64_t)M * S_;
-  kl_bwd_kernel<<<grid_for(groups, 8), 256, 0, S(stream)>>>(post, ldp, prior, ldq, M, S_, C, bal,
+  launch_k(kl_bwd_kernel, grid_for(groups, 8), 256, 0, S(stream), post, ldp, prior, ldq, M, S_, C, bal,
                                                             coef, scale, dpost, lddp, dprior, lddq);
   return launched("dd_kl_bwd");
 }
@@ -506,7 +516,7 @@ extern "C" int dd_mask_fwd(const float* pd, int ldpd, const float* ps, int ldps,
                            float* od, int ldod, float* os, int ldos, float* oa, int ldoa, int M,
                            int D, int SC, int A, dd_stream_t stream) {
   if (M <= 0) return 0;
-  mask_fwd_kernel<<<grid_for((int64_t)M * (D + SC + A), 256), 256, 0, S(stream)>>>(
+  launch_k(mask_fwd_kernel, grid_for((int64_t)M * (D + SC + A), 256), 256, 0, S(stream), 
       pd, ldpd, ps, ldps, act, lda, first, init_d, init_s, od, ldod, os, ldos, oa, ldoa, M, D, SC,
       A);
   return launched("dd_mask_fwd");
@@ -516,7 +526,7 @@ extern "C" int dd_mask_bwd(const float* dd_, int lddd, const float* ds, int ldds
                            const float* first, float* dpd, int lddpd, float* dps, int lddps,
                            float* dinit, int M, int D, int SC, dd_stream_t stream) {
   if (M <= 0) return 0;
-  mask_bwd_kernel<<<grid_for(D + SC, 128), 128, 0, S(stream)>>>(dd_, lddd, ds, ldds, first, dpd,
+  launch_k(mask_bwd_kernel, grid_for(D + SC, 128), 128, 0, S(stream), dd_, lddd, ds, ldds, first, dpd,
                                                                 lddpd, dps, lddps, dinit, M, D, SC);
   return launched("dd_mask_bwd");
 }

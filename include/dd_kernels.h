@@ -31,6 +31,10 @@ int dd_version(void);
 const char* dd_last_error(void);
 /* number of kernel launches enqueued by this library since process start */
 int64_t dd_launch_count(void);
+/* launch every kernel with programmatic stream serialization (PDL): consecutive
+ * launches overlap their launch latency, data dependences are unchanged.
+ * Returns the previous setting. */
+int dd_set_pdl(int on);
 
 /* ---- dense ------------------------------------------------------------ */
 /* C[M,N] = op(A) op(B) (+ bias[N]) + beta*C ; op = transpose when t*=1.

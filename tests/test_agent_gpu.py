@@ -237,3 +237,41 @@ def test_xarm_image_config_surface():
     out, state = a1.policy(ob, state, mode=mode)
     a = out['action']
     assert a.shape == (3, 6) and np.all(a.sum(-1) == 1.0) and set(np.unique(a)) <= {0.0, 1.0}
+
+
+def test_ur5_full_size_image_step_properties():
+  """BASELINE.json configs[2] at full size (ur5: 64x64x3 image + 19-dim proprio, B=32 L=50
+  H=15, cnn_depth 64, deter 512) -- too large for the CPU oracle, so size-independent
+  properties: identical images at both ends of the 1600-row batch give identical encoder
+  rows and identical decoder pixels (catches 32-bit index overflow in the 1.5M-row
+  im2col GEMMs), losses are finite, and a repeated batch lowers the image loss."""
+  from daydreamer_b200.agent import Agent
+  obs, act = xarm_like_spaces()
+  obs.pop('depth')
+  obs['joint_positions'] = Space((6,))
+  cfg = make_config('ur5', batch_size=32, replay_chunk=50)
+  agent = Agent(obs, act, None, cfg)
+  assert agent.spec.embed == 2560 and agent.spec.obs_total == 19
+  B, L = 32, 50
+  batch = xarm_like_batch(B, L, 6, seed=1)
+  batch.pop('depth')
+  batch['joint_positions'] = batch['joint_positions'][..., :6]
+  batch['image'][B - 1, L - 1] = batch['image'][0, 0]
+  first = None
+  for it in range(3):
+    _, _, mets = agent.train(batch, None)
+    first = first or mets
+    assert all(np.isfinite(mets[k]) for k in ('model_loss', 'image_loss_mean', 'actor_loss',
+                                               'extr_critic_loss', 'model_grad_norm'))
+  assert mets['image_loss_mean'] < first['image_loss_mean']
+  eng = agent._main
+  N = B * L
+  emb = eng.enc_cnn.H[-1].view(N, -1)
+  assert torch.equal(emb[0], emb[N - 1]), 'encoder rows of identical images differ'
+  assert float(emb.abs().max()) > 0
+  # decoder: force two identical feature rows and compare their reconstructions
+  eng.feat[N - 1].copy_(eng.feat[0])
+  out = eng.dec_cnn.fwd(eng.feat)
+  torch.cuda.synchronize()
+  assert torch.equal(out[0], out[N - 1]), 'decoder pixels of identical features differ'
+  assert agent.be.launch_count() > 0
