@@ -398,6 +398,9 @@ def main():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
   args = ap.parse_args()
+  if os.environ.get('DD_BENCH_VERBOSE'):      # where is it, if it ever stalls
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get('DD_BENCH_DUMP_S', '90')), exit=False)
   rank = int(os.environ.get('RANK', 0))
   world = int(os.environ.get('WORLD_SIZE', 1))
   local_rank = int(os.environ.get('LOCAL_RANK', 0))

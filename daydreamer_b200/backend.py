@@ -148,6 +148,8 @@ class CudaBackend:
     torch.cuda.set_device(self.device)
     if os.environ.get('DD_PDL', '') != '':
       self.lib.dd_set_pdl(int(os.environ['DD_PDL']))
+    if os.environ.get('DD_GEMM_TC_PERSISTENT', '') != '':
+      self.lib.dd_set_gemm_tc_persistent(int(os.environ['DD_GEMM_TC_PERSISTENT']))
 
   def set_pdl(self, on):
     return self.lib.dd_set_pdl(int(on))

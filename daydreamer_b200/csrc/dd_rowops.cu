@@ -418,6 +418,124 @@ __global__ void mask_bwd_kernel(const float* __restrict__ dd_, int lddd,
   }
 }
 
+// Narrow rows (N <= 128: the per-pixel channel LayerNorm of the conv stacks, millions
+// of rows): one warp per row, the row held in registers, warp-shuffle reductions.
+template <int PER>
+__global__ void __launch_bounds__(256) ln_fwd_warp_kernel(
+    const float* __restrict__ Z, int ldz, const float* __restrict__ scale,
+    const float* __restrict__ bias, float* __restrict__ H, int ldh, float* __restrict__ stats,
+    int M, int N, int act) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float sc[PER], bi[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int j = lane + 32 * i;
+    sc[i] = j < N ? scale[j] : 0.f;
+    bi[i] = j < N ? bias[j] : 0.f;
+  }
+  for (int64_t m = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); m < M;
+       m += (int64_t)gridDim.x * wpb) {
+    const float* z = Z + (size_t)m * ldz;
+    float v[PER], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int j = lane + 32 * i;
+      v[i] = j < N ? z[j] : 0.f;
+      s += v[i];
+    }
+    const float mean = warp_sum(s) / N;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const float d = (lane + 32 * i) < N ? v[i] - mean : 0.f;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / N + DD_LN_EPS);
+    float* h = H + (size_t)m * ldh;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int j = lane + 32 * i;
+      if (j < N) {
+        float y = (v[i] - mean) * rstd * sc[i] + bi[i];
+        if (act) y = y > 0.f ? y : expm1f(y);
+        h[j] = y;
+      }
+    }
+    if (lane == 0) {
+      stats[2 * m] = mean;
+      stats[2 * m + 1] = rstd;
+    }
+  }
+}
+
+template <int PER>
+__global__ void __launch_bounds__(256) ln_bwd_warp_kernel(
+    const float* __restrict__ dH, int lddh, const float* __restrict__ Z, int ldz,
+    const float* __restrict__ stats, const float* __restrict__ scale,
+    const float* __restrict__ bias, float* __restrict__ dZ, int lddz,
+    float* __restrict__ dscale, float* __restrict__ dbias, int M, int N, int act) {
+  pdl_prologue();
+  __shared__ float sh_s[8][32 * PER], sh_b[8][32 * PER];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float sc[PER], bi[PER], gs[PER], gb[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int j = lane + 32 * i;
+    sc[i] = j < N ? scale[j] : 0.f;
+    bi[i] = j < N ? bias[j] : 0.f;
+    gs[i] = gb[i] = 0.f;
+  }
+  for (int64_t m = blockIdx.x * (int64_t)wpb + warp; m < M; m += (int64_t)gridDim.x * wpb) {
+    const float mean = stats[2 * m], rstd = stats[2 * m + 1];
+    const float* z = Z + (size_t)m * ldz;
+    const float* dh = dH + (size_t)m * lddh;
+    float xh[PER], dx[PER], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int j = lane + 32 * i;
+      xh[i] = dx[i] = 0.f;
+      if (j < N) {
+        const float x = (z[j] - mean) * rstd;
+        float dy = dh[j];
+        if (act) {
+          const float y = x * sc[i] + bi[i];
+          if (y <= 0.f) dy *= expf(y);
+        }
+        gs[i] += dy * x;
+        gb[i] += dy;
+        xh[i] = x;
+        dx[i] = dy * sc[i];
+        s1 += dx[i];
+        s2 += dx[i] * x;
+      }
+    }
+    const float m1 = warp_sum(s1) / N, m2 = warp_sum(s2) / N;
+    float* dz = dZ + (size_t)m * lddz;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int j = lane + 32 * i;
+      if (j < N) dz[j] = rstd * (dx[i] - m1 - xh[i] * m2);
+    }
+  }
+  if (dscale == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    sh_s[warp][lane + 32 * i] = gs[i];
+    sh_b[warp][lane + 32 * i] = gb[i];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < wpb; ++w) {
+      a += sh_s[w][j];
+      b += sh_b[w][j];
+    }
+    atomicAdd(&dscale[j], a);
+    atomicAdd(&dbias[j], b);
+  }
+}
+
 }  // namespace dd
 
 using namespace dd;
@@ -426,6 +544,13 @@ extern "C" int dd_ln_fwd(const float* Z, int ldz, const float* scale, const floa
                          int ldh, float* stats, int M, int N, int act, dd_stream_t stream) {
   if (M <= 0) return 0;
   if (N > 12000) return fail("dd_ln_fwd", "row too wide for shared-memory staging");
+  if (N <= 128) {
+    const int grid = grid_for(M, 8, 148 * 16);
+    if (N <= 32) launch_k(ln_fwd_warp_kernel<1>, grid, 256, 0, S(stream), Z, ldz, scale, bias, H, ldh, stats, M, N, act);
+    else if (N <= 64) launch_k(ln_fwd_warp_kernel<2>, grid, 256, 0, S(stream), Z, ldz, scale, bias, H, ldh, stats, M, N, act);
+    else launch_k(ln_fwd_warp_kernel<4>, grid, 256, 0, S(stream), Z, ldz, scale, bias, H, ldh, stats, M, N, act);
+    return launched("dd_ln_fwd");
+  }
   const int block = N >= 2048 ? 512 : (N >= 256 ? 128 : 64);
   launch_k(ln_fwd_kernel, min(M, 148 * 32), block, N * sizeof(float), S(stream), 
       Z, ldz, scale, bias, H, ldh, stats, M, N, act);
@@ -440,7 +565,16 @@ extern "C" int dd_ln_bwd(const float* dH, int lddh, const float* Z, int ldz, con
 #define DD_LNB(PER, BLK)                                                                      \
   launch_k(ln_bwd_kernel<PER, BLK>, grid, BLK, 0, S(stream), dH, lddh, Z, ldz, stats, scale, bias, dZ, \
                                                   lddz, dscale, dbias, M, N, act)
-  if (N <= 128) DD_LNB(1, 128);
+  if (N <= 128) {
+    const int wgrid = grid_for(M, 8, 148 * 8);
+#define DD_LNW(PER)                                                                              \
+  launch_k(ln_bwd_warp_kernel<PER>, wgrid, 256, 0, S(stream), dH, lddh, Z, ldz, stats, scale, bias, \
+           dZ, lddz, dscale, dbias, M, N, act)
+    if (N <= 32) DD_LNW(1);
+    else if (N <= 64) DD_LNW(2);
+    else DD_LNW(4);
+#undef DD_LNW
+  }
   else if (N <= 512) DD_LNB(4, 128);
   else if (N <= 2048) DD_LNB(8, 256);
   else if (N <= 8192) DD_LNB(8, 1024);

@@ -17,10 +17,10 @@ def make_batch(spec, B, L, seed=0, term=0.05, mid_first=True):
   rng = np.random.default_rng(seed)
   b = {k: rng.standard_normal((B, L, d)).astype(np.float32)
        for k, d in spec.obs_dims.items()}
-  for k, shp in spec.cnn_keys.items():
+  for k, shp in getattr(spec, 'cnn_keys', {}).items():
     b[k] = rng.integers(0, 256, (B, L) + tuple(shp)).astype(np.uint8)
   b['action'] = rng.uniform(-1, 1, (B, L, spec.act_dim)).astype(np.float32)
-  if spec.discrete:            # one-hot actions (embodied OneHotAction wrapper)
+  if getattr(spec, 'discrete', False):            # one-hot actions (embodied OneHotAction wrapper)
     b['action'] = np.eye(spec.act_dim, dtype=np.float32)[rng.integers(0, spec.act_dim, (B, L))]
   b['reward'] = (0.1 * rng.standard_normal((B, L))).astype(np.float32)
   f = np.zeros((B, L), bool)
