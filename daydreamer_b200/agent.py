@@ -189,15 +189,20 @@ class Agent:
         eng.load_params(self._init_params)
         self._main = eng
       self._engines[key] = eng
-      eng.h_stage = {
-          k: torch.zeros(B, L, d, pin_memory=True)
-          for k, d in (('obs', self.spec.obs_total), ('action', self.spec.act_dim),
-                       ('first', 1), ('reward', 1), ('cont', 1))}
-      # images travel as uint8 and are scaled / channel-concatenated on the device
-      for k, shp in self.spec.cnn_keys.items():
-        eng.h_stage[f'img/{k}'] = torch.zeros(B, L, *shp, dtype=torch.uint8, pin_memory=True)
-      eng.d_stage = {k: torch.zeros_like(v, device=self.be.device) for k, v in eng.h_stage.items()}
+      self._attach_stage(eng)
     return self._engines[key]
+
+  def _attach_stage(self, eng):
+    """Pinned host + device staging buffers for one engine's [B, L, ...] inputs."""
+    B, L = eng.B, eng.L
+    eng.h_stage = {
+        k: torch.zeros(B, L, d, pin_memory=True)
+        for k, d in (('obs', self.spec.obs_total), ('action', self.spec.act_dim),
+                     ('first', 1), ('reward', 1), ('cont', 1))}
+    # images travel as uint8 and are scaled / channel-concatenated on the device
+    for k, shp in self.spec.cnn_keys.items():
+      eng.h_stage[f'img/{k}'] = torch.zeros(B, L, *shp, dtype=torch.uint8, pin_memory=True)
+    eng.d_stage = {k: torch.zeros_like(v, device=self.be.device) for k, v in eng.h_stage.items()}
 
   def _main_engine(self):
     if self._main is None:
@@ -358,7 +363,32 @@ class Agent:
       eng.launch_report()
     self._run(eng, 'report', launch)
     full = eng.read_metrics(report=True)
-    return {k: np.float32(v) for k, v in full.items()}
+    out = {k: np.float32(v) for k, v in full.items()}
+    if self.spec.cnn_keys and L > _engine.VideoReport.CONTEXT:
+      out.update(self._report_videos(data, min(6, B), L))
+    return out
+
+  def _report_videos(self, data, B6, L):
+    """openl_<key> / task_imag_<key> image summaries (A/agent.py:266-282,
+    A/behaviors.py:32-46) through engine.VideoReport."""
+    key = ('video', B6, L)
+    if key not in self._engines:
+      rep = _engine.VideoReport(self._main, B6, L)
+      self._attach_stage(rep.ctx)
+      self._engines[key] = rep
+    rep = self._engines[key]
+    C5 = rep.CONTEXT
+    sub = {k: np.asarray(v)[:B6, :C5] for k, v in data.items()
+           if k in self.spec.obs_dims or k in self.spec.cnn_keys or
+           k in ('action', 'is_first', 'reward', 'is_terminal')}
+    self._stage(rep.ctx, sub, None)
+    acts = np.asarray(data['action'], np.float32)[:B6, C5:].reshape(B6, L - C5, -1)
+    rep.actions.copy_(torch.from_numpy(np.ascontiguousarray(acts.swapaxes(0, 1))))
+    self._unstage(rep.ctx)
+    rep.launch()
+    self.be.sync()
+    truth = {k: np.asarray(data[k], np.float32)[:B6] / np.float32(255.0) for k in self.spec.cnn_keys}
+    return rep.videos(truth)
 
   def policy(self, obs, state=None, mode='train'):
     obs = {k: v for k, v in obs.items() if not k.startswith('log_')}

@@ -1021,7 +1021,10 @@ class Engine:
                     s.actor_minstd, s.actor_maxstd, self.taction[t],
                     self.tmean[t], self.tstd[t])
 
-  def imagine(self):
+  def imagine(self, actions=None):
+    """WorldModel.imagine (A/agent.py:234-261): the actor picks every action.  With
+    `actions` [H, N, A] given it is RSSM.imagine (A/nets.py:78-86): an open-loop
+    rollout of the prior along a recorded action sequence, no actor."""
     s, be, gm = self.spec, self.be, self.groups['model']
     N, H = self.N, self.H
     D, U, SC, A = s.deter, s.units, s.sc, s.act_dim
@@ -1030,10 +1033,12 @@ class Engine:
     be.copy_(self.tlogit[0], self.post_logit)
     Win = gm.P('rssm/img_in/kernel')
     Wgru = gm.P('rssm/gru_out/kernel')
-    self._actor_fwd(0)
+    if actions is None:
+      self._actor_fwd(0)
     for t in range(H):
       be.gemm(tf[t][:, D:], Win[:SC], self.i_zin[t])
-      be.gemm(self.taction[t], Win[SC:], self.i_zin[t], beta=1.0)
+      be.gemm(self.taction[t] if actions is None else actions[t], Win[SC:], self.i_zin[t],
+              beta=1.0)
       be.ln_fwd(self.i_zin[t], gm.P('rssm/img_in/norm/scale'),
                 gm.P('rssm/img_in/norm/bias'), self.i_xin[t], self.i_stin[t], 1)
       be.gemm(tf[t][:, :D], Wgru[:D], self.i_zgru[t])
@@ -1044,7 +1049,8 @@ class Engine:
       self._prior_stats_fwd(self.i_prior, t * N, (t + 1) * N, tf[t + 1][:, :D],
                             self.i_zs, self.g_img[t], self.tlogit[t + 1],
                             tf[t + 1][:, D:], None, 0)
-      self._actor_fwd(t + 1)
+      if actions is None:
+        self._actor_fwd(t + 1)
 
   # ==========================================================================
   # 3. trajectory heads, lambda-return, critic update (A/agent.py:398-454)
@@ -1303,6 +1309,82 @@ class Engine:
              actor_loss=mean('aloss'),
              actor_grad_norm=math.sqrt(sq['actor']), actor_grad_steps=int(cnt[C_ACTOR]))
     return m
+
+
+# ----------------------------------------------------------------------------
+# Image summaries of report(): open-loop prediction and imagined rollouts
+# ----------------------------------------------------------------------------
+
+class VideoReport:
+  """The image part of `Agent.report` for configs with cnn keys:
+    openl_<key>      WorldModel.report (A/agent.py:266-282): 5 context frames reconstructed
+                     from the posterior, the rest predicted open loop along the recorded
+                     actions; [truth | model | (model - truth + 1) / 2] stacked on the height axis
+    task_imag_<key>  Greedy.report (A/behaviors.py:32-46): decoded imagination rollout of the
+                     policy from the last context state
+  Both laid out by video_grid (A/tfutils.py:390-392): [T, H, B*W, C], B = min(6, batch).
+  Three small engines share the learner's parameters: `ctx` observes the context, `ol` rolls
+  the prior along the recorded actions, `im` imagines with the actor."""
+
+  CONTEXT = 5
+
+  def __init__(self, main: Engine, B: int, L: int):
+    spec, be = main.spec, main.be
+    if L <= self.CONTEXT:
+      raise ValueError(f'report() videos need sequences longer than {self.CONTEXT} steps')
+    self.main, self.be, self.spec = main, be, spec
+    self.B, self.L, self.T2 = B, L, L - self.CONTEXT
+    gm = main.groups['model']
+    self.ctx = Engine(spec, be, B, self.CONTEXT, seed=main.seed + 11, share=main)
+    self.ol = Engine(dataclasses.replace(spec, horizon=self.T2), be, B, 1,
+                     seed=main.seed + 12, share=main)
+    self.im = Engine(spec, be, B, 1, seed=main.seed + 13, share=main)
+    self.actions = be.zeros(self.T2, B, spec.act_dim)         # recorded actions, time-major
+    self.dec_ol = ConvDecoder(self.ol, gm, self.T2 * B, train=False)
+    self.dec_im = ConvDecoder(self.im, gm, (spec.horizon + 1) * B, train=False)
+    img = tuple(spec.img_shape)
+    self.recon = be.zeros(self.CONTEXT * B, *img)
+    self.openl = be.zeros(self.T2 * B, *img)
+    self.imag = be.zeros((spec.horizon + 1) * B, *img)
+
+  def launch(self, draw=True):
+    """Inputs: ctx.{obs,img,action,first} (context, time-major), self.actions (steps 5..L-1),
+    im.cont0.  Outputs: self.recon / self.openl / self.imag, sigmoid images, time-major."""
+    s, be = self.spec, self.be
+    ctx, ol, im = self.ctx, self.ol, self.im
+    B, C5 = self.B, self.CONTEXT
+    if draw:
+      for e in (ctx, ol, im):
+        e.draw_noise()
+    be.fill_(ctx.first0, 1.0)                 # observe(..., state=None): initial state
+    ctx.wm_forward()
+    be.sigmoid(ctx.dec_cnn.Z[-1], self.recon)
+    last = slice((C5 - 1) * B, C5 * B)
+    for e in (ol, im):                        # start = context[:, -1]
+      be.copy_(e.feat, ctx.feat[last])
+      be.copy_(e.post_logit, ctx.post_logit[last])
+    ol.imagine(actions=self.actions)
+    flat = ol.tfeat.view(-1, s.feat)
+    be.sigmoid(self.dec_ol.fwd(flat[B:(self.T2 + 1) * B]), self.openl)
+    im.imagine()
+    be.sigmoid(self.dec_im.fwd(im.tfeat.view(-1, s.feat)), self.imag)
+
+  def videos(self, truth):
+    """truth: {key: float [B, L, H, W, C] in [0,1]} -> dict of [T, H', B*W, C] arrays."""
+    s = self.spec
+    B, L, C5 = self.B, self.L, self.CONTEXT
+    grid = lambda v: v.transpose(1, 2, 0, 3, 4).reshape(v.shape[1], v.shape[2], -1, v.shape[4])
+    bt = lambda x, T: x.detach().cpu().numpy().reshape((T, B) + x.shape[1:]).swapaxes(0, 1)
+    model = np.concatenate([bt(self.recon, C5), bt(self.openl, self.T2)], 1)     # [B, L, H, W, C]
+    imag = bt(self.imag, s.horizon + 1)
+    out, c0 = {}, 0
+    for k, shp in s.cnn_keys.items():
+      m = model[..., c0:c0 + shp[2]]
+      t = np.asarray(truth[k], np.float32)
+      out[f'openl_{k}'] = grid(np.concatenate([t, m, (m - t + 1) / 2], 2))
+      out[f'task_imag_{k}'] = grid(imag[..., c0:c0 + shp[2]])
+      c0 += shp[2]
+    return out
 
 
 # ----------------------------------------------------------------------------

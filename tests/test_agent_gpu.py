@@ -206,7 +206,7 @@ def test_xarm_image_config_surface():
       'rssm.deter': 64, 'rssm.units': 64, 'rssm.stoch': 8, 'rssm.classes': 8,
       r'.*\.layers': 2, r'.*\.units': 64, 'encoder.mlp_layers': 2, 'encoder.mlp_units': 64,
       'decoder.mlp_layers': 2, 'decoder.mlp_units': 64, r'.*\.cnn_depth': 8, 'imag_horizon': 3,
-      'batch_size': 2, 'replay_chunk': 4})
+      'batch_size': 2, 'replay_chunk': 7})
   a1 = Agent(obs, act, None, cfg)
   a2 = Agent(obs, act, None, cfg)
   a2.use_graph = False
@@ -215,7 +215,7 @@ def test_xarm_image_config_surface():
   s1 = s2 = None
   first = None
   for it in range(4):
-    batch = xarm_like_batch(2, 4, 6, seed=0)
+    batch = xarm_like_batch(2, 7, 6, seed=0)
     _, s1, m1 = a1.train(batch, s1)
     _, s2, m2 = a2.train(batch, s2)
     s1 = s2 = None
@@ -229,6 +229,15 @@ def test_xarm_image_config_surface():
     assert np.isfinite(m1[k]) and m1[k] < first[k], (k, first[k], m1[k])
   rep = a1.report(batch)
   assert np.isfinite(rep['image_loss_mean'])
+  # image summaries: 5 context + 2 open-loop frames, [truth | model | error] on the height axis
+  assert rep['openl_image'].shape == (7, 3 * 64, 2 * 64, 3)
+  assert rep['openl_depth'].shape == (7, 3 * 64, 2 * 64, 1)
+  assert rep['task_imag_image'].shape == (4, 64, 2 * 64, 3)
+  truth = batch['image'][:2].astype(np.float32) / 255.0
+  assert np.array_equal(rep['openl_image'][:, :64], truth.transpose(1, 2, 0, 3, 4).reshape(7, 64, 128, 3))
+  for k in ('openl_image', 'openl_depth', 'task_imag_image', 'task_imag_depth'):
+    assert np.isfinite(rep[k]).all() and rep[k].min() >= 0.0 and rep[k].max() <= 1.0, k
+  assert all(np.ndim(v) in (0, 2, 3, 4) for v in rep.values())       # E/core/logger.py:30-33
   ob = {k: v[:, 0] for k, v in xarm_like_batch(3, 1, 6, seed=5).items() if k != 'action'}
   state = None
   for mode in ('train', 'eval', 'explore'):
