@@ -17,6 +17,12 @@ from tests import util
 from tests.hostsim import HostSim
 
 B, L, WORLD = 4, 5, 2
+SPECS = {
+    'proprio': {},
+    # image + one-hot actions (xarm/ur5 style): conv weight grads and the scalar entropy controller
+    'image_onehot': dict(discrete=True, act_dim=5, cnn_keys={'image': (10, 10, 3)}, cnn_depth=4,
+                         enc_kernels=(4, 4), dec_kernels=(4, 4)),
+}
 
 
 def shard(batch, noise, spec, rank):
@@ -31,11 +37,11 @@ def shard(batch, noise, spec, rank):
   return b, n
 
 
-def worker(rank, port, path):
+def worker(rank, port, path, name):
   os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
   dist.init_process_group('gloo', rank=rank, world_size=WORLD)
   torch.set_num_threads(1)
-  ospec = O.tiny_spec()
+  ospec = O.tiny_spec(**SPECS[name])
   spec = util.to_engine_spec(ospec)
   eng = E.Engine(spec, HostSim(), B // WORLD, L, world=WORLD,
                  allreduce=lambda t: dist.all_reduce(t))
@@ -56,8 +62,9 @@ def worker(rank, port, path):
   dist.destroy_process_group()
 
 
-def test_two_ranks_match_single_process():
-  ospec = O.tiny_spec()
+@pytest.mark.parametrize('name', list(SPECS))
+def test_two_ranks_match_single_process(name):
+  ospec = O.tiny_spec(**SPECS[name])
   spec = util.to_engine_spec(ospec)
   ref = E.Engine(spec, HostSim(), B, L)
   ref.load_params(O.init_params(ospec, seed=1))
@@ -70,7 +77,7 @@ def test_two_ranks_match_single_process():
   want = ref.get_params()
   with tempfile.TemporaryDirectory() as tmp:
     port = 29500 + os.getpid() % 2000
-    mp.spawn(worker, args=(port, tmp), nprocs=WORLD, join=True)
+    mp.spawn(worker, args=(port, tmp, name), nprocs=WORLD, join=True)
     ranks = [dict(np.load(os.path.join(tmp, f'rank{r}.npz'))) for r in range(WORLD)]
   for k in want:
     # replicas stay bit-identical to each other, and match the single-process update
