@@ -105,7 +105,10 @@ def test_rejects_unbuilt_configs_loudly():
   with pytest.raises(NotImplementedError):
     Agent(obs, act, None, make_config('a1', critic_type='qfunction'))
   with pytest.raises(NotImplementedError):
-    Agent(obs, act, None, make_config('xarm'))          # image keys
+    Agent(obs, act, None, make_config('a1', expl_behavior='Explore'))
+  with pytest.raises(NotImplementedError):
+    Agent(obs, act, None, make_config('a1', **{'encoder.cnn_keys': 'image', 'encoder.cnn': 'resnet',
+                                               'decoder.cnn_keys': 'image'}))
 
 
 def test_a1_full_size_properties():
