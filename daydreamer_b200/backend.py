@@ -90,6 +90,16 @@ class DdObserveFwd(ctypes.Structure):
               [('mix', ctypes.c_float)] + [(n, ctypes.c_void_p) for n in _PTRS])
 
 
+class DdObserveBwd(ctypes.Structure):
+  """Mirror of `struct DdObserveBwd` in include/dd_kernels.h."""
+  _PTRS = ('first', 'first0', 'post_logit', 'dpost_logit', 'z_obs', 'st_obs', 'ln_obs_s',
+           'ln_obs_b', 'y_gru', 'z_gru', 'st_gru', 'ln_gru_s', 'ln_gru_b', 'm_deter', 'z_in',
+           'st_in', 'ln_in_s', 'ln_in_b', 'Wst', 'Wobs', 'Wgru', 'Win', 'dfeat', 'dzs', 'dz_obs',
+           'dz_gru', 'dz_in', 'dh', 'dy_gru', 'dx', 'd_initdeter', 'partial', 'barrier')
+  _fields_ = ([(n, ctypes.c_int) for n in ('B', 'L', 'D', 'U', 'S', 'C', 'nsc', 'xk')] +
+              [('mix', ctypes.c_float)] + [(n, ctypes.c_void_p) for n in _PTRS])
+
+
 def load_library(path=LIB_PATH):
   """dlopen the kernel library and type every entry point.  Raises if absent."""
   path = pathlib.Path(path)
@@ -106,6 +116,10 @@ def load_library(path=LIB_PATH):
   lib.dd_observe_fwd_grid.restype = ctypes.c_int
   lib.dd_observe_fwd.argtypes = [ctypes.POINTER(DdObserveFwd), _P]
   lib.dd_observe_fwd.restype = ctypes.c_int
+  lib.dd_observe_bwd_grid.argtypes = [ctypes.POINTER(DdObserveBwd)]
+  lib.dd_observe_bwd_grid.restype = ctypes.c_int
+  lib.dd_observe_bwd.argtypes = [ctypes.POINTER(DdObserveBwd), _P]
+  lib.dd_observe_bwd.restype = ctypes.c_int
   lib.dd_version.restype = ctypes.c_int
   lib.dd_last_error.restype = ctypes.c_char_p
   lib.dd_launch_count.restype = ctypes.c_int64
@@ -269,6 +283,24 @@ class CudaBackend:
   def observe_fwd(self, dims, mix, tensors):
     p = self._observe_params(dims, mix, tensors)
     self._ck(self.lib.dd_observe_fwd(ctypes.byref(p), self.stream))
+
+  def _observe_bwd_params(self, dims, mix, tensors):
+    p = DdObserveBwd()
+    for k, v in dims.items():
+      setattr(p, k, int(v))
+    p.mix = float(mix)
+    for name in DdObserveBwd._PTRS:
+      t = tensors[name]
+      assert t.is_contiguous(), name
+      setattr(p, name, t.data_ptr())
+    return p
+
+  def observe_bwd_grid(self, dims, mix, tensors):
+    return int(self.lib.dd_observe_bwd_grid(ctypes.byref(self._observe_bwd_params(dims, mix, tensors))))
+
+  def observe_bwd(self, dims, mix, tensors):
+    p = self._observe_bwd_params(dims, mix, tensors)
+    self._ck(self.lib.dd_observe_bwd(ctypes.byref(p), self.stream))
 
   # -- observe masking --------------------------------------------------------
   def mask_fwd(self, pd, ps, act, first, init_d, init_s, od, os_, oa):

@@ -529,6 +529,301 @@ __global__ void __launch_bounds__(THREADS, 1) observe_fwd_kernel(DdObserveFwd p)
     for (int i = 0; i < 16; ++i) p.timing[i] = tacc[i];
 }
 
+// ---------------------------------------------------------------------------
+// Backward of the observe scan (BPTT), fused the same way: one persistent
+// cooperative kernel walks t = L-1 .. 0.  Weight-stationary TRANSPOSED slices (the
+// input-gradient GEMMs are dZ @ W^T, so a CTA that owns output columns owns rows
+// of W): obs_stats rows of its NU units, obs_out rows of its NJ deter units, the
+// gru_out rows of its NJ deter + NU x units, img_in rows of its stoch columns.
+// Per step (reference math = engine.Engine.wm_backward's per-step launches:
+// stats_bwd -> GEMM -> ln_bwd -> GEMM -> gru_bwd -> ln_bwd(joint 3D) -> 2 GEMMs ->
+// ln_bwd -> GEMM -> mask_bwd) 5 phases / 5 grid barriers:
+//   P1 straight-through + unimix backward of the posterior draw, dh = dzs @ Wst^T
+//   P2 LN backward (obs_out), d deter += dz_obs @ Wobs[:D]^T, GRU gate backward for
+//      my deter units, partial sums of the joint 3D LayerNorm backward
+//   P3 joint LN backward -> dz_gru for my gate columns
+//   P4 [d prev_deter | dx] = dz_gru @ Wgru^T ; is_first masking of the deter carry
+//   P5 LN backward (img_in), d prev_stoch = dz_in @ Win[:SC]^T ; masking
+// dzs / dz_obs / dz_gru / dz_in and the pre-LN gradients dh / dy / dx are written
+// time-major for the batched weight-gradient GEMMs and LN parameter gradients that
+// follow the kernel.
+// ---------------------------------------------------------------------------
+constexpr int NSW = 4;          // stoch columns per img_in chunk
+
+// LayerNorm(+elu) backward of rows 2w, 2w+1 held in X (in: dH, out: dZ), one warp.
+__device__ __forceinline__ void ln_bwd_rows(float* X, int ldx, int N, const float* Z,
+                                            const float* st, const float* __restrict__ scale,
+                                            const float* __restrict__ bias, int act, float* out,
+                                            int B, int warp, int lane) {
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int b = 2 * warp + r;
+    if (b >= B) continue;
+    float* x = X + (size_t)b * ldx;
+    const float* z = Z + (size_t)b * N;
+    const float mean = st[2 * b], rstd = st[2 * b + 1];
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = lane; k < N; k += 32) {
+      const float xh = (z[k] - mean) * rstd;
+      float dy = x[k];
+      const float sc = scale[k];
+      if (act) {
+        const float y = xh * sc + bias[k];
+        if (y <= 0.f) dy *= expf(y);
+      }
+      const float dxv = dy * sc;
+      x[k] = dxv;
+      s1 += dxv;
+      s2 += dxv * xh;
+    }
+    const float m1 = warp_sum(s1) / N, m2 = warp_sum(s2) / N;
+    for (int k = lane; k < N; k += 32) {
+      const float xh = (z[k] - mean) * rstd;
+      const float dz = rstd * (x[k] - m1 - xh * m2);
+      x[k] = dz;
+      if (out != nullptr) out[(size_t)b * N + k] = dz;
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int B = p.B, L = p.L, D = p.D, U = p.U, S = p.S, C = p.C;
+  const int SC = S * C, F = D + SC, G = gridDim.x, cta = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D3 = 3 * D;
+  const int nsc = p.nsc;                               // img_in chunks (of NSW columns) per CTA
+  const int XK = p.xk;                                 // staged row width (multiple of 4)
+  float* wst = smem_f;                                 // [SC][NU]
+  float* wobs = wst + (size_t)SC * NU;                 // [U][NJ]
+  float* wgru = wobs + (size_t)U * NJ;                 // [3D][NJ + NU]
+  float* win = wgru + (size_t)D3 * (NJ + NU);          // [nsc][U][NSW]
+  float* xs = win + (size_t)nsc * U * NSW;             // [MT][XK]
+  const int u0 = cta * NU, j0 = cta * NJ, n0 = cta * nsc * NSW;
+  const bool owner = cta == warp % G;                  // this CTA stores the full rows of warp `warp`
+
+  for (int e = tid; e < SC * NU; e += THREADS) {
+    const int k = e / NU, c = e % NU;
+    wst[e] = (u0 + c < U) ? p.Wst[(size_t)(u0 + c) * SC + k] : 0.f;
+  }
+  for (int e = tid; e < U * NJ; e += THREADS) {
+    const int k = e / NJ, c = e % NJ;
+    wobs[e] = (j0 + c < D) ? p.Wobs[(size_t)(j0 + c) * U + k] : 0.f;
+  }
+  for (int e = tid; e < D3 * (NJ + NU); e += THREADS) {
+    const int k = e / (NJ + NU), c = e % (NJ + NU);
+    float v = 0.f;
+    if (c < NJ) { if (j0 + c < D) v = p.Wgru[(size_t)(j0 + c) * D3 + k]; }
+    else if (u0 + c - NJ < U) v = p.Wgru[(size_t)(D + u0 + c - NJ) * D3 + k];
+    wgru[e] = v;
+  }
+  for (int e = tid; e < nsc * U * NSW; e += THREADS) {
+    const int ch = e / (U * NSW), k = (e / NSW) % U, c = e % NSW;
+    const int n = n0 + ch * NSW + c;
+    win[e] = (n < SC) ? p.Win[(size_t)n * U + k] : 0.f;
+  }
+  __syncthreads();
+
+  unsigned int epoch = 0;
+  const unsigned int uG = (unsigned int)G;
+  const float un = p.mix / C, om = 1.f - p.mix;
+
+  for (int t = L - 1; t >= 0; --t) {
+    const size_t row0 = (size_t)t * B;
+    const float* first = t == 0 ? p.first0 : p.first + row0;
+
+    // ===== P1: dzs = d(raw posterior logits); dh[:, my units] = dzs @ Wst^T =============
+    stage_my_rows(xs, XK, p.dfeat + row0 * F + D, F, B, SC, warp, lane);
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+      const int b = 2 * warp + r;
+      if (b >= B) continue;
+      float* xr = xs + (size_t)b * XK;
+      const float* lgr = p.post_logit + (row0 + b) * SC;
+      const float* dlr = p.dpost_logit + (row0 + b) * SC;
+      for (int sg = 0; sg < S; ++sg) {
+        const int c0 = sg * C + lane, c1 = c0 + 32;
+        const bool v0 = lane < C, v1 = lane + 32 < C;
+        const float q0 = v0 ? expf(lgr[c0]) : 0.f, q1 = v1 ? expf(lgr[c1]) : 0.f;
+        const float d0 = v0 ? xr[c0] : 0.f, d1 = v1 ? xr[c1] : 0.f;
+        const float dot = warp_sum(q0 * d0 + q1 * d1);
+        const float dl0 = q0 * (d0 - dot) + (v0 ? dlr[c0] : 0.f);
+        const float dl1 = q1 * (d1 - dot) + (v1 ? dlr[c1] : 0.f);
+        const float p0 = v0 ? (q0 - un) / om : 0.f, p1 = v1 ? (q1 - un) / om : 0.f;
+        const float dp0 = v0 ? om * dl0 / q0 : 0.f, dp1 = v1 ? om * dl1 / q1 : 0.f;
+        const float dot2 = warp_sum(p0 * dp0 + p1 * dp1);
+        const float dz0 = p0 * (dp0 - dot2), dz1 = p1 * (dp1 - dot2);
+        __syncwarp();
+        if (v0) xr[c0] = dz0;
+        if (v1) xr[c1] = dz1;
+        if (owner) {
+          if (v0) p.dzs[(row0 + b) * SC + c0] = dz0;
+          if (v1) p.dzs[(row0 + b) * SC + c1] = dz1;
+        }
+      }
+    }
+    __syncwarp();
+    {
+      float acc[2][NU];
+      rows_gemm<NU>(xs, XK, SC, wst, NU, warp, lane, acc);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int b = 2 * warp + r;
+        if (lane == 0 && b < B) {
+#pragma unroll
+          for (int c = 0; c < NU; ++c)
+            if (u0 + c < U) p.dh[(row0 + b) * U + u0 + c] = acc[r][c];
+        }
+      }
+    }
+    grid_barrier(p.barrier, epoch, uG);
+
+    // ===== P2: LN backward (obs_out) -> deter gradient -> GRU gates of my units ==========
+    stage_my_rows(xs, XK, p.dh + row0 * U, U, B, U, warp, lane);
+    ln_bwd_rows(xs, XK, U, p.z_obs + row0 * U, p.st_obs + row0 * 2, p.ln_obs_s, p.ln_obs_b, 1,
+                owner ? p.dz_obs + row0 * U : nullptr, B, warp, lane);
+    float ddir[2] = {0.f, 0.f};                        // direct path g*(1-u) of my deter unit
+    float dxg[2][3], xhg[2][3], rstd_g[2] = {0.f, 0.f};
+    {
+      float acc[2][NJ];
+      rows_gemm<NJ>(xs, XK, U, wobs, NJ, warp, lane, acc);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int b = 2 * warp + r;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int gate = 0; gate < 3; ++gate) dxg[r][gate] = xhg[r][gate] = 0.f;
+        if (b < B && lane < NJ && j0 + lane < D) {
+          const int j = j0 + lane;
+          float gsum = 0.f;
+#pragma unroll
+          for (int q = 0; q < NJ; ++q)
+            if (lane == q) gsum = acc[r][q];
+          const float g = gsum + __ldcg(p.dfeat + (row0 + b) * F + j);
+          const float* y = p.y_gru + (row0 + b) * D3;
+          const float yr = y[j], yc = y[D + j], yu = y[2 * D + j];
+          const float prev = p.m_deter[(row0 + b) * D + j];
+          const float rg = sigmoidf_(yr), cg = tanhf(rg * yc), ug = sigmoidf_(yu - 1.f);
+          const float dpre = g * ug * (1.f - cg * cg);
+          float dy[3];
+          dy[0] = dpre * yc * rg * (1.f - rg);
+          dy[1] = dpre * rg;
+          dy[2] = g * (cg - prev) * ug * (1.f - ug);
+          ddir[r] = g * (1.f - ug);
+          const float mean = p.st_gru[(row0 + b) * 2];
+          rstd_g[r] = p.st_gru[(row0 + b) * 2 + 1];
+#pragma unroll
+          for (int gate = 0; gate < 3; ++gate) {
+            const int col = gate * D + j;
+            p.dy_gru[(row0 + b) * D3 + col] = dy[gate];
+            xhg[r][gate] = (p.z_gru[(row0 + b) * D3 + col] - mean) * rstd_g[r];
+            dxg[r][gate] = dy[gate] * p.ln_gru_s[col];
+            s1 += dxg[r][gate];
+            s2 += dxg[r][gate] * xhg[r][gate];
+          }
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        if (lane == 0 && b < B) {
+          p.partial[((size_t)b * 148 + cta) * 2] = s1;
+          p.partial[((size_t)b * 148 + cta) * 2 + 1] = s2;
+        }
+      }
+    }
+    grid_barrier(p.barrier, epoch, uG);
+
+    // ===== P3: joint LayerNorm backward over 3D for my gate columns =======================
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int b = 2 * warp + r;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < (148 + 31) / 32; ++i) {
+        const int c = lane + 32 * i;
+        if (c < G && b < B) {
+          const float2 v = __ldcg(reinterpret_cast<const float2*>(p.partial) + (size_t)b * 148 + c);
+          s1 += v.x;
+          s2 += v.y;
+        }
+      }
+      const float m1 = warp_sum(s1) / D3, m2 = warp_sum(s2) / D3;
+      if (b < B && lane < NJ && j0 + lane < D) {
+#pragma unroll
+        for (int gate = 0; gate < 3; ++gate)
+          p.dz_gru[(row0 + b) * D3 + gate * D + j0 + lane] =
+              rstd_g[r] * (dxg[r][gate] - m1 - xhg[r][gate] * m2);
+      }
+    }
+    grid_barrier(p.barrier, epoch, uG);
+
+    // ===== P4: [d prev_deter | dx] = dz_gru @ Wgru^T ; deter carry masking ================
+    stage_my_rows(xs, XK, p.dz_gru + row0 * D3, D3, B, D3, warp, lane);
+    {
+      float acc[2][NJ + NU];
+      rows_gemm<NJ + NU>(xs, XK, D3, wgru, NJ + NU, warp, lane, acc);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int b = 2 * warp + r;
+        float mine = 0.f;
+#pragma unroll
+        for (int q = 0; q < NJ + NU; ++q)
+          if (lane == q) mine = acc[r][q];
+        if (b < B && lane < NJ && j0 + lane < D) {
+          const int j = j0 + lane;
+          const float dd = ddir[r] + mine, f = first[b];
+          if (f != 0.f) atomicAdd(p.d_initdeter + j, dd * f);
+          if (t > 0) {
+            float* q = p.dfeat + (row0 - B + b) * F + j;
+            *q = __ldcg(q) + dd * (1.f - f);
+          }
+        } else if (b < B && lane >= NJ && lane < NJ + NU && u0 + lane - NJ < U) {
+          p.dx[(row0 + b) * U + u0 + lane - NJ] = mine;
+        }
+      }
+    }
+    grid_barrier(p.barrier, epoch, uG);
+
+    // ===== P5: LN backward (img_in) ; d prev_stoch = dz_in @ Win[:SC]^T ; masking ==========
+    stage_my_rows(xs, XK, p.dx + row0 * U, U, B, U, warp, lane);
+    ln_bwd_rows(xs, XK, U, p.z_in + row0 * U, p.st_in + row0 * 2, p.ln_in_s, p.ln_in_b, 1,
+                owner ? p.dz_in + row0 * U : nullptr, B, warp, lane);
+    if (t > 0) {
+      for (int ch = 0; ch < nsc; ++ch) {
+        float acc[2][NSW];
+        rows_gemm<NSW>(xs, XK, U, win + (size_t)ch * U * NSW, NSW, warp, lane, acc);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int b = 2 * warp + r;
+          float mine = 0.f;
+#pragma unroll
+          for (int q = 0; q < NSW; ++q)
+            if (lane == q) mine = acc[r][q];
+          const int n = n0 + ch * NSW + lane;
+          if (b < B && lane < NSW && n < SC) {
+            float* q = p.dfeat + (row0 - B + b) * F + D + n;
+            *q = __ldcg(q) + mine * (1.f - first[b]);
+          }
+        }
+      }
+      grid_barrier(p.barrier, epoch, uG);
+    }
+  }
+}
+
+static size_t smem_bytes_bwd(const DdObserveBwd& p, int G, int* nsc_out, int* xk_out) {
+  const int SC = p.S * p.C;
+  const int per = (SC + G - 1) / G;
+  const int nsc = (per + NSW - 1) / NSW;
+  int xk = max(SC, max(3 * p.D, p.U));
+  xk = (xk + 3) / 4 * 4;
+  if (nsc_out) *nsc_out = nsc;
+  if (xk_out) *xk_out = xk;
+  size_t f = (size_t)SC * NU + (size_t)p.U * NJ + (size_t)3 * p.D * (NJ + NU) +
+             (size_t)nsc * p.U * NSW + (size_t)MT * xk;
+  return f * sizeof(float);
+}
+
 static size_t smem_bytes(const DdObserveFwd& p, int G) {
   const int SC = p.S * p.C, CP = p.C + 4, ngrp = (p.S + G - 1) / G;
   size_t f = (size_t)(SC + p.A) * NU + (size_t)(p.D + p.U) * 3 * NJ + (size_t)p.D * NU +
@@ -575,4 +870,39 @@ extern "C" int dd_observe_fwd(const DdObserveFwd* p, dd_stream_t stream) {
   cudaError_t e = cudaLaunchKernelEx(&cfg, scan::observe_fwd_kernel, params);
   if (e != cudaSuccess) return fail("dd_observe_fwd", cudaGetErrorString(e));
   return launched("dd_observe_fwd");
+}
+
+extern "C" int dd_observe_bwd_grid(const DdObserveBwd* p) {
+  if (p->B > scan::MT || p->C > 64 || p->B < 1) return 0;
+  const int G = max(max((p->D + scan::NJ - 1) / scan::NJ, (p->U + scan::NU - 1) / scan::NU), 1);
+  if (G > 148) return 0;
+  if (scan::smem_bytes_bwd(*p, G, nullptr, nullptr) > 220 * 1024) return 0;
+  return G;
+}
+
+extern "C" int dd_observe_bwd(const DdObserveBwd* p, dd_stream_t stream) {
+  const int G = dd_observe_bwd_grid(p);
+  if (G == 0) return fail("dd_observe_bwd", "shape not eligible for the fused scan");
+  DdObserveBwd params = *p;
+  const size_t smem = scan::smem_bytes_bwd(*p, G, &params.nsc, &params.xk);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(scan::observe_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         220 * 1024);
+    attr = true;
+  }
+  cudaMemsetAsync(p->barrier, 0, sizeof(unsigned int), S(stream));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(G);
+  cfg.blockDim = dim3(scan::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = S(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, scan::observe_bwd_kernel, params);
+  if (e != cudaSuccess) return fail("dd_observe_bwd", cudaGetErrorString(e));
+  return launched("dd_observe_bwd");
 }

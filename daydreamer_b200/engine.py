@@ -577,6 +577,11 @@ class Engine:
     self.fused_scan = True
     self.scan_partial = z(148 * 16 * 2)
     self.scan_barrier = z(4, dtype=torch.int32)
+    # fused BPTT kernel: pre-LN gradients of every step (LN parameter grads are batched after it)
+    self.fused_bptt = True
+    self.b_dh = z(N, U)
+    self.b_dy = z(N, 3 * D)
+    self.b_dx = z(N, U)
 
     # -- imagination buffers ------------------------------------------------
     ga, gc, gs = self.groups['actor'], self.groups['critic'], self.groups['slow_critic']
@@ -806,7 +811,7 @@ class Engine:
         post_idx=self.post_idx, partial=self.scan_partial, barrier=self.scan_barrier,
         timing=getattr(self, 'scan_timing', None))
     if not hasattr(self, '_scan_ok'):
-      self._scan_ok = be.observe_fwd_grid(dims, s.rssm_unimix, tensors) > 0
+      self._scan_ok = (be.observe_fwd_grid(dims, s.rssm_unimix, tensors) or 0) > 0
     if not self._scan_ok:
       return False
     be.observe_fwd(dims, s.rssm_unimix, tensors)
@@ -934,7 +939,7 @@ class Engine:
     Wgru = gm.P('rssm/gru_out/kernel')
     Wobs = gm.P('rssm/obs_out/kernel')
     Wst = gm.P('rssm/obs_stats/kernel')
-    for t in reversed(range(L)):
+    for t in ([] if self._bptt_fused() else reversed(range(L))):
       r = slice(t * B, (t + 1) * B)
       dh = self.tmp(0, B, U)
       dd = self.tmp(1, B, D)
@@ -994,6 +999,44 @@ class Engine:
     if s.obs_dims:
       be.gemm(self.dz_obs, Wobs[off:], self.d_embed, tb=True)
       self.enc.bwd(self.d_embed, 0, N, [(self.obs, 0)], [], True)
+
+  def _bptt_fused(self):
+    """All L reverse steps in one persistent cooperative kernel (csrc/dd_scan.cu) when the
+    backend has it and the shape is eligible; False -> per-step launches.  The LayerNorm
+    parameter gradients of the three scan norms come from the saved pre-LN gradients with one
+    batched ln_bwd each."""
+    be, s, gm = self.be, self.spec, self.groups['model']
+    if not (self.fused_bptt and hasattr(be, 'observe_bwd')):
+      return False
+    P = gm.P
+    dims = dict(B=self.B, L=self.L, D=s.deter, U=s.units, S=s.stoch, C=s.classes)
+    tensors = dict(
+        first=self.first, first0=self.first0, post_logit=self.post_logit,
+        dpost_logit=self.dpost_logit, z_obs=self.z_obs, st_obs=self.st_obs,
+        ln_obs_s=P('rssm/obs_out/norm/scale'), ln_obs_b=P('rssm/obs_out/norm/bias'),
+        y_gru=self.y_gru, z_gru=self.z_gru, st_gru=self.st_gru,
+        ln_gru_s=P('rssm/gru_out/norm/scale'), ln_gru_b=P('rssm/gru_out/norm/bias'),
+        m_deter=self.m_deter, z_in=self.z_in, st_in=self.st_in,
+        ln_in_s=P('rssm/img_in/norm/scale'), ln_in_b=P('rssm/img_in/norm/bias'),
+        Wst=P('rssm/obs_stats/kernel'), Wobs=P('rssm/obs_out/kernel'),
+        Wgru=P('rssm/gru_out/kernel'), Win=P('rssm/img_in/kernel'), dfeat=self.dfeat,
+        dzs=self.dzs, dz_obs=self.dz_obs, dz_gru=self.dz_gru, dz_in=self.dz_in, dh=self.b_dh,
+        dy_gru=self.b_dy, dx=self.b_dx, d_initdeter=self.d_initdeter,
+        partial=self.scan_partial, barrier=self.scan_barrier)
+    if not hasattr(self, '_bptt_ok'):
+      self._bptt_ok = (be.observe_bwd_grid(dims, s.rssm_unimix, tensors) or 0) > 0
+    if not self._bptt_ok:
+      return False
+    be.observe_bwd(dims, s.rssm_unimix, tensors)
+    N, U, D = self.N, s.units, s.deter
+    G = gm.G
+    for dH, Z, st, name, act, width in (
+        (self.b_dh, self.z_obs, self.st_obs, 'rssm/obs_out', 1, U),
+        (self.b_dy, self.z_gru, self.st_gru, 'rssm/gru_out', 0, 3 * D),
+        (self.b_dx, self.z_in, self.st_in, 'rssm/img_in', 1, U)):
+      be.ln_bwd(dH, Z, st, P(f'{name}/norm/scale'), P(f'{name}/norm/bias'), self.tmp(0, N, width),
+                G(f'{name}/norm/scale'), G(f'{name}/norm/bias'), act)
+    return True
 
   def opt_step(self, group, ci):
     s, be, g = self.spec, self.be, self.groups[group]

@@ -122,6 +122,29 @@ typedef struct DdObserveFwd {
 int dd_observe_fwd_grid(const DdObserveFwd* p);
 int dd_observe_fwd(const DdObserveFwd* p, dd_stream_t stream);
 
+/* ---- fused observe scan, backward (BPTT) --------------------------------
+ * One persistent cooperative kernel for all L reverse steps; per step exactly
+ * dd_stats_bwd -> dd_gemm(tb) -> dd_ln_bwd -> dd_gemm(tb) -> dd_gru_bwd ->
+ * dd_ln_bwd (joint 3D) -> 2x dd_gemm(tb) -> dd_ln_bwd -> dd_gemm(tb) -> dd_mask_bwd
+ * without the LayerNorm parameter gradients (the caller gets them from dh / dy_gru /
+ * dx with three batched dd_ln_bwd calls).  dfeat [L*B, D+SC] holds the head / prior
+ * gradients on entry and receives the carried gradients in place. */
+typedef struct DdObserveBwd {
+  int B, L, D, U, S, C;
+  int nsc, xk;             /* filled by the library */
+  float mix;
+  const float *first, *first0, *post_logit, *dpost_logit;
+  const float *z_obs, *st_obs, *ln_obs_s, *ln_obs_b;
+  const float *y_gru, *z_gru, *st_gru, *ln_gru_s, *ln_gru_b, *m_deter;
+  const float *z_in, *st_in, *ln_in_s, *ln_in_b;
+  const float *Wst, *Wobs, *Wgru, *Win;
+  float *dfeat, *dzs, *dz_obs, *dz_gru, *dz_in, *dh, *dy_gru, *dx, *d_initdeter;
+  float* partial;          /* workspace: 148 * 16 * 2 floats */
+  unsigned int* barrier;   /* workspace: 1 counter */
+} DdObserveBwd;
+int dd_observe_bwd_grid(const DdObserveBwd* p);
+int dd_observe_bwd(const DdObserveBwd* p, dd_stream_t stream);
+
 /* ---- observe-scan masking (A/nets.py:100-107) ------------------------ */
 int dd_mask_fwd(const float* pd, int ldpd, const float* ps, int ldps,
                 const float* act, int lda, const float* first,

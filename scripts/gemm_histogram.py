@@ -18,7 +18,7 @@ class Recorder:
 spec = E.Spec(obs_dims={'vector': 16})
 rec = Recorder()
 eng = E.Engine(spec, rec, 16, 64)
-eng.fused_scan = False
+eng.fused_scan = eng.fused_bptt = False
 rec.calls.clear(); rec.other.clear()
 eng.launch_step()
 tot = sum(2.0 * m * n * k * c for (m, n, k, *_), c in rec.calls.items())

@@ -33,7 +33,8 @@ def test_binding_covers_header(lib_path):
   from daydreamer_b200 import backend
   lib = backend.load_library(lib_path)
   typed = set(backend.SIGNATURES) | {'dd_version', 'dd_last_error', 'dd_launch_count',
-                                     'dd_observe_fwd', 'dd_observe_fwd_grid'}
+                                     'dd_observe_fwd', 'dd_observe_fwd_grid',
+                                     'dd_observe_bwd', 'dd_observe_bwd_grid'}
   assert typed == set(declared_symbols())
   assert lib.dd_version() >= 100
   assert lib.dd_launch_count() == 0
