@@ -184,3 +184,54 @@ def test_fused_observe_scan_equals_per_step_launches(name):
   for k in ('m_deter', 'm_stoch', 'm_act', 'z_in', 'st_in', 'st_gru', 'z_obs', 'st_obs', 'prior_logit'):
     assert rel(getattr(f, k).cpu().numpy(), getattr(u, k).cpu().numpy()) < 2e-5, k
   assert torch.equal(f.post_idx, u.post_idx)
+
+
+@pytest.mark.parametrize('name', ['tiny', 'ragged', 'medium', 'a1'])
+def test_fused_bptt_equals_per_step_launches(name):
+  """The persistent cooperative BPTT kernel (csrc/dd_scan.cu, observe_bwd_kernel) against the
+  same reverse scan issued as per-step launches: every world-model gradient, the saved
+  per-step dZ buffers and the gradient reaching the carried-in state agree to fp32 rounding.
+  Second pass: carried state with mid-chunk episode boundaries (is_first masking paths)."""
+  from daydreamer_b200.backend import CudaBackend
+  ospec, B, L = {
+      'tiny': (O.tiny_spec(), 3, 5),
+      'ragged': (O.tiny_spec(stoch=3, classes=48, deter=40, units=36, head_units=24, act_dim=2), 2, 4),
+      'medium': (O.Spec(obs_dims={'vector': 16}, act_dim=12, deter=128, units=128, stoch=16, classes=16,
+                        enc_layers=2, enc_units=64, head_layers=2, head_units=128, horizon=5), 8, 16),
+      'a1': (O.a1_spec(), 16, 64)}[name]
+  spec = util.to_engine_spec(ospec)
+  params = perturbed_params(ospec)
+  be = CudaBackend()
+  results = []
+  for fused in (True, False):
+    eng = E.Engine(spec, be, B, L)
+    eng.fused_bptt = fused
+    eng.load_params(params)
+    outs = []
+    state = None
+    for rnd in range(2):
+      batch = util.make_batch(ospec, B, L, seed=3 + rnd)
+      if rnd == 1:
+        batch['is_first'][:, 0] = False
+        batch['is_first'][0, 0] = True
+        batch['is_first'][B - 1, L // 2] = True
+      util.load_batch(eng, spec, batch, util.make_noise(ospec, B, L, seed=4 + rnd), state)
+      eng.be.stats_init(eng.mstat)
+      eng.wm_forward()
+      eng.wm_losses()
+      eng.wm_backward()
+      be.sync()
+      state = {'deter': eng.feat[(L - 1) * B:, :spec.deter].cpu().numpy().copy(),
+               'stoch': eng.feat[(L - 1) * B:, spec.deter:].cpu().numpy().copy()}
+      outs.append({'grads': eng.get_grads('model'),
+                   **{k: getattr(eng, k).cpu().numpy().copy()
+                      for k in ('dzs', 'dz_obs', 'dz_gru', 'dz_in', 'd_initdeter')},
+                   'dfeat_stoch': eng.dfeat[:, spec.deter:].cpu().numpy().copy()})
+    results.append((eng, outs))
+  (f, fo), (u, uo) = results
+  assert f._bptt_ok, 'fused BPTT was not eligible for this shape'
+  for rnd in range(2):
+    for k in ('dzs', 'dz_obs', 'dz_gru', 'dz_in', 'd_initdeter', 'dfeat_stoch'):
+      assert rel(fo[rnd][k], uo[rnd][k]) < 5e-5, (rnd, k, rel(fo[rnd][k], uo[rnd][k]))
+    for k, v in uo[rnd]['grads'].items():
+      assert rel(fo[rnd]['grads'][k], v) < 5e-5, (rnd, k, rel(fo[rnd]['grads'][k], v))
