@@ -95,7 +95,7 @@ class DdObserveBwd(ctypes.Structure):
   _PTRS = ('first', 'first0', 'post_logit', 'dpost_logit', 'z_obs', 'st_obs', 'ln_obs_s',
            'ln_obs_b', 'y_gru', 'z_gru', 'st_gru', 'ln_gru_s', 'ln_gru_b', 'm_deter', 'z_in',
            'st_in', 'ln_in_s', 'ln_in_b', 'Wst', 'Wobs', 'Wgru', 'Win', 'dfeat', 'dzs', 'dz_obs',
-           'dz_gru', 'dz_in', 'dh', 'dy_gru', 'dx', 'd_initdeter', 'partial', 'barrier')
+           'dz_gru', 'dz_in', 'dh', 'dy_gru', 'dx', 'd_initdeter', 'partial', 'barrier', 'timing')
   _fields_ = ([(n, ctypes.c_int) for n in ('B', 'L', 'D', 'U', 'S', 'C', 'nsc', 'xk')] +
               [('mix', ctypes.c_float)] + [(n, ctypes.c_void_p) for n in _PTRS])
 
@@ -290,7 +290,9 @@ class CudaBackend:
       setattr(p, k, int(v))
     p.mix = float(mix)
     for name in DdObserveBwd._PTRS:
-      t = tensors[name]
+      t = tensors.get(name)
+      if t is None:
+        continue                      # optional pointer (timing)
       assert t.is_contiguous(), name
       setattr(p, name, t.data_ptr())
     return p

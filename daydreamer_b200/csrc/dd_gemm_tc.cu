@@ -32,8 +32,12 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int LOADER_WARPS = 8;                 // two groups of 4 alternate k-blocks
-constexpr int GROUP_WARPS = 4;
+#ifndef DD_TC_GROUP_WARPS
+#define DD_TC_GROUP_WARPS 2
+#endif
+constexpr int GROUP_WARPS = DD_TC_GROUP_WARPS;   // 2 -> four loader groups: 4 k-blocks of L2 latency in flight
 constexpr int GROUP_THREADS = GROUP_WARPS * 32;
+constexpr int NGROUPS = 8 / GROUP_WARPS;
 constexpr int LOADER_THREADS = LOADER_WARPS * 32;
 constexpr int THREADS = LOADER_THREADS + 32;
 
@@ -248,7 +252,7 @@ gemm_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
       tile_gload<BM, A_MN>(A, lda, m0, M, kbeg + grp * BK, kend, gtid, ra);
       tile_gload<BN, B_MN>(B, ldb, n0, N, kbeg + grp * BK, kend, gtid, rb);
     }
-    for (int kb = grp; kb < nkb; kb += 2) {
+    for (int kb = grp; kb < nkb; kb += NGROUPS) {
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(empty0 + 8 * s, ph ^ 1);
@@ -266,8 +270,8 @@ gemm_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
           if (acc == 1.2345e-30f) *reinterpret_cast<float*>(st) = acc;
         }
       }
-      if (kb + 2 < nkb && !(dbg & 1) && !(dbg & 16)) {  // dbg 16: no global loads after the first
-        const int k1 = kbeg + (kb + 2) * BK;
+      if (kb + NGROUPS < nkb && !(dbg & 1) && !(dbg & 16)) {  // dbg 16: no global loads after the first
+        const int k1 = kbeg + (kb + NGROUPS) * BK;
         tile_gload<BM, A_MN>(A, lda, m0, M, k1, kend, gtid, ra);
         tile_gload<BN, B_MN>(B, ldb, n0, N, k1, kend, gtid, rb);
       }
@@ -465,16 +469,16 @@ gemm_tc_persistent_kernel(const float* __restrict__ A, int lda, const float* __r
       tile_gload<BM, A_MN>(A, lda, m0, M, k0, K, gtid, ra);
       tile_gload<BN, B_MN>(B, ldb, n0, N, k0, K, gtid, rb);
     }
-    for (long it = grp; it < total; it += 2) {
+    for (long it = grp; it < total; it += NGROUPS) {
       const int s = (int)(it % STAGES);
       const uint32_t ph = (uint32_t)((it / STAGES) & 1);
       mbar_wait(empty0 + 8 * s, ph ^ 1);
       char* st = smem + s * STAGE_BYTES;
       tile_split_store<BM, A_MN>(ra, st, st + A_BYTES, gtid);
       tile_split_store<BN, B_MN>(rb, st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES, gtid);
-      if (it + 2 < total) {
+      if (it + NGROUPS < total) {
         int m0, n0, k0;
-        coords(it + 2, m0, n0, k0);
+        coords(it + NGROUPS, m0, n0, k0);
         tile_gload<BM, A_MN>(A, lda, m0, M, k0, K, gtid, ra);
         tile_gload<BN, B_MN>(B, ldb, n0, N, k0, K, gtid, rb);
       }

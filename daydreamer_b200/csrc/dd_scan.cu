@@ -537,8 +537,9 @@ __global__ void __launch_bounds__(THREADS, 1) observe_fwd_kernel(DdObserveFwd p)
 // gru_out rows of its NJ deter + NU x units, img_in rows of its stoch columns.
 // Per step (reference math = engine.Engine.wm_backward's per-step launches:
 // stats_bwd -> GEMM -> ln_bwd -> GEMM -> gru_bwd -> ln_bwd(joint 3D) -> 2 GEMMs ->
-// ln_bwd -> GEMM -> mask_bwd) 5 phases / 5 grid barriers:
-//   P1 straight-through + unimix backward of the posterior draw, dh = dzs @ Wst^T
+// ln_bwd -> GEMM -> mask_bwd) 6 phases / 6 grid barriers:
+//   P1a straight-through + unimix backward of the posterior draw for my groups
+//   P1b dh = dzs @ Wst^T
 //   P2 LN backward (obs_out), d deter += dz_obs @ Wobs[:D]^T, GRU gate backward for
 //      my deter units, partial sums of the joint 3D LayerNorm backward
 //   P3 joint LN backward -> dz_gru for my gate columns
@@ -550,9 +551,10 @@ __global__ void __launch_bounds__(THREADS, 1) observe_fwd_kernel(DdObserveFwd p)
 // ---------------------------------------------------------------------------
 constexpr int NSW = 4;          // stoch columns per img_in chunk
 
-// LayerNorm(+elu) backward of rows 2w, 2w+1 held in X (in: dH, out: dZ), one warp.
-__device__ __forceinline__ void ln_bwd_rows(float* X, int ldx, int N, const float* Z,
-                                            const float* st, const float* __restrict__ scale,
+// LayerNorm(+elu) backward of rows 2w, 2w+1, one warp.  X[b][0:N] holds dH on entry and dZ on
+// exit; X[b][N:2N] holds the saved pre-norm row Z (both staged in shared memory).
+__device__ __forceinline__ void ln_bwd_rows(float* X, int ldx, int N, const float* st,
+                                            const float* __restrict__ scale,
                                             const float* __restrict__ bias, int act, float* out,
                                             int B, int warp, int lane) {
 #pragma unroll
@@ -560,7 +562,7 @@ __device__ __forceinline__ void ln_bwd_rows(float* X, int ldx, int N, const floa
     const int b = 2 * warp + r;
     if (b >= B) continue;
     float* x = X + (size_t)b * ldx;
-    const float* z = Z + (size_t)b * N;
+    const float* z = x + N;
     const float mean = st[2 * b], rstd = st[2 * b + 1];
     float s1 = 0.f, s2 = 0.f;
     for (int k = lane; k < N; k += 32) {
@@ -628,42 +630,61 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
   unsigned int epoch = 0;
   const unsigned int uG = (unsigned int)G;
   const float un = p.mix / C, om = 1.f - p.mix;
+  // optional phase timing (profiling aid): slots [P1a,B,P1b,B,P2,B,P3,B,P4,B,P5,B] of CTA 0
+  long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
+  int tslot = 0;
+#define DD_TICKB()                                      \
+  do {                                                  \
+    const long long now_ = clock64();                   \
+    tacc[tslot] += now_ - tlast;                        \
+    tlast = now_;                                       \
+    tslot = (tslot + 1) % 12;                           \
+  } while (0)
 
   for (int t = L - 1; t >= 0; --t) {
     const size_t row0 = (size_t)t * B;
     const float* first = t == 0 ? p.first0 : p.first + row0;
 
-    // ===== P1: dzs = d(raw posterior logits); dh[:, my units] = dzs @ Wst^T =============
-    stage_my_rows(xs, XK, p.dfeat + row0 * F + D, F, B, SC, warp, lane);
-#pragma unroll 1
-    for (int r = 0; r < 2; ++r) {
-      const int b = 2 * warp + r;
-      if (b >= B) continue;
-      float* xr = xs + (size_t)b * XK;
-      const float* lgr = p.post_logit + (row0 + b) * SC;
-      const float* dlr = p.dpost_logit + (row0 + b) * SC;
-      for (int sg = 0; sg < S; ++sg) {
-        const int c0 = sg * C + lane, c1 = c0 + 32;
-        const bool v0 = lane < C, v1 = lane + 32 < C;
-        const float q0 = v0 ? expf(lgr[c0]) : 0.f, q1 = v1 ? expf(lgr[c1]) : 0.f;
-        const float d0 = v0 ? xr[c0] : 0.f, d1 = v1 ? xr[c1] : 0.f;
-        const float dot = warp_sum(q0 * d0 + q1 * d1);
-        const float dl0 = q0 * (d0 - dot) + (v0 ? dlr[c0] : 0.f);
-        const float dl1 = q1 * (d1 - dot) + (v1 ? dlr[c1] : 0.f);
+    // ===== P1a: dzs = d(raw posterior logits) for my categorical groups ===================
+    // (straight-through + unimix backward; lanes = classes, warps = row pairs)
+    for (int g = cta; g < S; g += G) {
+      const int c0 = g * C + lane, c1 = c0 + 32;
+      const bool v0 = lane < C, v1 = lane + 32 < C;
+      float lg[2][2], dlg[2][2], dst[2][2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {                      // every load of both rows up front
+        const int b = 2 * warp + r;
+        const size_t rr = row0 + (b < B ? b : 0);
+        lg[r][0] = v0 ? p.post_logit[rr * SC + c0] : 0.f;
+        lg[r][1] = v1 ? p.post_logit[rr * SC + c1] : 0.f;
+        dlg[r][0] = v0 ? p.dpost_logit[rr * SC + c0] : 0.f;
+        dlg[r][1] = v1 ? p.dpost_logit[rr * SC + c1] : 0.f;
+        dst[r][0] = v0 ? __ldcg(p.dfeat + rr * F + D + c0) : 0.f;
+        dst[r][1] = v1 ? __ldcg(p.dfeat + rr * F + D + c1) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int b = 2 * warp + r;
+        const float q0 = v0 ? expf(lg[r][0]) : 0.f, q1 = v1 ? expf(lg[r][1]) : 0.f;
+        const float dot = warp_sum(q0 * dst[r][0] + q1 * dst[r][1]);
+        const float dl0 = q0 * (dst[r][0] - dot) + dlg[r][0];
+        const float dl1 = q1 * (dst[r][1] - dot) + dlg[r][1];
         const float p0 = v0 ? (q0 - un) / om : 0.f, p1 = v1 ? (q1 - un) / om : 0.f;
         const float dp0 = v0 ? om * dl0 / q0 : 0.f, dp1 = v1 ? om * dl1 / q1 : 0.f;
         const float dot2 = warp_sum(p0 * dp0 + p1 * dp1);
-        const float dz0 = p0 * (dp0 - dot2), dz1 = p1 * (dp1 - dot2);
-        __syncwarp();
-        if (v0) xr[c0] = dz0;
-        if (v1) xr[c1] = dz1;
-        if (owner) {
-          if (v0) p.dzs[(row0 + b) * SC + c0] = dz0;
-          if (v1) p.dzs[(row0 + b) * SC + c1] = dz1;
+        if (b < B) {
+          if (v0) p.dzs[(row0 + b) * SC + c0] = p0 * (dp0 - dot2);
+          if (v1) p.dzs[(row0 + b) * SC + c1] = p1 * (dp1 - dot2);
         }
       }
     }
-    __syncwarp();
+    DD_TICKB();
+    grid_barrier(p.barrier, epoch, uG);
+    DD_TICKB();
+
+    // ===== P1b: dh[:, my units] = dzs @ Wst^T ============================================
+    stage_my_rows(xs, XK, p.dzs + row0 * SC, SC, B, SC, warp, lane);
     {
       float acc[2][NU];
       rows_gemm<NU>(xs, XK, SC, wst, NU, warp, lane, acc);
@@ -677,11 +698,14 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
         }
       }
     }
+    DD_TICKB();
     grid_barrier(p.barrier, epoch, uG);
+    DD_TICKB();
 
     // ===== P2: LN backward (obs_out) -> deter gradient -> GRU gates of my units ==========
     stage_my_rows(xs, XK, p.dh + row0 * U, U, B, U, warp, lane);
-    ln_bwd_rows(xs, XK, U, p.z_obs + row0 * U, p.st_obs + row0 * 2, p.ln_obs_s, p.ln_obs_b, 1,
+    stage_my_rows(xs + U, XK, p.z_obs + row0 * U, U, B, U, warp, lane);
+    ln_bwd_rows(xs, XK, U, p.st_obs + row0 * 2, p.ln_obs_s, p.ln_obs_b, 1,
                 owner ? p.dz_obs + row0 * U : nullptr, B, warp, lane);
     float ddir[2] = {0.f, 0.f};                        // direct path g*(1-u) of my deter unit
     float dxg[2][3], xhg[2][3], rstd_g[2] = {0.f, 0.f};
@@ -731,7 +755,9 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
         }
       }
     }
+    DD_TICKB();
     grid_barrier(p.barrier, epoch, uG);
+    DD_TICKB();
 
     // ===== P3: joint LayerNorm backward over 3D for my gate columns =======================
 #pragma unroll
@@ -755,7 +781,9 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
               rstd_g[r] * (dxg[r][gate] - m1 - xhg[r][gate] * m2);
       }
     }
+    DD_TICKB();
     grid_barrier(p.barrier, epoch, uG);
+    DD_TICKB();
 
     // ===== P4: [d prev_deter | dx] = dz_gru @ Wgru^T ; deter carry masking ================
     stage_my_rows(xs, XK, p.dz_gru + row0 * D3, D3, B, D3, warp, lane);
@@ -782,11 +810,14 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
         }
       }
     }
+    DD_TICKB();
     grid_barrier(p.barrier, epoch, uG);
+    DD_TICKB();
 
     // ===== P5: LN backward (img_in) ; d prev_stoch = dz_in @ Win[:SC]^T ; masking ==========
     stage_my_rows(xs, XK, p.dx + row0 * U, U, B, U, warp, lane);
-    ln_bwd_rows(xs, XK, U, p.z_in + row0 * U, p.st_in + row0 * 2, p.ln_in_s, p.ln_in_b, 1,
+    stage_my_rows(xs + U, XK, p.z_in + row0 * U, U, B, U, warp, lane);
+    ln_bwd_rows(xs, XK, U, p.st_in + row0 * 2, p.ln_in_s, p.ln_in_b, 1,
                 owner ? p.dz_in + row0 * U : nullptr, B, warp, lane);
     if (t > 0) {
       for (int ch = 0; ch < nsc; ++ch) {
@@ -806,7 +837,9 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
           }
         }
       }
-      grid_barrier(p.barrier, epoch, uG);
+      DD_TICKB();
+    grid_barrier(p.barrier, epoch, uG);
+    DD_TICKB();
     }
   }
 }
@@ -815,7 +848,7 @@ static size_t smem_bytes_bwd(const DdObserveBwd& p, int G, int* nsc_out, int* xk
   const int SC = p.S * p.C;
   const int per = (SC + G - 1) / G;
   const int nsc = (per + NSW - 1) / NSW;
-  int xk = max(SC, max(3 * p.D, p.U));
+  int xk = max(SC, max(3 * p.D, 2 * p.U));
   xk = (xk + 3) / 4 * 4;
   if (nsc_out) *nsc_out = nsc;
   if (xk_out) *xk_out = xk;

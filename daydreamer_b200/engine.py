@@ -1022,7 +1022,8 @@ class Engine:
         Wgru=P('rssm/gru_out/kernel'), Win=P('rssm/img_in/kernel'), dfeat=self.dfeat,
         dzs=self.dzs, dz_obs=self.dz_obs, dz_gru=self.dz_gru, dz_in=self.dz_in, dh=self.b_dh,
         dy_gru=self.b_dy, dx=self.b_dx, d_initdeter=self.d_initdeter,
-        partial=self.scan_partial, barrier=self.scan_barrier)
+        partial=self.scan_partial, barrier=self.scan_barrier,
+        timing=getattr(self, 'bptt_timing', None))
     if not hasattr(self, '_bptt_ok'):
       self._bptt_ok = (be.observe_bwd_grid(dims, s.rssm_unimix, tensors) or 0) > 0
     if not self._bptt_ok:

@@ -141,6 +141,7 @@ typedef struct DdObserveBwd {
   float *dfeat, *dzs, *dz_obs, *dz_gru, *dz_in, *dh, *dy_gru, *dx, *d_initdeter;
   float* partial;          /* workspace: 148 * 16 * 2 floats */
   unsigned int* barrier;   /* workspace: 1 counter */
+  long long* timing;       /* optional: 12 per-phase SM-clock totals of CTA 0, or NULL */
 } DdObserveBwd;
 int dd_observe_bwd_grid(const DdObserveBwd* p);
 int dd_observe_bwd(const DdObserveBwd* p, dd_stream_t stream);

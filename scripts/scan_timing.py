@@ -18,3 +18,15 @@ tot = t.sum()
 for n, v in zip(names, t):
   print(f'{n:22s} {v/64:9.0f} cycles/step  {100*v/tot:5.1f}%')
 print('total cycles/step', tot / 64, ' (~%.1f us at 1.9 GHz)' % (tot / 64 / 1900))
+# ---- backward (BPTT) kernel phase split
+eng.bptt_timing = torch.zeros(12, dtype=torch.int64, device='cuda')
+for i in range(2):
+  _, st, _ = agent.train(bench.synthetic_batch(16, i + 3), st)
+torch.cuda.synchronize()
+t = eng.bptt_timing.cpu().numpy().astype(float)
+names = ['P1a stats_bwd', 'B', 'P1b dzs@Wst^T', 'B', 'P2 LN+gemm+gru', 'B', 'P3 joint LN', 'B', 'P4 gemm Wgru^T', 'B',
+         'P5 LN+gemm Win^T', 'B']
+tot = t.sum()
+for n, v in zip(names, t):
+  print(f'bwd {n:20s} {v/64:9.0f} cycles/step  {100*v/tot:5.1f}%')
+print('bwd total cycles/step', tot / 64, ' (~%.1f us at 1.9 GHz)' % (tot / 64 / 1900))
