@@ -33,9 +33,10 @@ constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int LOADER_WARPS = 8;                 // two groups of 4 alternate k-blocks
 #ifndef DD_TC_GROUP_WARPS
-#define DD_TC_GROUP_WARPS 2
+#define DD_TC_GROUP_WARPS 4
 #endif
-constexpr int GROUP_WARPS = DD_TC_GROUP_WARPS;   // 2 -> four loader groups: 4 k-blocks of L2 latency in flight
+constexpr int GROUP_WARPS = DD_TC_GROUP_WARPS;   // loader groups = 8 / GROUP_WARPS; must be <= STAGES (r01: 4 groups with
+                                                 // 3 stages alias the mbarrier parity and hang; with 4 stages no faster)
 constexpr int GROUP_THREADS = GROUP_WARPS * 32;
 constexpr int NGROUPS = 8 / GROUP_WARPS;
 constexpr int LOADER_THREADS = LOADER_WARPS * 32;

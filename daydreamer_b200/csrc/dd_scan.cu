@@ -553,7 +553,8 @@ constexpr int NSW = 4;          // stoch columns per img_in chunk
 
 // LayerNorm(+elu) backward of rows 2w, 2w+1, one warp.  X[b][0:N] holds dH on entry and dZ on
 // exit; X[b][N:2N] holds the saved pre-norm row Z (both staged in shared memory).
-__device__ __forceinline__ void ln_bwd_rows(float* X, int ldx, int N, const float* st,
+__device__ __forceinline__ void ln_bwd_rows(float* X, int ldx, int N, const float* Zg,
+                                            const float* st,
                                             const float* __restrict__ scale,
                                             const float* __restrict__ bias, int act, float* out,
                                             int B, int warp, int lane) {
@@ -562,7 +563,7 @@ __device__ __forceinline__ void ln_bwd_rows(float* X, int ldx, int N, const floa
     const int b = 2 * warp + r;
     if (b >= B) continue;
     float* x = X + (size_t)b * ldx;
-    const float* z = x + N;
+    const float* z = Zg != nullptr ? Zg + (size_t)b * N : x + N;   // Zg: read Z from global instead
     const float mean = st[2 * b], rstd = st[2 * b + 1];
     float s1 = 0.f, s2 = 0.f;
     for (int k = lane; k < N; k += 32) {
@@ -630,6 +631,8 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
   unsigned int epoch = 0;
   const unsigned int uG = (unsigned int)G;
   const float un = p.mix / C, om = 1.f - p.mix;
+  const bool dist_p1 = (p.flags & 1) != 0;             // distributed straight-through backward (P1a)
+  const bool staged_z = (p.flags & 2) != 0;            // LayerNorm inputs staged in shared memory
   // optional phase timing (profiling aid): slots [P1a,B,P1b,B,P2,B,P3,B,P4,B,P5,B] of CTA 0
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
@@ -648,6 +651,7 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
 
     // ===== P1a: dzs = d(raw posterior logits) for my categorical groups ===================
     // (straight-through + unimix backward; lanes = classes, warps = row pairs)
+    if (dist_p1) {
     for (int g = cta; g < S; g += G) {
       const int c0 = g * C + lane, c1 = c0 + 32;
       const bool v0 = lane < C, v1 = lane + 32 < C;
@@ -682,9 +686,43 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
     DD_TICKB();
     grid_barrier(p.barrier, epoch, uG);
     DD_TICKB();
+    }
 
     // ===== P1b: dh[:, my units] = dzs @ Wst^T ============================================
-    stage_my_rows(xs, XK, p.dzs + row0 * SC, SC, B, SC, warp, lane);
+    if (dist_p1) {
+      stage_my_rows(xs, XK, p.dzs + row0 * SC, SC, B, SC, warp, lane);
+    } else {
+      // redundant variant: every CTA recomputes all groups of its staged rows in place
+      stage_my_rows(xs, XK, p.dfeat + row0 * F + D, F, B, SC, warp, lane);
+#pragma unroll 1
+      for (int r = 0; r < 2; ++r) {
+        const int b = 2 * warp + r;
+        if (b >= B) continue;
+        float* xr = xs + (size_t)b * XK;
+        const float* lgr = p.post_logit + (row0 + b) * SC;
+        const float* dlr = p.dpost_logit + (row0 + b) * SC;
+        for (int sg = 0; sg < S; ++sg) {
+          const int c0 = sg * C + lane, c1 = c0 + 32;
+          const bool v0 = lane < C, v1 = lane + 32 < C;
+          const float q0 = v0 ? expf(lgr[c0]) : 0.f, q1 = v1 ? expf(lgr[c1]) : 0.f;
+          const float d0 = v0 ? xr[c0] : 0.f, d1 = v1 ? xr[c1] : 0.f;
+          const float dot = warp_sum(q0 * d0 + q1 * d1);
+          const float dl0 = q0 * (d0 - dot) + (v0 ? dlr[c0] : 0.f);
+          const float dl1 = q1 * (d1 - dot) + (v1 ? dlr[c1] : 0.f);
+          const float p0 = v0 ? (q0 - un) / om : 0.f, p1 = v1 ? (q1 - un) / om : 0.f;
+          const float dp0 = v0 ? om * dl0 / q0 : 0.f, dp1 = v1 ? om * dl1 / q1 : 0.f;
+          const float dot2 = warp_sum(p0 * dp0 + p1 * dp1);
+          const float dz0 = p0 * (dp0 - dot2), dz1 = p1 * (dp1 - dot2);
+          if (v0) xr[c0] = dz0;
+          if (v1) xr[c1] = dz1;
+          if (owner) {
+            if (v0) p.dzs[(row0 + b) * SC + c0] = dz0;
+            if (v1) p.dzs[(row0 + b) * SC + c1] = dz1;
+          }
+        }
+      }
+      __syncwarp();
+    }
     {
       float acc[2][NU];
       rows_gemm<NU>(xs, XK, SC, wst, NU, warp, lane, acc);
@@ -704,8 +742,9 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
 
     // ===== P2: LN backward (obs_out) -> deter gradient -> GRU gates of my units ==========
     stage_my_rows(xs, XK, p.dh + row0 * U, U, B, U, warp, lane);
-    stage_my_rows(xs + U, XK, p.z_obs + row0 * U, U, B, U, warp, lane);
-    ln_bwd_rows(xs, XK, U, p.st_obs + row0 * 2, p.ln_obs_s, p.ln_obs_b, 1,
+    if (staged_z) stage_my_rows(xs + U, XK, p.z_obs + row0 * U, U, B, U, warp, lane);
+    ln_bwd_rows(xs, XK, U, staged_z ? nullptr : p.z_obs + row0 * U, p.st_obs + row0 * 2,
+                p.ln_obs_s, p.ln_obs_b, 1,
                 owner ? p.dz_obs + row0 * U : nullptr, B, warp, lane);
     float ddir[2] = {0.f, 0.f};                        // direct path g*(1-u) of my deter unit
     float dxg[2][3], xhg[2][3], rstd_g[2] = {0.f, 0.f};
@@ -816,8 +855,9 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
 
     // ===== P5: LN backward (img_in) ; d prev_stoch = dz_in @ Win[:SC]^T ; masking ==========
     stage_my_rows(xs, XK, p.dx + row0 * U, U, B, U, warp, lane);
-    stage_my_rows(xs + U, XK, p.z_in + row0 * U, U, B, U, warp, lane);
-    ln_bwd_rows(xs, XK, U, p.st_in + row0 * 2, p.ln_in_s, p.ln_in_b, 1,
+    if (staged_z) stage_my_rows(xs + U, XK, p.z_in + row0 * U, U, B, U, warp, lane);
+    ln_bwd_rows(xs, XK, U, staged_z ? nullptr : p.z_in + row0 * U, p.st_in + row0 * 2,
+                p.ln_in_s, p.ln_in_b, 1,
                 owner ? p.dz_in + row0 * U : nullptr, B, warp, lane);
     if (t > 0) {
       for (int ch = 0; ch < nsc; ++ch) {
@@ -838,10 +878,13 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
         }
       }
       DD_TICKB();
-    grid_barrier(p.barrier, epoch, uG);
-    DD_TICKB();
+      grid_barrier(p.barrier, epoch, uG);
+      DD_TICKB();
     }
   }
+#undef DD_TICKB
+  if (cta == 0 && tid == 0 && p.timing != nullptr)
+    for (int i = 0; i < 12; ++i) p.timing[i] = tacc[i];
 }
 
 static size_t smem_bytes_bwd(const DdObserveBwd& p, int G, int* nsc_out, int* xk_out) {
