@@ -96,7 +96,7 @@ class DdObserveBwd(ctypes.Structure):
            'ln_obs_b', 'y_gru', 'z_gru', 'st_gru', 'ln_gru_s', 'ln_gru_b', 'm_deter', 'z_in',
            'st_in', 'ln_in_s', 'ln_in_b', 'Wst', 'Wobs', 'Wgru', 'Win', 'dfeat', 'dzs', 'dz_obs',
            'dz_gru', 'dz_in', 'dh', 'dy_gru', 'dx', 'd_initdeter', 'partial', 'barrier', 'timing')
-  _fields_ = ([(n, ctypes.c_int) for n in ('B', 'L', 'D', 'U', 'S', 'C', 'nsc', 'xk', 'flags')] +
+  _fields_ = ([(n, ctypes.c_int) for n in ('B', 'L', 'D', 'U', 'S', 'C', 'nsc', 'xk')] +
               [('mix', ctypes.c_float)] + [(n, ctypes.c_void_p) for n in _PTRS])
 
 

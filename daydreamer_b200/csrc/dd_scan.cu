@@ -95,26 +95,45 @@ __device__ __forceinline__ void rows_gemm(const float* __restrict__ X, int ldx, 
 // K-split GEMM only ever touch the warp's own rows), so staging needs no block
 // barrier.  Loads come from L2 (ld.global.cg: other CTAs wrote them this step),
 // as float4 when the row is 16-byte aligned.
+template <int UN>
 __device__ __forceinline__ void stage_my_rows(float* X, int ldx, const float* g, int ld, int B,
                                               int N, int warp, int lane) {
   const bool vec = ((ld & 3) == 0) && ((N & 3) == 0) && ((ldx & 3) == 0) &&
                    ((reinterpret_cast<uintptr_t>(g) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  const int b0 = 2 * warp, b1 = b0 + 1;
+  float* x0 = X + (size_t)b0 * ldx;
+  float* x1 = x0 + ldx;
+  // rows past B read row 0 and are zeroed on the way into shared memory
+  const float* s0 = g + (size_t)(b0 < B ? b0 : 0) * ld;
+  const float* s1 = g + (size_t)(b1 < B ? b1 : 0) * ld;
+  const float m0 = b0 < B ? 1.f : 0.f, m1 = b1 < B ? 1.f : 0.f;
+  if (vec) {
+    // both rows, UN float4 each: 2*UN independent L2 loads in flight per lane per round trip
+    // (r01: with 4 in flight the 1536-wide rows of the BPTT kernel cost 6 round trips)
+    for (int k0 = lane * 4; k0 < N; k0 += 128 * UN) {
+      float4 a[UN], c[UN];
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int b = 2 * warp + r;
-    float* x = X + (size_t)b * ldx;
-    if (b < B) {
-      const float* src = g + (size_t)b * ld;
-      if (vec) {
-#pragma unroll 4
-        for (int k = lane * 4; k < N; k += 128)
-          *reinterpret_cast<float4*>(x + k) = __ldcg(reinterpret_cast<const float4*>(src + k));
-      } else {
-        for (int k = lane; k < N; k += 32) x[k] = __ldcg(src + k);
+      for (int u = 0; u < UN; ++u) {
+        const int k = k0 + u * 128;
+        if (k < N) {
+          a[u] = __ldcg(reinterpret_cast<const float4*>(s0 + k));
+          c[u] = __ldcg(reinterpret_cast<const float4*>(s1 + k));
+        }
       }
-    } else {
-      for (int k = lane; k < N; k += 32) x[k] = 0.f;
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int k = k0 + u * 128;
+        if (k < N) {
+          *reinterpret_cast<float4*>(x0 + k) = make_float4(a[u].x * m0, a[u].y * m0, a[u].z * m0, a[u].w * m0);
+          *reinterpret_cast<float4*>(x1 + k) = make_float4(c[u].x * m1, c[u].y * m1, c[u].z * m1, c[u].w * m1);
+        }
+      }
+    }
+  } else {
+    for (int k = lane; k < N; k += 32) {
+      x0[k] = __ldcg(s0 + k) * m0;
+      x1[k] = __ldcg(s1 + k) * m1;
     }
   }
   __syncwarp();
@@ -279,8 +298,8 @@ __global__ void __launch_bounds__(THREADS, 1) observe_fwd_kernel(DdObserveFwd p)
     DD_TICK(1);
 
     // ===== P2: x = elu(LN(z_in)); z_gru[:, my gate cols] = [m_deter | x] @ Wgru slice =====
-    stage_my_rows(sm.x + D, XK, p.z_in + row0 * U, U, B, U, warp, lane);
-    stage_my_rows(sm.x, XK, p.m_deter + row0 * D, D, B, D, warp, lane);
+    stage_my_rows<2>(sm.x + D, XK, p.z_in + row0 * U, U, B, U, warp, lane);
+    stage_my_rows<2>(sm.x, XK, p.m_deter + row0 * D, D, B, D, warp, lane);
     DD_TICK(12);
     {
 #pragma unroll
@@ -406,7 +425,7 @@ __global__ void __launch_bounds__(THREADS, 1) observe_fwd_kernel(DdObserveFwd p)
     DD_TICK(5);
 
     // ===== P4: z_obs[:, u0..] += deter_t @ Wobs[:D] slice  (embed part already there) ====
-    stage_my_rows(sm.x, XK, p.feat + row0 * (D + SC), D + SC, B, D, warp, lane);
+    stage_my_rows<2>(sm.x, XK, p.feat + row0 * (D + SC), D + SC, B, D, warp, lane);
     {
       float zo[2][NU];
       rows_gemm<NU>(sm.x, XK, D, sm.wobs, NU, warp, lane, zo);
@@ -426,7 +445,7 @@ __global__ void __launch_bounds__(THREADS, 1) observe_fwd_kernel(DdObserveFwd p)
 
     // ===== P5: h = elu(LN(z_obs)); logits of my groups; unimix; Gumbel-argmax ==========
     if (cta < S) {
-      stage_my_rows(sm.x, XK, p.z_obs + row0 * U, U, B, U, warp, lane);
+      stage_my_rows<2>(sm.x, XK, p.z_obs + row0 * U, U, B, U, warp, lane);
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int b = 2 * warp + r;
@@ -553,38 +572,49 @@ constexpr int NSW = 4;          // stoch columns per img_in chunk
 
 // LayerNorm(+elu) backward of rows 2w, 2w+1, one warp.  X[b][0:N] holds dH on entry and dZ on
 // exit; X[b][N:2N] holds the saved pre-norm row Z (both staged in shared memory).
-__device__ __forceinline__ void ln_bwd_rows(float* X, int ldx, int N, const float* Zg,
-                                            const float* st,
+__device__ __forceinline__ void ln_bwd_rows(float* X, int ldx, int N, const float* st,
                                             const float* __restrict__ scale,
                                             const float* __restrict__ bias, int act, float* out,
                                             int B, int warp, int lane) {
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int b = 2 * warp + r;
-    if (b >= B) continue;
-    float* x = X + (size_t)b * ldx;
-    const float* z = Zg != nullptr ? Zg + (size_t)b * N : x + N;   // Zg: read Z from global instead
-    const float mean = st[2 * b], rstd = st[2 * b + 1];
-    float s1 = 0.f, s2 = 0.f;
-    for (int k = lane; k < N; k += 32) {
-      const float xh = (z[k] - mean) * rstd;
-      float dy = x[k];
-      const float sc = scale[k];
-      if (act) {
-        const float y = xh * sc + bias[k];
-        if (y <= 0.f) dy *= expf(y);
-      }
-      const float dxv = dy * sc;
-      x[k] = dxv;
-      s1 += dxv;
-      s2 += dxv * xh;
+  // both rows of the warp advance together: two independent dependency chains per lane
+  const int b0 = 2 * warp, b1 = b0 + 1;
+  const bool a0 = b0 < B, a1 = b1 < B;
+  if (!a0) return;                                       // b1 >= B as well
+  float* x0 = X + (size_t)b0 * ldx;
+  float* x1 = x0 + ldx;
+  const float* z0 = x0 + N;
+  const float* z1 = x1 + N;
+  const float mean0 = st[2 * b0], rstd0 = st[2 * b0 + 1];
+  const float mean1 = a1 ? st[2 * b1] : 0.f, rstd1 = a1 ? st[2 * b1 + 1] : 0.f;
+  float s10 = 0.f, s20 = 0.f, s11 = 0.f, s21 = 0.f;
+#pragma unroll 4
+  for (int k = lane; k < N; k += 32) {
+    const float sc = scale[k], bi = bias[k];
+    const float xh0 = (z0[k] - mean0) * rstd0, xh1 = (z1[k] - mean1) * rstd1;
+    float dy0 = x0[k], dy1 = x1[k];
+    if (act) {
+      const float y0 = xh0 * sc + bi, y1 = xh1 * sc + bi;
+      if (y0 <= 0.f) dy0 *= expf(y0);
+      if (y1 <= 0.f) dy1 *= expf(y1);
     }
-    const float m1 = warp_sum(s1) / N, m2 = warp_sum(s2) / N;
-    for (int k = lane; k < N; k += 32) {
-      const float xh = (z[k] - mean) * rstd;
-      const float dz = rstd * (x[k] - m1 - xh * m2);
-      x[k] = dz;
-      if (out != nullptr) out[(size_t)b * N + k] = dz;
+    const float d0 = dy0 * sc, d1 = dy1 * sc;
+    x0[k] = d0;
+    x1[k] = d1;
+    s10 += d0; s20 += d0 * xh0;
+    s11 += d1; s21 += d1 * xh1;
+  }
+  const float m10 = warp_sum(s10) / N, m20 = warp_sum(s20) / N;
+  const float m11 = warp_sum(s11) / N, m21 = warp_sum(s21) / N;
+#pragma unroll 4
+  for (int k = lane; k < N; k += 32) {
+    const float xh0 = (z0[k] - mean0) * rstd0, xh1 = (z1[k] - mean1) * rstd1;
+    const float dz0 = rstd0 * (x0[k] - m10 - xh0 * m20);
+    const float dz1 = a1 ? rstd1 * (x1[k] - m11 - xh1 * m21) : 0.f;
+    x0[k] = dz0;
+    x1[k] = dz1;
+    if (out != nullptr) {
+      out[(size_t)b0 * N + k] = dz0;
+      if (a1) out[(size_t)b1 * N + k] = dz1;
     }
   }
   __syncwarp();
@@ -631,8 +661,6 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
   unsigned int epoch = 0;
   const unsigned int uG = (unsigned int)G;
   const float un = p.mix / C, om = 1.f - p.mix;
-  const bool dist_p1 = (p.flags & 1) != 0;             // distributed straight-through backward (P1a)
-  const bool staged_z = (p.flags & 2) != 0;            // LayerNorm inputs staged in shared memory
   // optional phase timing (profiling aid): slots [P1a,B,P1b,B,P2,B,P3,B,P4,B,P5,B] of CTA 0
   long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
@@ -651,7 +679,6 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
 
     // ===== P1a: dzs = d(raw posterior logits) for my categorical groups ===================
     // (straight-through + unimix backward; lanes = classes, warps = row pairs)
-    if (dist_p1) {
     for (int g = cta; g < S; g += G) {
       const int c0 = g * C + lane, c1 = c0 + 32;
       const bool v0 = lane < C, v1 = lane + 32 < C;
@@ -686,43 +713,9 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
     DD_TICKB();
     grid_barrier(p.barrier, epoch, uG);
     DD_TICKB();
-    }
 
     // ===== P1b: dh[:, my units] = dzs @ Wst^T ============================================
-    if (dist_p1) {
-      stage_my_rows(xs, XK, p.dzs + row0 * SC, SC, B, SC, warp, lane);
-    } else {
-      // redundant variant: every CTA recomputes all groups of its staged rows in place
-      stage_my_rows(xs, XK, p.dfeat + row0 * F + D, F, B, SC, warp, lane);
-#pragma unroll 1
-      for (int r = 0; r < 2; ++r) {
-        const int b = 2 * warp + r;
-        if (b >= B) continue;
-        float* xr = xs + (size_t)b * XK;
-        const float* lgr = p.post_logit + (row0 + b) * SC;
-        const float* dlr = p.dpost_logit + (row0 + b) * SC;
-        for (int sg = 0; sg < S; ++sg) {
-          const int c0 = sg * C + lane, c1 = c0 + 32;
-          const bool v0 = lane < C, v1 = lane + 32 < C;
-          const float q0 = v0 ? expf(lgr[c0]) : 0.f, q1 = v1 ? expf(lgr[c1]) : 0.f;
-          const float d0 = v0 ? xr[c0] : 0.f, d1 = v1 ? xr[c1] : 0.f;
-          const float dot = warp_sum(q0 * d0 + q1 * d1);
-          const float dl0 = q0 * (d0 - dot) + (v0 ? dlr[c0] : 0.f);
-          const float dl1 = q1 * (d1 - dot) + (v1 ? dlr[c1] : 0.f);
-          const float p0 = v0 ? (q0 - un) / om : 0.f, p1 = v1 ? (q1 - un) / om : 0.f;
-          const float dp0 = v0 ? om * dl0 / q0 : 0.f, dp1 = v1 ? om * dl1 / q1 : 0.f;
-          const float dot2 = warp_sum(p0 * dp0 + p1 * dp1);
-          const float dz0 = p0 * (dp0 - dot2), dz1 = p1 * (dp1 - dot2);
-          if (v0) xr[c0] = dz0;
-          if (v1) xr[c1] = dz1;
-          if (owner) {
-            if (v0) p.dzs[(row0 + b) * SC + c0] = dz0;
-            if (v1) p.dzs[(row0 + b) * SC + c1] = dz1;
-          }
-        }
-      }
-      __syncwarp();
-    }
+    stage_my_rows<4>(xs, XK, p.dzs + row0 * SC, SC, B, SC, warp, lane);
     {
       float acc[2][NU];
       rows_gemm<NU>(xs, XK, SC, wst, NU, warp, lane, acc);
@@ -741,10 +734,9 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
     DD_TICKB();
 
     // ===== P2: LN backward (obs_out) -> deter gradient -> GRU gates of my units ==========
-    stage_my_rows(xs, XK, p.dh + row0 * U, U, B, U, warp, lane);
-    if (staged_z) stage_my_rows(xs + U, XK, p.z_obs + row0 * U, U, B, U, warp, lane);
-    ln_bwd_rows(xs, XK, U, staged_z ? nullptr : p.z_obs + row0 * U, p.st_obs + row0 * 2,
-                p.ln_obs_s, p.ln_obs_b, 1,
+    stage_my_rows<4>(xs, XK, p.dh + row0 * U, U, B, U, warp, lane);
+    stage_my_rows<4>(xs + U, XK, p.z_obs + row0 * U, U, B, U, warp, lane);
+    ln_bwd_rows(xs, XK, U, p.st_obs + row0 * 2, p.ln_obs_s, p.ln_obs_b, 1,
                 owner ? p.dz_obs + row0 * U : nullptr, B, warp, lane);
     float ddir[2] = {0.f, 0.f};                        // direct path g*(1-u) of my deter unit
     float dxg[2][3], xhg[2][3], rstd_g[2] = {0.f, 0.f};
@@ -825,7 +817,7 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
     DD_TICKB();
 
     // ===== P4: [d prev_deter | dx] = dz_gru @ Wgru^T ; deter carry masking ================
-    stage_my_rows(xs, XK, p.dz_gru + row0 * D3, D3, B, D3, warp, lane);
+    stage_my_rows<4>(xs, XK, p.dz_gru + row0 * D3, D3, B, D3, warp, lane);
     {
       float acc[2][NJ + NU];
       rows_gemm<NJ + NU>(xs, XK, D3, wgru, NJ + NU, warp, lane, acc);
@@ -854,10 +846,9 @@ __global__ void __launch_bounds__(THREADS, 1) observe_bwd_kernel(DdObserveBwd p)
     DD_TICKB();
 
     // ===== P5: LN backward (img_in) ; d prev_stoch = dz_in @ Win[:SC]^T ; masking ==========
-    stage_my_rows(xs, XK, p.dx + row0 * U, U, B, U, warp, lane);
-    if (staged_z) stage_my_rows(xs + U, XK, p.z_in + row0 * U, U, B, U, warp, lane);
-    ln_bwd_rows(xs, XK, U, staged_z ? nullptr : p.z_in + row0 * U, p.st_in + row0 * 2,
-                p.ln_in_s, p.ln_in_b, 1,
+    stage_my_rows<4>(xs, XK, p.dx + row0 * U, U, B, U, warp, lane);
+    stage_my_rows<4>(xs + U, XK, p.z_in + row0 * U, U, B, U, warp, lane);
+    ln_bwd_rows(xs, XK, U, p.st_in + row0 * 2, p.ln_in_s, p.ln_in_b, 1,
                 owner ? p.dz_in + row0 * U : nullptr, B, warp, lane);
     if (t > 0) {
       for (int ch = 0; ch < nsc; ++ch) {

@@ -580,7 +580,6 @@ class Engine:
     self.scan_barrier = z(4, dtype=torch.int32)
     # fused BPTT kernel: pre-LN gradients of every step (LN parameter grads are batched after it)
     self.fused_bptt = True
-    self.bptt_flags = int(os.environ.get('DD_BPTT_FLAGS', '0'))
     self.b_dh = z(N, U)
     self.b_dy = z(N, 3 * D)
     self.b_dx = z(N, U)
@@ -1011,8 +1010,7 @@ class Engine:
     if not (self.fused_bptt and hasattr(be, 'observe_bwd')):
       return False
     P = gm.P
-    dims = dict(B=self.B, L=self.L, D=s.deter, U=s.units, S=s.stoch, C=s.classes,
-                flags=self.bptt_flags)
+    dims = dict(B=self.B, L=self.L, D=s.deter, U=s.units, S=s.stoch, C=s.classes)
     tensors = dict(
         first=self.first, first0=self.first0, post_logit=self.post_logit,
         dpost_logit=self.dpost_logit, z_obs=self.z_obs, st_obs=self.st_obs,

@@ -132,7 +132,6 @@ int dd_observe_fwd(const DdObserveFwd* p, dd_stream_t stream);
 typedef struct DdObserveBwd {
   int B, L, D, U, S, C;
   int nsc, xk;             /* filled by the library */
-  int flags;               /* bit 0: distributed P1 (one more barrier), bit 1: LN inputs staged in smem */
   float mix;
   const float *first, *first0, *post_logit, *dpost_logit;
   const float *z_obs, *st_obs, *ln_obs_s, *ln_obs_b;
