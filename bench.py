@@ -328,13 +328,18 @@ def run_ours(args, rank, world, local_rank):
       if world > 1:
         eng.allreduce = saved
     peaks = load_peaks()
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'tc_gemm_traffic.json')
+    if os.path.exists(tpath):          # per-launch DRAM bytes of the dominant kernel from the ncu capture
+      tj = json.load(open(tpath))
+      traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
     tf = probe.flops / gemm_s / 1e12
     scan_bytes = 222.4e6        # fused observe+imagine scan, a1, per GPU
     roofline = {
         'kernel': 'dd::tc::gemm_tc_kernel (tcgen05 kind::tf32 x3 = fp32-accurate) + fp32 SIMT/skinny '
                   'fallbacks: every dd_gemm launch of one step', 'bound': 'tensor', 'achieved': tf,
         'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': tf / peaks['tflops'],
-        'traffic': None, 'peak_source': peaks['source'],
+        'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peaks['source'],
         'launches_per_step': probe.calls, 'avg_launch_us': gemm_s / probe.calls * 1e6,
         'flops_per_step': probe.flops, 'share_of_step': gemm_s / dt,
         'step_hbm': {'algorithmic_bytes': scan_bytes,
