@@ -180,6 +180,8 @@ static int launch(const float* A, int lda, int ta, const float* B, int ldb, int 
   return launched("dd_gemm");
 }
 
+int gemm_thin_try(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
+                  int ldc, int M, int N, int K, float beta, const float* bias, cudaStream_t st);
 int gemm_skinny_try(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
                     int ldc, int M, int N, int K, float beta, const float* bias,
                     cudaStream_t st);
@@ -212,6 +214,10 @@ extern "C" int dd_gemm(const float* A, int lda, int ta, const float* B, int ldb,
   cudaStream_t st = S(stream);
   {
     const int r = gemm_skinny_try(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias, st);
+    if (r != 0) return r > 0 ? 0 : r;
+  }
+  {
+    const int r = gemm_thin_try(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias, st);
     if (r != 0) return r > 0 ? 0 : r;
   }
   if (tc_enabled()) {

@@ -418,8 +418,12 @@ __global__ void mask_bwd_kernel(const float* __restrict__ dd_, int lddd,
   }
 }
 
-// Narrow rows (N <= 128: the per-pixel channel LayerNorm of the conv stacks, millions
-// of rows): one warp per row, the row held in registers, warp-shuffle reductions.
+// Rows of up to 512 values (the per-pixel channel LayerNorm of the conv stacks with millions of
+// rows, and every 512-wide MLP layer): one warp per row, the row held in registers (<= 16 values
+// per lane), warp-shuffle reductions, no block barriers.  dd_set_ln_warp_max(128) restores the
+// block-per-row kernel for the wider rows.
+int g_ln_warp_max = 512;
+
 template <int PER>
 __global__ void __launch_bounds__(256) ln_fwd_warp_kernel(
     const float* __restrict__ Z, int ldz, const float* __restrict__ scale,
@@ -544,11 +548,15 @@ extern "C" int dd_ln_fwd(const float* Z, int ldz, const float* scale, const floa
                          int ldh, float* stats, int M, int N, int act, dd_stream_t stream) {
   if (M <= 0) return 0;
   if (N > 12000) return fail("dd_ln_fwd", "row too wide for shared-memory staging");
-  if (N <= 128) {
+  if (N <= g_ln_warp_max) {
     const int grid = grid_for(M, 8, 148 * 16);
-    if (N <= 32) launch_k(ln_fwd_warp_kernel<1>, grid, 256, 0, S(stream), Z, ldz, scale, bias, H, ldh, stats, M, N, act);
-    else if (N <= 64) launch_k(ln_fwd_warp_kernel<2>, grid, 256, 0, S(stream), Z, ldz, scale, bias, H, ldh, stats, M, N, act);
-    else launch_k(ln_fwd_warp_kernel<4>, grid, 256, 0, S(stream), Z, ldz, scale, bias, H, ldh, stats, M, N, act);
+#define DD_LNF(PER) launch_k(ln_fwd_warp_kernel<PER>, grid, 256, 0, S(stream), Z, ldz, scale, bias, H, ldh, stats, M, N, act)
+    if (N <= 32) DD_LNF(1);
+    else if (N <= 64) DD_LNF(2);
+    else if (N <= 128) DD_LNF(4);
+    else if (N <= 256) DD_LNF(8);
+    else DD_LNF(16);
+#undef DD_LNF
     return launched("dd_ln_fwd");
   }
   const int block = N >= 2048 ? 512 : (N >= 256 ? 128 : 64);
@@ -565,16 +573,19 @@ extern "C" int dd_ln_bwd(const float* dH, int lddh, const float* Z, int ldz, con
 #define DD_LNB(PER, BLK)                                                                      \
   launch_k(ln_bwd_kernel<PER, BLK>, grid, BLK, 0, S(stream), dH, lddh, Z, ldz, stats, scale, bias, dZ, \
                                                   lddz, dscale, dbias, M, N, act)
-  if (N <= 128) {
+  if (N <= g_ln_warp_max) {
     const int wgrid = grid_for(M, 8, 148 * 8);
 #define DD_LNW(PER)                                                                              \
   launch_k(ln_bwd_warp_kernel<PER>, wgrid, 256, 0, S(stream), dH, lddh, Z, ldz, stats, scale, bias, \
            dZ, lddz, dscale, dbias, M, N, act)
     if (N <= 32) DD_LNW(1);
     else if (N <= 64) DD_LNW(2);
-    else DD_LNW(4);
+    else if (N <= 128) DD_LNW(4);
+    else if (N <= 256) DD_LNW(8);
+    else DD_LNW(16);
 #undef DD_LNW
   }
+  else if (N <= 128) DD_LNB(1, 128);
   else if (N <= 512) DD_LNB(4, 128);
   else if (N <= 2048) DD_LNB(8, 256);
   else if (N <= 8192) DD_LNB(8, 1024);
@@ -663,4 +674,10 @@ extern "C" int dd_mask_bwd(const float* dd_, int lddd, const float* ds, int ldds
   launch_k(mask_bwd_kernel, grid_for(D + SC, 128), 128, 0, S(stream), dd_, lddd, ds, ldds, first, dpd,
                                                                 lddpd, dps, lddps, dinit, M, D, SC);
   return launched("dd_mask_bwd");
+}
+
+extern "C" int dd_set_ln_warp_max(int n) {
+  const int prev = g_ln_warp_max;
+  g_ln_warp_max = n < 0 ? 0 : (n > 512 ? 512 : n);
+  return prev;
 }

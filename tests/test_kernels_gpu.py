@@ -56,6 +56,29 @@ def test_gemm(backends, M, N, K, ta, tb):
   both(backends, case, rtol=1e-4, atol=1e-4 * np.sqrt(K))
 
 
+@pytest.mark.parametrize('M,N,K', [(1024, 12, 512), (1024, 24, 512), (1024, 512, 12), (15360, 1, 512),
+                                   (15360, 512, 1), (1000, 3, 300), (70, 32, 1536), (333, 5, 20),
+                                   (1024, 1536, 12), (900, 2, 16), (257, 31, 33)])
+@pytest.mark.parametrize('tb', [False, True])
+def test_gemm_thin(backends, M, N, K, tb):
+  """Thin shapes (N <= 32 or K <= 32, many rows) on the streaming kernels of dd_gemm_thin.cu,
+  contiguous (vector path) and row-strided operands, bias / beta combinations."""
+  def case(be, T):
+    out = {}
+    for pad in (0, 3):
+      A = T(rnd(M, K + pad, seed=1))[:, :K]
+      B = T(rnd(*((N, K + pad) if tb else (K, N + pad)), seed=2))
+      B = B[:, :K] if tb else B[:, :N]
+      C = T(rnd(M, N + pad, seed=3))[:, :N]
+      bias = T(rnd(N + 4, seed=4))[:N] if pad == 0 else None
+      be.gemm(A, B, C, tb=tb, beta=0.0, bias=bias)
+      out[f'c0_{pad}'] = C.clone()
+      be.gemm(A, B, C, tb=tb, beta=1.0)
+      out[f'c1_{pad}'] = C.clone()
+    return out
+  both(backends, case, rtol=1e-4, atol=1e-4 * np.sqrt(K))
+
+
 def test_gemm_splitk_wgrad(backends):
   def case(be, T):
     X = T(rnd(16384, 200, seed=1))
@@ -67,7 +90,8 @@ def test_gemm_splitk_wgrad(backends):
 
 
 @pytest.mark.parametrize('M,N,act', [(16, 512, 1), (1000, 1536, 0), (3, 20, 1), (70, 6144, 0),
-                                     (257, 72, 1)])
+                                     (257, 72, 1), (1024, 512, 1), (777, 256, 0), (16384, 512, 1),
+                                     (300, 200, 1), (50, 640, 1)])
 def test_ln(backends, M, N, act):
   def case(be, T):
     Z = T(rnd(M, N + 4, seed=1, scale=2.0))[:, 2:2 + N]
