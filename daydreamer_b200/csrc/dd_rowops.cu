@@ -420,9 +420,11 @@ __global__ void mask_bwd_kernel(const float* __restrict__ dd_, int lddd,
 
 // Rows of up to 512 values (the per-pixel channel LayerNorm of the conv stacks with millions of
 // rows, and every 512-wide MLP layer): one warp per row, the row held in registers (<= 16 values
-// per lane), warp-shuffle reductions, no block barriers.  dd_set_ln_warp_max(128) restores the
-// block-per-row kernel for the wider rows.
-int g_ln_warp_max = 512;
+// per lane), warp-shuffle reductions, no block barriers.  Default limit 128 columns: measured on
+// the a1 step (r01), the warp kernels at N = 512 were SLOWER than block-per-row (fewer warps in
+// flight per SM: imagine +0.5 ms, actor_update +2 ms), so wider rows use them only on request
+// (dd_set_ln_warp_max(512)).
+int g_ln_warp_max = 128;
 
 template <int PER>
 __global__ void __launch_bounds__(256) ln_fwd_warp_kernel(

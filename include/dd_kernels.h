@@ -52,7 +52,7 @@ int dd_set_gemm_tc(int on);
 int dd_set_gemm_tc_persistent(int on);
 /* thin GEMMs (N <= 32 or K <= 32 with many rows) on dedicated streaming kernels (default on) */
 int dd_set_gemm_thin(int on);
-/* widest row the warp-per-row LayerNorm kernels take (<= 512, default 512) */
+/* widest row the warp-per-row LayerNorm kernels take (<= 512, default 128) */
 int dd_set_ln_warp_max(int n);
 /* profiling aid: bit 0 = skip operand loads, bit 1 = skip MMA issue (garbage results) */
 int dd_set_gemm_tc_debug(int bits);
