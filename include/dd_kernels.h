@@ -50,7 +50,7 @@ int dd_set_gemm_tc(int on);
 /* 1 (default): GEMMs with more 128x128 tiles than ~1.5x the SM count use the persistent
  * tensor-core kernel (double-buffered TMEM, overlapped epilogue).  Returns previous. */
 int dd_set_gemm_tc_persistent(int on);
-/* thin GEMMs (N <= 32 or K <= 32 with many rows) on dedicated streaming kernels (default on) */
+/* thin GEMMs (N <= 32 or K <= 32 with many rows) on dedicated streaming kernels (default off) */
 int dd_set_gemm_thin(int on);
 /* widest row the warp-per-row LayerNorm kernels take (<= 512, default 128) */
 int dd_set_ln_warp_max(int n);

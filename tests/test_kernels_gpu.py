@@ -65,6 +65,7 @@ def test_gemm_thin(backends, M, N, K, tb):
   contiguous (vector path) and row-strided operands, bias / beta combinations."""
   def case(be, T):
     out = {}
+    prev = be.lib.dd_set_gemm_thin(1) if hasattr(be, 'lib') else None     # off by default
     for pad in (0, 3):
       A = T(rnd(M, K + pad, seed=1))[:, :K]
       B = T(rnd(*((N, K + pad) if tb else (K, N + pad)), seed=2))
@@ -75,6 +76,8 @@ def test_gemm_thin(backends, M, N, K, tb):
       out[f'c0_{pad}'] = C.clone()
       be.gemm(A, B, C, tb=tb, beta=1.0)
       out[f'c1_{pad}'] = C.clone()
+    if prev is not None:
+      be.lib.dd_set_gemm_thin(prev)
     return out
   both(backends, case, rtol=1e-4, atol=1e-4 * np.sqrt(K))
 
@@ -92,8 +95,10 @@ def test_gemm_splitk_wgrad(backends):
 @pytest.mark.parametrize('M,N,act', [(16, 512, 1), (1000, 1536, 0), (3, 20, 1), (70, 6144, 0),
                                      (257, 72, 1), (1024, 512, 1), (777, 256, 0), (16384, 512, 1),
                                      (300, 200, 1), (50, 640, 1)])
-def test_ln(backends, M, N, act):
+@pytest.mark.parametrize('warp_max', [128, 512])
+def test_ln(backends, M, N, act, warp_max):
   def case(be, T):
+    prev = be.lib.dd_set_ln_warp_max(warp_max) if hasattr(be, 'lib') else None
     Z = T(rnd(M, N + 4, seed=1, scale=2.0))[:, 2:2 + N]
     sc, bi = T(1 + 0.2 * rnd(N, seed=2)), T(0.3 * rnd(N, seed=3))
     H, st = T(torch.zeros(M, N)), T(torch.zeros(M, 2))
@@ -103,6 +108,8 @@ def test_ln(backends, M, N, act):
     be.ln_bwd(dH, Z, st, sc, bi, dZ, ds, db, act)
     dZ2 = T(torch.zeros(M, N))
     be.ln_bwd(dH, Z, st, sc, bi, dZ2, None, None, act)
+    if prev is not None:
+      be.lib.dd_set_ln_warp_max(prev)
     return {'H': H, 'st': st, 'dZ': dZ, 'ds': ds, 'db': db, 'dZ2': dZ2}
   both(backends, case, rtol=1e-4, atol=1e-4 * np.sqrt(M))
 
