@@ -88,10 +88,11 @@ def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
     raise NotImplementedError(f'encoder keys {list(enc)} must equal decoder keys {list(dec)}')
   heads = [g(f'{h}.layers') for h in ('reward_head', 'cont_head', 'actor', 'critic')]
   units = [g(f'{h}.units') for h in ('reward_head', 'cont_head', 'actor', 'critic')]
-  heads.append(g('decoder.mlp_layers'))
-  units.append(g('decoder.mlp_units'))
   if len(set(heads)) != 1 or len(set(units)) != 1:
-    raise NotImplementedError('heads must share layers/units')
+    raise NotImplementedError('reward / cont / actor / critic heads must share layers and units')
+  for h in ('decoder', 'reward_head', 'cont_head', 'actor', 'critic'):
+    if g(f'{h}.act') != 'elu' or g(f'{h}.norm') != 'layer':
+      raise NotImplementedError(f'{h}: only act=elu, norm=layer are built')
   opts = [tuple(g(f'{o}.{k}') for k in ('lr', 'eps', 'clip', 'wd', 'warmup'))
           for o in ('model_opt', 'actor_opt', 'critic_opt')]
   if len(set(opts)) != 1 or opts[0][4]:
@@ -102,7 +103,8 @@ def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
       classes=int(g('rssm.classes')), prior_layers=int(g('rssm.prior_layers')),
       rssm_unimix=float(g('rssm.unimix')), enc_layers=int(g('encoder.mlp_layers')),
       enc_units=int(g('encoder.mlp_units')), head_layers=int(heads[0]),
-      head_units=int(units[0]), horizon=int(g('imag_horizon')), discount=float(g('discount')),
+      head_units=int(units[0]), dec_layers=int(g('decoder.mlp_layers')),
+      dec_units=int(g('decoder.mlp_units')), horizon=int(g('imag_horizon')), discount=float(g('discount')),
       lam=float(g('return_lambda')), kl_balance=float(g('wmkl_balance')),
       wmkl_target=float(g('wmkl.target')), wmkl_min=float(g('wmkl.min')),
       wmkl_max=float(g('wmkl.max')), actent_target=float(g('actent.target')),
@@ -153,13 +155,17 @@ class Agent:
 
   configs = _configs.CONFIGS
 
-  def __init__(self, obs_space, act_space, step, config, seed=None):
+  def __init__(self, obs_space, act_space, step, config, seed=None, backend=None):
+    """`backend` is a test seam: the product path always constructs CudaBackend (which raises
+    without a GPU / the kernel library); tests/test_reference_loop.py passes the torch-CPU
+    primitive simulator to drive the reference's own run loop where there is no GPU."""
     self.config = config
     self.obs_space = obs_space
     self.act_space = act_space['action'] if isinstance(act_space, dict) else act_space
     self.step = step
     self.spec = spec_from_config(config, obs_space, act_space)
-    self.be = CudaBackend()                     # raises without GPU / .so
+    self.be = backend if backend is not None else CudaBackend()   # raises without GPU / .so
+    self._on_gpu = self.be.device.type == 'cuda'
     self.seed = int(_get(config, 'seed')) if seed is None else int(seed)
     self.world, self.rank, self._allreduce = 1, 0, None
     if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -173,7 +179,7 @@ class Agent:
     self._graphs = {}
     self._calls = {}
     self._slow_updates = -1           # host mirror of the device slow-target counter
-    self.use_graph = True
+    self.use_graph = self._on_gpu
     self._init_params = _engine.init_params(self.spec, seed=self.seed + 1)
     self.expl_noise = float(_get(config, 'expl_noise'))
     self.eval_noise = float(_get(config, 'eval_noise'))
@@ -195,13 +201,14 @@ class Agent:
   def _attach_stage(self, eng):
     """Pinned host + device staging buffers for one engine's [B, L, ...] inputs."""
     B, L = eng.B, eng.L
+    pin = self._on_gpu
     eng.h_stage = {
-        k: torch.zeros(B, L, d, pin_memory=True)
+        k: torch.zeros(B, L, d, pin_memory=pin)
         for k, d in (('obs', self.spec.obs_total), ('action', self.spec.act_dim),
                      ('first', 1), ('reward', 1), ('cont', 1))}
     # images travel as uint8 and are scaled / channel-concatenated on the device
     for k, shp in self.spec.cnn_keys.items():
-      eng.h_stage[f'img/{k}'] = torch.zeros(B, L, *shp, dtype=torch.uint8, pin_memory=True)
+      eng.h_stage[f'img/{k}'] = torch.zeros(B, L, *shp, dtype=torch.uint8, pin_memory=pin)
     eng.d_stage = {k: torch.zeros_like(v, device=self.be.device) for k, v in eng.h_stage.items()}
 
   def _main_engine(self):
@@ -418,10 +425,10 @@ class Agent:
     self._run(pol, 'policy', pol.launch)
     noise = self.expl_noise
     if mode == 'eval':
-      action = pol.mean.cpu().numpy()
+      action = pol.mean.cpu().numpy().copy()
       noise = self.eval_noise
     else:
-      action = pol.action.cpu().numpy()
+      action = pol.action.cpu().numpy().copy()
     if noise and self.spec.discrete:                              # A/tfutils.py:85-93
       probs = noise / action.shape[-1] + (1 - noise) * action
       draw = (probs.cumsum(-1) > np.random.uniform(size=action.shape[:-1] + (1,))).argmax(-1)

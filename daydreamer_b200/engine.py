@@ -51,6 +51,8 @@ class Spec:
   enc_units: int = 512
   head_layers: int = 4
   head_units: int = 512
+  dec_layers: int = 0                 # decoder.mlp_layers / mlp_units when they differ (0 = as heads)
+  dec_units: int = 0
   horizon: int = 15
   discount: float = 0.995
   lam: float = 0.95
@@ -84,6 +86,14 @@ class Spec:
   @property
   def sc(self):
     return self.stoch * self.classes
+
+  def trunk(self, prefix):
+    """(layers, units) of the MLP trunk called `prefix`."""
+    if prefix == 'dec':
+      return (self.dec_layers or self.head_layers, self.dec_units or self.head_units)
+    if prefix == 'enc':
+      return (self.enc_layers, self.enc_units)
+    return (self.head_layers, self.head_units)
 
   @property
   def img_shape(self):
@@ -193,8 +203,8 @@ def param_shapes(spec: Spec) -> Dict[str, Tuple[int, ...]]:
       s[f'{name}/norm/scale'] = (co,)
       s[f'{name}/norm/bias'] = (co,)
   if spec.obs_dims:
-    mlp('dec', spec.feat, spec.head_layers, spec.head_units)
-    out('dec/dist_out/out', spec.head_units, spec.obs_total)
+    mlp('dec', spec.feat, *spec.trunk('dec'))
+    out('dec/dist_out/out', spec.trunk('dec')[1], spec.obs_total)
   for name in ('reward', 'cont'):
     mlp(name, spec.feat, spec.head_layers, spec.head_units)
     out(f'{name}/dist_out/out', spec.head_units, 1)
@@ -519,7 +529,7 @@ class Engine:
 
     # shared temporaries for backward ping-pong (largest row count x widest)
     R = (H + 1) * N
-    wide = max(3 * D, SC, U, s.head_units, E)
+    wide = max(3 * D, SC, U, s.head_units, s.trunk('dec')[1], E)
     self._tmp = [z(R * wide) for _ in range(3)]
 
     # -- world model buffers -------------------------------------------------
@@ -551,7 +561,7 @@ class Engine:
     self.post_idx = z(N, s.stoch, dtype=torch.int32)
     self.prior = Trunk(self, gm, 'rssm/priorp', s.prior_layers, U, N)
     self.prior_logit = z(N, SC)
-    self.heads = {k: Trunk(self, gm, k, s.head_layers, s.head_units, N)
+    self.heads = {k: Trunk(self, gm, k, *s.trunk(k), N)
                   for k in (('dec',) if s.obs_dims else ()) + ('reward', 'cont')}
     self.out_dec = z(N, s.obs_total)
     self.out_rew = z(N, 1)
@@ -923,7 +933,7 @@ class Engine:
       if name not in self.heads:
         continue
       tr = self.heads[name]
-      dH = self.tmp(0, N, hu)
+      dH = self.tmp(0, N, tr.units)
       self._out_bwd(gm, f'{name}/dist_out/out', tr.H[-1], dOut, dH, True)
       tr.bwd(dH, 0, N, [(feat, 0)], [(dfeat, 0, beta)], True)
       beta = 1.0

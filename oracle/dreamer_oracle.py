@@ -52,8 +52,10 @@ class Spec:
   rssm_unimix: float = 0.01
   enc_layers: int = 4
   enc_units: int = 512
-  head_layers: int = 4                # reward / cont / actor / critic / decoder
+  head_layers: int = 4                # reward / cont / actor / critic (and decoder MLP unless set below)
   head_units: int = 512
+  dec_layers: int = 0                 # decoder.mlp_layers / mlp_units when they differ (0 = as heads)
+  dec_units: int = 0
   horizon: int = 15
   discount: float = 0.995
   lam: float = 0.95
@@ -87,6 +89,14 @@ class Spec:
   @property
   def sc(self):
     return self.stoch * self.classes
+
+  def trunk(self, prefix):
+    """(layers, units) of the MLP trunk called `prefix`."""
+    if prefix == 'dec':
+      return (self.dec_layers or self.head_layers, self.dec_units or self.head_units)
+    if prefix == 'enc':
+      return (self.enc_layers, self.enc_units)
+    return (self.head_layers, self.head_units)
 
   @property
   def img_shape(self):
@@ -215,8 +225,8 @@ def param_shapes(spec: Spec) -> Dict[str, Tuple[int, ...]]:
       s[f'{name}/norm/scale'] = (co,)
       s[f'{name}/norm/bias'] = (co,)
   if spec.obs_dims:
-    mlp('dec', spec.feat, spec.head_layers, spec.head_units)
-    out('dec/dist_out/out', spec.head_units, spec.obs_total)
+    mlp('dec', spec.feat, *spec.trunk('dec'))
+    out('dec/dist_out/out', spec.trunk('dec')[1], spec.obs_total)
   for name in ('reward', 'cont'):
     mlp(name, spec.feat, spec.head_layers, spec.head_units)
     out(f'{name}/dist_out/out', spec.head_units, 1)
@@ -439,7 +449,7 @@ def feat_of(state, spec: Spec):
 
 
 def head(feat, p, prefix, spec: Spec, out='out'):
-  x = mlp_trunk(feat, p, prefix, spec.head_layers)
+  x = mlp_trunk(feat, p, prefix, spec.trunk('critic' if prefix == 'slow_critic' else prefix)[0])
   return linear_bias(x, p, f'{prefix}/dist_out/{out}')
 
 

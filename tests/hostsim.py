@@ -169,7 +169,8 @@ class HostSim:
     dst.fill_(value)
 
   def transpose01(self, src, dst):
-    dst.copy_(src.transpose(0, 1))
+    A, B = src.shape[0], src.shape[1]
+    dst.view(B, A, -1).copy_(src.reshape(A, B, -1).transpose(0, 1))
 
   def colsum(self, X, out, acc=False):
     s = X.sum(0)

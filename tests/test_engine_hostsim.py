@@ -22,6 +22,8 @@ def rel(a, b):
     # image + depth CNN encoder/decoder next to the proprio MLP (xarm-style), one-hot actor
     (2, 4, 2, dict(discrete=True, act_dim=5, cnn_keys={'image': (18, 18, 3), 'depth': (18, 18, 1)},
                    cnn_depth=4, enc_kernels=(4, 4), dec_kernels=(3, 4, 4))),
+    # decoder MLP sized differently from the other heads (the reference's `debug` block)
+    (2, 4, 1, dict(dec_layers=3, dec_units=12)),
     # image only, continuous actions
     (2, 3, 1, dict(obs_dims={}, cnn_keys={'image': (10, 10, 3)}, cnn_depth=4, enc_kernels=(4, 4),
                    dec_kernels=(4, 4))),
