@@ -11,7 +11,7 @@ B="python bench.py --steps 10 --warmup 3 --no-cpu"
 timeout -k 5 150 env DD_BENCH_VERBOSE=1 DD_GEMM_TC_PERSISTENT=0 $B > gpurun_out/bench_np.json 2> gpurun_out/bench_np.err; rc=$?; el bench_nopersist $rc
 if [ $rc -eq 0 ]; then
   timeout -k 5 150 env DD_BENCH_VERBOSE=1 $B > gpurun_out/bench_p.json 2> gpurun_out/bench_p.err; el bench_persist $?
-  ./scripts/micro/pdl_chain > gpurun_out/pdl_chain.txt 2>&1; el pdl_chain $?
+  (cd scripts/micro && nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o pdl_chain pdl_chain.cu) && ./scripts/micro/pdl_chain > gpurun_out/pdl_chain.txt 2>&1; el pdl_chain $?
   timeout -k 5 150 env DD_BENCH_VERBOSE=1 DD_GEMM_TC_PERSISTENT=0 DD_PDL=1 $B > gpurun_out/bench_pdl.json 2> gpurun_out/bench_pdl.err; el bench_pdl $?
 fi
 timeout -k 5 500 python -m pytest tests/test_train_gpu.py tests/test_agent_gpu.py -q -x --timeout 150 -k "not a1" --durations=10 > gpurun_out/new_tests.log 2>&1; el new_tests $?
