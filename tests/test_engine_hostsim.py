@@ -79,3 +79,47 @@ def test_train_step_matches_oracle(B, L, steps, kw):
       else:
         assert abs(em[k] - v) <= 2e-4 * max(1.0, abs(v)), (it, k, em[k], v)
     assert set(em) == set(omets)
+
+
+@pytest.mark.parametrize('case', ['all_first', 'L1', 'B1', 'all_terminal', 'no_terminal_no_first'])
+def test_edge_case_batches_match_oracle(case):
+  """Edge cases of the replay batch: every step an episode start (the carry is reset at each
+  step), chunks of a single step, a single sequence, every step terminal (cont = 0 everywhere:
+  imagination weights vanish after the start), and a continuation chunk without any boundary."""
+  B, L = {'L1': (3, 1), 'B1': (1, 5)}.get(case, (2, 4))
+  ospec = O.tiny_spec()
+  spec = util.to_engine_spec(ospec)
+  params = O.init_params(ospec, seed=2)
+  ol = O.Learner(ospec, params)
+  eng = E.Engine(spec, HostSim(), B, L)
+  eng.load_params(params)
+  ostate = estate = None
+  for it in range(2):
+    batch = util.make_batch(ospec, B, L, seed=30 + it, mid_first=False)
+    if case == 'all_first':
+      batch['is_first'][:] = True
+    if case == 'all_terminal':
+      batch['is_terminal'][:] = True
+      batch['is_last'][:] = True
+    if case == 'no_terminal_no_first':
+      batch['is_terminal'][:] = False
+      if it > 0:
+        batch['is_first'][:] = False
+    noise = util.make_noise(ospec, B, L, seed=40 + it)
+    _, ostate, omets, aux = ol.train_step(batch, noise, ostate, keep=True)
+    util.load_batch(eng, spec, batch, noise, estate)
+    eng.launch_step(draw=False, slow_refreshed=eng.slow_refresh_due(int(eng.counters[E.C_SLOW])))
+    estate = {'deter': eng.prev_deter.numpy().copy(), 'stoch': eng.prev_stoch.numpy().copy()}
+    post_stoch = util.tm(aux['post']['stoch'].numpy().reshape(B, L, -1))
+    assert np.array_equal(eng.feat[:, spec.deter:].numpy(), post_stoch)
+    for group in ('model', 'critic', 'actor'):
+      eg = eng.get_grads(group)
+      for k, v in aux[f'{group}_grads'].items():
+        scale = max(np.abs(v.numpy()).max(), 1e-6)
+        assert np.abs(eg[k] - v.numpy()).max() <= 2e-4 * scale + 1e-9, (case, it, group, k)
+    em = eng.read_metrics()
+    for k, v in omets.items():
+      if np.isnan(v):
+        assert np.isnan(em[k]), (case, k)
+      else:
+        assert abs(em[k] - v) <= 2e-4 * max(1.0, abs(v)), (case, it, k, em[k], v)
