@@ -123,8 +123,12 @@ class Batcher:
   """zip() over `batch_size` replay generators with worker threads: the role of
   embodied.Prefetch (embodied/core/prefetch.py:6-67) in Agent.dataset()."""
 
-  def __init__(self, generator, batch_size, workers=8, prefetch=4):
+  def __init__(self, generator, batch_size, workers=8, prefetch=4, keys=None):
+    """keys: the batch keys the learner reads; everything else a replay step carries (e.g. a1's
+    unused 12 KB camera image per step, `log_*` entries) is dropped BEFORE stacking, so the host
+    never assembles or copies it."""
     self._queues = [queuelib.Queue(prefetch) for _ in range(batch_size)]
+    self._keys = None if keys is None else set(keys)
     self._running = True
     for w in range(min(workers, batch_size)):
       qs = self._queues[w::workers]
@@ -136,19 +140,22 @@ class Batcher:
       while self._running:
         for it, q in zip(its, queues):
           q.put(next(it))
-    except Exception as e:      # surface worker errors to the consumer
-      queues[0].put(e)
-      raise
+    except Exception as e:      # surface worker errors to the consumer (it may be blocked on any
+      for q in queues:          # of this worker's queues); the worker then ends
+        q.put(e)
 
   def __iter__(self):
     return self
 
   def __next__(self):
-    elems = [q.get() for q in self._queues]
-    for e in elems:
+    elems = []
+    for q in self._queues:
+      e = q.get()
       if isinstance(e, Exception):
         raise e
-    return {k: np.stack([e[k] for e in elems], 0) for k in elems[0]}
+      elems.append(e)
+    keys = [k for k in elems[0] if self._keys is None or k in self._keys]
+    return {k: np.stack([e[k] for e in elems], 0) for k in keys}
 
 
 class Agent:
@@ -320,8 +327,15 @@ class Agent:
     return segs
 
   # -- embodied.Agent surface -------------------------------------------------
+  def batch_keys(self):
+    """Every batch key train() / report() read."""
+    keys = set(self.spec.obs_dims) | set(self.spec.cnn_keys)
+    keys |= {'action', 'reward', 'is_first', 'is_last', 'is_terminal', 'key', 'prob'}
+    keys.add(str(_get(self.config, 'priority')))
+    return keys
+
   def dataset(self, generator):
-    return Batcher(generator, int(_get(self.config, 'batch_size')))
+    return Batcher(generator, int(_get(self.config, 'batch_size')), keys=self.batch_keys())
 
   def train(self, data, state=None):
     B, L = np.asarray(data['is_first']).shape[:2]

@@ -89,3 +89,28 @@ def test_large_rssm_config():
 def test_unbuilt_settings_raise(override):
   with pytest.raises(NotImplementedError):
     spec_from_config(make_config('a1', **override), *a1_spaces())
+
+
+def test_batcher_drops_unused_keys_and_surfaces_errors():
+  """Agent.dataset(): zip over batch_size replay generators (the role of embodied.Prefetch,
+  E/core/prefetch.py:6-67); keys the learner never reads are dropped before stacking."""
+  from daydreamer_b200.agent import Batcher
+
+  def gen():
+    i = 0
+    while True:
+      yield {'vector': np.full((5, 16), i, np.float32), 'image': np.zeros((5, 64, 64, 3), np.uint8),
+             'action': np.zeros((5, 12), np.float32), 'log_extra': np.zeros((5,), np.float32)}
+      i += 1
+  it = iter(Batcher(gen, 4, keys={'vector', 'action', 'reward'}))
+  b = next(it)
+  assert set(b) == {'vector', 'action'} and b['vector'].shape == (4, 5, 16)
+  assert set(next(iter(Batcher(gen, 3)))) == {'vector', 'image', 'action', 'log_extra'}
+
+  def bad():
+    yield {'vector': np.zeros((5, 16), np.float32)}
+    raise RuntimeError('replay failed')
+  it = iter(Batcher(bad, 2, workers=1))
+  next(it)
+  with pytest.raises(RuntimeError):
+    next(it)
