@@ -25,7 +25,6 @@ from __future__ import annotations
 
 import dataclasses
 import math
-import os
 from typing import Dict, List, Tuple
 
 import numpy as np
