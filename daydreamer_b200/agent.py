@@ -84,8 +84,10 @@ def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
       raise NotImplementedError('encoder.cnn_depth must equal decoder.cnn_depth')
   enc = vec_keys(g('encoder.mlp_keys'), enc_ex, (0, 1))
   dec = vec_keys(g('decoder.mlp_keys'), dec_ex, (1,))
-  if list(enc) != list(dec) or not (enc or enc_cnn):
-    raise NotImplementedError(f'encoder keys {list(enc)} must equal decoder keys {list(dec)}')
+  if not (enc or enc_cnn):
+    raise NotImplementedError('the encoder matches no observation key')
+  if not (dec or dec_cnn):
+    raise NotImplementedError('the decoder matches no observation key')
   heads = [g(f'{h}.layers') for h in ('reward_head', 'cont_head', 'actor', 'critic')]
   units = [g(f'{h}.units') for h in ('reward_head', 'cont_head', 'actor', 'critic')]
   if len(set(heads)) != 1 or len(set(units)) != 1:
@@ -98,7 +100,8 @@ def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
   if len(set(opts)) != 1 or opts[0][4]:
     raise NotImplementedError('optimizers must share lr/eps/clip/wd and warmup=0')
   return _engine.Spec(
-      obs_dims=enc, act_dim=int(np.prod(_space_shape(act))), discrete=discrete,
+      obs_dims=enc, dec_dims=None if list(enc.items()) == list(dec.items()) else dec,
+      act_dim=int(np.prod(_space_shape(act))), discrete=discrete,
       deter=int(g('rssm.deter')), units=int(g('rssm.units')), stoch=int(g('rssm.stoch')),
       classes=int(g('rssm.classes')), prior_layers=int(g('rssm.prior_layers')),
       rssm_unimix=float(g('rssm.unimix')), enc_layers=int(g('encoder.mlp_layers')),
@@ -213,6 +216,8 @@ class Agent:
         k: torch.zeros(B, L, d, pin_memory=pin)
         for k, d in (('obs', self.spec.obs_total), ('action', self.spec.act_dim),
                      ('first', 1), ('reward', 1), ('cont', 1))}
+    if self.spec.dec_dims is not None:          # decoder targets differ from the encoder input
+      eng.h_stage['dec'] = torch.zeros(B, L, self.spec.dec_total, pin_memory=pin)
     # images travel as uint8 and are scaled / channel-concatenated on the device
     for k, shp in self.spec.cnn_keys.items():
       eng.h_stage[f'img/{k}'] = torch.zeros(B, L, *shp, dtype=torch.uint8, pin_memory=pin)
@@ -235,6 +240,12 @@ class Agent:
       h['obs'][:, :, off:off + d] = torch.from_numpy(
           np.asarray(data[k], np.float32).reshape(B, L, d))
       off += d
+    if s.dec_dims is not None:
+      off = 0
+      for k, d in s.dec_dims.items():
+        h['dec'][:, :, off:off + d] = torch.from_numpy(
+            np.asarray(data[k], np.float32).reshape(B, L, d))
+        off += d
     for k, shp in s.cnn_keys.items():
       arr = np.asarray(data[k])
       if arr.dtype != np.uint8:
@@ -261,6 +272,8 @@ class Agent:
     be, d = eng.be, eng.d_stage
     if eng.spec.obs_dims:
       be.transpose01(d['obs'], eng.obs)
+    if eng.spec.dec_dims is not None and eng.spec.dec_total:
+      be.transpose01(d['dec'], eng.dec_tgt)
     c0 = 0
     for k, shp in eng.spec.cnn_keys.items():
       be.image_stage(d[f'img/{k}'], eng.img, c0, 1.0 / 255.0)
@@ -329,7 +342,7 @@ class Agent:
   # -- embodied.Agent surface -------------------------------------------------
   def batch_keys(self):
     """Every batch key train() / report() read."""
-    keys = set(self.spec.obs_dims) | set(self.spec.cnn_keys)
+    keys = set(self.spec.obs_dims) | set(self.spec.dec_vec) | set(self.spec.cnn_keys)
     keys |= {'action', 'reward', 'is_first', 'is_last', 'is_terminal', 'key', 'prob'}
     keys.add(str(_get(self.config, 'priority')))
     return keys
@@ -400,7 +413,7 @@ class Agent:
     rep = self._engines[key]
     C5 = rep.CONTEXT
     sub = {k: np.asarray(v)[:B6, :C5] for k, v in data.items()
-           if k in self.spec.obs_dims or k in self.spec.cnn_keys or
+           if k in self.spec.obs_dims or k in self.spec.dec_vec or k in self.spec.cnn_keys or
            k in ('action', 'is_first', 'reward', 'is_terminal')}
     self._stage(rep.ctx, sub, None)
     acts = np.asarray(data['action'], np.float32)[:B6, C5:].reshape(B6, L - C5, -1)

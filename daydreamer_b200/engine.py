@@ -25,7 +25,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
-from typing import Dict, List, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -52,6 +52,10 @@ class Spec:
   head_units: int = 512
   dec_layers: int = 0                 # decoder.mlp_layers / mlp_units when they differ (0 = as heads)
   dec_units: int = 0
+  # decoder vector keys when they differ from the encoder's (None = the same keys).  The reference's
+  # default `mlp_keys: '.*'` feeds the encoder every rank-0/1 key (reward, is_terminal, counters)
+  # but decodes only rank-1 observation keys (A/nets.py:192-201, :241-250).
+  dec_dims: Optional[Dict[str, int]] = None
   horizon: int = 15
   discount: float = 0.995
   lam: float = 0.95
@@ -158,6 +162,15 @@ class Spec:
   def obs_total(self):
     return int(sum(self.obs_dims.values()))
 
+  @property
+  def dec_vec(self):
+    """Vector keys the decoder MLP reconstructs."""
+    return self.obs_dims if self.dec_dims is None else self.dec_dims
+
+  @property
+  def dec_total(self):
+    return int(sum(self.dec_vec.values()))
+
 
 def param_shapes(spec: Spec) -> Dict[str, Tuple[int, ...]]:
   """Every trainable tensor (+ slow critic), reference names and shapes
@@ -201,9 +214,9 @@ def param_shapes(spec: Spec) -> Dict[str, Tuple[int, ...]]:
     if i < len(dshapes) - 1:
       s[f'{name}/norm/scale'] = (co,)
       s[f'{name}/norm/bias'] = (co,)
-  if spec.obs_dims:
+  if spec.dec_vec:
     mlp('dec', spec.feat, *spec.trunk('dec'))
-    out('dec/dist_out/out', spec.trunk('dec')[1], spec.obs_total)
+    out('dec/dist_out/out', spec.trunk('dec')[1], spec.dec_total)
   for name in ('reward', 'cont'):
     mlp(name, spec.feat, spec.head_layers, spec.head_units)
     out(f'{name}/dist_out/out', spec.head_units, 1)
@@ -512,6 +525,8 @@ class Engine:
 
     # inputs (time-major)
     self.obs = z(N, s.obs_total)
+    # decoder targets: the encoder's vector input unless the decoder has its own key set
+    self.dec_tgt = self.obs if s.dec_dims is None else z(N, s.dec_total)
     self.img = z(N, *s.img_shape) if s.cnn_keys else None     # f32 in [0,1], channel-concat
     self.action = z(N, A)
     self.first = z(N)
@@ -561,17 +576,17 @@ class Engine:
     self.prior = Trunk(self, gm, 'rssm/priorp', s.prior_layers, U, N)
     self.prior_logit = z(N, SC)
     self.heads = {k: Trunk(self, gm, k, *s.trunk(k), N)
-                  for k in (('dec',) if s.obs_dims else ()) + ('reward', 'cont')}
-    self.out_dec = z(N, s.obs_total)
+                  for k in (('dec',) if s.dec_vec else ()) + ('reward', 'cont')}
+    self.out_dec = z(N, s.dec_total)
     self.out_rew = z(N, 1)
     self.out_con = z(N, 1)
-    self.d_dec = z(N, s.obs_total)
+    self.d_dec = z(N, s.dec_total)
     self.d_rew = z(N, 1)
     self.d_con = z(N, 1)
     self.kl_row = z(N)
     self.ent_post = z(N)
     self.ent_prior = z(N)
-    self.loss_rows = {k: z(N) for k in list(s.cnn_keys) + list(s.obs_dims) +
+    self.loss_rows = {k: z(N) for k in list(s.cnn_keys) + list(s.dec_vec) +
                       ['reward', 'cont', 'total']}
     self.kl_sum = z(1)
     self.dfeat = z(N, D + SC)
@@ -646,7 +661,7 @@ class Engine:
     # metrics: rows of 8 doubles written by `stats`/`balance`
     self.mnames = [
         'kl', 'ent_post', 'ent_prior', 'reward_loss', 'cont_loss', 'total_loss',
-        *[f'loss_{k}' for k in list(s.cnn_keys) + list(s.obs_dims)], 'bal_reward', 'bal_cont',
+        *[f'loss_{k}' for k in list(s.cnn_keys) + list(s.dec_vec)], 'bal_reward', 'bal_cont',
         'imag_reward', 'imag_critic', 'imag_return', 'closs', 'score', 'adv_ctrl',
         'ret_ctrl', 'score_ctrl', 'ent', 'aloss']
     self.mstat = z(len(self.mnames), 8, dtype=torch.float64)
@@ -793,7 +808,7 @@ class Engine:
     xs = [(feat, 0)]
     if s.cnn_keys:
       self.dec_cnn.fwd(feat)
-    if s.obs_dims:
+    if s.dec_vec:
       self._out_fwd(gm, 'dec/dist_out/out', self.heads['dec'].fwd(xs, 0, N), self.out_dec)
     self._out_fwd(gm, 'reward/dist_out/out', self.heads['reward'].fwd(xs, 0, N), self.out_rew)
     self._out_fwd(gm, 'cont/dist_out/out', self.heads['cont'].fwd(xs, 0, N), self.out_con)
@@ -888,8 +903,8 @@ class Engine:
       be.add_(tot, self.loss_rows[k])
       off += shp[2]
     off = 0
-    for k, d in s.obs_dims.items():
-      be.head_loss(0, self.out_dec[:, off:off + d], self.obs[:, off:off + d], None,
+    for k, d in s.dec_vec.items():
+      be.head_loss(0, self.out_dec[:, off:off + d], self.dec_tgt[:, off:off + d], None,
                    coef, self.loss_rows[k], self.d_dec[:, off:off + d])
       be.add_(tot, self.loss_rows[k])
       off += d
@@ -907,7 +922,7 @@ class Engine:
     self._stat(self.loss_rows['reward'], 'reward_loss')
     self._stat(self.loss_rows['cont'], 'cont_loss')
     self._stat(tot, 'total_loss')
-    for k in list(s.cnn_keys) + list(s.obs_dims):
+    for k in list(s.cnn_keys) + list(s.dec_vec):
       self._stat(self.loss_rows[k], f'loss_{k}')
     be.balance(1, self.out_rew, self.loss_rows['reward'], self.reward, 0.1,
                self.mstat[self.midx['bal_reward']])
@@ -1333,7 +1348,7 @@ class Engine:
     m = {}
     m.update(wmkl_mean=mean('kl'), wmkl_std=std('kl'), wmkl_scale_mean=wm,
              wmkl_scale_std=0.0, kl_loss_mean=wm * mean('kl'), kl_loss_std=wm * std('kl'))
-    for k in list(s.cnn_keys) + list(s.obs_dims):
+    for k in list(s.cnn_keys) + list(s.dec_vec):
       m[f'{k}_loss_mean'], m[f'{k}_loss_std'] = mean(f'loss_{k}'), std(f'loss_{k}')
     for k in ('reward', 'cont'):
       m[f'{k}_loss_mean'], m[f'{k}_loss_std'] = mean(f'{k}_loss'), std(f'{k}_loss')

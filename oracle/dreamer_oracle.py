@@ -26,7 +26,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
-from typing import Dict, Tuple
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -56,6 +56,10 @@ class Spec:
   head_units: int = 512
   dec_layers: int = 0                 # decoder.mlp_layers / mlp_units when they differ (0 = as heads)
   dec_units: int = 0
+  # decoder vector keys when they differ from the encoder's (None = the same keys).  The reference's
+  # default `mlp_keys: '.*'` feeds the encoder every rank-0/1 key (reward, is_terminal, counters)
+  # but decodes only rank-1 observation keys (A/nets.py:192-201, :241-250).
+  dec_dims: Optional[Dict[str, int]] = None
   horizon: int = 15
   discount: float = 0.995
   lam: float = 0.95
@@ -158,6 +162,15 @@ class Spec:
   def obs_total(self):
     return int(sum(self.obs_dims.values()))
 
+  @property
+  def dec_vec(self):
+    """Vector keys the decoder MLP reconstructs."""
+    return self.obs_dims if self.dec_dims is None else self.dec_dims
+
+  @property
+  def dec_total(self):
+    return int(sum(self.dec_vec.values()))
+
 
 def a1_spec(**kw) -> Spec:
   """BASELINE.json configs[1]: a1 proprio, deter=units=512, stoch 32x32, A=12."""
@@ -224,9 +237,9 @@ def param_shapes(spec: Spec) -> Dict[str, Tuple[int, ...]]:
     if i < len(dshapes) - 1:
       s[f'{name}/norm/scale'] = (co,)
       s[f'{name}/norm/bias'] = (co,)
-  if spec.obs_dims:
+  if spec.dec_vec:
     mlp('dec', spec.feat, *spec.trunk('dec'))
-    out('dec/dist_out/out', spec.trunk('dec')[1], spec.obs_total)
+    out('dec/dist_out/out', spec.trunk('dec')[1], spec.dec_total)
   for name in ('reward', 'cont'):
     mlp(name, spec.feat, spec.head_layers, spec.head_units)
     out(f'{name}/dist_out/out', spec.head_units, 1)
@@ -667,9 +680,9 @@ class Learner:
         embed, data['action'], data['is_first'], state, p, spec, g_post)
     feat = feat_of(post, spec)
     dec = recon = None
-    if spec.obs_dims:
+    if spec.dec_vec:
       target = torch.cat([data[k].reshape(data[k].shape[:2] + (-1,))
-                          for k in spec.obs_dims], -1)
+                          for k in spec.dec_vec], -1)
       dec = head(feat, p, 'dec', spec)
     if spec.cnn_keys:
       recon = image_decoder(feat.reshape(-1, spec.feat), p, spec)
@@ -692,7 +705,7 @@ class Learner:
       losses[k] = ((recon[..., off:off + c] - data[k]) ** 2).sum((-1, -2, -3))
       off += c
     off = 0
-    for k, d in spec.obs_dims.items():
+    for k, d in spec.dec_vec.items():
       losses[k] = ((dec[..., off:off + d] - target[..., off:off + d]) ** 2).sum(-1)
       off += d
     losses['reward'] = (rew - symlog(data['reward'])) ** 2

@@ -84,7 +84,7 @@ def test_large_rssm_config():
     {'actor_dist_cont': 'trunc_normal'}, {'rssm.act': 'gelu'}, {'reward_head.dist': 'mse'},
     {'model_opt.lr': 3e-4}, {'actor.layers': 3}, {'retnorm.impl': 'mean_std'},
     {'encoder.cnn_keys': 'image', 'decoder.cnn_keys': 'image', 'encoder.cnn': 'resnet'},
-    {'encoder.mlp_keys': '.*'},      # encoder would take reward / is_terminal, decoder does not
+    {'encoder.mlp_keys': '$^', 'decoder.mlp_keys': '$^'},      # nothing left to encode
 ])
 def test_unbuilt_settings_raise(override):
   with pytest.raises(NotImplementedError):
@@ -114,3 +114,16 @@ def test_batcher_drops_unused_keys_and_surfaces_errors():
   next(it)
   with pytest.raises(RuntimeError):
     next(it)
+
+
+def test_default_key_regexes_give_the_encoder_more_keys_than_the_decoder():
+  """Reference defaults `mlp_keys: '.*'` (A/configs.yaml:54-55): the encoder MLP takes every
+  rank-0/1 key except is_first / is_last (A/nets.py:192-201: vector, reward, is_terminal), the
+  decoder only rank-1 keys outside its exclusion list (A/nets.py:241-250: vector)."""
+  obs, act = a1_spaces()
+  cfg = make_config('a1', **{'encoder.mlp_keys': '.*', 'decoder.mlp_keys': '.*'})
+  spec = spec_from_config(cfg, obs, act)
+  assert spec.obs_dims == {'vector': 16, 'reward': 1, 'is_terminal': 1}
+  assert spec.dec_dims == {'vector': 16} and spec.dec_total == 16 and spec.obs_total == 18
+  shapes = E.param_shapes(spec)
+  assert shapes['enc/dense0/kernel'] == (18, 512) and shapes['dec/dist_out/out/kernel'] == (512, 16)

@@ -24,6 +24,8 @@ def rel(a, b):
                    cnn_depth=4, enc_kernels=(4, 4), dec_kernels=(3, 4, 4))),
     # decoder MLP sized differently from the other heads (the reference's `debug` block)
     (2, 4, 1, dict(dec_layers=3, dec_units=12)),
+    # the encoder sees more vector keys than the decoder reconstructs (reference default key regexes)
+    (2, 4, 2, dict(obs_dims={'vector': 5, 'aux': 1, 'count': 1}, dec_dims={'vector': 5})),
     # image only, continuous actions
     (2, 3, 1, dict(obs_dims={}, cnn_keys={'image': (10, 10, 3)}, cnn_depth=4, enc_kernels=(4, 4),
                    dec_kernels=(4, 4))),

@@ -97,8 +97,9 @@ def test_reference_learner_process_loop(embodied, tmp_path):
   config = config.update(Agent.configs['debug'])
   config = embodied.Flags(config).parse([
       '--task', 'dummy_discrete', '--logdir', str(tmp_path), '--run', 'learning',
-      '--encoder.mlp_keys', 'vector', '--decoder.mlp_keys', 'vector',
-      '--encoder.cnn_keys', '$^', '--decoder.cnn_keys', '$^', '--rssm.deter', '32',
+      # key regexes left at the reference defaults ('.*'): the encoder MLP takes vector, step,
+      # reward and is_terminal, the decoder reconstructs vector and image only
+      '--rssm.deter', '32', '--encoder.cnn_depth', '4', '--decoder.cnn_depth', '4',
       '--batch_size', '2', '--replay_chunk', '6', '--imag_horizon', '3', '--env.length', '12',
       '--train.train_fill', '30', '--train.sync_every', '-1', '--train.eval_every', '3',
       '--train.eval_samples', '1', '--train.steps', '6'])
@@ -114,6 +115,8 @@ def test_reference_learner_process_loop(embodied, tmp_path):
   driver.on_step(replay.add)
   driver(embodied.RandomAgent(env.act_space).policy, steps=40, episodes=1)
   agent = Agent(env.obs_space, env.act_space, step, config, backend=HostSim())
+  assert list(agent.spec.obs_dims) == ['vector', 'step', 'reward', 'is_terminal']
+  assert agent.spec.dec_dims == {'vector': 7} and list(agent.spec.cnn_keys) == ['image']
   env.close()
   embodied.run.learning(agent, replay, replay, logger, args)
   assert int(step) == 6

@@ -15,8 +15,9 @@ def make_batch(spec, B, L, seed=0, term=0.05, mid_first=True):
   """SURVEY.md 8(d) synthetic replay: N(0,1) vectors, U(-1,1) actions,
   0.1*N(0,1) rewards, is_first[:,0]=True, Bernoulli is_terminal."""
   rng = np.random.default_rng(seed)
-  b = {k: rng.standard_normal((B, L, d)).astype(np.float32)
-       for k, d in spec.obs_dims.items()}
+  vec = dict(spec.obs_dims)
+  vec.update(getattr(spec, 'dec_dims', None) or {})
+  b = {k: rng.standard_normal((B, L, d)).astype(np.float32) for k, d in vec.items()}
   for k, shp in getattr(spec, 'cnn_keys', {}).items():
     b[k] = rng.integers(0, 256, (B, L) + tuple(shp)).astype(np.uint8)
   b['action'] = rng.uniform(-1, 1, (B, L, spec.act_dim)).astype(np.float32)
@@ -67,6 +68,10 @@ def load_batch(eng, spec, batch, noise=None, state=None):
     obs = np.concatenate([np.asarray(batch[k], np.float32).reshape(B, L, -1)
                           for k in spec.obs_dims], -1)
     put(eng.obs, tm(obs))
+  if getattr(spec, 'dec_dims', None) is not None and spec.dec_total:
+    tgt = np.concatenate([np.asarray(batch[k], np.float32).reshape(B, L, -1)
+                          for k in spec.dec_dims], -1)
+    put(eng.dec_tgt, tm(tgt))
   if spec.cnn_keys:
     img = np.concatenate([np.asarray(batch[k], np.float32) / np.float32(255.0)
                           for k in spec.cnn_keys], -1)
