@@ -37,8 +37,8 @@ def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
   g = lambda p: _get(config, p)
   act = act_space['action'] if isinstance(act_space, dict) else act_space
   discrete = bool(getattr(act, 'discrete', False))
-  if g('task_behavior') != 'Greedy' or g('expl_behavior') != 'None':
-    raise NotImplementedError('only task_behavior=Greedy, expl_behavior=None are built')
+  if g('task_behavior') != 'Greedy' or g('expl_behavior') not in ('None', 'Random'):
+    raise NotImplementedError('only task_behavior=Greedy with expl_behavior=None|Random are built')
   if g('critic_type') != 'vfunction':
     raise NotImplementedError('only critic_type=vfunction is built')
   checks = {
@@ -191,6 +191,8 @@ class Agent:
     self._slow_updates = -1           # host mirror of the device slow-target counter
     self.use_graph = self._on_gpu
     self._init_params = _engine.init_params(self.spec, seed=self.seed + 1)
+    # behaviors.Random (A/behaviors.py:97-120): uniform actions in 'explore' mode, nothing to train
+    self.expl_random = str(_get(config, 'expl_behavior')) == 'Random'
     self.expl_noise = float(_get(config, 'expl_noise'))
     self.eval_noise = float(_get(config, 'eval_noise'))
 
@@ -454,6 +456,12 @@ class Agent:
     if mode == 'eval':
       action = pol.mean.cpu().numpy().copy()
       noise = self.eval_noise
+    elif mode == 'explore' and self.expl_random:
+      shape = (P,) + tuple(self.act_space.shape)
+      if self.spec.discrete:
+        action = np.eye(shape[-1], dtype=np.float32)[np.random.randint(0, shape[-1], shape[:-1])]
+      else:
+        action = np.random.uniform(-1, 1, shape).astype(np.float32)
     else:
       action = pol.action.cpu().numpy().copy()
     if noise and self.spec.discrete:                              # A/tfutils.py:85-93

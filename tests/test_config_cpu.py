@@ -80,7 +80,7 @@ def test_large_rssm_config():
 
 
 @pytest.mark.parametrize('override', [
-    {'critic_type': 'qfunction'}, {'expl_behavior': 'Explore'}, {'rssm.classes': 0},
+    {'critic_type': 'qfunction'}, {'expl_behavior': 'Explore'}, {'task_behavior': 'Random'}, {'rssm.classes': 0},
     {'actor_dist_cont': 'trunc_normal'}, {'rssm.act': 'gelu'}, {'reward_head.dist': 'mse'},
     {'model_opt.lr': 3e-4}, {'actor.layers': 3}, {'retnorm.impl': 'mean_std'},
     {'encoder.cnn_keys': 'image', 'decoder.cnn_keys': 'image', 'encoder.cnn': 'resnet'},

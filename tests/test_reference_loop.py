@@ -46,7 +46,9 @@ def test_reference_train_loop_drives_the_agent(embodied, task, tmp_path):
       '--rssm.deter', '32', '--encoder.cnn_depth', '4', '--decoder.cnn_depth', '4',
       '--batch_size', '2', '--replay_chunk', '6', '--imag_horizon', '3', '--env.length', '12',
       '--train.train_fill', '40', '--train.train_every', '8', '--train.log_every', '16',
-      '--train.eval_every', '24', '--train.steps', '48', '--train.log_keys_video', 'image'])
+      '--train.eval_every', '24', '--train.steps', '48', '--train.log_keys_video', 'image',
+      # run/train.py asks for mode='explore' while step < expl_until: exercise behaviors.Random too
+      '--expl_behavior', 'Random', '--train.expl_until', '20'])
   args = embodied.Config(logdir=config.logdir, **config.train)
   args = args.update(expl_until=args.expl_until // config.env.repeat)
   step = embodied.Counter()
