@@ -29,6 +29,7 @@ SIGNATURES = {
     'dd_set_gemm_tc': [_I],
     'dd_set_gemm_tc_debug': [_I],
     'dd_set_gemm_tc_persistent': [_I],
+    'dd_set_gemm_tc_staged': [_I],
     'dd_set_pdl': [_I],
     'dd_set_gemm_thin': [_I],
     'dd_set_ln_warp_max': [_I],
@@ -168,6 +169,8 @@ class CudaBackend:
       self.lib.dd_set_ln_warp_max(int(os.environ['DD_LN_WARP_MAX']))
     if os.environ.get('DD_GEMM_THIN', '') != '':
       self.lib.dd_set_gemm_thin(int(os.environ['DD_GEMM_THIN']))
+    if os.environ.get('DD_GEMM_TC_STAGED', '') != '':
+      self.lib.dd_set_gemm_tc_staged(int(os.environ['DD_GEMM_TC_STAGED']))
     if os.environ.get('DD_GEMM_TC_PERSISTENT', '') != '':
       self.lib.dd_set_gemm_tc_persistent(int(os.environ['DD_GEMM_TC_PERSISTENT']))
 

@@ -27,6 +27,7 @@
 namespace dd {
 int g_tc_debug = 0;
 int g_tc_persistent = 1;
+int g_tc_staged = 0;        // experimental cp.async-staged operand loader for the 64-wide tile (not yet measured)
 namespace tc {
 
 constexpr int BM = 128;
@@ -196,7 +197,53 @@ __device__ __forceinline__ void tile_split_store(const float4 (&v)[TileMap<R, MN
   }
 }
 
-template <int BN, int STAGES, bool TA, bool TB>
+// ---- staged loader (experimental, dd_set_gemm_tc_staged) ----------------------------------
+// Same unit map as tile_gload, but the 16-byte units go global -> shared with cp.async into a
+// per-thread slot of a raw ring instead of into registers, so a loader group can keep RD
+// k-blocks of L2 latency in flight instead of one.  Each thread later re-reads exactly the
+// units it copied itself (after cp.async.wait_group), so no cross-thread synchronisation is
+// added.  Ring layout: [slot][unit][thread] x 16 B (consecutive threads -> consecutive banks).
+template <int R, bool MNMAJ>
+__device__ __forceinline__ void tile_cpasync(const float* __restrict__ g, int ld, int r0, int rmax,
+                                             int k0, int kmax, int ltid, uint32_t raw_unit0) {
+  const int lane = ltid & 31, warp = ltid >> 5;
+#pragma unroll
+  for (int it = 0; it < TileMap<R, MNMAJ>::PER; ++it) {
+    int r, k;
+    uint32_t off;
+    TileMap<R, MNMAJ>::at(warp + it * GROUP_WARPS, lane, r, k, off);
+    const int gr = r0 + r, gk = k0 + k;
+    const bool in = gr < rmax && gk < kmax;
+    const float* p = in ? (MNMAJ ? g + (size_t)gk * ld + gr : g + (size_t)gr * ld + gk) : g;
+    const uint32_t dst = raw_unit0 + (uint32_t)it * GROUP_THREADS * 16;
+    const uint32_t bytes = in ? 16u : 0u;               // 0 -> the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(p), "r"(bytes)
+                 : "memory");
+  }
+}
+
+template <int R, bool MNMAJ>
+__device__ __forceinline__ void tile_split_store_raw(const char* raw_unit0, char* s_hi, char* s_lo,
+                                                     int ltid) {
+  const int lane = ltid & 31, warp = ltid >> 5;
+#pragma unroll
+  for (int it = 0; it < TileMap<R, MNMAJ>::PER; ++it) {
+    int r, k;
+    uint32_t off;
+    TileMap<R, MNMAJ>::at(warp + it * GROUP_WARPS, lane, r, k, off);
+    const float4 v = *reinterpret_cast<const float4*>(raw_unit0 + (size_t)it * GROUP_THREADS * 16);
+    float4 hi, lo;
+    hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
+    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+    *reinterpret_cast<float4*>(s_hi + off) = hi;
+    *reinterpret_cast<float4*>(s_lo + off) = lo;
+  }
+}
+
+constexpr int RAW_DEPTH = 2;       // raw k-blocks in flight per loader group (staged loader)
+constexpr int RAW_OFFSET = 1024;   // raw ring starts this far after the hi/lo stages (barriers live there)
+
+template <int BN, int STAGES, bool TA, bool TB, bool STAGED = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                float* __restrict__ C, int ldc, int M, int N, int K, float beta,
@@ -248,12 +295,50 @@ gemm_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
     // global loads of its NEXT block in flight while it splits/stores the current
     // one, so ~4 k-blocks of L2 latency overlap with the tensor-core work.
     const int grp = warp / GROUP_WARPS, gtid = tid % GROUP_THREADS;
+    if constexpr (STAGED) {
+      static_assert(NGROUPS <= STAGES, "a producer may not run two mbarrier phases ahead");
+      constexpr int UA = TileMap<BM, A_MN>::PER, UB = TileMap<BN, B_MN>::PER;
+      constexpr uint32_t SLOT_BYTES = (uint32_t)(UA + UB) * GROUP_THREADS * 16;
+      char* rawbase = smem + STAGES * STAGE_BYTES + RAW_OFFSET;
+      auto slot_ptr = [&](int slot) { return rawbase + (size_t)slot * SLOT_BYTES + (size_t)gtid * 16; };
+      auto issue = [&](int kbp, int slot) {
+        const uint32_t u0 = smem_u32(slot_ptr(slot));
+        tile_cpasync<BM, A_MN>(A, lda, m0, M, kbeg + kbp * BK, kend, gtid, u0);
+        tile_cpasync<BN, B_MN>(B, ldb, n0, N, kbeg + kbp * BK, kend, gtid,
+                               u0 + (uint32_t)UA * GROUP_THREADS * 16);
+      };
+#pragma unroll
+      for (int d = 0; d < RAW_DEPTH; ++d) {             // one commit group per k-block, even if empty
+        const int kbp = grp + NGROUPS * d;
+        if (kbp < nkb) issue(kbp, grp * RAW_DEPTH + d);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      int i = 0;
+      for (int kb = grp; kb < nkb; kb += NGROUPS, ++i) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(RAW_DEPTH - 1) : "memory");
+        const int slot = grp * RAW_DEPTH + (i % RAW_DEPTH);
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        char* st = smem + s * STAGE_BYTES;
+        const char* ru = slot_ptr(slot);
+        tile_split_store_raw<BM, A_MN>(ru, st, st + A_BYTES, gtid);
+        tile_split_store_raw<BN, B_MN>(ru + (size_t)UA * GROUP_THREADS * 16, st + 2 * A_BYTES,
+                                       st + 2 * A_BYTES + B_BYTES, gtid);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(full0 + 8 * s);
+        const int kbn = kb + NGROUPS * RAW_DEPTH;        // refill the slot this thread just drained
+        if (kbn < nkb) issue(kbn, slot);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     float4 ra[TileMap<BM, A_MN>::PER], rb[TileMap<BN, B_MN>::PER];
-    if (grp < nkb && !(dbg & 1)) {
+    if (!STAGED && grp < nkb && !(dbg & 1)) {
       tile_gload<BM, A_MN>(A, lda, m0, M, kbeg + grp * BK, kend, gtid, ra);
       tile_gload<BN, B_MN>(B, ldb, n0, N, kbeg + grp * BK, kend, gtid, rb);
     }
-    for (int kb = grp; kb < nkb; kb += NGROUPS) {
+    for (int kb = grp; !STAGED && kb < nkb; kb += NGROUPS) {
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(empty0 + 8 * s, ph ^ 1);
@@ -659,6 +744,38 @@ static int launch(const float* A, int lda, int ta, const float* B, int ldb, int 
   return launched("dd_gemm_tc");
 }
 
+// Staged-loader launch (BN = 64 only: two hi/lo stages + a raw ring of NGROUPS * RAW_DEPTH
+// k-blocks fit the 227 KB of one SM; the 128-wide tile has no room for the ring).
+static int launch_staged(const float* A, int lda, int ta, const float* B, int ldb, int tb, float* C,
+                         int ldc, int M, int N, int K, float beta, const float* bias, int splits,
+                         cudaStream_t st) {
+  constexpr int BN = 64, STAGES = 2;
+  constexpr int STAGE_BYTES = 2 * BM * BK * 4 + 2 * BN * BK * 4;
+  constexpr int UNITS = (BM / 8) * (BK / 16) / GROUP_WARPS + (BN / 8) * (BK / 16) / GROUP_WARPS;
+  constexpr int SMEM = STAGES * STAGE_BYTES + RAW_OFFSET + NGROUPS * RAW_DEPTH * UNITS * GROUP_THREADS * 16;
+  static_assert(SMEM <= 227 * 1024, "staged loader ring does not fit");
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
+  int klen = (K + splits - 1) / splits;
+  klen = (klen + BK - 1) / BK * BK;
+  const int atomic = splits > 1 ? 1 : 0;
+#define DD_TCS(TA_, TB_)                                                                       \
+  do {                                                                                         \
+    static bool attr_set = false;                                                              \
+    auto kern = gemm_tc_kernel<BN, STAGES, TA_, TB_, true>;                                    \
+    if (!attr_set) {                                                                           \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);           \
+      attr_set = true;                                                                         \
+    }                                                                                          \
+    launch_k(kern, grid, THREADS, SMEM, st, A, lda, B, ldb, C, ldc, M, N, K, beta, bias, klen, atomic, 0); \
+  } while (0)
+  if (!ta && !tb) DD_TCS(false, false);
+  else if (ta && !tb) DD_TCS(true, false);
+  else if (!ta && tb) DD_TCS(false, true);
+  else DD_TCS(true, true);
+#undef DD_TCS
+  return launched("dd_gemm_tc_staged");
+}
+
 }  // namespace tc
 
 // Returns 1 if the tensor-core path took the call, 0 if the shape/alignment is
@@ -693,6 +810,9 @@ int gemm_tc_try(const float* A, int lda, int ta, const float* B, int ldb, int tb
   } else if (tiles128 >= kNumSm / 2) {
     rc = tc::launch<128, 3>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias,
                             pick_splits(tiles128), st);
+  } else if (g_tc_staged) {
+    rc = tc::launch_staged(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias,
+                           pick_splits(tiles64), st);
   } else {
     rc = tc::launch<64, 4>(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, beta, bias,
                            pick_splits(tiles64), st);
@@ -705,6 +825,12 @@ int gemm_tc_try(const float* A, int lda, int ta, const float* B, int ldb, int tb
 extern "C" int dd_set_gemm_tc_persistent(int on) {
   const int prev = dd::g_tc_persistent;
   dd::g_tc_persistent = on ? 1 : 0;
+  return prev;
+}
+
+extern "C" int dd_set_gemm_tc_staged(int on) {
+  const int prev = dd::g_tc_staged;
+  dd::g_tc_staged = on ? 1 : 0;
   return prev;
 }
 

@@ -50,6 +50,9 @@ int dd_set_gemm_tc(int on);
 /* 1 (default): GEMMs with more 128x128 tiles than ~1.5x the SM count use the persistent
  * tensor-core kernel (double-buffered TMEM, overlapped epilogue).  Returns previous. */
 int dd_set_gemm_tc_persistent(int on);
+/* EXPERIMENTAL (round 2, not yet run on a GPU): cp.async-staged operand loader for the 64-wide
+ * tensor-core tile, four k-blocks of L2 latency in flight instead of two (default off) */
+int dd_set_gemm_tc_staged(int on);
 /* thin GEMMs (N <= 32 or K <= 32 with many rows) on dedicated streaming kernels (default off) */
 int dd_set_gemm_thin(int on);
 /* widest row the warp-per-row LayerNorm kernels take (<= 512, default 128) */

@@ -443,3 +443,26 @@ def test_gemm_skinny(backends, M, N, K, tb):
     be.gemm(A, B, c, tb=tb, beta=1.0)
     return {'c0': c1, 'c1': c.clone(), 'pad': C[:, N:].clone()}
   both(backends, case, rtol=1e-4, atol=2e-5 * np.sqrt(K))
+
+
+@pytest.mark.skipif(not __import__('os').environ.get('DD_TEST_EXPERIMENTAL'),
+                    reason='experimental kernels run only on request (DD_TEST_EXPERIMENTAL=1)')
+@pytest.mark.parametrize('M,N,K', [(1024, 512, 512), (1024, 512, 1536), (1024, 1024, 512), (130, 72, 100),
+                                   (1000, 64, 36), (512, 512, 1024)])
+@pytest.mark.parametrize('ta,tb', [(False, False), (False, True), (True, False), (True, True)])
+def test_gemm_tc_staged_loader(backends, M, N, K, ta, tb):
+  """Round-2 work in progress: the cp.async-staged operand loader of the 64-wide tcgen05 tile
+  (dd_set_gemm_tc_staged) against fp64, same bound as the register-staged loader."""
+  hs, cu = backends
+  A = rnd(*((K, M) if ta else (M, K)), seed=1).to(cu.device)
+  B = rnd(*((N, K) if tb else (K, N)), seed=2).to(cu.device)
+  C = torch.zeros(M, N, device=cu.device)
+  prev = cu.lib.dd_set_gemm_tc_staged(1)
+  try:
+    cu.gemm(A, B, C, ta=ta, tb=tb)
+    cu.sync()
+  finally:
+    cu.lib.dd_set_gemm_tc_staged(prev)
+  ref = (A.t() if ta else A).double() @ (B.t() if tb else B).double()
+  err = float((C.double() - ref).abs().max() / ref.abs().max())
+  assert err < 2e-5 * max(1.0, K / 512), err
