@@ -57,6 +57,17 @@ def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
       raise NotImplementedError(f'config {key}={g(key)!r} is not built (only {want!r})')
   if not g('rssm.classes'):
     raise NotImplementedError('continuous (Gaussian) latents are not built')
+  # settings the kernels would otherwise ignore silently
+  if float(g('priority_correct')) != 0.0:
+    raise NotImplementedError('priority_correct != 0 (importance-weighted model loss) is not built')
+  scales = g('loss_scales')
+  for key in (scales.keys() if hasattr(scales, 'keys') else []):
+    if float(scales[key]) != 1.0:
+      raise NotImplementedError(f'loss_scales.{key}={scales[key]} is not built (only 1.0)')
+  if not {'decoder', 'reward', 'cont'} <= set(g('grad_heads')):
+    raise NotImplementedError('grad_heads must contain decoder, reward and cont')
+  if float(g('actent.vel')) != float(g('wmkl.vel')):
+    raise NotImplementedError('actent.vel must equal wmkl.vel (one controller velocity is built)')
   shapes = {k: _space_shape(v) for k, v in obs_space.items() if not k.startswith('log_')}
 
   def vec_keys(pattern, excluded, ranks):

@@ -82,7 +82,8 @@ def test_large_rssm_config():
 @pytest.mark.parametrize('override', [
     {'critic_type': 'qfunction'}, {'expl_behavior': 'Explore'}, {'task_behavior': 'Random'}, {'rssm.classes': 0},
     {'actor_dist_cont': 'trunc_normal'}, {'rssm.act': 'gelu'}, {'reward_head.dist': 'mse'},
-    {'model_opt.lr': 3e-4}, {'actor.layers': 3}, {'retnorm.impl': 'mean_std'},
+    {'model_opt.lr': 3e-4}, {'actor.layers': 3}, {'retnorm.impl': 'mean_std'}, {'priority_correct': 0.5},
+    {'loss_scales.kl': 0.5}, {'grad_heads': ['decoder', 'reward']}, {'actent.vel': 0.2},
     {'encoder.cnn_keys': 'image', 'decoder.cnn_keys': 'image', 'encoder.cnn': 'resnet'},
     {'encoder.mlp_keys': '$^', 'decoder.mlp_keys': '$^'},      # nothing left to encode
 ])
