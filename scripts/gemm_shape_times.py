@@ -12,11 +12,16 @@ from daydreamer_b200 import engine as E
 
 class Recorder:
   device = torch.device('cpu')
-  def __init__(self): self.gemms = []
+  def __init__(self): self.gemms, self.seq, self.rows = [], [], []
   def zeros(self, *shape, dtype=torch.float32): return torch.empty(*shape, dtype=dtype)
   def gemm(self, A, B, C, ta=False, tb=False, beta=0.0, bias=None):
     K = A.shape[0] if ta else A.shape[1]
+    self.seq.append(len(self.rows))           # row-op calls issued before this GEMM
     self.gemms.append((C.shape[0], C.shape[1], K, int(ta), int(tb), int(beta), int(bias is not None)))
+  def ln_fwd(self, Z, scale, bias, H, stats, act):
+    self.rows.append(('ln_fwd', Z.shape[0], Z.shape[1], 2))       # read Z, write H
+  def ln_bwd(self, dH, Z, stats, scale, bias, dZ, dscale, dbias, act):
+    self.rows.append(('ln_bwd', Z.shape[0], Z.shape[1], 3))       # read dH, Z, write dZ
   def observe_fwd_grid(self, *a): return 128
   def observe_bwd_grid(self, *a): return 128
   def __getattr__(self, name):
@@ -69,6 +74,7 @@ def main(path):
   best = max(range(n), key=score)
   print(f'# window starts at call {best} of the step; {score(best)}/{len(names)} launches match the expected kernel')
   rec.gemms = rec.gemms[best:] + rec.gemms[:best]
+  row0 = rec.seq[best]
   by = collections.OrderedDict()
   for shape, (name, us) in zip(rec.gemms, gk):
     key = shape + (re.sub(r'^tc::', '', name),)
@@ -80,6 +86,20 @@ def main(path):
     print(f'{M:6d} {N:5d} {K:6d}  {ta}  {tb}  {beta}    {bias}  {len(v):4d} {mean:9.1f} {sum(v)/1e3:9.3f} {100*sum(v)/tot:6.1f}% '
           f'{2.0*M*N*K/mean/1e6:8.1f}  {name}')
   print(f'# total {tot/1e3:.2f} ms over {sum(len(v) for v in by.values())} launches')
+  # LayerNorm(+elu) kernels: HBM/L2 streaming, algorithmic bytes = passes * M * N * 4
+  rows = rec.rows[row0:] + rec.rows[:row0]
+  lk = [(n, v) for n, v in launches if re.match(r'ln_(fwd|bwd)', n)]
+  print(f'#\n# {len(rows)} LayerNorm calls in the replayed step, {len(lk)} ln_* launches in the list')
+  agg = collections.OrderedDict()
+  ok = 0
+  for (kind, M, N, passes), (name, us) in zip(rows, lk):
+    ok += name.startswith(kind)
+    agg.setdefault((kind, M, N, passes), []).append(us)
+  print(f'# {ok}/{len(lk)} launches match the expected kernel family')
+  print('# kernel   M      N   x   mean us  total ms   GB/s (algorithmic bytes / time; measured copy peak 6573)')
+  for (kind, M, N, passes), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+    mean = sum(v) / len(v)
+    print(f'{kind}  {M:6d} {N:5d} {len(v):4d} {mean:8.1f} {sum(v)/1e3:8.3f} {passes*M*N*4/mean/1e3:8.0f}')
 
 
 if __name__ == '__main__':
