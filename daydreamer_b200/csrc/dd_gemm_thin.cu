@@ -29,7 +29,7 @@ __device__ __forceinline__ void stage_b(float* Bs, const float* __restrict__ B, 
   }
 }
 
-template <int NN>     // N <= NN <= 4
+template <int NN>     // N <= NN; NN in {1, 4} (level 1) or {8, 16} (level 2, experimental)
 __global__ void __launch_bounds__(256) thin_n_small_kernel(
     const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, int tb,
     float* __restrict__ C, int ldc, int M, int N, int K, float beta,
@@ -193,15 +193,24 @@ int gemm_thin_try(const float* A, int lda, int ta, const float* B, int ldb, int 
   if (!once) {
     cudaFuncSetAttribute(thin_n_small_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, THIN_SMEM);
     cudaFuncSetAttribute(thin_n_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, THIN_SMEM);
+    cudaFuncSetAttribute(thin_n_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, THIN_SMEM);
+    cudaFuncSetAttribute(thin_n_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, THIN_SMEM);
     cudaFuncSetAttribute(thin_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, THIN_SMEM);
     cudaFuncSetAttribute(thin_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, THIN_SMEM);
     once = true;
   }
-  if (N <= 4 && (size_t)K * N * 4 <= THIN_SMEM && K >= 16) {
+  // level 2 (experimental, written after the r01 measurement, not yet run): the row-per-warp kernel
+  // also takes N <= 16 (the action heads), where the 4-rows-per-warp shuffle kernel measured slow
+  const int nsmall = g_thin_on >= 2 ? 16 : 4;
+  if (N <= nsmall && (size_t)K * N * 4 <= THIN_SMEM && K >= 16) {
     const int grid = grid_for(M, 8, 148 * 8);
     const size_t smem = (size_t)K * N * 4;
-    if (N == 1) launch_k(thin_n_small_kernel<1>, grid, 256, smem, st, A, lda, B, ldb, tb, C, ldc, M, N, K, beta, bias);
-    else launch_k(thin_n_small_kernel<4>, grid, 256, smem, st, A, lda, B, ldb, tb, C, ldc, M, N, K, beta, bias);
+#define DD_THIN_S(NN) launch_k(thin_n_small_kernel<NN>, grid, 256, smem, st, A, lda, B, ldb, tb, C, ldc, M, N, K, beta, bias)
+    if (N == 1) DD_THIN_S(1);
+    else if (N <= 4) DD_THIN_S(4);
+    else if (N <= 8) DD_THIN_S(8);
+    else DD_THIN_S(16);
+#undef DD_THIN_S
     return launched("dd_gemm_thin_n") == 0 ? 1 : -1;
   }
   if (K <= 32 && (size_t)K * ((N + 3) / 4 * 4) * 4 <= THIN_SMEM) {
@@ -225,6 +234,6 @@ int gemm_thin_try(const float* A, int lda, int ta, const float* B, int ldb, int 
 
 extern "C" int dd_set_gemm_thin(int on) {
   const int prev = dd::g_thin_on;
-  dd::g_thin_on = on ? 1 : 0;
+  dd::g_thin_on = on < 0 ? 0 : (on > 2 ? 2 : on);       // 0 off, 1 r01 kernels, 2 + row-per-warp up to N = 16
   return prev;
 }

@@ -60,12 +60,14 @@ def test_gemm(backends, M, N, K, ta, tb):
                                    (15360, 512, 1), (1000, 3, 300), (70, 32, 1536), (333, 5, 20),
                                    (1024, 1536, 12), (900, 2, 16), (257, 31, 33)])
 @pytest.mark.parametrize('tb', [False, True])
-def test_gemm_thin(backends, M, N, K, tb):
+@pytest.mark.parametrize('level', [1, pytest.param(2, marks=pytest.mark.skipif(
+    not __import__('os').environ.get('DD_TEST_EXPERIMENTAL'), reason='experimental (DD_TEST_EXPERIMENTAL=1)'))])
+def test_gemm_thin(backends, M, N, K, tb, level):
   """Thin shapes (N <= 32 or K <= 32, many rows) on the streaming kernels of dd_gemm_thin.cu,
   contiguous (vector path) and row-strided operands, bias / beta combinations."""
   def case(be, T):
     out = {}
-    prev = be.lib.dd_set_gemm_thin(1) if hasattr(be, 'lib') else None     # off by default
+    prev = be.lib.dd_set_gemm_thin(level) if hasattr(be, 'lib') else None     # off by default
     for pad in (0, 3):
       A = T(rnd(M, K + pad, seed=1))[:, :K]
       B = T(rnd(*((N, K + pad) if tb else (K, N + pad)), seed=2))
