@@ -210,3 +210,23 @@ def test_image_geometry_and_loss():
   g = torch.zeros(L, B, small.stoch, small.classes)
   _, aux, mets = learner.wm_loss(learner.params, data, None, g, training=False)
   assert abs(float(mets['image_loss_mean']) - 10 * 10 * 3 * 0.25) < 1e-3
+
+
+def test_oracle_matches_committed_golden_steps():
+  """tests/golden/oracle_steps.npz (made by tests/golden/make_oracle_golden.py): two seeded
+  train steps of three small configurations.  Guards the oracle against drift between rounds;
+  categorical indices must be identical, sums agree to fp32 reduction noise."""
+  import importlib.util
+  import pathlib
+  here = pathlib.Path(__file__).parent / 'golden'
+  spec = importlib.util.spec_from_file_location('make_oracle_golden', here / 'make_oracle_golden.py')
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  want = np.load(here / 'oracle_steps.npz')
+  got = mod.build()
+  assert set(got) == set(want.files)
+  for k in want.files:
+    if k.endswith('_idx'):
+      assert np.array_equal(got[k], want[k]), k
+    else:
+      assert np.allclose(got[k], want[k], rtol=2e-4, atol=1e-5), (k, np.abs(got[k] - want[k]).max())
