@@ -176,8 +176,8 @@ class Agent:
 
   configs = _configs.CONFIGS
 
-  def __init__(self, obs_space, act_space, step, config, seed=None, backend=None):
-    """`backend` is a test seam: the product path always constructs CudaBackend (which raises
+  def __init__(self, obs_space, act_space, step, config, seed=None, _backend_for_tests=None):
+    """`_backend_for_tests` is a test seam, never a fallback: the product path always constructs CudaBackend (which raises
     without a GPU / the kernel library); tests/test_reference_loop.py passes the torch-CPU
     primitive simulator to drive the reference's own run loop where there is no GPU."""
     self.config = config
@@ -185,7 +185,7 @@ class Agent:
     self.act_space = act_space['action'] if isinstance(act_space, dict) else act_space
     self.step = step
     self.spec = spec_from_config(config, obs_space, act_space)
-    self.be = backend if backend is not None else CudaBackend()   # raises without GPU / .so
+    self.be = _backend_for_tests if _backend_for_tests is not None else CudaBackend()  # raises without GPU / .so
     self._on_gpu = self.be.device.type == 'cuda'
     self.seed = int(_get(config, 'seed')) if seed is None else int(seed)
     self.world, self.rank, self._allreduce = 1, 0, None

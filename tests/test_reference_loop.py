@@ -1,7 +1,7 @@
 """CPU: the REFERENCE's own run loop (embodied/run/train.py: Driver + replay + Checkpoint +
 Timer.wrap + Logger, read from /root/reference, never copied) drives daydreamer_b200.Agent
 unchanged -- the drop-in claim of INTEGRATION.md, exercised where there is no GPU by handing the
-Agent the torch-CPU primitive simulator (tests/hostsim.py) through its `backend` test seam.
+Agent the torch-CPU primitive simulator (tests/hostsim.py) through its `_backend_for_tests` seam.
 Covers: Agent.configs through embodied.Config + flags, spaces from the reference's Dummy env
 (continuous and one-hot actions, image + vector observations), dataset() over the reference's
 FixedLength replay, train/report/policy through Timer.wrap re-binding, report() outputs accepted
@@ -62,7 +62,7 @@ def test_reference_train_loop_drives_the_agent(embodied, task, tmp_path):
   env = embodied.envs.load_env(
       config.task, mode='train', logdir=str(tmp_path), amount=1, parallel='none',
       size=(64, 64), length=config.env.length)
-  agent = Agent(env.obs_space, env.act_space, step, config, backend=HostSim())
+  agent = Agent(env.obs_space, env.act_space, step, config, _backend_for_tests=HostSim())
   assert agent.spec.discrete == (task == 'dummy_discrete')
   assert list(agent.spec.cnn_keys) == ['image'] and list(agent.spec.obs_dims) == ['vector']
   store = embodied.replay.Stats(embodied.replay.RAMStore(1000))
@@ -81,7 +81,7 @@ def test_reference_train_loop_drives_the_agent(embodied, task, tmp_path):
   vid = [v for _, n, v in records if n == 'report/openl_image'][-1]
   assert np.asarray(vid).shape == (6, 3 * 64, 2 * 64, 3)          # [T, 3H, B*W, C]
   # the checkpoint the loop wrote round-trips into a fresh agent (embodied.Checkpoint pickles save())
-  other = Agent(env.obs_space, env.act_space, embodied.Counter(), config, backend=HostSim())
+  other = Agent(env.obs_space, env.act_space, embodied.Counter(), config, _backend_for_tests=HostSim())
   import pickle
   with open(pathlib.Path(str(tmp_path)) / 'checkpoint.pkl', 'rb') as f:     # what Checkpoint.load reads
     other.load(pickle.load(f)['agent'])
@@ -116,7 +116,7 @@ def test_reference_learner_process_loop(embodied, tmp_path):
   driver = embodied.Driver(env)
   driver.on_step(replay.add)
   driver(embodied.RandomAgent(env.act_space).policy, steps=40, episodes=1)
-  agent = Agent(env.obs_space, env.act_space, step, config, backend=HostSim())
+  agent = Agent(env.obs_space, env.act_space, step, config, _backend_for_tests=HostSim())
   assert list(agent.spec.obs_dims) == ['vector', 'step', 'reward', 'is_terminal']
   assert agent.spec.dec_dims == {'vector': 7} and list(agent.spec.cnn_keys) == ['image']
   env.close()
