@@ -125,3 +125,44 @@ def test_edge_case_batches_match_oracle(case):
         assert np.isnan(em[k]), (case, k)
       else:
         assert abs(em[k] - v) <= 2e-4 * max(1.0, abs(v)), (case, it, k, em[k], v)
+
+
+@pytest.mark.parametrize('kw', [
+    dict(prior_layers=1, enc_layers=1, head_layers=1, horizon=1),
+    dict(stoch=1, classes=2, act_dim=1, deter=8, units=12),
+    dict(obs_dims={'a': 1, 'b': 3, 'c': 2}, stoch=5, classes=3, prior_layers=2, horizon=2),
+    dict(discrete=True, act_dim=2, stoch=2, classes=7, head_units=8, enc_units=8, horizon=4),
+    dict(kl_balance=0.5, discount=0.9, lam=0.5, rssm_unimix=0.1, actor_minstd=0.3, clip=0.5, wd=0.0),
+])
+def test_odd_sizes_and_hyperparameters_match_oracle(kw):
+  """Degenerate layer counts, single-group / two-class latents, one-dimensional actions, several
+  vector keys, a gradient clip that is active, no weight decay."""
+  B, L = 2, 3
+  ospec = O.tiny_spec(**kw)
+  spec = util.to_engine_spec(ospec)
+  params = O.init_params(ospec, seed=4)
+  rng = np.random.default_rng(6)
+  for k, v in params.items():
+    if not k.endswith('/kernel'):
+      params[k] = (v + 0.1 * rng.standard_normal(v.shape)).astype(np.float32)
+  ol = O.Learner(ospec, params)
+  eng = E.Engine(spec, HostSim(), B, L)
+  eng.load_params(params)
+  ostate = estate = None
+  for it in range(2):
+    batch = util.make_batch(ospec, B, L, seed=50 + it)
+    noise = util.make_noise(ospec, B, L, seed=60 + it)
+    _, ostate, omets, aux = ol.train_step(batch, noise, ostate, keep=True)
+    util.load_batch(eng, spec, batch, noise, estate)
+    eng.launch_step(draw=False, slow_refreshed=eng.slow_refresh_due(int(eng.counters[E.C_SLOW])))
+    estate = {'deter': eng.prev_deter.numpy().copy(), 'stoch': eng.prev_stoch.numpy().copy()}
+    for group in ('model', 'critic', 'actor'):
+      eg = eng.get_grads(group)
+      for k, v in aux[f'{group}_grads'].items():
+        assert rel(eg[k], v.numpy()) < 3e-4 or np.abs(eg[k] - v.numpy()).max() < 1e-8, (it, group, k)
+    ep = eng.get_params()
+    for k, v in ol.params.items():
+      assert rel(ep[k], v.numpy()) < 1e-5, (it, k)
+    em = eng.read_metrics()
+    for k, v in omets.items():
+      assert (np.isnan(v) and np.isnan(em[k])) or abs(em[k] - v) <= 2e-4 * max(1.0, abs(v)), (it, k, em[k], v)
