@@ -33,6 +33,7 @@ SIGNATURES = {
     'dd_set_pdl': [_I],
     'dd_set_gemm_thin': [_I],
     'dd_set_ln_warp_max': [_I],
+    'dd_set_ln_vec': [_I],
     'dd_ln_fwd': [_P, _I, _P, _P, _P, _I, _P, _I, _I, _I, _P],
     'dd_ln_bwd': [_P, _I, _P, _I, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _P],
     'dd_gru_fwd': [_P, _I, _P, _I, _P, _I, _I, _I, _P],
@@ -165,6 +166,8 @@ class CudaBackend:
     torch.cuda.set_device(self.device)
     if os.environ.get('DD_PDL', '') != '':
       self.lib.dd_set_pdl(int(os.environ['DD_PDL']))
+    if os.environ.get('DD_LN_VEC', '') != '':
+      self.lib.dd_set_ln_vec(int(os.environ['DD_LN_VEC']))
     if os.environ.get('DD_LN_WARP_MAX', '') != '':
       self.lib.dd_set_ln_warp_max(int(os.environ['DD_LN_WARP_MAX']))
     if os.environ.get('DD_GEMM_THIN', '') != '':

@@ -542,6 +542,152 @@ __global__ void __launch_bounds__(256) ln_bwd_warp_kernel(
   }
 }
 
+// ---- EXPERIMENTAL (round 2, not yet run on a GPU; dd_set_ln_vec) -----------------------------
+// r01 measured the block-per-row kernels at 26-29 % of the HBM copy peak for M ~ 15K rows and
+// latency bound (7-10 us) at M = 1024 (profiles/r01_gemm_shape_times.txt): three block barriers
+// per row, scalar 4-byte accesses, ~32 KB in flight per SM.  Variant for N % 128 == 0, N <= 512:
+// one warp per row, float4 accesses (lane owns columns 4*lane + 128*i), no block barrier, register
+// budget capped so 3-4 CTAs of 8 warps are resident per SM.
+int g_ln_vec = 0;
+
+template <int V>
+__global__ void __launch_bounds__(256, 4) ln_fwd_vec_kernel(
+    const float* __restrict__ Z, int ldz, const float* __restrict__ scale,
+    const float* __restrict__ bias, float* __restrict__ H, int ldh, float* __restrict__ stats,
+    int M, int N, int act) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const float4* sc4 = reinterpret_cast<const float4*>(scale);
+  const float4* bi4 = reinterpret_cast<const float4*>(bias);
+  for (int64_t m = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); m < M;
+       m += (int64_t)gridDim.x * wpb) {
+    const float4* z4 = reinterpret_cast<const float4*>(Z + (size_t)m * ldz);
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i] = z4[lane + 32 * i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / N;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / N + DD_LN_EPS);
+    float4* h4 = reinterpret_cast<float4*>(H + (size_t)m * ldh);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 sc = sc4[lane + 32 * i], bi = bi4[lane + 32 * i];
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * sc.x + bi.x;
+      y.y = (v[i].y - mean) * rstd * sc.y + bi.y;
+      y.z = (v[i].z - mean) * rstd * sc.z + bi.z;
+      y.w = (v[i].w - mean) * rstd * sc.w + bi.w;
+      if (act) {
+        y.x = y.x > 0.f ? y.x : expm1f(y.x);
+        y.y = y.y > 0.f ? y.y : expm1f(y.y);
+        y.z = y.z > 0.f ? y.z : expm1f(y.z);
+        y.w = y.w > 0.f ? y.w : expm1f(y.w);
+      }
+      h4[lane + 32 * i] = y;
+    }
+    if (lane == 0) {
+      stats[2 * m] = mean;
+      stats[2 * m + 1] = rstd;
+    }
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256, 2) ln_bwd_vec_kernel(
+    const float* __restrict__ dH, int lddh, const float* __restrict__ Z, int ldz,
+    const float* __restrict__ stats, const float* __restrict__ scale,
+    const float* __restrict__ bias, float* __restrict__ dZ, int lddz,
+    float* __restrict__ dscale, float* __restrict__ dbias, int M, int N, int act) {
+  pdl_prologue();
+  __shared__ float sh_s[8][128 * V], sh_b[8][128 * V];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const float4* sc4 = reinterpret_cast<const float4*>(scale);
+  const float4* bi4 = reinterpret_cast<const float4*>(bias);
+  float gs[V][4], gb[V][4];
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gs[i][j] = gb[i][j] = 0.f;
+  for (int64_t m = blockIdx.x * (int64_t)wpb + warp; m < M; m += (int64_t)gridDim.x * wpb) {
+    const float mean = stats[2 * m], rstd = stats[2 * m + 1];
+    const float4* z4 = reinterpret_cast<const float4*>(Z + (size_t)m * ldz);
+    const float4* d4 = reinterpret_cast<const float4*>(dH + (size_t)m * lddh);
+    float xh[V][4], dx[V][4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 z = z4[lane + 32 * i], dh = d4[lane + 32 * i];
+      const float4 sc = sc4[lane + 32 * i];
+      const float zz[4] = {z.x, z.y, z.z, z.w}, dd[4] = {dh.x, dh.y, dh.z, dh.w};
+      const float ss[4] = {sc.x, sc.y, sc.z, sc.w};
+      float bb[4] = {0.f, 0.f, 0.f, 0.f};
+      if (act) {
+        const float4 bi = bi4[lane + 32 * i];
+        bb[0] = bi.x; bb[1] = bi.y; bb[2] = bi.z; bb[3] = bi.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = (zz[j] - mean) * rstd;
+        float dy = dd[j];
+        if (act) {
+          const float y = x * ss[j] + bb[j];
+          if (y <= 0.f) dy *= expf(y);
+        }
+        gs[i][j] += dy * x;
+        gb[i][j] += dy;
+        xh[i][j] = x;
+        dx[i][j] = dy * ss[j];
+        s1 += dx[i][j];
+        s2 += dx[i][j] * x;
+      }
+    }
+    const float m1 = warp_sum(s1) / N, m2 = warp_sum(s2) / N;
+    float4* o4 = reinterpret_cast<float4*>(dZ + (size_t)m * lddz);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 o;
+      o.x = rstd * (dx[i][0] - m1 - xh[i][0] * m2);
+      o.y = rstd * (dx[i][1] - m1 - xh[i][1] * m2);
+      o.z = rstd * (dx[i][2] - m1 - xh[i][2] * m2);
+      o.w = rstd * (dx[i][3] - m1 - xh[i][3] * m2);
+      o4[lane + 32 * i] = o;
+    }
+  }
+  if (dscale == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < V; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sh_s[warp][4 * (lane + 32 * i) + j] = gs[i][j];
+      sh_b[warp][4 * (lane + 32 * i) + j] = gb[i][j];
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < wpb; ++w) {
+      a += sh_s[w][c];
+      b += sh_b[w][c];
+    }
+    atomicAdd(&dscale[c], a);
+    atomicAdd(&dbias[c], b);
+  }
+}
+
+static bool ln_vec_ok(const void* a, int lda, const void* b, int ldb, const void* c, const void* d,
+                      int N) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return g_ln_vec && N % 128 == 0 && N <= 512 && (lda & 3) == 0 && (ldb & 3) == 0 && al(a) && al(b) &&
+         al(c) && al(d);
+}
+
 }  // namespace dd
 
 using namespace dd;
@@ -550,6 +696,16 @@ extern "C" int dd_ln_fwd(const float* Z, int ldz, const float* scale, const floa
                          int ldh, float* stats, int M, int N, int act, dd_stream_t stream) {
   if (M <= 0) return 0;
   if (N > 12000) return fail("dd_ln_fwd", "row too wide for shared-memory staging");
+  if (ln_vec_ok(Z, ldz, H, ldh, scale, bias, N)) {
+    const int grid = grid_for(M, 8, 148 * 4);
+#define DD_LNV(V) launch_k(ln_fwd_vec_kernel<V>, grid, 256, 0, S(stream), Z, ldz, scale, bias, H, ldh, stats, M, N, act)
+    if (N == 128) DD_LNV(1);
+    else if (N == 256) DD_LNV(2);
+    else if (N == 384) DD_LNV(3);
+    else DD_LNV(4);
+#undef DD_LNV
+    return launched("dd_ln_fwd");
+  }
   if (N <= g_ln_warp_max) {
     const int grid = grid_for(M, 8, 148 * 16);
 #define DD_LNF(PER) launch_k(ln_fwd_warp_kernel<PER>, grid, 256, 0, S(stream), Z, ldz, scale, bias, H, ldh, stats, M, N, act)
@@ -575,6 +731,17 @@ extern "C" int dd_ln_bwd(const float* dH, int lddh, const float* Z, int ldz, con
 #define DD_LNB(PER, BLK)                                                                      \
   launch_k(ln_bwd_kernel<PER, BLK>, grid, BLK, 0, S(stream), dH, lddh, Z, ldz, stats, scale, bias, dZ, \
                                                   lddz, dscale, dbias, M, N, act)
+  if (ln_vec_ok(dH, lddh, Z, ldz, scale, bias, N) && (lddz & 3) == 0 &&
+      (reinterpret_cast<uintptr_t>(dZ) & 15) == 0) {
+    const int vgrid = grid_for(M, 8, 148 * 2);
+#define DD_LNBV(V) launch_k(ln_bwd_vec_kernel<V>, vgrid, 256, 0, S(stream), dH, lddh, Z, ldz, stats, scale, bias, dZ, lddz, dscale, dbias, M, N, act)
+    if (N == 128) DD_LNBV(1);
+    else if (N == 256) DD_LNBV(2);
+    else if (N == 384) DD_LNBV(3);
+    else DD_LNBV(4);
+#undef DD_LNBV
+    return launched("dd_ln_bwd");
+  }
   if (N <= g_ln_warp_max) {
     const int wgrid = grid_for(M, 8, 148 * 8);
 #define DD_LNW(PER)                                                                              \
@@ -681,5 +848,11 @@ extern "C" int dd_mask_bwd(const float* dd_, int lddd, const float* ds, int ldds
 extern "C" int dd_set_ln_warp_max(int n) {
   const int prev = g_ln_warp_max;
   g_ln_warp_max = n < 0 ? 0 : (n > 512 ? 512 : n);
+  return prev;
+}
+
+extern "C" int dd_set_ln_vec(int on) {
+  const int prev = g_ln_vec;
+  g_ln_vec = on ? 1 : 0;
   return prev;
 }

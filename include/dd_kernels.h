@@ -57,6 +57,9 @@ int dd_set_gemm_tc_staged(int on);
 int dd_set_gemm_thin(int on);
 /* widest row the warp-per-row LayerNorm kernels take (<= 512, default 128) */
 int dd_set_ln_warp_max(int n);
+/* EXPERIMENTAL (round 2, not yet run on a GPU): float4 warp-per-row LayerNorm kernels for
+ * N % 128 == 0, N <= 512 (default off) */
+int dd_set_ln_vec(int on);
 /* profiling aid: bit 0 = skip operand loads, bit 1 = skip MMA issue (garbage results) */
 int dd_set_gemm_tc_debug(int bits);
 

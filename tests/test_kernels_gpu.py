@@ -116,6 +116,31 @@ def test_ln(backends, M, N, act, warp_max):
   both(backends, case, rtol=1e-4, atol=1e-4 * np.sqrt(M))
 
 
+@pytest.mark.skipif(not __import__('os').environ.get('DD_TEST_EXPERIMENTAL'),
+                    reason='experimental kernels run only on request (DD_TEST_EXPERIMENTAL=1)')
+@pytest.mark.parametrize('M,N,act', [(1024, 512, 1), (15360, 512, 1), (777, 256, 0), (50, 128, 1),
+                                     (333, 384, 0), (16, 512, 1)])
+def test_ln_vec_experimental(backends, M, N, act):
+  """Round-2 work in progress: the float4 warp-per-row LayerNorm kernels (dd_set_ln_vec) on
+  contiguous, 16-byte aligned rows (the only layout they accept)."""
+  def case(be, T):
+    if hasattr(be, 'lib'):
+      be.lib.dd_set_ln_vec(1)
+    Z = T(rnd(M, N, seed=1, scale=2.0))
+    sc, bi = T(1 + 0.2 * rnd(N, seed=2)), T(0.3 * rnd(N, seed=3))
+    H, st = T(torch.zeros(M, N)), T(torch.zeros(M, 2))
+    be.ln_fwd(Z, sc, bi, H, st, act)
+    dH = T(rnd(M, N, seed=4))
+    dZ, ds, db = T(torch.zeros(M, N)), T(0.1 * rnd(N, seed=5)), T(0.1 * rnd(N, seed=6))
+    be.ln_bwd(dH, Z, st, sc, bi, dZ, ds, db, act)
+    dZ2 = T(torch.zeros(M, N))
+    be.ln_bwd(dH, Z, st, sc, bi, dZ2, None, None, act)
+    if hasattr(be, 'lib'):
+      be.lib.dd_set_ln_vec(0)
+    return {'H': H, 'st': st, 'dZ': dZ, 'ds': ds, 'db': db, 'dZ2': dZ2}
+  both(backends, case, rtol=1e-4, atol=1e-4 * np.sqrt(M))
+
+
 @pytest.mark.parametrize('M,D', [(16, 512), (1024, 24), (7, 5)])
 def test_gru(backends, M, D):
   def case(be, T):
