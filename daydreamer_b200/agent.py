@@ -361,7 +361,11 @@ class Agent:
     return keys
 
   def dataset(self, generator):
-    return Batcher(generator, int(_get(self.config, 'batch_size')), keys=self.batch_keys())
+    """Batches of `batch_size` sequences; under data parallelism `batch_size` is the GLOBAL batch
+    (as in the reference, A/tfagent.py:112-116) and every rank draws its own batch_size / world
+    sequences from its own replay."""
+    per_rank = max(1, int(_get(self.config, 'batch_size')) // self.world)
+    return Batcher(generator, per_rank, keys=self.batch_keys())
 
   def train(self, data, state=None):
     B, L = np.asarray(data['is_first']).shape[:2]
