@@ -37,9 +37,17 @@ __global__ void __launch_bounds__(256) thin_n_small_kernel(
   pdl_prologue();
   extern __shared__ __align__(16) float thin_smem[];
   float* Bs = thin_smem;                                   // [N][K] (row n contiguous over k)
-  for (int e = threadIdx.x; e < K * N; e += blockDim.x) {
-    const int n = e / K, k = e % K;
-    Bs[e] = tb ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n];
+  if (NN > 4 && !tb) {
+    // (level 2) B is [K, N] row-major: walk it in memory order so the global reads coalesce
+    for (int e = threadIdx.x; e < K * N; e += blockDim.x) {
+      const int k = e / N, n = e % N;
+      Bs[n * K + k] = B[(size_t)k * ldb + n];
+    }
+  } else {
+    for (int e = threadIdx.x; e < K * N; e += blockDim.x) {
+      const int n = e / K, k = e % K;
+      Bs[e] = tb ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n];
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
