@@ -16,7 +16,7 @@ namespace dd {
 // generic SIMT tile kernel is FASTER on these shapes than this first version (step 28.8 ms vs
 // 29.2 ms with the thin kernels); the 27 us per launch that motivated them is the cold-cache,
 // serialised ncu figure, not the in-graph cost.  Kept (and tested) behind dd_set_gemm_thin(1).
-int g_thin_on = 0;
+int g_thin_on = 2;
 
 constexpr int THIN_SMEM = 96 * 1024;
 

@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(256) ln_bwd_warp_kernel(
 // per row, scalar 4-byte accesses, ~32 KB in flight per SM.  Variant for N % 128 == 0, N <= 512:
 // one warp per row, float4 accesses (lane owns columns 4*lane + 128*i), no block barrier, register
 // budget capped so 3-4 CTAs of 8 warps are resident per SM.
-int g_ln_vec = 0;
+int g_ln_vec = 1;
 
 template <int V>
 __global__ void __launch_bounds__(256, 4) ln_fwd_vec_kernel(

@@ -60,8 +60,7 @@ def test_gemm(backends, M, N, K, ta, tb):
                                    (15360, 512, 1), (1000, 3, 300), (70, 32, 1536), (333, 5, 20),
                                    (1024, 1536, 12), (900, 2, 16), (257, 31, 33)])
 @pytest.mark.parametrize('tb', [False, True])
-@pytest.mark.parametrize('level', [1, pytest.param(2, marks=pytest.mark.skipif(
-    not __import__('os').environ.get('DD_TEST_EXPERIMENTAL'), reason='experimental (DD_TEST_EXPERIMENTAL=1)'))])
+@pytest.mark.parametrize('level', [1, 2])
 def test_gemm_thin(backends, M, N, K, tb, level):
   """Thin shapes (N <= 32 or K <= 32, many rows) on the streaming kernels of dd_gemm_thin.cu,
   contiguous (vector path) and row-strided operands, bias / beta combinations."""
@@ -116,8 +115,6 @@ def test_ln(backends, M, N, act, warp_max):
   both(backends, case, rtol=1e-4, atol=1e-4 * np.sqrt(M))
 
 
-@pytest.mark.skipif(not __import__('os').environ.get('DD_TEST_EXPERIMENTAL'),
-                    reason='experimental kernels run only on request (DD_TEST_EXPERIMENTAL=1)')
 @pytest.mark.parametrize('M,N,act', [(1024, 512, 1), (15360, 512, 1), (777, 256, 0), (50, 128, 1),
                                      (333, 384, 0), (16, 512, 1)])
 def test_ln_vec_experimental(backends, M, N, act):
@@ -472,8 +469,6 @@ def test_gemm_skinny(backends, M, N, K, tb):
   both(backends, case, rtol=1e-4, atol=2e-5 * np.sqrt(K))
 
 
-@pytest.mark.skipif(not __import__('os').environ.get('DD_TEST_EXPERIMENTAL'),
-                    reason='experimental kernels run only on request (DD_TEST_EXPERIMENTAL=1)')
 @pytest.mark.parametrize('M,N,K', [(1024, 512, 512), (1024, 512, 1536), (1024, 1024, 512), (130, 72, 100),
                                    (1000, 64, 36), (512, 512, 1024)])
 @pytest.mark.parametrize('ta,tb', [(False, False), (False, True), (True, False), (True, True)])
