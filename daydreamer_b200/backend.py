@@ -80,6 +80,9 @@ SIGNATURES = {
     'dd_counter_inc': [_P, _I, _P],
     'dd_fill_gumbel': [_P, _L, _U64, _U32, _P, _I, _P],
     'dd_fill_normal': [_P, _L, _U64, _U32, _P, _I, _P],
+    'dd_program_run': [_P, _I, _I, _P],
+    'dd_split_lo': [_P, _I, _P, _I, _I, _I, _P],
+    'dd_transpose_lo': [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
 }
 
 
@@ -104,6 +107,28 @@ class DdObserveBwd(ctypes.Structure):
               [('mix', ctypes.c_float)] + [(n, ctypes.c_void_p) for n in _PTRS])
 
 
+class DdSeg(ctypes.Structure):
+  """Mirror of `struct DdSeg` in include/dd_kernels.h."""
+  _fields_ = [('a', _P), ('a_lo', _P), ('lda', _I), ('k', _I), ('wk0', _I)]
+
+
+class DdLayer(ctypes.Structure):
+  """Mirror of `struct DdLayer` in include/dd_kernels.h."""
+  _fields_ = [('nseg', _I), ('seg', DdSeg * 2), ('w', _P), ('w_lo', _P), ('ldw', _I),
+              ('wrows', _I), ('wcols', _I), ('wn0', _I), ('N', _I), ('epi', _I), ('act', _I),
+              ('add', _P), ('ld_add', _I), ('bias', _P), ('gamma', _P), ('beta', _P), ('z', _P),
+              ('ld_z', _I), ('st', _P), ('out', _P), ('out_lo', _P), ('ld_out', _I),
+              ('dgamma', _P), ('dbeta', _P)]
+
+
+class ProgramHandle:
+  """A compiled layer program: the device table with its TMA descriptors plus references that
+  keep every tensor the descriptors point at alive."""
+
+  def __init__(self, table, nlayers, rows, layers):
+    self.table, self.nlayers, self.rows, self.layers = table, nlayers, rows, layers
+
+
 def load_library(path=LIB_PATH):
   """dlopen the kernel library and type every entry point.  Raises if absent."""
   path = pathlib.Path(path)
@@ -124,6 +149,12 @@ def load_library(path=LIB_PATH):
   lib.dd_observe_bwd_grid.restype = ctypes.c_int
   lib.dd_observe_bwd.argtypes = [ctypes.POINTER(DdObserveBwd), _P]
   lib.dd_observe_bwd.restype = ctypes.c_int
+  lib.dd_program_bytes.argtypes = [_I]
+  lib.dd_program_bytes.restype = ctypes.c_size_t
+  lib.dd_program_build.argtypes = [ctypes.POINTER(DdLayer), _I, _I, _P]
+  lib.dd_program_build.restype = ctypes.c_int
+  lib.dd_program_debug.argtypes = [ctypes.POINTER(ctypes.c_uint)]
+  lib.dd_program_debug.restype = ctypes.c_int
   lib.dd_version.restype = ctypes.c_int
   lib.dd_last_error.restype = ctypes.c_char_p
   lib.dd_launch_count.restype = ctypes.c_int64
@@ -523,6 +554,71 @@ class CudaBackend:
 
   def counter_inc(self, counters, ci):
     self._ck(self.lib.dd_counter_inc(counters.data_ptr(), int(ci), self.stream))
+
+  # -- layer machine -------------------------------------------------------------
+  def program_build(self, layers, rows):
+    """Compile a list of program.Layer into a device table (TMA descriptors are encoded here:
+    synchronous, call outside stream capture)."""
+    n = len(layers)
+    arr = (DdLayer * n)()
+    for i, L in enumerate(layers):
+      d = arr[i]
+      d.nseg = len(L.segs)
+      assert 1 <= d.nseg <= 2
+      for g, sg in enumerate(L.segs):
+        pa, r, k, lda = _mat(sg.a)
+        assert r == rows, (sg.a.shape, rows)
+        d.seg[g].a, d.seg[g].lda, d.seg[g].k, d.seg[g].wk0 = pa, lda, k, int(sg.wk0)
+        if sg.a_lo is not None:
+          pl, _, _, ldl = _mat(sg.a_lo)
+          assert ldl == lda and sg.a_lo.shape == sg.a.shape
+          d.seg[g].a_lo = pl
+      pw, wrows, wcols, ldw = _mat(L.w)
+      pwl, _, _, ldwl = _mat(L.w_lo)
+      assert ldwl == ldw and L.w_lo.shape == L.w.shape
+      d.w, d.w_lo, d.ldw, d.wrows, d.wcols, d.wn0 = pw, pwl, ldw, wrows, wcols, int(L.wn0)
+      d.N, d.epi, d.act = int(L.N), int(L.epi), int(L.act)
+      if L.add is not None:
+        d.add, _, _, d.ld_add = _mat(L.add)
+      d.bias, d.gamma, d.beta = _ptr(L.bias), _ptr(L.gamma), _ptr(L.beta)
+      if L.z is not None:
+        d.z, _, _, d.ld_z = _mat(L.z)
+      d.st = _ptr(L.st)
+      d.out, _, _, d.ld_out = _mat(L.out)
+      if L.out_lo is not None:
+        pl, _, _, ldl = _mat(L.out_lo)
+        assert ldl == d.ld_out
+        d.out_lo = pl
+      d.dgamma, d.dbeta = _ptr(L.dgamma), _ptr(L.dbeta)
+    nbytes = int(self.lib.dd_program_bytes(n))
+    table = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+    torch.cuda.synchronize(self.device)
+    self._ck(self.lib.dd_program_build(arr, n, int(rows), table.data_ptr()))
+    return ProgramHandle(table, n, int(rows), list(layers))
+
+  def program_run(self, h):
+    self._ck(self.lib.dd_program_run(h.table.data_ptr(), h.nlayers, h.rows, self.stream))
+
+  def program_debug(self):
+    """Diagnostic words of a stuck wait inside the layer machine (after a failed sync)."""
+    out = (ctypes.c_uint * 8)()
+    stuck = self.lib.dd_program_debug(out)
+    return bool(stuck), [int(x) for x in out]
+
+  def split_lo(self, x, lo):
+    px, r, c, ldx = _mat(x)
+    pl, _, _, ldl = _mat(lo)
+    self._ck(self.lib.dd_split_lo(px, ldx, pl, ldl, r, c, self.stream))
+
+  def transpose_lo(self, p, pt, pt_lo, jobs):
+    """jobs: list of (src offset, rows, cols, dst offset, dst row stride, mode); mode 0 writes the
+    transpose of the [rows, cols] matrix at p[src:], mode 1 a re-strided copy; both with x_lo."""
+    for i in range(0, len(jobs), 64):
+      part = jobs[i:i + 64]
+      n = len(part)
+      cols = [(ctypes.c_int * n)(*[int(j[q]) for j in part]) for q in range(6)]
+      self._ck(self.lib.dd_transpose_lo(p.data_ptr(), pt.data_ptr(), pt_lo.data_ptr(), n,
+                                        *cols, self.stream))
 
   # -- noise ------------------------------------------------------------------
   def fill_gumbel(self, buf, seed, stream_id, counters, ci):

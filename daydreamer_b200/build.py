@@ -11,7 +11,7 @@ ROOT = pathlib.Path(__file__).resolve().parent
 CSRC = ROOT / 'csrc'
 LIBDIR = ROOT / 'lib'
 LIB = LIBDIR / 'libdd_kernels.so'
-SOURCES = ['dd_gemm.cu', 'dd_gemm_tc.cu', 'dd_gemm_skinny.cu', 'dd_gemm_thin.cu', 'dd_rowops.cu', 'dd_scan.cu', 'dd_elem.cu', 'dd_conv.cu', 'dd_ctrl.cu', 'dd_rng.cu']
+SOURCES = ['dd_gemm.cu', 'dd_gemm_tc.cu', 'dd_gemm_skinny.cu', 'dd_gemm_thin.cu', 'dd_rowops.cu', 'dd_scan.cu', 'dd_elem.cu', 'dd_conv.cu', 'dd_ctrl.cu', 'dd_rng.cu', 'dd_machine.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
     '-std=c++17', '-Xcompiler', '-fPIC', '-shared',

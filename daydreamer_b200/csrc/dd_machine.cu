@@ -1,0 +1,1035 @@
+// The "layer machine": chains of  Y = epilogue(X . W)  layers executed by ONE persistent
+// kernel, one thread-block cluster per 128-row tile.
+//
+// Why: the imagination rollout (A/agent.py:234-261), every MLP trunk (A/nets.py:408-416) and
+// their reverse passes are chains of dependent [rows x K] . [K x N] products with a LayerNorm
+// (over the FULL row) between them, and each 128-row tile of the batch runs through such a
+// chain independently of every other tile.  So a cluster of CL = 8 CTAs owns a row tile: CTA r
+// computes column slice r of every layer (tcgen05 kind::tf32 tiles 128 x bn, accumulators in
+// TMEM), the 8 CTAs exchange the per-row LayerNorm partials through distributed shared memory,
+// and the only synchronisation between consecutive layers is cluster-local (mbarriers with
+// release/acquire at cluster scope) -- no grid barrier, no kernel boundary.
+//
+// Operands reach the tensor core straight from TMA (cp.async.bulk.tensor, SWIZZLE_128B K-major
+// tiles; SASS: UTMALDG): fp32-accurate 3xTF32 needs x = hi + lo with both halves in shared
+// memory, so every operand exists in global memory as a pair (x, x_lo): the tensor core reads
+// the top 19 bits of x itself as `hi` and x_lo = tf32(x - trunc19(x)) is written once by the
+// producer of x (the previous layer's epilogue, or the optimizer for weights).  The A tile (the
+// activations, identical for the 8 column-slice CTAs) is fetched ONCE per cluster: each CTA
+// loads a 16-row slice and multicasts it to all 8; weights (B) are private column slices.
+//
+//   warp 0    TMA producer (one lane issues): 4-stage ring {A_hi, A_lo, B_hi, B_lo}
+//   warp 1    TMEM allocator + MMA issuer (one lane): per k-step hi.hi -> main accumulator,
+//             lo.hi + hi.lo -> cross accumulator (separate TMEM columns), tcgen05.commit
+//             multicast to the `empty` barrier of all 8 CTAs (they all receive my A slices)
+//   warps 2-5 epilogue, one accumulator row per thread: tcgen05.ld, bias / addend, LayerNorm
+//             forward (+elu) or backward with the cross-CTA row reduction over DSMEM, writes x and
+//             x_lo for the next layer through a per-warp transposing staging buffer (coalesced)
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "dd_common.cuh"
+
+namespace dd {
+namespace lm {
+
+constexpr int CL = 8;                 // CTAs per cluster = column slices of one row tile
+constexpr int BM = 128;               // rows per tile (= TMEM lanes)
+constexpr int BK = 32;                // k-block: 32 fp32 = one 128-byte swizzle row
+constexpr int BNMAX = 64;             // widest per-CTA column chunk
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 4;                       // 16 KB
+constexpr int B_BYTES = BNMAX * BK * 4;                    // 8 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;     // 48 KB: A_hi | A_lo | B_hi | B_lo
+constexpr int SLICE_ROWS = BM / CL;                        // 16 rows of A loaded by each CTA
+constexpr int SLICE_BYTES = SLICE_ROWS * BK * 4;           // 2 KB = two 8-row swizzle groups
+constexpr int OFF_STATS = STAGES * STAGE_BYTES;            // float2 [2 parity][CL][BM]
+constexpr int STATS_BYTES = 2 * CL * BM * 8;
+constexpr int OFF_STG = OFF_STATS + STATS_BYTES;           // per-warp 32 x 36 floats
+constexpr int STG_LD = 36;
+constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;
+constexpr int OFF_BAR = OFF_STG + 4 * STG_WARP_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 256;        // 2 buffers x (main 64 | cross 64)
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+
+enum { BAR_FULL = 0, BAR_EMPTY = 32, BAR_ACCF = 64, BAR_ACCE = 80, BAR_STATS = 96, BAR_READY = 104,
+       BAR_TMEM = 112 };
+
+// device-side layer descriptor (built on the host by dd_program_build)
+struct alignas(64) LmLayer {
+  CUtensorMap a_hi[2], a_lo[2];   // per A segment: [rows, k] fp32, box {32, 16}, SWIZZLE_128B
+  CUtensorMap w_hi, w_lo;         // B operand [n rows, k cols], box {32, bn}
+  int nseg, seg_k[2], seg_wk0[2], seg_exact[2];
+  int wn0;                        // first row of the B operand used by this layer
+  int N, bn, nchunk, chunk_stride, nactive;
+  int epi, act;
+  int ld_add, ld_out, ld_z;
+  const float* add;               // [M, N] added to the accumulator (beta = 1 / skip input)
+  const float* bias;              // [N]
+  const float* gamma;             // LayerNorm scale / bias
+  const float* beta;
+  float* z;                       // LN fwd: pre-norm output (saved for backward); LN bwd: saved pre-norm input
+  float* st;                      // [M, 2] (mean, rstd): output of LN fwd, input of LN bwd
+  float* out;                     // primary output  (x)
+  float* out_lo;                  // its tf32 remainder (x_lo), or null
+  float* dgamma;                  // LN bwd: parameter gradients (+=), or null
+  float* dbeta;
+};
+
+// ---- PTX helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  const uint32_t ra = mapa(bar, rank);
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+
+// Diagnostics of a stuck wait: a wait that does not complete within ~2 s writes what it was
+// waiting for into `dbg` (mapped host memory, survives the trap) and kills the kernel, so a
+// protocol bug shows up as an error with a location instead of a hung GPU box.
+struct Ctx {
+  unsigned* dbg;
+  int pair;          // (tile, layer) pair index being processed
+};
+__device__ __noinline__ void stuck(const Ctx& cx, int code, uint32_t parity) {
+  if (cx.dbg != nullptr) {
+    cx.dbg[1] = (unsigned)code;
+    cx.dbg[2] = blockIdx.x;
+    cx.dbg[3] = threadIdx.x;
+    cx.dbg[4] = parity;
+    cx.dbg[5] = (unsigned)cx.pair;
+    cx.dbg[0] = 0xDEADBEEFu;
+    __threadfence_system();
+  }
+  __trap();
+}
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const Ctx& cx, int code) {
+  uint32_t done = 0;
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    if (CLUSTER)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    else
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+    if ((spin & 1023u) == 1023u) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) stuck(cx, code, parity);
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                            uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmap_acquire(const CUtensorMap* map) {
+  // the descriptor table is written by a host copy before the launch
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;"
+               ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// K-major SWIZZLE_128B operand tile (rows x 32 fp32, 128-byte rows, 8-row groups 1024 B apart):
+// start >> 4 [0,14), LBO >> 4 [16,30) (=1, unused for swizzled K-major), SBO >> 4 [32,46),
+// version 1 [46,48), layout SWIZZLE_128B = 2 [61,64)   (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// kind::tf32 instruction descriptor: D = F32 [4,6), A = B = TF32 (2) [7,10) [10,13), both K-major,
+// N >> 3 [17,23), M >> 4 [24,29)   (cute::UMMA::InstrDescriptor)
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// tf32 remainder of x: the tensor core uses the top 19 bits of x as `hi`; lo is rounded to tf32
+// here so that the hardware's truncation of it is exact.
+__device__ __forceinline__ float lo_of(float x) {
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  const float lo = x - hi;
+  return __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ float elu_f(float y) { return y > 0.f ? y : expm1f(y); }
+
+// ---- 32 x 32 sub-tile I/O through the warp's staging buffer ----------------------------------
+// Thread `lane` owns row `lane` of the sub-tile in registers; global rows are `ld` floats apart.
+// Vector path (ld % 4 == 0, 16-byte aligned, all 32 columns valid): each global access covers 4
+// rows x 128 contiguous bytes.  Otherwise a guarded scalar path (narrow heads, N = 1 ... 31).
+__device__ __forceinline__ void sub_store(float* stg, const float (&v)[32], float* g, int ld,
+                                          int rows_valid, int cols_valid, int lane) {
+  const bool vec = cols_valid >= 32 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+  if (vec) {
+    float4* srow = reinterpret_cast<float4*>(stg + lane * STG_LD);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + (lane >> 3), c4 = (lane & 7) * 4;
+      const float4 x = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4);
+      if (r < rows_valid) *reinterpret_cast<float4*>(g + (size_t)r * ld + c4) = x;
+    }
+    __syncwarp();
+  } else if (lane < rows_valid) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < cols_valid) g[(size_t)lane * ld + j] = v[j];
+  }
+}
+__device__ __forceinline__ void sub_load(float* stg, float (&v)[32], const float* g, int ld,
+                                         int rows_valid, int cols_valid, int lane) {
+  const bool vec = cols_valid >= 32 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+  if (vec) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + (lane >> 3), c4 = (lane & 7) * 4;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows_valid) x = *reinterpret_cast<const float4*>(g + (size_t)r * ld + c4);
+      *reinterpret_cast<float4*>(stg + r * STG_LD + c4) = x;
+    }
+    __syncwarp();
+    const float4* srow = reinterpret_cast<const float4*>(stg + lane * STG_LD);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 x = srow[j];
+      v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+    }
+    __syncwarp();
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      v[j] = (lane < rows_valid && j < cols_valid) ? g[(size_t)lane * ld + j] : 0.f;
+  }
+}
+
+// column sums over the warp's 32 rows: on return lane j holds sum_rows a_row[j] in a[0]
+__device__ __forceinline__ void warp_colsum32(float (&a)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? a[i] : a[i + off];
+      const float keep = up ? a[i + off] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+// ---- roles ------------------------------------------------------------------------------------
+struct Shared {
+  char* smem;
+  uint32_t base;      // shared-window address of smem
+  uint32_t bars;      // of the barrier block
+};
+
+__device__ __forceinline__ int layer_kblocks(const LmLayer& L) {
+  int kb = (L.seg_k[0] + BK - 1) / BK;
+  if (L.nseg > 1) kb += (L.seg_k[1] + BK - 1) / BK;
+  return kb;
+}
+
+__device__ void producer(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
+                         int cluster_id, int nclusters, int lane, Ctx cx) {
+  const int ntiles = (M + BM - 1) / BM;
+  uint32_t it = 0;
+  int pair = 0;
+  for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+    const int m0 = tile * BM;
+    for (int l = 0; l < nlayers; ++l, ++pair) {
+      const LmLayer& L = layers[l];
+      cx.pair = pair;
+      if (lane == 0) {
+        for (int s = 0; s < L.nseg; ++s) {
+          tmap_acquire(&L.a_hi[s]);
+          if (!L.seg_exact[s]) tmap_acquire(&L.a_lo[s]);
+        }
+        tmap_acquire(&L.w_hi);
+        tmap_acquire(&L.w_lo);
+      }
+      __syncwarp();
+      const int kb0 = (L.seg_k[0] + BK - 1) / BK;
+      const int kbc = layer_kblocks(L);
+      const int total = kbc * L.nchunk;
+      const bool active = rank < L.nactive;
+      bool need_ready = l > 0;
+      int j = 0;
+      while (j < total) {
+        const int batch = need_ready ? min(STAGES, total - j) : 1;
+        // weights first: they do not depend on the previous layer
+        for (int b = 0; b < batch; ++b) {
+          const int jj = j + b, c = jj / kbc, r = jj % kbc;
+          const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
+          const uint32_t itb = it + b, s = itb % STAGES, ph = (itb / STAGES) & 1;
+          const uint32_t full = sh.bars + BAR_FULL + 8 * s, empty = sh.bars + BAR_EMPTY + 8 * s;
+          mbar_wait<true>(empty, ph ^ 1, cx, 1);
+          if (lane == 0) {
+            const uint32_t bytes = (L.seg_exact[seg] ? 1u : 2u) * A_BYTES +
+                                   (active ? 2u * (uint32_t)L.bn * BK * 4 : 0u);
+            mbar_arrive_tx(full, bytes);
+            if (active) {
+              const uint32_t st = sh.base + s * STAGE_BYTES + 2 * A_BYTES;
+              const int k = L.seg_wk0[seg] + kb * BK;
+              const int n = L.wn0 + c * L.chunk_stride + rank * L.bn;
+              tma_load(st, &L.w_hi, k, n, full);
+              tma_load(st + B_BYTES, &L.w_lo, k, n, full);
+            }
+          }
+          __syncwarp();
+        }
+        if (need_ready) {       // the previous layer's outputs of all 8 CTAs are in global memory
+          mbar_wait<true>(sh.bars + BAR_READY, (uint32_t)(pair - 1) & 1, cx, 2);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          need_ready = false;
+        }
+        // activations: my 16-row slice of the tile, multicast to the whole cluster
+        for (int b = 0; b < batch; ++b) {
+          const int jj = j + b, r = jj % kbc;
+          const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
+          const uint32_t itb = it + b, s = itb % STAGES;
+          const uint32_t full = sh.bars + BAR_FULL + 8 * s;
+          if (lane == 0) {
+            const uint32_t st = sh.base + s * STAGE_BYTES + rank * SLICE_BYTES;
+            const int k = kb * BK, m = m0 + rank * SLICE_ROWS;
+            tma_load_mc(st, &L.a_hi[seg], k, m, full, (uint16_t)0xFF);
+            if (!L.seg_exact[seg]) tma_load_mc(st + A_BYTES, &L.a_lo[seg], k, m, full, (uint16_t)0xFF);
+          }
+          __syncwarp();
+        }
+        it += batch;
+        j += batch;
+      }
+    }
+  }
+}
+
+__device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
+                           int cluster_id, int nclusters, int lane, uint32_t tmem_base, Ctx cx) {
+  const int ntiles = (M + BM - 1) / BM;
+  uint32_t it = 0, ac = 0;
+  int pair = 0;
+  for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+    for (int l = 0; l < nlayers; ++l, ++pair) {
+      const LmLayer& L = layers[l];
+      cx.pair = pair;
+      const int kb0 = (L.seg_k[0] + BK - 1) / BK;
+      const int kbc = layer_kblocks(L);
+      const bool active = rank < L.nactive;
+      const uint32_t idesc = make_idesc(L.bn);
+      for (int c = 0; c < L.nchunk; ++c) {
+        const uint32_t buf = ac & 1;
+        if (active) {
+          mbar_wait<false>(sh.bars + BAR_ACCE + 8 * buf, ((ac >> 1) & 1) ^ 1, cx, 3);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t d_main = tmem_base + buf * 128, d_cross = d_main + 64;
+        uint32_t acc_main = 0, acc_cross = 0;
+        for (int r = 0; r < kbc; ++r, ++it) {
+          const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait<false>(sh.bars + BAR_FULL + 8 * s, ph, cx, 4);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            if (active) {
+              const uint32_t a_hi = sh.base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
+              const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+              const int kvalid = min(BK, L.seg_k[seg] - kb * BK);
+              const int ksteps = (kvalid + 7) >> 3;
+              const bool exact = L.seg_exact[seg] != 0;
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t dah = make_desc(a_hi + ks * 32), dbh = make_desc(b_hi + ks * 32);
+                const uint64_t dbl = make_desc(b_lo + ks * 32);
+                // the small cross terms accumulate apart from the main sum
+                if (!exact) {
+                  mma_tf32(d_cross, make_desc(a_lo + ks * 32), dbh, idesc, acc_cross);
+                  acc_cross = 1;
+                }
+                mma_tf32(d_cross, dah, dbl, idesc, acc_cross);
+                acc_cross = 1;
+                mma_tf32(d_main, dah, dbh, idesc, acc_main);
+                acc_main = 1;
+              }
+            }
+            // this stage may be refilled once every CTA of the cluster has read it
+            umma_commit_mc(sh.bars + BAR_EMPTY + 8 * s, (uint16_t)0xFF);
+            if (active && r == kbc - 1) umma_commit(sh.bars + BAR_ACCF + 8 * buf);
+          }
+          __syncwarp();
+        }
+        if (active) ++ac;
+      }
+    }
+  }
+}
+
+struct EpiState {
+  uint32_t ac;        // accumulator buffers consumed
+  uint32_t xc;        // cross-CTA row reductions done
+};
+
+// main + cross accumulator columns [cc*32, cc*32+32) of buffer `buf`, this thread's row
+__device__ __forceinline__ void acc_load32(uint32_t tmem_base, uint32_t buf, int quad, int cc,
+                                           float (&v)[32]) {
+  uint32_t a[32], b[32];
+  const uint32_t t = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + cc * 32;
+  tmem_ld32_nowait(t, a);
+  tmem_ld32_nowait(t + 64, b);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
+}
+
+// publish this thread's pair of row partials to every CTA of the cluster, then collect all 8
+__device__ __forceinline__ void row_exchange(const Shared& sh, EpiState& es, int rank, int trow,
+                                             int lane, float a, float b, float2 (&parts)[CL],
+                                             const Ctx& cx) {
+  const uint32_t par = es.xc & 1;
+  const uint32_t slot = sh.base + OFF_STATS + ((par * CL + rank) * BM + trow) * 8;
+#pragma unroll
+  for (int d = 0; d < CL; ++d) {
+    const uint32_t ra = mapa(slot, d);
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(ra), "f"(a), "f"(b) : "memory");
+  }
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < CL; ++d) mbar_arrive_remote(sh.bars + BAR_STATS, d);
+  }
+  mbar_wait<true>(sh.bars + BAR_STATS, par, cx, 5);
+  const float2* mine = reinterpret_cast<const float2*>(sh.smem + OFF_STATS) + par * CL * BM + trow;
+#pragma unroll
+  for (int d = 0; d < CL; ++d) parts[d] = mine[d * BM];
+  ++es.xc;
+}
+
+__device__ __forceinline__ void acc_wait(const Shared& sh, const EpiState& es, const Ctx& cx) {
+  mbar_wait<false>(sh.bars + BAR_ACCF + 8 * (es.ac & 1), (es.ac >> 1) & 1, cx, 6);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void acc_release(const Shared& sh, EpiState& es, int lane) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) mbar_arrive(sh.bars + BAR_ACCE + 8 * (es.ac & 1));
+  ++es.ac;
+}
+
+// accumulator (+ addend + bias) of one 32-column sub-tile
+__device__ __forceinline__ void fetch_sub(const LmLayer& L, uint32_t tmem_base, uint32_t buf, int quad,
+                                          int half, float* stg, int wrow0, int rows_valid, int cb,
+                                          int cols_valid, int lane, float (&v)[32]) {
+  acc_load32(tmem_base, buf, quad, half, v);
+  if (L.add != nullptr) {
+    float a[32];
+    sub_load(stg, a, L.add + (size_t)wrow0 * L.ld_add + cb, L.ld_add, rows_valid, cols_valid, lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += a[j];
+  }
+  if (L.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < cols_valid) v[j] += L.bias[cb + j];
+  }
+}
+
+__device__ __forceinline__ void store_with_lo(const LmLayer& L, float* stg, float (&v)[32], int wrow0,
+                                              int rows_valid, int cb, int cols_valid, int lane) {
+  sub_store(stg, v, L.out + (size_t)wrow0 * L.ld_out + cb, L.ld_out, rows_valid, cols_valid, lane);
+  if (L.out_lo != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = lo_of(v[j]);
+    sub_store(stg, v, L.out_lo + (size_t)wrow0 * L.ld_out + cb, L.ld_out, rows_valid, cols_valid, lane);
+  }
+}
+
+// E_PLAIN: out = acc (+ add) (+ bias)
+__device__ void epi_plain(const Shared& sh, const LmLayer& L, EpiState& es, uint32_t tmem_base,
+                          int rank, int quad, int lane, float* stg, int wrow0, int rows_valid,
+                          const Ctx& cx) {
+  const int halves = L.bn >> 5;
+  for (int c = 0; c < L.nchunk; ++c) {
+    acc_wait(sh, es, cx);
+    const int col0 = c * L.chunk_stride + rank * L.bn;
+    for (int h = 0; h < halves; ++h) {
+      const int cb = col0 + h * 32;
+      const int cols_valid = min(32, L.N - cb);
+      float v[32];
+      fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, cols_valid, lane, v);
+      if (cols_valid > 0) store_with_lo(L, stg, v, wrow0, rows_valid, cb, cols_valid, lane);
+    }
+    acc_release(sh, es, lane);
+  }
+}
+
+// E_LN: z = acc (+add)(+bias); out = act(LayerNorm(z) * gamma + beta)   (A/nets.py:585-602)
+__device__ void epi_ln_fwd(const Shared& sh, const LmLayer& L, EpiState& es, uint32_t tmem_base,
+                           int rank, int quad, int lane, float* stg, int wrow0, int rows_valid,
+                           int trow, const Ctx& cx) {
+  const int halves = L.bn >> 5;
+  const bool single = L.nchunk == 1 && halves <= 2;
+  float keep[64];
+  float mean = 0.f, m2 = 0.f, cnt = 0.f;
+  for (int c = 0; c < L.nchunk; ++c) {
+    acc_wait(sh, es, cx);
+    const int col0 = c * L.chunk_stride + rank * L.bn;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h < halves) {
+        const int cb = col0 + h * 32;
+        float v[32];
+        fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, 32, lane, v);
+        if (L.z != nullptr)
+          sub_store(stg, v, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s += v[j];
+        const float mu = s * (1.f / 32.f);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { const float d = v[j] - mu; q += d * d; }
+        const float delta = mu - mean, tot = cnt + 32.f;
+        mean += delta * (32.f / tot);
+        m2 += q + delta * delta * (cnt * 32.f / tot);
+        cnt = tot;
+        if (single) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) keep[h * 32 + j] = v[j];
+        }
+      }
+    }
+    acc_release(sh, es, lane);
+  }
+  float2 parts[CL];
+  row_exchange(sh, es, rank, trow, lane, mean, m2, parts, cx);
+  float gm = 0.f;
+  for (int d = 0; d < L.nactive; ++d) gm += parts[d].x;
+  gm /= (float)L.nactive;
+  float gq = 0.f;
+  for (int d = 0; d < L.nactive; ++d) { const float dl = parts[d].x - gm; gq += parts[d].y + cnt * dl * dl; }
+  const float rstd = rsqrtf(gq / (float)L.N + DD_LN_EPS);
+  if (L.st != nullptr && rank == 0 && lane < rows_valid) {
+    L.st[(size_t)(wrow0 + lane) * 2] = gm;
+    L.st[(size_t)(wrow0 + lane) * 2 + 1] = rstd;
+  }
+  for (int c = 0; c < L.nchunk; ++c) {
+    const int col0 = c * L.chunk_stride + rank * L.bn;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h < halves) {
+        const int cb = col0 + h * 32;
+        float v[32];
+        if (single) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = keep[h * 32 + j];
+        } else {
+          sub_load(stg, v, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float y = (v[j] - gm) * rstd * L.gamma[cb + j] + L.beta[cb + j];
+          v[j] = L.act ? elu_f(y) : y;
+        }
+        store_with_lo(L, stg, v, wrow0, rows_valid, cb, 32, lane);
+      }
+    }
+  }
+}
+
+// E_LNBWD: dh = acc (+add); dz = LayerNorm'(act'(.) dh) given the saved pre-norm z and (mean, rstd)
+// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy  (optional)
+__device__ void epi_ln_bwd(const Shared& sh, const LmLayer& L, EpiState& es, uint32_t tmem_base,
+                           int rank, int quad, int lane, float* stg, int wrow0, int rows_valid,
+                           int trow, const Ctx& cx) {
+  const int halves = L.bn >> 5;
+  const bool single = L.nchunk == 1 && halves <= 2;
+  const bool rowok = lane < rows_valid;
+  float mean = 0.f, rstd = 0.f;
+  if (rowok) {
+    mean = L.st[(size_t)(wrow0 + lane) * 2];
+    rstd = L.st[(size_t)(wrow0 + lane) * 2 + 1];
+  }
+  float keep[64];
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = 0; c < L.nchunk; ++c) {
+    acc_wait(sh, es, cx);
+    const int col0 = c * L.chunk_stride + rank * L.bn;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h < halves) {
+        const int cb = col0 + h * 32;
+        float v[32], z[32];
+        fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, 32, lane, v);
+        sub_load(stg, z, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
+        float dyv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float g = L.gamma[cb + j];
+          const float xh = (z[j] - mean) * rstd;
+          float dy = rowok ? v[j] : 0.f;
+          if (L.act) {
+            const float y = xh * g + L.beta[cb + j];
+            dy = y > 0.f ? dy : dy * expf(y);
+          }
+          const float dx = dy * g;
+          s1 += dx;
+          s2 += dx * xh;
+          v[j] = dx;
+          z[j] = dy * xh;
+          dyv[j] = dy;
+        }
+        if (L.dgamma != nullptr) {       // column sums over the warp's rows, one atomic per column
+          warp_colsum32(z, lane);
+          warp_colsum32(dyv, lane);
+          atomicAdd(L.dgamma + cb + lane, z[0]);
+          atomicAdd(L.dbeta + cb + lane, dyv[0]);
+        }
+        if (single) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) keep[h * 32 + j] = v[j];
+        } else {
+          sub_store(stg, v, L.out + (size_t)wrow0 * L.ld_out + cb, L.ld_out, rows_valid, 32, lane);
+        }
+      }
+    }
+    acc_release(sh, es, lane);
+  }
+  float2 parts[CL];
+  row_exchange(sh, es, rank, trow, lane, s1, s2, parts, cx);
+  float t1 = 0.f, t2 = 0.f;
+  for (int d = 0; d < L.nactive; ++d) { t1 += parts[d].x; t2 += parts[d].y; }
+  t1 /= (float)L.N;
+  t2 /= (float)L.N;
+  for (int c = 0; c < L.nchunk; ++c) {
+    const int col0 = c * L.chunk_stride + rank * L.bn;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h < halves) {
+        const int cb = col0 + h * 32;
+        float v[32], z[32];
+        if (single) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = keep[h * 32 + j];
+        } else {
+          sub_load(stg, v, L.out + (size_t)wrow0 * L.ld_out + cb, L.ld_out, rows_valid, 32, lane);
+        }
+        sub_load(stg, z, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float xh = (z[j] - mean) * rstd;
+          v[j] = rstd * (v[j] - t1 - xh * t2);
+        }
+        store_with_lo(L, stg, v, wrow0, rows_valid, cb, 32, lane);
+      }
+    }
+  }
+}
+
+__device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
+                         int cluster_id, int nclusters, int warp, int lane, uint32_t tmem_base,
+                         Ctx cx) {
+  const int ntiles = (M + BM - 1) / BM;
+  const int quad = warp & 3;                      // TMEM lane quadrant this warp may read
+  float* stg = reinterpret_cast<float*>(sh.smem + OFF_STG + (warp - 2) * STG_WARP_BYTES);
+  EpiState es = {0u, 0u};
+  int pair = 0;
+  for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+    const int wrow0 = tile * BM + quad * 32;      // first global row of this warp
+    const int rows_valid = max(0, min(32, M - wrow0));
+    const int trow = quad * 32 + lane;
+    for (int l = 0; l < nlayers; ++l, ++pair) {
+      const LmLayer& L = layers[l];
+      cx.pair = pair;
+      const bool active = rank < L.nactive;
+      if (L.epi == DD_EPI_PLAIN) {
+        if (active) epi_plain(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, cx);
+      } else if (L.epi == DD_EPI_LN) {
+        if (active) epi_ln_fwd(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, trow, cx);
+      } else {
+        if (active) epi_ln_bwd(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, trow, cx);
+      }
+      // my rows of this layer's outputs are written: tell every CTA's producer.  The barrier
+      // counts 32 arrivals per (tile, layer) pair; a CTA running ahead (a first layer does not wait
+      // for `ready`) must not add its arrivals to the phase of a pair a slower CTA has not finished.
+      if (pair > 0) mbar_wait<true>(sh.bars + BAR_READY, (uint32_t)(pair - 1) & 1, cx, 7);
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < CL; ++d) mbar_arrive_remote(sh.bars + BAR_READY, d);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg) {
+  extern __shared__ __align__(1024) char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_rank();
+  const int cluster_id = blockIdx.x / CL, nclusters = gridDim.x / CL;
+  Shared sh;
+  sh.smem = smem;
+  sh.base = smem_u32(smem);
+  sh.bars = sh.base + OFF_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + BAR_TMEM);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(sh.bars + BAR_FULL + 8 * s, 1);
+      mbar_init(sh.bars + BAR_EMPTY + 8 * s, CL);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sh.bars + BAR_ACCF + 8 * b, 1);
+      mbar_init(sh.bars + BAR_ACCE + 8 * b, 4);
+    }
+    mbar_init(sh.bars + BAR_STATS, CL * 4);
+    mbar_init(sh.bars + BAR_READY, CL * 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                // every CTA's barriers exist before anyone multicasts
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  Ctx cx = {dbg, 0};
+  if ((sh.base & 1023u) != 0u) stuck(cx, 9, sh.base);      // SWIZZLE_128B tiles need 1 KB alignment
+
+  if (warp == 0) {
+    producer(sh, layers, nlayers, M, rank, cluster_id, nclusters, lane, cx);
+  } else if (warp == 1) {
+    mma_issuer(sh, layers, nlayers, M, rank, cluster_id, nclusters, lane, tmem_base, cx);
+  } else {
+    epilogue(sh, layers, nlayers, M, rank, cluster_id, nclusters, warp, lane, tmem_base, cx);
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();                // nobody exits while a peer may still write into it
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ---- operand preparation ------------------------------------------------------------------
+__global__ void split_lo_kernel(const float* __restrict__ x, int ldx, float* __restrict__ lo,
+                                int ldlo, int rows, int cols) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    lo[(size_t)r * ldlo + c] = lo_of(x[(size_t)r * ldx + c]);
+  }
+}
+
+struct TrJobs {
+  int n;
+  int src[DD_MAX_TRANSPOSE_JOBS], rows[DD_MAX_TRANSPOSE_JOBS], cols[DD_MAX_TRANSPOSE_JOBS];
+  int dst[DD_MAX_TRANSPOSE_JOBS], ldd[DD_MAX_TRANSPOSE_JOBS], mode[DD_MAX_TRANSPOSE_JOBS];
+  int tile0[DD_MAX_TRANSPOSE_JOBS + 1];
+};
+
+// per job, for the row-major [rows, cols] matrix at p + src:
+//   mode 0 (transpose): pt[dst + c*ldd + r] = p[src + r*cols + c]
+//   mode 1 (copy):      pt[dst + r*ldd + c] = p[src + r*cols + c]     (re-strided copy)
+// and the tf32 remainder of the same element into pt_lo; 32 x 32 tiles
+__global__ void transpose_lo_kernel(const float* __restrict__ p, float* __restrict__ pt,
+                                    float* __restrict__ pt_lo, TrJobs jobs) {
+  __shared__ float t[32][33];
+  int j = 0;
+  while (j + 1 < jobs.n && (int)blockIdx.x >= jobs.tile0[j + 1]) ++j;
+  const int rows = jobs.rows[j], cols = jobs.cols[j], ldd = jobs.ldd[j];
+  const int tiles_c = (cols + 31) / 32;
+  const int tl = (int)blockIdx.x - jobs.tile0[j];
+  const int r0 = (tl / tiles_c) * 32, c0 = (tl % tiles_c) * 32;
+  const float* src = p + jobs.src[j];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+  if (jobs.mode[j] == 1) {
+    for (int i = ty; i < 32; i += 8) {
+      const int r = r0 + i, c = c0 + tx;
+      if (r < rows && c < cols) {
+        const float x = src[(size_t)r * cols + c];
+        pt[(size_t)jobs.dst[j] + (size_t)r * ldd + c] = x;
+        pt_lo[(size_t)jobs.dst[j] + (size_t)r * ldd + c] = lo_of(x);
+      }
+    }
+    return;
+  }
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    t[i][tx] = (r < rows && c < cols) ? src[(size_t)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) {
+      const float x = t[tx][i];
+      pt[(size_t)jobs.dst[j] + (size_t)c * ldd + r] = x;
+      pt_lo[(size_t)jobs.dst[j] + (size_t)c * ldd + r] = lo_of(x);
+    }
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols], row stride ld floats, box {32 cols, box_rows}, SWIZZLE_128B,
+// out-of-bounds elements read as zero
+static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld,
+                    int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail("dd_program_build", "cuTensorMapEncodeTiled unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 3))
+    return fail("dd_program_build", "operand base / row stride must be 16-byte aligned");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[64];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return fail("dd_program_build", msg);
+  }
+  return 0;
+}
+
+static unsigned* g_dbg_host = nullptr;
+static unsigned* g_dbg_dev = nullptr;
+
+}  // namespace lm
+}  // namespace dd
+
+using namespace dd;
+
+extern "C" size_t dd_program_bytes(int nlayers) { return sizeof(lm::LmLayer) * (size_t)nlayers; }
+
+extern "C" int dd_program_build(const DdLayer* layers, int nlayers, int rows, void* table_dev) {
+  if (nlayers < 1 || rows < 1) return fail("dd_program_build", "empty program");
+  lm::LmLayer* host = static_cast<lm::LmLayer*>(calloc(nlayers, sizeof(lm::LmLayer)));
+  if (host == nullptr) return fail("dd_program_build", "out of host memory");
+  int rc = 0;
+  for (int i = 0; i < nlayers && rc == 0; ++i) {
+    const DdLayer& s = layers[i];
+    lm::LmLayer& d = host[i];
+    if (s.nseg < 1 || s.nseg > 2) { rc = fail("dd_program_build", "1 or 2 A segments"); break; }
+    // column tiling across the 8 CTAs
+    if (s.N % (lm::CL * 64) == 0) {
+      d.bn = 64; d.nchunk = s.N / (lm::CL * 64); d.nactive = lm::CL;
+    } else if (s.N % (lm::CL * 32) == 0) {
+      d.bn = 32; d.nchunk = s.N / (lm::CL * 32); d.nactive = lm::CL;
+    } else if (s.N <= 64 && s.epi == DD_EPI_PLAIN) {
+      d.bn = s.N <= 32 ? 32 : 64; d.nchunk = 1; d.nactive = 1;
+    } else {
+      rc = fail("dd_program_build", "N must be a multiple of 256 (or <= 64 for plain layers)");
+      break;
+    }
+    d.N = s.N;
+    d.chunk_stride = d.nactive == 1 ? 0 : s.N / d.nchunk;
+    d.nseg = s.nseg;
+    for (int g = 0; g < s.nseg && rc == 0; ++g) {
+      const DdSeg& sg = s.seg[g];
+      if (sg.k < 1) { rc = fail("dd_program_build", "empty segment"); break; }
+      d.seg_k[g] = sg.k;
+      d.seg_wk0[g] = sg.wk0;
+      d.seg_exact[g] = sg.a_lo == nullptr ? 1 : 0;
+      rc = lm::make_map(&d.a_hi[g], sg.a, rows, sg.k, sg.lda, lm::SLICE_ROWS);
+      if (rc == 0 && sg.a_lo != nullptr)
+        rc = lm::make_map(&d.a_lo[g], sg.a_lo, rows, sg.k, sg.lda, lm::SLICE_ROWS);
+    }
+    if (rc != 0) break;
+    if (s.w == nullptr || s.w_lo == nullptr) { rc = fail("dd_program_build", "B operand needs (w, w_lo)"); break; }
+    rc = lm::make_map(&d.w_hi, s.w, s.wrows, s.wcols, s.ldw, d.bn);
+    if (rc == 0) rc = lm::make_map(&d.w_lo, s.w_lo, s.wrows, s.wcols, s.ldw, d.bn);
+    if (rc != 0) break;
+    d.wn0 = s.wn0;
+    d.epi = s.epi;
+    d.act = s.act;
+    d.ld_add = s.ld_add; d.ld_out = s.ld_out; d.ld_z = s.ld_z;
+    d.add = s.add; d.bias = s.bias; d.gamma = s.gamma; d.beta = s.beta;
+    d.z = s.z; d.st = s.st; d.out = s.out; d.out_lo = s.out_lo;
+    d.dgamma = s.dgamma; d.dbeta = s.dbeta;
+    if (s.out == nullptr) { rc = fail("dd_program_build", "layer without output"); break; }
+    if (s.epi == DD_EPI_LN && (s.gamma == nullptr || s.beta == nullptr))
+      rc = fail("dd_program_build", "LayerNorm layer without scale / bias");
+    if (s.epi == DD_EPI_LN && s.z == nullptr && !(d.nchunk == 1))
+      rc = fail("dd_program_build", "multi-chunk LayerNorm needs the pre-norm buffer z");
+    if (s.epi == DD_EPI_LNBWD && (s.gamma == nullptr || s.beta == nullptr || s.z == nullptr || s.st == nullptr))
+      rc = fail("dd_program_build", "LayerNorm backward needs scale, bias, z and stats");
+    if ((s.dgamma == nullptr) != (s.dbeta == nullptr))
+      rc = fail("dd_program_build", "dgamma and dbeta come together");
+  }
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpy(table_dev, host, sizeof(lm::LmLayer) * (size_t)nlayers, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = fail("dd_program_build", cudaGetErrorString(e));
+  }
+  free(host);
+  if (rc == 0 && lm::g_dbg_host == nullptr) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&lm::g_dbg_host), 64, cudaHostAllocMapped) == cudaSuccess) {
+      memset(lm::g_dbg_host, 0, 64);
+      cudaHostGetDevicePointer(reinterpret_cast<void**>(&lm::g_dbg_dev), lm::g_dbg_host, 0);
+    }
+  }
+  return rc;
+}
+
+extern "C" int dd_program_run(const void* table_dev, int nlayers, int rows, dd_stream_t stream) {
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    cudaFuncSetAttribute(lm::lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lm::SMEM_BYTES);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(lm::CL * 16);
+    cfg.blockDim = dim3(lm::THREADS);
+    cfg.dynamicSmemBytes = lm::SMEM_BYTES;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, lm::lm_kernel, &cfg) != cudaSuccess || n < 1) {
+      cudaGetLastError();
+      n = 8;
+    }
+    max_clusters = n;
+  }
+  const int ntiles = (rows + lm::BM - 1) / lm::BM;
+  const int nclusters = ntiles < max_clusters ? ntiles : max_clusters;
+  lm::lm_kernel<<<dim3(lm::CL * nclusters), dim3(lm::THREADS), lm::SMEM_BYTES, S(stream)>>>(
+      static_cast<const lm::LmLayer*>(table_dev), nlayers, rows, lm::g_dbg_dev);
+  return launched("dd_program_run");
+}
+
+extern "C" int dd_program_debug(unsigned* out8) {
+  if (lm::g_dbg_host == nullptr) return 0;
+  for (int i = 0; i < 8; ++i) out8[i] = lm::g_dbg_host[i];
+  return lm::g_dbg_host[0] == 0xDEADBEEFu ? 1 : 0;
+}
+
+extern "C" int dd_split_lo(const float* x, int ldx, float* lo, int ldlo, int rows, int cols,
+                           dd_stream_t stream) {
+  if (rows < 1 || cols < 1) return 0;
+  lm::split_lo_kernel<<<grid_for((int64_t)rows * cols, 256), 256, 0, S(stream)>>>(x, ldx, lo, ldlo, rows, cols);
+  return launched("dd_split_lo");
+}
+
+extern "C" int dd_transpose_lo(const float* p, float* pt, float* pt_lo, int njobs, const int* src,
+                               const int* rows, const int* cols, const int* dst, const int* ldd,
+                               const int* mode, dd_stream_t stream) {
+  if (njobs < 1) return 0;
+  if (njobs > DD_MAX_TRANSPOSE_JOBS) return fail("dd_transpose_lo", "too many matrices in one call");
+  lm::TrJobs jobs;
+  jobs.n = njobs;
+  int tiles = 0;
+  for (int j = 0; j < njobs; ++j) {
+    jobs.src[j] = src[j]; jobs.rows[j] = rows[j]; jobs.cols[j] = cols[j]; jobs.dst[j] = dst[j];
+    jobs.ldd[j] = ldd[j]; jobs.mode[j] = mode[j];
+    jobs.tile0[j] = tiles;
+    tiles += ((rows[j] + 31) / 32) * ((cols[j] + 31) / 32);
+  }
+  jobs.tile0[njobs] = tiles;
+  lm::transpose_lo_kernel<<<tiles, 256, 0, S(stream)>>>(p, pt, pt_lo, jobs);
+  return launched("dd_transpose_lo");
+}

@@ -19,6 +19,7 @@
 #ifndef DD_KERNELS_H_
 #define DD_KERNELS_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -287,6 +288,71 @@ int dd_fill_gumbel(float* buf, int64_t n, uint64_t seed, uint32_t stream_id,
                    const int64_t* counters, int ci, dd_stream_t stream);
 int dd_fill_normal(float* buf, int64_t n, uint64_t seed, uint32_t stream_id,
                    const int64_t* counters, int ci, dd_stream_t stream);
+
+/* ---- layer machine: chains of GEMM + full-row epilogue layers in one persistent kernel ----
+ * (csrc/dd_machine.cu).  One thread-block cluster (8 CTAs) owns a 128-row tile and runs every
+ * layer of the program on it: TMA-fed tcgen05 3xTF32 tiles, LayerNorm row reductions over
+ * distributed shared memory, cluster-local synchronisation between layers.  Replaces the
+ * Linear -> LayerNorm -> elu stacks of A/nets.py:408-416, :566-602 (forward) and their reverse
+ * chains.  Every GEMM operand is a pair (x, x_lo): x_lo = tf32(x - top19bits(x)), produced by
+ * the layer that wrote x (out_lo), by dd_split_lo, or by dd_transpose_lo for weights.
+ *   layer:  acc[M,N] = sum_seg  A_seg[M,k] . B[wn0 : wn0+N, wk0_seg : wk0_seg+k]^T
+ *           B is a row-major [wrows, wcols] matrix (row stride ldw): the TRANSPOSED kernel for a
+ *           forward Linear (x @ W), the kernel itself for an input gradient (dY @ W^T)
+ *   DD_EPI_PLAIN   out = acc (+ add) (+ bias)
+ *   DD_EPI_LN      z = acc (+ add) (+ bias); (mean, rstd) -> st; out = act(LN(z) * gamma + beta)
+ *   DD_EPI_LNBWD   dh = acc (+ add); out = dz of  h = act(LN(z) * gamma + beta)  given the saved
+ *                  z and st; dgamma / dbeta (+=) optional
+ * a_lo == NULL marks an operand that is exact in tf32 (one-hot latents): its lo terms are skipped. */
+#define DD_EPI_PLAIN 0
+#define DD_EPI_LN 1
+#define DD_EPI_LNBWD 2
+#define DD_MAX_TRANSPOSE_JOBS 64
+typedef struct DdSeg {
+  const float* a;
+  const float* a_lo;
+  int lda, k, wk0;
+} DdSeg;
+typedef struct DdLayer {
+  int nseg;
+  DdSeg seg[2];
+  const float* w;
+  const float* w_lo;
+  int ldw, wrows, wcols, wn0;
+  int N, epi, act;
+  const float* add;
+  int ld_add;
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  float* z;
+  int ld_z;
+  float* st;
+  float* out;
+  float* out_lo;
+  int ld_out;
+  float* dgamma;
+  float* dbeta;
+} DdLayer;
+/* bytes of device memory a compiled program of `nlayers` layers occupies */
+size_t dd_program_bytes(int nlayers);
+/* encodes the TMA descriptors and copies the program into table_dev (synchronous; call once,
+ * outside stream capture).  rows = M of every layer. */
+int dd_program_build(const DdLayer* layers, int nlayers, int rows, void* table_dev);
+int dd_program_run(const void* table_dev, int nlayers, int rows, dd_stream_t stream);
+/* after a failed run: 1 and the 8 diagnostic words of the stuck wait, else 0 */
+int dd_program_debug(unsigned* out8);
+/* lo[r, c] = tf32(x - top19bits(x)) for a row-strided matrix */
+int dd_split_lo(const float* x, int ldx, float* lo, int ldlo, int rows, int cols,
+                dd_stream_t stream);
+/* for each job j over the row-major [rows_j, cols_j] matrix at p + src_j:
+ *   mode 0: pt[dst_j + c*ldd_j + r] = p[src_j + r*cols_j + c]   (transposed copy, row stride ldd_j)
+ *   mode 1: pt[dst_j + r*ldd_j + c] = p[src_j + r*cols_j + c]   (re-strided copy)
+ * and the tf32 remainder of each element into pt_lo at the same index.  This is how the
+ * optimizer's flat parameter buffer becomes the (w, w_lo) B operands of dd_program_build. */
+int dd_transpose_lo(const float* p, float* pt, float* pt_lo, int njobs, const int* src,
+                    const int* rows, const int* cols, const int* dst, const int* ldd,
+                    const int* mode, dd_stream_t stream);
 
 #ifdef __cplusplus
 }

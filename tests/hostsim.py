@@ -90,6 +90,59 @@ class HostSim:
     dp = dOut * (1.0 - u)
     dPrev.copy_(dPrev + dp if acc else dp)
 
+  # -- layer machine (csrc/dd_machine.cu) --------------------------------------
+  def program_build(self, layers, rows):
+    return (list(layers), int(rows))
+
+  def program_run(self, h):
+    """Each layer: acc = sum_seg A_seg @ B[wn0:wn0+N, wk0:wk0+k].T with every operand
+    reconstructed from its (x, x_lo) pair exactly as the tensor core sees it, so a stale or
+    missing x_lo shows up as a numerical error in the CPU tests."""
+    from daydreamer_b200 import program as P
+    layers, rows = h
+    for L in layers:
+      acc = torch.zeros(rows, L.N, dtype=torch.float64)
+      for sg in L.segs:
+        k = sg.a.shape[1]
+        a = P.trunc19(sg.a).double() + (0.0 if sg.a_lo is None else sg.a_lo.double())
+        if sg.a_lo is None:
+          assert torch.equal(P.trunc19(sg.a), sg.a.contiguous()), 'operand declared exact is not'
+        wsl = (slice(L.wn0, L.wn0 + L.N), slice(sg.wk0, sg.wk0 + k))
+        b = P.trunc19(L.w[wsl]).double() + L.w_lo[wsl].double()
+        acc += a @ b.t()
+      acc = acc.float()
+      if L.add is not None:
+        acc = acc + L.add
+      if L.bias is not None:
+        acc = acc + L.bias
+      if L.epi == P.EPI_PLAIN:
+        out = acc
+      elif L.epi == P.EPI_LN:
+        if L.z is not None:
+          L.z.copy_(acc)
+        st = L.st if L.st is not None else torch.zeros(rows, 2)
+        out = torch.zeros(rows, L.N)
+        self.ln_fwd(acc, L.gamma, L.beta, out, st, L.act)
+      else:
+        out = torch.zeros(rows, L.N)
+        self.ln_bwd(acc, L.z, L.st, L.gamma, L.beta, out, L.dgamma, L.dbeta, L.act)
+      L.out.copy_(out)
+      if L.out_lo is not None:
+        L.out_lo.copy_(P.lo_of(out))
+
+  def split_lo(self, x, lo):
+    from daydreamer_b200 import program as P
+    lo.copy_(P.lo_of(x))
+
+  def transpose_lo(self, p, pt, pt_lo, jobs):
+    from daydreamer_b200 import program as P
+    for src, rows, cols, dst, ldd, mode in jobs:
+      m = p[src:src + rows * cols].view(rows, cols)
+      t = (m if mode == 1 else m.t()).contiguous()
+      r, c = t.shape
+      for buf, val in ((pt, t), (pt_lo, P.lo_of(t))):
+        buf[dst:dst + (r - 1) * ldd + c].as_strided((r, c), (ldd, 1)).copy_(val)
+
   # -- categorical latent ---------------------------------------------------
   def stats_fwd(self, Z, G, logit, stoch, idx, S, C, mix, mode):
     """mode 0: idx = argmax(logit + G); 1: idx = argmax(logit); 2: no draw."""
