@@ -188,6 +188,7 @@ class Agent:
     self.be = _backend_for_tests if _backend_for_tests is not None else CudaBackend()  # raises without GPU / .so
     self._on_gpu = self.be.device.type == 'cuda'
     self.seed = int(_get(config, 'seed')) if seed is None else int(seed)
+    self._rng = np.random.default_rng(self.seed)      # exploration / action noise draws
     self.world, self.rank, self._allreduce = 1, 0, None
     if torch.distributed.is_available() and torch.distributed.is_initialized():
       self.world = torch.distributed.get_world_size()
@@ -276,7 +277,9 @@ class Agent:
       eng.first0.fill_(1.0)
     else:
       eng.first0.copy_(torch.from_numpy(first[:, 0, 0].copy()), non_blocking=True)
-      if state['deter'].data_ptr() != eng.prev_deter.data_ptr():
+      # the returned state is a snapshot; skip the copy back only when the engine's buffers still
+      # hold exactly that snapshot (no other train() call on this engine since)
+      if state.get('_version') != (id(eng), getattr(eng, '_state_version', -1)):
         eng.prev_deter.copy_(torch.as_tensor(state['deter']).to(self.be.device))
         eng.prev_stoch.copy_(torch.as_tensor(state['stoch']).to(self.be.device).reshape(B, -1))
 
@@ -386,7 +389,9 @@ class Agent:
     outs = {}
     if 'key' in data:                    # prioritized replay hook (A/agent.py:90-92)
       outs = {'key': data['key'], 'priority': self._criterion(eng, data)}
-    state = {'deter': eng.prev_deter, 'stoch': eng.prev_stoch}
+    eng._state_version = getattr(eng, '_state_version', 0) + 1
+    state = {'deter': eng.prev_deter.clone(), 'stoch': eng.prev_stoch.clone(),
+             '_version': (id(eng), eng._state_version)}
     return outs, state, metrics
 
   def _criterion(self, eng, data):
@@ -461,10 +466,11 @@ class Agent:
       first = np.ones(P, np.float32)
       pol.prev_action.zero_()
     else:
+      # the caller's state is its own copy (two drivers with the same number of environments
+      # share this PolicyEngine but not their recurrent state): always load it
       pol.prev_action.copy_(torch.from_numpy(np.asarray(state['action'], np.float32)))
-      if state['deter'].data_ptr() != pol.prev_deter.data_ptr():
-        pol.prev_deter.copy_(state['deter'])
-        pol.prev_stoch.copy_(state['stoch'])
+      pol.prev_deter.copy_(state['deter'])
+      pol.prev_stoch.copy_(state['stoch'])
     pol.first.copy_(torch.from_numpy(first))
     self._run(pol, 'policy', pol.launch)
     noise = self.expl_noise
@@ -474,19 +480,19 @@ class Agent:
     elif mode == 'explore' and self.expl_random:
       shape = (P,) + tuple(self.act_space.shape)
       if self.spec.discrete:
-        action = np.eye(shape[-1], dtype=np.float32)[np.random.randint(0, shape[-1], shape[:-1])]
+        action = np.eye(shape[-1], dtype=np.float32)[self._rng.integers(0, shape[-1], shape[:-1])]
       else:
-        action = np.random.uniform(-1, 1, shape).astype(np.float32)
+        action = self._rng.uniform(-1, 1, shape).astype(np.float32)
     else:
       action = pol.action.cpu().numpy().copy()
     if noise and self.spec.discrete:                              # A/tfutils.py:85-93
       probs = noise / action.shape[-1] + (1 - noise) * action
-      draw = (probs.cumsum(-1) > np.random.uniform(size=action.shape[:-1] + (1,))).argmax(-1)
+      draw = (probs.cumsum(-1) > self._rng.uniform(size=action.shape[:-1] + (1,))).argmax(-1)
       action = np.eye(action.shape[-1], dtype=np.float32)[draw]
     elif noise:
-      action = np.clip(action + noise * np.random.standard_normal(action.shape), -1, 1)
+      action = np.clip(action + noise * self._rng.standard_normal(action.shape), -1, 1)
     action = action.astype(np.float32).reshape((P,) + tuple(self.act_space.shape))
-    state = {'deter': pol.prev_deter, 'stoch': pol.prev_stoch, 'action': action}
+    state = {'deter': pol.prev_deter.clone(), 'stoch': pol.prev_stoch.clone(), 'action': action}
     return {'action': action}, state
 
   # -- checkpointing (embodied/core/checkpoint.py:20-24,41-60) ----------------

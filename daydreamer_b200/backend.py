@@ -81,6 +81,8 @@ SIGNATURES = {
     'dd_fill_gumbel': [_P, _L, _U64, _U32, _P, _I, _P],
     'dd_fill_normal': [_P, _L, _U64, _U32, _P, _I, _P],
     'dd_program_run': [_P, _I, _I, _P],
+    'dd_set_machine_debug': [_I],
+    'dd_machine_prof': [_I, _P, _I],
     'dd_split_lo': [_P, _I, _P, _I, _I, _I, _P],
     'dd_transpose_lo': [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
 }
@@ -564,7 +566,7 @@ class CudaBackend:
     for i, L in enumerate(layers):
       d = arr[i]
       d.nseg = len(L.segs)
-      assert 1 <= d.nseg <= 2
+      assert 0 <= d.nseg <= 2
       for g, sg in enumerate(L.segs):
         pa, r, k, lda = _mat(sg.a)
         assert r == rows, (sg.a.shape, rows)
@@ -573,10 +575,11 @@ class CudaBackend:
           pl, _, _, ldl = _mat(sg.a_lo)
           assert ldl == lda and sg.a_lo.shape == sg.a.shape
           d.seg[g].a_lo = pl
-      pw, wrows, wcols, ldw = _mat(L.w)
-      pwl, _, _, ldwl = _mat(L.w_lo)
-      assert ldwl == ldw and L.w_lo.shape == L.w.shape
-      d.w, d.w_lo, d.ldw, d.wrows, d.wcols, d.wn0 = pw, pwl, ldw, wrows, wcols, int(L.wn0)
+      if L.segs:
+        pw, wrows, wcols, ldw = _mat(L.w)
+        pwl, _, _, ldwl = _mat(L.w_lo)
+        assert ldwl == ldw and L.w_lo.shape == L.w.shape
+        d.w, d.w_lo, d.ldw, d.wrows, d.wcols, d.wn0 = pw, pwl, ldw, wrows, wcols, int(L.wn0)
       d.N, d.epi, d.act = int(L.N), int(L.epi), int(L.act)
       if L.add is not None:
         d.add, _, _, d.ld_add = _mat(L.add)

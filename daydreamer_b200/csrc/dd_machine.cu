@@ -50,7 +50,9 @@ constexpr int OFF_STG = OFF_STATS + STATS_BYTES;           // per-warp 32 x 36 f
 constexpr int STG_LD = 36;
 constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;
 constexpr int OFF_BAR = OFF_STG + 4 * STG_WARP_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int OFF_EP = OFF_BAR + 128;                      // per-epilogue-warp copy of the layer's epilogue view
+constexpr int EP_BYTES = 160;
+constexpr int SMEM_BYTES = OFF_EP + 4 * EP_BYTES;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 256;        // 2 buffers x (main 64 | cross 64)
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -113,13 +115,31 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
 
+// `ready` is a monotonically increasing counter, not an mbarrier: a producer that skips the wait of
+// a first layer may be several layers away from the epilogues, which a one-bit phase cannot express
+// (ptxas turns every .release.cluster / .acquire.cluster into MEMBAR.ALL.GPU / CCTL.IVALL, so the
+// signal is ONE fence.acq_rel.cluster by one thread per CTA followed by relaxed remote adds)
+__device__ __forceinline__ void count_add_remote(uint32_t addr, uint32_t rank) {
+  const uint32_t ra = mapa(addr, rank);
+  asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(ra), "r"(1u) : "memory");
+}
+
 // Diagnostics of a stuck wait: a wait that does not complete within ~2 s writes what it was
 // waiting for into `dbg` (mapped host memory, survives the trap) and kills the kernel, so a
 // protocol bug shows up as an error with a location instead of a hung GPU box.
 struct Ctx {
   unsigned* dbg;
-  int pair;          // (tile, layer) pair index being processed
+  int pair;                    // (tile, layer) pair index being processed
+  unsigned long long* prof;    // optional: per-CTA wait-cycle totals by wait code (dd_set_machine_prof)
+  int flags;                   // profiling switches (dd_set_machine_debug), results are garbage
+  unsigned long long* trace;   // optional (CTA 0 only): clock64 at pipeline events, [role][event]
 };
+constexpr int TRACE_N = 2048;    // events per role
+__device__ __forceinline__ void trace_ev(const Ctx& cx, int role, uint32_t idx) {
+  if (cx.trace != nullptr && idx < (uint32_t)TRACE_N && (threadIdx.x & 31) == 0)
+    cx.trace[role * TRACE_N + idx] = (unsigned long long)clock64();
+}
+enum { F_NOMMA = 1, F_NOA = 2, F_LOCALA = 4, F_NOB = 8, F_TMFENCE = 16 };
 __device__ __noinline__ void stuck(const Ctx& cx, int code, uint32_t parity) {
   if (cx.dbg != nullptr) {
     cx.dbg[1] = (unsigned)code;
@@ -136,6 +156,7 @@ template <bool CLUSTER>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const Ctx& cx, int code) {
   uint32_t done = 0;
   unsigned long long t0 = 0;
+  const long long c0 = cx.prof != nullptr ? clock64() : 0;
   for (uint32_t spin = 0;; ++spin) {
     if (CLUSTER)
       asm volatile(
@@ -149,12 +170,38 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const C
           "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
           "selp.b32 %0, 1, 0, p;\n\t}"
           : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) return;
+    if (done) {
+      if (cx.prof != nullptr && (threadIdx.x & 31) == 0)
+        atomicAdd(cx.prof + code, (unsigned long long)(clock64() - c0));
+      return;
+    }
     if ((spin & 1023u) == 1023u) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t0 == 0) t0 = t;
       else if (t - t0 > 2000000000ull) stuck(cx, code, parity);
+    }
+  }
+}
+
+__device__ __forceinline__ void count_wait(uint32_t addr, uint32_t target, const Ctx& cx, int code) {
+  unsigned long long t0 = 0;
+  const long long c0 = cx.prof != nullptr ? clock64() : 0;
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t v;
+    asm volatile("ld.relaxed.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    if (v >= target) {
+      asm volatile("fence.acq_rel.cluster;" ::: "memory");
+      if (cx.prof != nullptr && (threadIdx.x & 31) == 0)
+        atomicAdd(cx.prof + code, (unsigned long long)(clock64() - c0));
+      return;
+    }
+    __nanosleep(32);
+    if ((spin & 1023u) == 1023u) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) stuck(cx, code, target);
     }
   }
 }
@@ -175,10 +222,14 @@ __device__ __forceinline__ void tma_load_mc(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tmap_acquire(const CUtensorMap* map) {
-  // the descriptor table is written by a host copy before the launch
-  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;"
-               ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+__device__ __forceinline__ void tmap_acquire(const CUtensorMap* map, bool fence) {
+  // The descriptor table is written once by a host copy that completes before any launch and
+  // its memory is never reused for other descriptors (dd_program_build owns it), so the
+  // descriptor cache cannot hold a stale copy; the explicit tensormap-proxy fence (several
+  // microseconds per descriptor) is kept only as a debugging switch.
+  if (fence)
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;"
+                 ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
@@ -308,6 +359,7 @@ struct Shared {
 };
 
 __device__ __forceinline__ int layer_kblocks(const LmLayer& L) {
+  if (L.nseg == 0) return 0;
   int kb = (L.seg_k[0] + BK - 1) / BK;
   if (L.nseg > 1) kb += (L.seg_k[1] + BK - 1) / BK;
   return kb;
@@ -324,15 +376,18 @@ __device__ void producer(const Shared& sh, const LmLayer* layers, int nlayers, i
       const LmLayer& L = layers[l];
       cx.pair = pair;
       if (lane == 0) {
+        const bool fence = (cx.flags & F_TMFENCE) != 0;
         for (int s = 0; s < L.nseg; ++s) {
-          tmap_acquire(&L.a_hi[s]);
-          if (!L.seg_exact[s]) tmap_acquire(&L.a_lo[s]);
+          tmap_acquire(&L.a_hi[s], fence);
+          if (!L.seg_exact[s]) tmap_acquire(&L.a_lo[s], fence);
         }
-        tmap_acquire(&L.w_hi);
-        tmap_acquire(&L.w_lo);
+        if (L.nseg > 0) {
+          tmap_acquire(&L.w_hi, fence);
+          tmap_acquire(&L.w_lo, fence);
+        }
       }
       __syncwarp();
-      const int kb0 = (L.seg_k[0] + BK - 1) / BK;
+      const int kb0 = L.nseg > 0 ? (L.seg_k[0] + BK - 1) / BK : 0;
       const int kbc = layer_kblocks(L);
       const int total = kbc * L.nchunk;
       const bool active = rank < L.nactive;
@@ -346,23 +401,25 @@ __device__ void producer(const Shared& sh, const LmLayer* layers, int nlayers, i
           const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
           const uint32_t itb = it + b, s = itb % STAGES, ph = (itb / STAGES) & 1;
           const uint32_t full = sh.bars + BAR_FULL + 8 * s, empty = sh.bars + BAR_EMPTY + 8 * s;
-          mbar_wait<true>(empty, ph ^ 1, cx, 1);
+          mbar_wait<false>(empty, ph ^ 1, cx, 1);     // protects shared-memory reuse only
+          trace_ev(cx, 0, 4 * itb);
           if (lane == 0) {
-            const uint32_t bytes = (L.seg_exact[seg] ? 1u : 2u) * A_BYTES +
-                                   (active ? 2u * (uint32_t)L.bn * BK * 4 : 0u);
+            const uint32_t bytes = ((cx.flags & F_NOA) ? 0u : (L.seg_exact[seg] ? 1u : 2u) * A_BYTES) +
+                                   ((active && !(cx.flags & F_NOB)) ? 2u * (uint32_t)L.bn * BK * 4 : 0u);
             mbar_arrive_tx(full, bytes);
-            if (active) {
+            if (active && !(cx.flags & F_NOB)) {
               const uint32_t st = sh.base + s * STAGE_BYTES + 2 * A_BYTES;
               const int k = L.seg_wk0[seg] + kb * BK;
               const int n = L.wn0 + c * L.chunk_stride + rank * L.bn;
               tma_load(st, &L.w_hi, k, n, full);
-              tma_load(st + B_BYTES, &L.w_lo, k, n, full);
+              tma_load(st + (uint32_t)L.bn * (BK * 4), &L.w_lo, k, n, full);   // rows [bn, 2 bn) of one tile
             }
           }
           __syncwarp();
+          trace_ev(cx, 0, 4 * itb + 1);
         }
         if (need_ready) {       // the previous layer's outputs of all 8 CTAs are in global memory
-          mbar_wait<true>(sh.bars + BAR_READY, (uint32_t)(pair - 1) & 1, cx, 2);
+          count_wait(sh.bars + BAR_READY, (uint32_t)pair * CL, cx, 2);
           asm volatile("fence.proxy.async;" ::: "memory");
           need_ready = false;
         }
@@ -372,13 +429,22 @@ __device__ void producer(const Shared& sh, const LmLayer* layers, int nlayers, i
           const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
           const uint32_t itb = it + b, s = itb % STAGES;
           const uint32_t full = sh.bars + BAR_FULL + 8 * s;
-          if (lane == 0) {
-            const uint32_t st = sh.base + s * STAGE_BYTES + rank * SLICE_BYTES;
-            const int k = kb * BK, m = m0 + rank * SLICE_ROWS;
-            tma_load_mc(st, &L.a_hi[seg], k, m, full, (uint16_t)0xFF);
-            if (!L.seg_exact[seg]) tma_load_mc(st + A_BYTES, &L.a_lo[seg], k, m, full, (uint16_t)0xFF);
+          if (lane == 0 && !(cx.flags & F_NOA)) {
+            if (cx.flags & F_LOCALA) {       // profiling: every CTA fetches the whole tile itself
+              for (int q = 0; q < CL; ++q) {
+                const uint32_t st = sh.base + s * STAGE_BYTES + q * SLICE_BYTES;
+                tma_load(st, &L.a_hi[seg], kb * BK, m0 + q * SLICE_ROWS, full);
+                if (!L.seg_exact[seg]) tma_load(st + A_BYTES, &L.a_lo[seg], kb * BK, m0 + q * SLICE_ROWS, full);
+              }
+            } else {
+              const uint32_t st = sh.base + s * STAGE_BYTES + rank * SLICE_BYTES;
+              const int k = kb * BK, m = m0 + rank * SLICE_ROWS;
+              tma_load_mc(st, &L.a_hi[seg], k, m, full, (uint16_t)0xFF);
+              if (!L.seg_exact[seg]) tma_load_mc(st + A_BYTES, &L.a_lo[seg], k, m, full, (uint16_t)0xFF);
+            }
           }
           __syncwarp();
+          trace_ev(cx, 0, 4 * itb + 2);
         }
         it += batch;
         j += batch;
@@ -399,39 +465,37 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
       const int kb0 = (L.seg_k[0] + BK - 1) / BK;
       const int kbc = layer_kblocks(L);
       const bool active = rank < L.nactive;
-      const uint32_t idesc = make_idesc(L.bn);
+      const uint32_t idesc = make_idesc(L.bn), idesc2 = make_idesc(2 * L.bn);
+      if (L.nseg == 0) continue;                 // epilogue-only layer
       for (int c = 0; c < L.nchunk; ++c) {
         const uint32_t buf = ac & 1;
         if (active) {
           mbar_wait<false>(sh.bars + BAR_ACCE + 8 * buf, ((ac >> 1) & 1) ^ 1, cx, 3);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        const uint32_t d_main = tmem_base + buf * 128, d_cross = d_main + 64;
-        uint32_t acc_main = 0, acc_cross = 0;
+        // accumulator buffer: columns [0, bn) main (hi.hi), [bn, 2 bn) the small cross terms
+        const uint32_t d_main = tmem_base + buf * 128, d_cross = d_main + (uint32_t)L.bn;
+        uint32_t acc = 0;
         for (int r = 0; r < kbc; ++r, ++it) {
           const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait<false>(sh.bars + BAR_FULL + 8 * s, ph, cx, 4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          trace_ev(cx, 1, 4 * it);
           if (lane == 0) {
-            if (active) {
+            if (active && !(cx.flags & F_NOMMA)) {
               const uint32_t a_hi = sh.base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
-              const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+              const uint32_t b_hi = a_hi + 2 * A_BYTES;
               const int kvalid = min(BK, L.seg_k[seg] - kb * BK);
               const int ksteps = (kvalid + 7) >> 3;
               const bool exact = L.seg_exact[seg] != 0;
               for (int ks = 0; ks < ksteps; ++ks) {
                 const uint64_t dah = make_desc(a_hi + ks * 32), dbh = make_desc(b_hi + ks * 32);
-                const uint64_t dbl = make_desc(b_lo + ks * 32);
-                // the small cross terms accumulate apart from the main sum
-                if (!exact) {
-                  mma_tf32(d_cross, make_desc(a_lo + ks * 32), dbh, idesc, acc_cross);
-                  acc_cross = 1;
-                }
-                mma_tf32(d_cross, dah, dbl, idesc, acc_cross);
-                acc_cross = 1;
-                mma_tf32(d_main, dah, dbh, idesc, acc_main);
-                acc_main = 1;
+                // B_hi and B_lo are rows [0, bn) and [bn, 2 bn) of ONE K-major tile: a single
+                // N = 2 bn product gives hi.hi (main) and hi.lo (cross) with one read of A_hi
+                mma_tf32(d_main, dah, dbh, idesc2, acc);
+                acc = 1;
+                if (!exact) mma_tf32(d_cross, make_desc(a_lo + ks * 32), dbh, idesc, 1u);
               }
             }
             // this stage may be refilled once every CTA of the cluster has read it
@@ -439,6 +503,7 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
             if (active && r == kbc - 1) umma_commit(sh.bars + BAR_ACCF + 8 * buf);
           }
           __syncwarp();
+          trace_ev(cx, 1, 4 * it + 1);
         }
         if (active) ++ac;
       }
@@ -452,56 +517,96 @@ struct EpiState {
 };
 
 // main + cross accumulator columns [cc*32, cc*32+32) of buffer `buf`, this thread's row
-__device__ __forceinline__ void acc_load32(uint32_t tmem_base, uint32_t buf, int quad, int cc,
+__device__ __forceinline__ void acc_load32(uint32_t tmem_base, uint32_t buf, int quad, int cc, int bn,
                                            float (&v)[32]) {
   uint32_t a[32], b[32];
   const uint32_t t = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + cc * 32;
   tmem_ld32_nowait(t, a);
-  tmem_ld32_nowait(t + 64, b);
+  tmem_ld32_nowait(t + (uint32_t)bn, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
 }
 
-// publish this thread's pair of row partials to every CTA of the cluster, then collect all 8
+// publish this thread's pair of row partials to every CTA of the cluster, then collect all 8.
+// The remote stores carry their own completion (st.async ... mbarrier::complete_tx): the destination's
+// barrier counts the bytes, so no fence and no separate arrive is needed.
 __device__ __forceinline__ void row_exchange(const Shared& sh, EpiState& es, int rank, int trow,
-                                             int lane, float a, float b, float2 (&parts)[CL],
-                                             const Ctx& cx) {
+                                             int warp, int lane, float a, float b,
+                                             float2 (&parts)[CL], const Ctx& cx) {
   const uint32_t par = es.xc & 1;
+  const uint32_t bar = sh.bars + BAR_STATS;
+  if (warp == 2 && lane == 0) mbar_arrive_tx(bar, CL * BM * 8);      // bytes this CTA will receive
   const uint32_t slot = sh.base + OFF_STATS + ((par * CL + rank) * BM + trow) * 8;
 #pragma unroll
   for (int d = 0; d < CL; ++d) {
-    const uint32_t ra = mapa(slot, d);
-    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(ra), "f"(a), "f"(b) : "memory");
+    const uint32_t ra = mapa(slot, d), rb = mapa(bar, d);
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+                 ::"r"(ra), "f"(a), "f"(b), "r"(rb) : "memory");
   }
-  __syncwarp();
-  if (lane == 0) {
-#pragma unroll
-    for (int d = 0; d < CL; ++d) mbar_arrive_remote(sh.bars + BAR_STATS, d);
-  }
-  mbar_wait<true>(sh.bars + BAR_STATS, par, cx, 5);
+  mbar_wait<false>(bar, par, cx, 5);
   const float2* mine = reinterpret_cast<const float2*>(sh.smem + OFF_STATS) + par * CL * BM + trow;
 #pragma unroll
   for (int d = 0; d < CL; ++d) parts[d] = mine[d * BM];
   ++es.xc;
 }
 
-__device__ __forceinline__ void acc_wait(const Shared& sh, const EpiState& es, const Ctx& cx) {
+__device__ __forceinline__ void acc_wait(const Shared& sh, const EpiState& es, const Ctx& cx,
+                                         bool has_acc) {
+  if (!has_acc) return;
   mbar_wait<false>(sh.bars + BAR_ACCF + 8 * (es.ac & 1), (es.ac >> 1) & 1, cx, 6);
+  if ((threadIdx.x >> 5) == 2) trace_ev(cx, 2, 4 * cx.pair + 3);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void acc_release(const Shared& sh, EpiState& es, int lane) {
+__device__ __forceinline__ void acc_release(const Shared& sh, EpiState& es, int lane, bool has_acc) {
+  if (!has_acc) return;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncwarp();
   if (lane == 0) mbar_arrive(sh.bars + BAR_ACCE + 8 * (es.ac & 1));
   ++es.ac;
 }
 
+// the epilogue's view of a layer, copied into shared memory once per (tile, layer) and warp: the
+// descriptor itself lives in global memory and would be re-read after every global store
+struct EP {
+  int nseg, N, bn, nchunk, chunk_stride, nactive, epi, act, ld_add, ld_out, ld_z;
+  const float *add, *bias, *gamma, *beta;
+  float *z, *st, *out, *out_lo, *dgamma, *dbeta;
+};
+static_assert(sizeof(EP) <= EP_BYTES, "EP slot");
+__device__ __forceinline__ EP load_ep(const LmLayer& L) {
+  EP e;
+  e.nseg = L.nseg; e.N = L.N; e.bn = L.bn; e.nchunk = L.nchunk; e.chunk_stride = L.chunk_stride;
+  e.nactive = L.nactive; e.epi = L.epi; e.act = L.act;
+  e.ld_add = L.ld_add; e.ld_out = L.ld_out; e.ld_z = L.ld_z;
+  e.add = L.add; e.bias = L.bias; e.gamma = L.gamma; e.beta = L.beta;
+  e.z = L.z; e.st = L.st; e.out = L.out; e.out_lo = L.out_lo; e.dgamma = L.dgamma; e.dbeta = L.dbeta;
+  return e;
+}
+// 32 consecutive per-column parameters (16-byte aligned: offsets are multiples of 32 floats)
+__device__ __forceinline__ void load32(const float* p, float (&o)[32]) {
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 x = reinterpret_cast<const float4*>(p)[q];
+      o[4 * q] = x.x; o[4 * q + 1] = x.y; o[4 * q + 2] = x.z; o[4 * q + 3] = x.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = p[j];
+  }
+}
+
 // accumulator (+ addend + bias) of one 32-column sub-tile
-__device__ __forceinline__ void fetch_sub(const LmLayer& L, uint32_t tmem_base, uint32_t buf, int quad,
+__device__ __forceinline__ void fetch_sub(const EP& L, uint32_t tmem_base, uint32_t buf, int quad,
                                           int half, float* stg, int wrow0, int rows_valid, int cb,
                                           int cols_valid, int lane, float (&v)[32]) {
-  acc_load32(tmem_base, buf, quad, half, v);
+  if (L.nseg > 0) {
+    acc_load32(tmem_base, buf, quad, half, L.bn, v);
+  } else {                                     // epilogue-only layer: the input is `add`
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  }
   if (L.add != nullptr) {
     float a[32];
     sub_load(stg, a, L.add + (size_t)wrow0 * L.ld_add + cb, L.ld_add, rows_valid, cols_valid, lane);
@@ -509,13 +614,20 @@ __device__ __forceinline__ void fetch_sub(const LmLayer& L, uint32_t tmem_base, 
     for (int j = 0; j < 32; ++j) v[j] += a[j];
   }
   if (L.bias != nullptr) {
+    if (cols_valid >= 32) {
+      float b[32];
+      load32(L.bias + cb, b);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < cols_valid) v[j] += L.bias[cb + j];
+      for (int j = 0; j < 32; ++j) v[j] += b[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < cols_valid) v[j] += L.bias[cb + j];
+    }
   }
 }
 
-__device__ __forceinline__ void store_with_lo(const LmLayer& L, float* stg, float (&v)[32], int wrow0,
+__device__ __forceinline__ void store_with_lo(const EP& L, float* stg, float (&v)[32], int wrow0,
                                               int rows_valid, int cb, int cols_valid, int lane) {
   sub_store(stg, v, L.out + (size_t)wrow0 * L.ld_out + cb, L.ld_out, rows_valid, cols_valid, lane);
   if (L.out_lo != nullptr) {
@@ -526,12 +638,12 @@ __device__ __forceinline__ void store_with_lo(const LmLayer& L, float* stg, floa
 }
 
 // E_PLAIN: out = acc (+ add) (+ bias)
-__device__ void epi_plain(const Shared& sh, const LmLayer& L, EpiState& es, uint32_t tmem_base,
+__device__ void epi_plain(const Shared& sh, const EP& L, EpiState& es, uint32_t tmem_base,
                           int rank, int quad, int lane, float* stg, int wrow0, int rows_valid,
                           const Ctx& cx) {
   const int halves = L.bn >> 5;
   for (int c = 0; c < L.nchunk; ++c) {
-    acc_wait(sh, es, cx);
+    acc_wait(sh, es, cx, L.nseg > 0);
     const int col0 = c * L.chunk_stride + rank * L.bn;
     for (int h = 0; h < halves; ++h) {
       const int cb = col0 + h * 32;
@@ -540,12 +652,12 @@ __device__ void epi_plain(const Shared& sh, const LmLayer& L, EpiState& es, uint
       fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, cols_valid, lane, v);
       if (cols_valid > 0) store_with_lo(L, stg, v, wrow0, rows_valid, cb, cols_valid, lane);
     }
-    acc_release(sh, es, lane);
+    acc_release(sh, es, lane, L.nseg > 0);
   }
 }
 
 // E_LN: z = acc (+add)(+bias); out = act(LayerNorm(z) * gamma + beta)   (A/nets.py:585-602)
-__device__ void epi_ln_fwd(const Shared& sh, const LmLayer& L, EpiState& es, uint32_t tmem_base,
+__device__ void epi_ln_fwd(const Shared& sh, const EP& L, EpiState& es, uint32_t tmem_base,
                            int rank, int quad, int lane, float* stg, int wrow0, int rows_valid,
                            int trow, const Ctx& cx) {
   const int halves = L.bn >> 5;
@@ -553,7 +665,7 @@ __device__ void epi_ln_fwd(const Shared& sh, const LmLayer& L, EpiState& es, uin
   float keep[64];
   float mean = 0.f, m2 = 0.f, cnt = 0.f;
   for (int c = 0; c < L.nchunk; ++c) {
-    acc_wait(sh, es, cx);
+    acc_wait(sh, es, cx, L.nseg > 0);
     const int col0 = c * L.chunk_stride + rank * L.bn;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -580,10 +692,10 @@ __device__ void epi_ln_fwd(const Shared& sh, const LmLayer& L, EpiState& es, uin
         }
       }
     }
-    acc_release(sh, es, lane);
+    acc_release(sh, es, lane, L.nseg > 0);
   }
   float2 parts[CL];
-  row_exchange(sh, es, rank, trow, lane, mean, m2, parts, cx);
+  row_exchange(sh, es, rank, trow, 2 + ((quad + 2) & 3), lane, mean, m2, parts, cx);
   float gm = 0.f;
   for (int d = 0; d < L.nactive; ++d) gm += parts[d].x;
   gm /= (float)L.nactive;
@@ -607,10 +719,13 @@ __device__ void epi_ln_fwd(const Shared& sh, const LmLayer& L, EpiState& es, uin
         } else {
           sub_load(stg, v, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
         }
+        const float* gp = L.gamma + cb;
+        const float* bp = L.beta + cb;
+        const int act = L.act;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float y = (v[j] - gm) * rstd * L.gamma[cb + j] + L.beta[cb + j];
-          v[j] = L.act ? elu_f(y) : y;
+          const float y = (v[j] - gm) * rstd * __ldg(gp + j) + __ldg(bp + j);
+          v[j] = act ? elu_f(y) : y;
         }
         store_with_lo(L, stg, v, wrow0, rows_valid, cb, 32, lane);
       }
@@ -620,7 +735,7 @@ __device__ void epi_ln_fwd(const Shared& sh, const LmLayer& L, EpiState& es, uin
 
 // E_LNBWD: dh = acc (+add); dz = LayerNorm'(act'(.) dh) given the saved pre-norm z and (mean, rstd)
 // dgamma += sum_rows dy * xhat, dbeta += sum_rows dy  (optional)
-__device__ void epi_ln_bwd(const Shared& sh, const LmLayer& L, EpiState& es, uint32_t tmem_base,
+__device__ void epi_ln_bwd(const Shared& sh, const EP& L, EpiState& es, uint32_t tmem_base,
                            int rank, int quad, int lane, float* stg, int wrow0, int rows_valid,
                            int trow, const Ctx& cx) {
   const int halves = L.bn >> 5;
@@ -634,7 +749,7 @@ __device__ void epi_ln_bwd(const Shared& sh, const LmLayer& L, EpiState& es, uin
   float keep[64];
   float s1 = 0.f, s2 = 0.f;
   for (int c = 0; c < L.nchunk; ++c) {
-    acc_wait(sh, es, cx);
+    acc_wait(sh, es, cx, L.nseg > 0);
     const int col0 = c * L.chunk_stride + rank * L.bn;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -644,13 +759,16 @@ __device__ void epi_ln_bwd(const Shared& sh, const LmLayer& L, EpiState& es, uin
         fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, 32, lane, v);
         sub_load(stg, z, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
         float dyv[32];
+        const float* gp = L.gamma + cb;
+        const float* bp = L.beta + cb;
+        const int act = L.act;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float g = L.gamma[cb + j];
+          const float g = __ldg(gp + j);
           const float xh = (z[j] - mean) * rstd;
           float dy = rowok ? v[j] : 0.f;
-          if (L.act) {
-            const float y = xh * g + L.beta[cb + j];
+          if (act) {
+            const float y = xh * g + __ldg(bp + j);
             dy = y > 0.f ? dy : dy * expf(y);
           }
           const float dx = dy * g;
@@ -674,10 +792,10 @@ __device__ void epi_ln_bwd(const Shared& sh, const LmLayer& L, EpiState& es, uin
         }
       }
     }
-    acc_release(sh, es, lane);
+    acc_release(sh, es, lane, L.nseg > 0);
   }
   float2 parts[CL];
-  row_exchange(sh, es, rank, trow, lane, s1, s2, parts, cx);
+  row_exchange(sh, es, rank, trow, 2 + ((quad + 2) & 3), lane, s1, s2, parts, cx);
   float t1 = 0.f, t2 = 0.f;
   for (int d = 0; d < L.nactive; ++d) { t1 += parts[d].x; t2 += parts[d].y; }
   t1 /= (float)L.N;
@@ -713,6 +831,7 @@ __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, i
   const int ntiles = (M + BM - 1) / BM;
   const int quad = warp & 3;                      // TMEM lane quadrant this warp may read
   float* stg = reinterpret_cast<float*>(sh.smem + OFF_STG + (warp - 2) * STG_WARP_BYTES);
+  EP* ep_slot = reinterpret_cast<EP*>(sh.smem + OFF_EP + (warp - 2) * EP_BYTES);
   EpiState es = {0u, 0u};
   int pair = 0;
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
@@ -720,9 +839,15 @@ __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, i
     const int rows_valid = max(0, min(32, M - wrow0));
     const int trow = quad * 32 + lane;
     for (int l = 0; l < nlayers; ++l, ++pair) {
-      const LmLayer& L = layers[l];
+      __syncwarp();
+      if (lane == 0) *ep_slot = load_ep(layers[l]);
+      __syncwarp();
+      const EP& L = *ep_slot;
       cx.pair = pair;
       const bool active = rank < L.nactive;
+      if (L.nseg == 0 && l > 0)       // no producer wait protects its inputs: wait here
+        count_wait(sh.bars + BAR_READY, (uint32_t)pair * CL, cx, 8);
+      if (warp == 2) trace_ev(cx, 2, 4 * pair);
       if (L.epi == DD_EPI_PLAIN) {
         if (active) epi_plain(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, cx);
       } else if (L.epi == DD_EPI_LN) {
@@ -730,23 +855,26 @@ __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, i
       } else {
         if (active) epi_ln_bwd(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, trow, cx);
       }
-      // my rows of this layer's outputs are written: tell every CTA's producer.  The barrier
-      // counts 32 arrivals per (tile, layer) pair; a CTA running ahead (a first layer does not wait
-      // for `ready`) must not add its arrivals to the phase of a pair a slower CTA has not finished.
-      if (pair > 0) mbar_wait<true>(sh.bars + BAR_READY, (uint32_t)(pair - 1) & 1, cx, 7);
+      // this CTA's rows of the layer's outputs are written: tell every CTA's producer.  Each
+      // writer orders its stores against the async proxy (TMA reads them), the four epilogue warps
+      // meet at a named barrier, then one thread publishes with a single cluster-scope fence.
+      if (warp == 2) trace_ev(cx, 2, 4 * pair + 1);
       asm volatile("fence.proxy.async;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
 #pragma unroll
-        for (int d = 0; d < CL; ++d) mbar_arrive_remote(sh.bars + BAR_READY, d);
+        for (int d = 0; d < CL; ++d) count_add_remote(sh.bars + BAR_READY, d);
       }
+      if (warp == 2) trace_ev(cx, 2, 4 * pair + 2);
       __syncwarp();
     }
   }
 }
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
-lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg) {
+lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg,
+          unsigned long long* prof, int flags) {
   extern __shared__ __align__(1024) char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_rank();
@@ -766,8 +894,8 @@ lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg)
       mbar_init(sh.bars + BAR_ACCF + 8 * b, 1);
       mbar_init(sh.bars + BAR_ACCE + 8 * b, 4);
     }
-    mbar_init(sh.bars + BAR_STATS, CL * 4);
-    mbar_init(sh.bars + BAR_READY, CL * 4);
+    mbar_init(sh.bars + BAR_STATS, 1);
+    *reinterpret_cast<volatile unsigned long long*>(smem + OFF_BAR + BAR_READY) = 0ull;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -780,7 +908,10 @@ lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg)
   cluster_sync_all();                // every CTA's barriers exist before anyone multicasts
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  Ctx cx = {dbg, 0};
+  const long long kstart = clock64();
+  Ctx cx = {dbg, 0, prof != nullptr ? prof + (size_t)blockIdx.x * 16 : nullptr, flags,
+            (prof != nullptr && blockIdx.x == 0) ? prof + 148 * 16 : nullptr};
+  if (tid == 0) trace_ev(cx, 3, 0);
   if ((sh.base & 1023u) != 0u) stuck(cx, 9, sh.base);      // SWIZZLE_128B tiles need 1 KB alignment
 
   if (warp == 0) {
@@ -791,9 +922,13 @@ lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg)
     epilogue(sh, layers, nlayers, M, rank, cluster_id, nclusters, warp, lane, tmem_base, cx);
   }
 
+  if (tid % 32 == 0) trace_ev(cx, 3, 1 + warp);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (tid == 0) trace_ev(cx, 3, 8);
   cluster_sync_all();                // nobody exits while a peer may still write into it
+  if (tid == 0) trace_ev(cx, 3, 9);
+  if (tid == 0 && cx.prof != nullptr) cx.prof[0] += (unsigned long long)(clock64() - kstart);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
@@ -903,6 +1038,9 @@ static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t col
 
 static unsigned* g_dbg_host = nullptr;
 static unsigned* g_dbg_dev = nullptr;
+static unsigned long long* g_prof_dev = nullptr;     // [148 CTAs][16] wait-cycle totals
+static int g_prof_on = 0;
+static int g_flags = 0;
 
 }  // namespace lm
 }  // namespace dd
@@ -919,7 +1057,8 @@ extern "C" int dd_program_build(const DdLayer* layers, int nlayers, int rows, vo
   for (int i = 0; i < nlayers && rc == 0; ++i) {
     const DdLayer& s = layers[i];
     lm::LmLayer& d = host[i];
-    if (s.nseg < 1 || s.nseg > 2) { rc = fail("dd_program_build", "1 or 2 A segments"); break; }
+    if (s.nseg < 0 || s.nseg > 2) { rc = fail("dd_program_build", "0, 1 or 2 A segments"); break; }
+    if (s.nseg == 0 && s.add == nullptr) { rc = fail("dd_program_build", "epilogue-only layer without input (add)"); break; }
     // column tiling across the 8 CTAs
     if (s.N % (lm::CL * 64) == 0) {
       d.bn = 64; d.nchunk = s.N / (lm::CL * 64); d.nactive = lm::CL;
@@ -945,10 +1084,12 @@ extern "C" int dd_program_build(const DdLayer* layers, int nlayers, int rows, vo
         rc = lm::make_map(&d.a_lo[g], sg.a_lo, rows, sg.k, sg.lda, lm::SLICE_ROWS);
     }
     if (rc != 0) break;
-    if (s.w == nullptr || s.w_lo == nullptr) { rc = fail("dd_program_build", "B operand needs (w, w_lo)"); break; }
-    rc = lm::make_map(&d.w_hi, s.w, s.wrows, s.wcols, s.ldw, d.bn);
-    if (rc == 0) rc = lm::make_map(&d.w_lo, s.w_lo, s.wrows, s.wcols, s.ldw, d.bn);
-    if (rc != 0) break;
+    if (s.nseg > 0) {
+      if (s.w == nullptr || s.w_lo == nullptr) { rc = fail("dd_program_build", "B operand needs (w, w_lo)"); break; }
+      rc = lm::make_map(&d.w_hi, s.w, s.wrows, s.wcols, s.ldw, d.bn);
+      if (rc == 0) rc = lm::make_map(&d.w_lo, s.w_lo, s.wrows, s.wcols, s.ldw, d.bn);
+      if (rc != 0) break;
+    }
     d.wn0 = s.wn0;
     d.epi = s.epi;
     d.act = s.act;
@@ -998,7 +1139,8 @@ extern "C" int dd_program_run(const void* table_dev, int nlayers, int rows, dd_s
   const int ntiles = (rows + lm::BM - 1) / lm::BM;
   const int nclusters = ntiles < max_clusters ? ntiles : max_clusters;
   lm::lm_kernel<<<dim3(lm::CL * nclusters), dim3(lm::THREADS), lm::SMEM_BYTES, S(stream)>>>(
-      static_cast<const lm::LmLayer*>(table_dev), nlayers, rows, lm::g_dbg_dev);
+      static_cast<const lm::LmLayer*>(table_dev), nlayers, rows, lm::g_dbg_dev,
+      lm::g_prof_on ? lm::g_prof_dev : nullptr, lm::g_flags);
   return launched("dd_program_run");
 }
 
@@ -1006,6 +1148,27 @@ extern "C" int dd_program_debug(unsigned* out8) {
   if (lm::g_dbg_host == nullptr) return 0;
   for (int i = 0; i < 8; ++i) out8[i] = lm::g_dbg_host[i];
   return lm::g_dbg_host[0] == 0xDEADBEEFu ? 1 : 0;
+}
+
+/* profiling aids (not part of the product path): per-CTA wait-cycle counters and switches that
+ * drop parts of the pipeline (results become garbage) */
+extern "C" int dd_set_machine_debug(int flags) {
+  const int prev = lm::g_flags;
+  lm::g_flags = flags;
+  return prev;
+}
+extern "C" int dd_machine_prof(int on, unsigned long long* out, int n) {
+  if (lm::g_prof_dev == nullptr) {
+    if (cudaMalloc(reinterpret_cast<void**>(&lm::g_prof_dev), (148 * 16 + 4 * lm::TRACE_N) * 8) != cudaSuccess) return -1;
+    cudaMemset(lm::g_prof_dev, 0, (148 * 16 + 4 * lm::TRACE_N) * 8);
+  }
+  if (out != nullptr && n > 0) {
+    const int cap = 148 * 16 + 4 * lm::TRACE_N;
+    cudaMemcpy(out, lm::g_prof_dev, (size_t)(n < cap ? n : cap) * 8, cudaMemcpyDeviceToHost);
+    cudaMemset(lm::g_prof_dev, 0, (size_t)cap * 8);
+  }
+  lm::g_prof_on = on;
+  return 0;
 }
 
 extern "C" int dd_split_lo(const float* x, int ldx, float* lo, int ldlo, int rows, int cols,

@@ -25,10 +25,13 @@ from __future__ import annotations
 
 import dataclasses
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
+
+from . import program as PG
 
 
 # ----------------------------------------------------------------------------
@@ -262,10 +265,30 @@ def init_params(spec: Spec, seed=1) -> Dict[str, np.ndarray]:
   return out
 
 
+def _ceil4(n):
+  return (n + 3) // 4 * 4
+
+
+def _strided(buf, off, rows, cols, ld):
+  return buf[off:off + (rows - 1) * ld + cols].as_strided((rows, cols), (ld, 1))
+
+
+def _mview_ok(t):
+  """A 2-D view the layer machine's TMA descriptors accept: unit column stride, row stride a
+  multiple of 16 bytes, 16-byte aligned base."""
+  return (t is not None and t.dim() == 2 and (t.shape[1] == 1 or t.stride(1) == 1) and
+          t.stride(0) % 4 == 0 and t.data_ptr() % 16 == 0)
+
+
 class ParamGroup:
   """One optimizer group as flat fp32 buffers [params | grads | m | v]; tensors
   matching the weight-decay pattern 'kernel' (A/tfutils.py:292) come first so
-  the fused Adam kernel decays a prefix."""
+  the fused Adam kernel decays a prefix.
+
+  For the layer machine (csrc/dd_machine.cu) the group also keeps GEMM-operand copies,
+  refreshed by prep() after every update: `p_lo` (tf32 remainder of every parameter, same
+  offsets) and, per 2-D kernel [K, N], the transposed copy [N, ld >= K] with its remainder (B
+  operand of x @ W) and, when N % 4 != 0, a row-padded copy [K, ld >= N] (B operand of dY @ W^T)."""
 
   def __init__(self, be, names_shapes: List[Tuple[str, Tuple[int, ...]]], opt=True):
     decayed = [(n, s) for n, s in names_shapes if 'kernel' in n]
@@ -286,6 +309,27 @@ class ParamGroup:
     self.m = be.zeros(self.size) if opt else None
     self.v = be.zeros(self.size) if opt else None
     self.sumsq = be.zeros(1, dtype=torch.float64) if opt else None
+    self.machine = hasattr(be, 'program_build')
+    self.t_off, self.b_off, self.jobs = {}, {}, []
+    if self.machine:
+      off = 0
+      for n, s in self.order:
+        if not (n.endswith('/kernel') and len(s) == 2):
+          continue
+        K, N = s
+        src = self.offsets[n][0]
+        ldt = _ceil4(K)
+        self.t_off[n] = (off, ldt)
+        self.jobs.append((src, K, N, off, ldt, 0))
+        off += _ceil4(N * ldt)
+        if N % 4:
+          ldb = _ceil4(N)
+          self.b_off[n] = (off, ldb)
+          self.jobs.append((src, K, N, off, ldb, 1))
+          off += K * ldb
+      self.p_lo = be.zeros(self.size)
+      self.pt = be.zeros(max(off, 4))
+      self.pt_lo = be.zeros(max(off, 4))
 
   def view(self, flat, name):
     off, shape = self.offsets[name]
@@ -297,6 +341,28 @@ class ParamGroup:
   def G(self, name):
     return self.view(self.g, name)
 
+  def prep(self, be):
+    """Refresh the machine's operand copies from the current parameters."""
+    if not self.machine:
+      return
+    be.split_lo(self.p, self.p_lo)
+    if self.jobs:
+      be.transpose_lo(self.p, self.pt, self.pt_lo, self.jobs)
+
+  def PT(self, name):
+    """(W^T, its remainder) as [N, K] views: the B operand of x @ W."""
+    off, ldt = self.t_off[name]
+    K, N = self.offsets[name][1]
+    return _strided(self.pt, off, N, K, ldt), _strided(self.pt_lo, off, N, K, ldt)
+
+  def PB(self, name):
+    """(W, its remainder) as [K, N] views with a 16-byte row stride: the B operand of dY @ W^T."""
+    K, N = self.offsets[name][1]
+    if name in self.b_off:
+      off, ldb = self.b_off[name]
+      return _strided(self.pt, off, K, N, ldb), _strided(self.pt_lo, off, K, N, ldb)
+    return self.P(name), self.view(self.p_lo, name)
+
 
 # ----------------------------------------------------------------------------
 # MLP trunk with saved activations
@@ -305,9 +371,14 @@ class ParamGroup:
 class Trunk:
   """`layers` x (Linear(no bias) -> LayerNorm(eps 1e-3) -> elu) over a fixed
   number of rows, keeping pre-norm Z, output H and (mean, rstd) per layer for
-  the backward pass (A/nets.py:408-416, :566-582)."""
+  the backward pass (A/nets.py:408-416, :566-582).
 
-  def __init__(self, eng, group, prefix, layers, units, rows, param_prefix=None):
+  Inputs are lists of (X, first weight row[, X_lo]): a third element (a tensor, or None for an
+  operand that is exact in tf32 such as the one-hot latent) makes the trunk eligible for the layer
+  machine, which runs the whole stack -- and optional output layers -- as ONE program
+  (csrc/dd_machine.cu); otherwise every layer is a dd_gemm + dd_ln_fwd pair."""
+
+  def __init__(self, eng, group, prefix, layers, units, rows, param_prefix=None, names=None):
     be = eng.be
     self.eng, self.group, self.prefix = eng, group, prefix
     self.pp = param_prefix or prefix
@@ -315,26 +386,61 @@ class Trunk:
     self.Z = [be.zeros(rows, units) for _ in range(layers)]
     self.H = [be.zeros(rows, units) for _ in range(layers)]
     self.st = [be.zeros(rows, 2) for _ in range(layers)]
+    self._names_fn = names
+    self.machine = bool(getattr(eng, 'machine', False)) and units % 256 == 0 and rows >= 1
+    self.Hlo = [be.zeros(rows, units) for _ in range(layers)] if self.machine else None
+    self._progs = {}
 
   def _names(self, i):
+    if self._names_fn is not None:
+      return self._names_fn(i)
     b = f'{self.pp}/dense{i}'
     return f'{b}/kernel', f'{b}/norm/scale', f'{b}/norm/bias'
 
-  def fwd(self, xs, r0, r1, group=None):
-    """xs: list of (X[r1-r0, k], first weight row).  Returns H[-1][r0:r1]."""
+  def _machine_xs(self, xs):
+    return (self.machine and 1 <= len(xs) <= 2 and all(len(x) == 3 for x in xs) and
+            all(_mview_ok(x[0]) and (x[2] is None or _mview_ok(x[2])) for x in xs))
+
+  def fwd(self, xs, r0, r1, group=None, heads=()):
+    """xs: list of (X[r1-r0, k], first weight row[, X_lo]).  heads: (kernel name, bias name, out
+    view) output layers applied to the last hidden layer.  Returns H[-1][r0:r1]."""
     be, g = self.eng.be, group or self.group
+    if self._machine_xs(xs) and all(_mview_ok(h[2]) or h[2].shape[1] < 4 for h in heads):
+      key = ('f', r0, r1, id(g), tuple((x[0].data_ptr(), x[1]) for x in xs),
+             tuple((h[0], h[2].data_ptr()) for h in heads))
+      prog = self._progs.get(key)
+      if prog is None:
+        layers = []
+        for i in range(self.layers):
+          kn, sn, bn = self._names(i)
+          wt, wtlo = g.PT(kn)
+          segs = ([PG.Seg(X, lo, w0) for X, w0, lo in xs] if i == 0 else
+                  [PG.Seg(self.H[i - 1][r0:r1], self.Hlo[i - 1][r0:r1], 0)])
+          layers.append(PG.Layer(segs, wt, wtlo, self.units, PG.EPI_LN, act=1, gamma=g.P(sn),
+                                 beta=g.P(bn), z=self.Z[i][r0:r1], st=self.st[i][r0:r1],
+                                 out=self.H[i][r0:r1], out_lo=self.Hlo[i][r0:r1]))
+        last = PG.Seg(self.H[-1][r0:r1], self.Hlo[-1][r0:r1], 0)
+        for kn, bn, out in heads:
+          wt, wtlo = g.PT(kn)
+          layers.append(PG.Layer([last], wt, wtlo, out.shape[1], PG.EPI_PLAIN, bias=g.P(bn), out=out))
+        prog = self._progs[key] = be.program_build(layers, r1 - r0)
+      be.program_run(prog)
+      return self.H[-1][r0:r1]
     for i in range(self.layers):
       kn, sn, bn = self._names(i)
       W = g.P(kn)
       Z = self.Z[i][r0:r1]
       if i == 0:
         beta = 0.0
-        for X, w0 in xs:
+        for x in xs:
+          X, w0 = x[0], x[1]
           be.gemm(X, W[w0:w0 + X.shape[1]], Z, beta=beta)
           beta = 1.0
       else:
         be.gemm(self.H[i - 1][r0:r1], W, Z)
       be.ln_fwd(Z, g.P(sn), g.P(bn), self.H[i][r0:r1], self.st[i][r0:r1], 1)
+    for kn, bn, out in heads:
+      be.gemm(self.H[-1][r0:r1], g.P(kn), out, bias=g.P(bn))
     return self.H[-1][r0:r1]
 
   def bwd(self, dH, r0, r1, xs, dxs, wgrad, group=None):
@@ -343,6 +449,41 @@ class Trunk:
     grads to produce.  wgrad: accumulate parameter grads into the group."""
     eng, be, g = self.eng, self.eng.be, group or self.group
     n = r1 - r0
+    if (self.machine and _mview_ok(dH) and
+        all(_mview_ok(d[0]) and PG.eligible_width(d[0].shape[1], PG.EPI_PLAIN) for d in dxs)):
+      key = ('b', r0, r1, id(g), dH.data_ptr(), bool(wgrad),
+             tuple((d[0].data_ptr(), d[1], float(d[2])) for d in dxs))
+      prog = self._progs.get(key)
+      dZ = [eng.dz_buf(i, n, self.units) for i in range(self.layers)]
+      if prog is None:
+        layers = []
+        for i in reversed(range(self.layers)):
+          kn, sn, bn = self._names(i)
+          common = dict(act=1, gamma=g.P(sn), beta=g.P(bn), z=self.Z[i][r0:r1], st=self.st[i][r0:r1],
+                        out=dZ[i][0], out_lo=dZ[i][1], dgamma=g.G(sn) if wgrad else None,
+                        dbeta=g.G(bn) if wgrad else None)
+          if i == self.layers - 1:
+            layers.append(PG.Layer([], None, None, self.units, PG.EPI_LNBWD, add=dH, **common))
+          else:
+            w, wlo = g.PB(self._names(i + 1)[0])
+            layers.append(PG.Layer([PG.Seg(dZ[i + 1][0], dZ[i + 1][1], 0)], w, wlo, self.units,
+                                   PG.EPI_LNBWD, **common))
+        w, wlo = g.PB(self._names(0)[0])
+        for dX, w0, beta in dxs:
+          layers.append(PG.Layer([PG.Seg(dZ[0][0], dZ[0][1], 0)], w, wlo, dX.shape[1], PG.EPI_PLAIN,
+                                 wn0=w0, add=dX if beta else None, out=dX))
+        prog = self._progs[key] = be.program_build(layers, n)
+      be.program_run(prog)
+      if wgrad:
+        for i in range(self.layers):
+          GW = g.G(self._names(i)[0])
+          if i == 0:
+            for x in xs:
+              X, w0 = x[0], x[1]
+              be.gemm(X, dZ[0][0], GW[w0:w0 + X.shape[1]], ta=True, beta=1.0)
+          else:
+            be.gemm(self.H[i - 1][r0:r1], dZ[i][0], GW, ta=True, beta=1.0)
+      return
     tA = dH
     for i in reversed(range(self.layers)):
       kn, sn, bn = self._names(i)
@@ -353,7 +494,8 @@ class Trunk:
       if wgrad:
         GW = g.G(kn)
         if i == 0:
-          for X, w0 in xs:
+          for x in xs:
+            X, w0 = x[0], x[1]
             be.gemm(X, tB, GW[w0:w0 + X.shape[1]], ta=True, beta=1.0)
         else:
           be.gemm(self.H[i - 1][r0:r1], tB, GW, ta=True, beta=1.0)
@@ -499,6 +641,9 @@ class Engine:
     self.seed = seed
     self.world = world
     self.allreduce = allreduce            # callable(flat tensor) -> sum over ranks
+    # layer machine (csrc/dd_machine.cu): trunks, the prior stack and the rollout's img_in / GRU
+    # layers run as fused programs wherever their shapes tile across its 8-CTA clusters
+    self.machine = hasattr(be, 'program_build') and os.environ.get('DD_MACHINE', '1') != '0'
     s, N, H = spec, self.N, self.H
     D, U, SC, A, E = s.deter, s.units, s.sc, s.act_dim, s.enc_units
     z = be.zeros
@@ -545,6 +690,13 @@ class Engine:
     R = (H + 1) * N
     wide = max(3 * D, SC, U, s.head_units, s.trunk('dec')[1], E)
     self._tmp = [z(R * wide) for _ in range(3)]
+    # machine: per-layer dZ (+ remainder) of the trunk being differentiated (trunks run one after
+    # another, so one pool serves them all), remainders of the GEMM-operand activations
+    umax = max(U, s.head_units, s.trunk('dec')[1], E)
+    nl = max(s.head_layers, s.enc_layers, s.prior_layers, s.trunk('dec')[0])
+    self._dzp = [z(R * umax) for _ in range(2 * nl)] if self.machine else []
+    self.obs_lo = z(N, s.obs_total) if self.machine and s.obs_total else None
+    self.feat_lo = z(N, D) if self.machine else None
 
     # -- world model buffers -------------------------------------------------
     self.enc = Trunk(self, gm, 'enc', s.enc_layers, E, N) if s.obs_dims else None
@@ -553,7 +705,7 @@ class Engine:
     self.d_img = z(N, *s.img_shape) if s.cnn_keys else None
     self.d_cnn = z(N, s.cnn_out) if s.cnn_keys else None
     self.init_deter = z(1, D)
-    self.init_trunk = Trunk(self, gm, 'rssm/initp', s.prior_layers, U, 1)
+    self.init_trunk = Trunk(self, gm, 'rssm/initp', s.prior_layers, U, 1, names=self._prior_names)
     self.init_zs = z(1, SC)
     self.init_logit = z(1, SC)
     self.init_stoch = z(1, SC)
@@ -573,7 +725,7 @@ class Engine:
     self.zs_tmp = z(N, SC)
     self.post_logit = z(N, SC)
     self.post_idx = z(N, s.stoch, dtype=torch.int32)
-    self.prior = Trunk(self, gm, 'rssm/priorp', s.prior_layers, U, N)
+    self.prior = Trunk(self, gm, 'rssm/priorp', s.prior_layers, U, N, names=self._prior_names)
     self.prior_logit = z(N, SC)
     self.heads = {k: Trunk(self, gm, k, *s.trunk(k), N)
                   for k in (('dec',) if s.dec_vec else ()) + ('reward', 'cont')}
@@ -612,6 +764,9 @@ class Engine:
     ga, gc, gs = self.groups['actor'], self.groups['critic'], self.groups['slow_critic']
     T = H + 1
     self.tfeat = z(T, N, D + SC)
+    self.tfeat_lo = z(T, N, D) if self.machine else None       # deter part; the latent is one-hot
+    self.taction_lo = z(T, N, A) if self.machine else None
+    self.i_xin_lo = z(H, N, U) if self.machine else None
     self.tlogit = z(T, N, SC)
     self.taction = z(T, N, A)
     self.tmean = z(T, N, A)
@@ -626,7 +781,7 @@ class Engine:
     self.i_zgru = z(H, N, 3 * D)
     self.i_ygru = z(H, N, 3 * D)
     self.i_stgru = z(H, N, 2)
-    self.i_prior = Trunk(self, gm, 'rssm/priorp', s.prior_layers, U, H * N)
+    self.i_prior = Trunk(self, gm, 'rssm/priorp', s.prior_layers, U, H * N, names=self._prior_names)
     self.i_zs = z(N, SC)
     self.t_reward = Trunk(self, gm, 'reward', s.head_layers, s.head_units, T * N)
     self.t_cont = Trunk(self, gm, 'cont', s.head_layers, s.head_units, T * N)
@@ -676,6 +831,24 @@ class Engine:
     i = 1 if cur.data_ptr() == self._tmp[0].data_ptr() else 0
     return self.tmp(i, rows, cols)
 
+  def dz_buf(self, i, rows, cols):
+    """(dZ, dZ_lo) of layer i of the trunk currently being differentiated."""
+    return (self._dzp[2 * i][:rows * cols].view(rows, cols),
+            self._dzp[2 * i + 1][:rows * cols].view(rows, cols))
+
+  def prep_weights(self, names=None):
+    """Refresh the machine's (w, w_lo) operand copies of the given groups from the parameters."""
+    for n in (names or self.groups):
+      self.groups[n].prep(self.be)
+
+  def fsegs(self, X, Xlo):
+    """[deter | stoch] feature rows as the two A segments of a first trunk layer: the deter part
+    with its remainder, the one-hot latent exact.  Without the machine: the plain (X, 0) input."""
+    D = self.spec.deter
+    if not self.machine or Xlo is None:
+      return [(X, 0)]
+    return [(X[:, :D], 0, Xlo), (X[:, D:], D, None)]
+
   def reset_state(self):
     be = self.be
     be.fill_(self.wmkl_scale, 1.0)
@@ -687,6 +860,7 @@ class Engine:
     for g in self.groups.values():
       for n, _ in g.order:
         g.P(n).copy_(torch.as_tensor(np.asarray(params[n], np.float32)).to(g.p.device))
+    self.prep_weights()
 
   def get_params(self) -> Dict[str, np.ndarray]:
     out = {}
@@ -718,46 +892,21 @@ class Engine:
       be.colsum(dOut, g.G(f'{prefix}/bias'), acc=True)
     be.gemm(dOut, g.P(f'{prefix}/kernel'), dX, tb=True)
 
-  def _prior_stats_fwd(self, trunk, r0, r1, X, zs, G, logit, stoch, idx, mode):
+  def _prior_stats_fwd(self, trunk, r0, r1, X, zs, G, logit, stoch, idx, mode, Xlo=None):
     """img_out_0..k -> img_stats -> unimix logits (+ draw)  (A/nets.py:132-137)."""
-    s, gm = self.spec, self.groups['model']
-    h = self._prior_trunk_fwd(trunk, r0, r1, X)
-    self._out_fwd(gm, 'rssm/img_stats', h, zs)
+    s = self.spec
+    xs = [(X, 0, Xlo)] if (self.machine and Xlo is not None) else [(X, 0)]
+    trunk.fwd(xs, r0, r1, heads=[('rssm/img_stats/kernel', 'rssm/img_stats/bias', zs)])
     self.be.stats_fwd(zs, G, logit, stoch, idx, s.stoch, s.classes, s.rssm_unimix, mode)
 
   def _prior_names(self, i):
     b = f'rssm/img_out_{i}'
     return f'{b}/kernel', f'{b}/norm/scale', f'{b}/norm/bias'
 
-  def _prior_trunk_fwd(self, trunk, r0, r1, X):
-    be, gm = self.be, self.groups['model']
-    for i in range(trunk.layers):
-      kn, sn, bn = self._prior_names(i)
-      src = X if i == 0 else trunk.H[i - 1][r0:r1]
-      be.gemm(src, gm.P(kn), trunk.Z[i][r0:r1])
-      be.ln_fwd(trunk.Z[i][r0:r1], gm.P(sn), gm.P(bn), trunk.H[i][r0:r1],
-                trunk.st[i][r0:r1], 1)
-    return trunk.H[-1][r0:r1]
-
-  def _prior_trunk_bwd(self, trunk, r0, r1, X, dH, dX, beta, wgrad):
+  def _prior_trunk_bwd(self, trunk, r0, r1, X, dH, dX, beta, wgrad, Xlo=None):
     """Backward of img_out_* trunk; dH clobbered; dX (+)= grad wrt X."""
-    be, gm = self.be, self.groups['model']
-    n = r1 - r0
-    tA = dH
-    for i in reversed(range(trunk.layers)):
-      kn, sn, bn = self._prior_names(i)
-      tB = self.tmp_other(tA, n, trunk.units)
-      be.ln_bwd(tA, trunk.Z[i][r0:r1], trunk.st[i][r0:r1], gm.P(sn), gm.P(bn), tB,
-                gm.G(sn) if wgrad else None, gm.G(bn) if wgrad else None, 1)
-      src = X if i == 0 else trunk.H[i - 1][r0:r1]
-      if wgrad:
-        be.gemm(src, tB, gm.G(kn), ta=True, beta=1.0)
-      if i == 0:
-        if dX is not None:
-          be.gemm(tB, gm.P(kn), dX, tb=True, beta=beta)
-      else:
-        tA = self.tmp_other(tB, n, trunk.units)
-        be.gemm(tB, gm.P(kn), tA, tb=True)
+    xs = [(X, 0, Xlo)] if (self.machine and Xlo is not None) else [(X, 0)]
+    trunk.bwd(dH, r0, r1, xs, [(dX, 0, beta)] if dX is not None else [], wgrad)
 
   # -- noise ------------------------------------------------------------------
   def draw_noise(self):
@@ -786,7 +935,11 @@ class Engine:
     if s.cnn_keys:
       self.embed_parts.append(self.enc_cnn.fwd(self.img))
     if s.obs_dims:
-      self.embed_parts.append(self.enc.fwd([(self.obs, 0)], 0, N))
+      if self.machine and self.enc.machine and _mview_ok(self.obs):
+        be.split_lo(self.obs, self.obs_lo)
+        self.embed_parts.append(self.enc.fwd([(self.obs, 0, self.obs_lo)], 0, N))
+      else:
+        self.embed_parts.append(self.enc.fwd([(self.obs, 0)], 0, N))
     off, beta = D, 0.0
     for part in self.embed_parts:
       be.gemm(part, Wobs[off:off + part.shape[1]], self.z_obs, beta=beta)
@@ -799,19 +952,21 @@ class Engine:
 
     if not self._observe_fused():
       self._observe_steps()
+    if self.machine:
+      be.split_lo(feat[:, :D], self.feat_lo)
 
     # prior logits for every step at once (the prior draw is unused by observe)
     self._prior_stats_fwd(self.prior, 0, N, feat[:, :D], self.zs_tmp, None,
-                          self.prior_logit, None, None, 2)
+                          self.prior_logit, None, None, 2, Xlo=self.feat_lo)
 
     # heads on the posterior features (A/agent.py:170-176)
-    xs = [(feat, 0)]
+    xs = self.fsegs(feat, self.feat_lo)
     if s.cnn_keys:
       self.dec_cnn.fwd(feat)
-    if s.dec_vec:
-      self._out_fwd(gm, 'dec/dist_out/out', self.heads['dec'].fwd(xs, 0, N), self.out_dec)
-    self._out_fwd(gm, 'reward/dist_out/out', self.heads['reward'].fwd(xs, 0, N), self.out_rew)
-    self._out_fwd(gm, 'cont/dist_out/out', self.heads['cont'].fwd(xs, 0, N), self.out_con)
+    for name, out in ((('dec', self.out_dec),) if s.dec_vec else ()) + (
+        ('reward', self.out_rew), ('cont', self.out_con)):
+      self.heads[name].fwd(xs, 0, N, heads=[(f'{name}/dist_out/out/kernel',
+                                             f'{name}/dist_out/out/bias', out)])
 
   def _observe_fused(self):
     """All L obs_steps in one persistent cooperative kernel (csrc/dd_scan.cu) when
@@ -949,7 +1104,7 @@ class Engine:
       tr = self.heads[name]
       dH = self.tmp(0, N, tr.units)
       self._out_bwd(gm, f'{name}/dist_out/out', tr.H[-1], dOut, dH, True)
-      tr.bwd(dH, 0, N, [(feat, 0)], [(dfeat, 0, beta)], True)
+      tr.bwd(dH, 0, N, self.fsegs(feat, self.feat_lo), [(dfeat, 0, beta)], True)
       beta = 1.0
 
     # prior chain (all steps at once): dprior_logit -> ... -> dfeat[:, :D]
@@ -957,7 +1112,8 @@ class Engine:
                  s.classes, s.rssm_unimix)
     dH = self.tmp(0, N, U)
     self._out_bwd(gm, 'rssm/img_stats', self.prior.H[-1], self.dzs, dH, True)
-    self._prior_trunk_bwd(self.prior, 0, N, feat[:, :D], dH, dfeat[:, :D], 1.0, True)
+    self._prior_trunk_bwd(self.prior, 0, N, feat[:, :D], dH, dfeat[:, :D], 1.0, True,
+                          Xlo=self.feat_lo)
 
     # reverse scan (BPTT)
     Win = gm.P('rssm/img_in/kernel')
@@ -1071,6 +1227,7 @@ class Engine:
     be.sumsq(g.g, g.sumsq)
     be.adam(g.p, g.g, g.m, g.v, g.n_decay, s.lr, s.beta1, s.beta2, s.adam_eps,
             s.wd, s.clip, 1.0, g.sumsq, self.counters, ci)
+    g.prep(be)
 
   # ==========================================================================
   # 2. imagination rollout (A/agent.py:234-261)
@@ -1079,16 +1236,20 @@ class Engine:
     s, be, ga = self.spec, self.be, self.groups['actor']
     N = self.N
     r0, r1 = t * N, (t + 1) * N
-    h = self.actor.fwd([(self.tfeat[t], 0)], r0, r1)
-    self._out_fwd(ga, 'actor/dist_out/out', h, self.a_mraw[r0:r1])
+    heads = [('actor/dist_out/out/kernel', 'actor/dist_out/out/bias', self.a_mraw[r0:r1])]
+    if not s.discrete:
+      heads.append(('actor/dist_out/std/kernel', 'actor/dist_out/std/bias', self.a_sraw[r0:r1]))
+    self.actor.fwd(self.fsegs(self.tfeat[t], self.tfeat_lo[t] if self.machine else None), r0, r1,
+                   heads=heads)
     if s.discrete:       # OneHotDist over unimix logits, straight-through sample (A/nets.py:480-491)
       be.stats_fwd(self.a_mraw[r0:r1], self.eps_act[t], self.talogit[t], self.taction[t],
                    None, 1, s.act_dim, s.actor_unimix, 0)
       return
-    self._out_fwd(ga, 'actor/dist_out/std', h, self.a_sraw[r0:r1])
     be.actor_sample(self.a_mraw[r0:r1], self.a_sraw[r0:r1], self.eps_act[t],
                     s.actor_minstd, s.actor_maxstd, self.taction[t],
                     self.tmean[t], self.tstd[t])
+    if self.machine:
+      be.split_lo(self.taction[t], self.taction_lo[t])
 
   def imagine(self, actions=None):
     """WorldModel.imagine (A/agent.py:234-261): the actor picks every action.  With
@@ -1100,34 +1261,86 @@ class Engine:
     tf = self.tfeat
     be.copy_(tf[0], self.feat)
     be.copy_(self.tlogit[0], self.post_logit)
+    if self.machine:
+      be.copy_(self.tfeat_lo[0], self.feat_lo)
     Win = gm.P('rssm/img_in/kernel')
     Wgru = gm.P('rssm/gru_out/kernel')
     if actions is None:
       self._actor_fwd(0)
     for t in range(H):
-      be.gemm(tf[t][:, D:], Win[:SC], self.i_zin[t])
-      be.gemm(self.taction[t] if actions is None else actions[t], Win[SC:], self.i_zin[t],
-              beta=1.0)
-      be.ln_fwd(self.i_zin[t], gm.P('rssm/img_in/norm/scale'),
-                gm.P('rssm/img_in/norm/bias'), self.i_xin[t], self.i_stin[t], 1)
-      be.gemm(tf[t][:, :D], Wgru[:D], self.i_zgru[t])
-      be.gemm(self.i_xin[t], Wgru[D:], self.i_zgru[t], beta=1.0)
-      be.ln_fwd(self.i_zgru[t], gm.P('rssm/gru_out/norm/scale'),
-                gm.P('rssm/gru_out/norm/bias'), self.i_ygru[t], self.i_stgru[t], 0)
+      act = self.taction[t] if actions is None else actions[t]
+      if not self._cell_program(t, act, actions is None):
+        be.gemm(tf[t][:, D:], Win[:SC], self.i_zin[t])
+        be.gemm(act, Win[SC:], self.i_zin[t], beta=1.0)
+        be.ln_fwd(self.i_zin[t], gm.P('rssm/img_in/norm/scale'),
+                  gm.P('rssm/img_in/norm/bias'), self.i_xin[t], self.i_stin[t], 1)
+        be.gemm(tf[t][:, :D], Wgru[:D], self.i_zgru[t])
+        be.gemm(self.i_xin[t], Wgru[D:], self.i_zgru[t], beta=1.0)
+        be.ln_fwd(self.i_zgru[t], gm.P('rssm/gru_out/norm/scale'),
+                  gm.P('rssm/gru_out/norm/bias'), self.i_ygru[t], self.i_stgru[t], 0)
       be.gru_fwd(self.i_ygru[t], tf[t][:, :D], tf[t + 1][:, :D])
+      if self.machine:
+        be.split_lo(tf[t + 1][:, :D], self.tfeat_lo[t + 1])
       self._prior_stats_fwd(self.i_prior, t * N, (t + 1) * N, tf[t + 1][:, :D],
                             self.i_zs, self.g_img[t], self.tlogit[t + 1],
-                            tf[t + 1][:, D:], None, 0)
+                            tf[t + 1][:, D:], None, 0,
+                            Xlo=self.tfeat_lo[t + 1] if self.machine else None)
       if actions is None:
         self._actor_fwd(t + 1)
+
+  def _cell_program(self, t, act, own_action):
+    """img_in (Linear + LayerNorm + elu over [stoch, action]) and the GRU's Linear + joint
+    LayerNorm of rollout step t as one 2-layer machine program (A/nets.py:129, :153-154).
+    False when the shapes do not tile (the caller then issues the per-op launches)."""
+    s, be, gm = self.spec, self.be, self.groups['model']
+    D, U, SC = s.deter, s.units, s.sc
+    if not (self.machine and U % 256 == 0 and (3 * D) % 256 == 0 and D % 4 == 0 and SC % 4 == 0):
+      return False
+    if not hasattr(self, '_cell_progs'):
+      self._cell_progs = {}
+    prog = self._cell_progs.get(t)
+    if prog is None:
+      if own_action:
+        act_lo = self.taction_lo[t]
+      else:                      # recorded actions (report): remainders computed on the fly
+        if not hasattr(self, '_act_lo'):
+          self._act_lo = be.zeros(*self.taction.shape)
+        act_lo = self._act_lo[t]
+      if not (_mview_ok(act) and _mview_ok(act_lo)):
+        self._cell_progs[t] = False
+        return False
+      tf = self.tfeat
+      wt, wtlo = gm.PT('rssm/img_in/kernel')
+      gt, gtlo = gm.PT('rssm/gru_out/kernel')
+      layers = [
+          PG.Layer([PG.Seg(tf[t][:, D:], None, 0), PG.Seg(act, act_lo, SC)], wt, wtlo, U, PG.EPI_LN,
+                   act=1, gamma=gm.P('rssm/img_in/norm/scale'), beta=gm.P('rssm/img_in/norm/bias'),
+                   z=self.i_zin[t], st=self.i_stin[t], out=self.i_xin[t], out_lo=self.i_xin_lo[t]),
+          PG.Layer([PG.Seg(tf[t][:, :D], self.tfeat_lo[t], 0), PG.Seg(self.i_xin[t], self.i_xin_lo[t], D)],
+                   gt, gtlo, 3 * D, PG.EPI_LN, act=0, gamma=gm.P('rssm/gru_out/norm/scale'),
+                   beta=gm.P('rssm/gru_out/norm/bias'), z=self.i_zgru[t], st=self.i_stgru[t],
+                   out=self.i_ygru[t])]
+      prog = self._cell_progs[t] = (be.program_build(layers, self.N), act_lo, own_action)
+    if prog is False:
+      return False
+    if not prog[2]:
+      be.split_lo(act, prog[1])
+    be.program_run(prog[0])
+    return True
 
   # ==========================================================================
   # 3. trajectory heads, lambda-return, critic update (A/agent.py:398-454)
   # ==========================================================================
-  def _traj_head(self, trunk, group, prefix, out, r0, r1):
+  def _tsegs(self, r0, r1):
+    """Trajectory feature rows [r0, r1) of the flattened [T*N, D+SC] rollout as trunk inputs."""
     flat = self.tfeat.view(-1, self.spec.feat)
-    h = trunk.fwd([(flat[r0:r1], 0)], r0, r1, group)
-    self._out_fwd(group, f'{prefix}/dist_out/out', h, out.view(-1, 1)[r0:r1])
+    lo = self.tfeat_lo.view(-1, self.spec.deter)[r0:r1] if self.machine else None
+    return self.fsegs(flat[r0:r1], lo)
+
+  def _traj_head(self, trunk, group, prefix, out, r0, r1):
+    trunk.fwd(self._tsegs(r0, r1), r0, r1, group,
+              heads=[(f'{prefix}/dist_out/out/kernel', f'{prefix}/dist_out/out/bias',
+                      out.view(-1, 1)[r0:r1])])
 
   def traj_values(self, slow_only=False):
     s, be = self.spec, self.be
@@ -1145,15 +1358,15 @@ class Engine:
     N, H = self.N, self.H
     M = H * N
     flat = self.tfeat.view(-1, s.feat)[:M]
-    h = self.t_critic.fwd([(flat, 0)], 0, M)
-    self._out_fwd(gc, 'critic/dist_out/out', h, self.vpred)
+    h = self.t_critic.fwd(self._tsegs(0, M), 0, M,
+                          heads=[('critic/dist_out/out/kernel', 'critic/dist_out/out/bias', self.vpred)])
     coef = 1.0 / (M * self.world)
     be.head_loss(1, self.vpred, self.r_ret.view(M, 1), self.r_weight.view(-1)[:M],
                  coef, self.closs_row, self.d_vpred)
     be.fill_(gc.g, 0.0)
     dH = self.tmp(0, M, s.head_units)
     self._out_bwd(gc, 'critic/dist_out/out', h, self.d_vpred, dH, True)
-    self.t_critic.bwd(dH, 0, M, [(flat, 0)], [], True)
+    self.t_critic.bwd(dH, 0, M, self._tsegs(0, M), [], True)
     # metrics before the update changes anything
     self._stat(self.r_reward, 'imag_reward')
     be.symexp(self.vpred, self.vsym)
@@ -1162,6 +1375,7 @@ class Engine:
     self._stat(self.closs_row, 'closs')
     self.opt_step('critic', C_CRITIC)
     be.slow_sync(gc.p, self.groups['slow_critic'].p, self.counters, C_SLOW, s.slow_every)
+    self.groups['slow_critic'].prep(be)
 
   # ==========================================================================
   # 4. actor update (A/agent.py:326-381), gradients through the dynamics
@@ -1217,7 +1431,7 @@ class Engine:
       n = T * N - r0
       dH = self.tmp(0, n, hu)
       self._out_bwd(g, f'{prefix}/dist_out/out', trunk.H[-1][r0:], dOut.view(-1, 1)[r0:], dH, False)
-      trunk.bwd(dH, r0, T * N, [(flat[r0:], 0)], [(dtf[r0:], 0, beta)], False, g)
+      trunk.bwd(dH, r0, T * N, self._tsegs(r0, T * N), [(dtf[r0:], 0, beta)], False, g)
 
     # reverse through the rollout: t = H .. 1
     Win = gm.P('rssm/img_in/kernel')
@@ -1230,7 +1444,8 @@ class Engine:
       dH = self.tmp(0, N, U)
       self._out_bwd(gm, 'rssm/img_stats', self.i_prior.H[-1][k * N:(k + 1) * N], dzs, dH, False)
       self._prior_trunk_bwd(self.i_prior, k * N, (k + 1) * N, self.tfeat[t][:, :D], dH,
-                            self.dtfeat[t][:, :D], 1.0, False)
+                            self.dtfeat[t][:, :D], 1.0, False,
+                            Xlo=self.tfeat_lo[t] if self.machine else None)
       dy = self.tmp(0, N, 3 * D)
       dzg = self.tmp(1, N, 3 * D)
       be.gru_bwd(self.dtfeat[t][:, :D], self.i_ygru[k], self.tfeat[k][:, :D], dy,
@@ -1262,7 +1477,7 @@ class Engine:
     be.colsum(self.d_sraw, ga.G('actor/dist_out/std/bias'), acc=True)
     be.gemm(self.d_mraw, ga.P('actor/dist_out/out/kernel'), dH, tb=True)
     be.gemm(self.d_sraw, ga.P('actor/dist_out/std/kernel'), dH, tb=True, beta=1.0)
-    self.actor.bwd(dH, 0, M, [(flat[:M], 0)], [], True)
+    self.actor.bwd(dH, 0, M, self._tsegs(0, M), [], True)
     self.opt_step('actor', C_ACTOR)
 
   def _actor_update_reinforce(self):
@@ -1289,8 +1504,7 @@ class Engine:
     h = self.actor.H[-1][:M]
     dH = self.tmp(0, M, s.head_units)
     self._out_bwd(ga, 'actor/dist_out/out', h, self.d_mraw, dH, True)
-    flat = self.tfeat.view(-1, s.feat)
-    self.actor.bwd(dH, 0, M, [(flat[:M], 0)], [], True)
+    self.actor.bwd(dH, 0, M, self._tsegs(0, M), [], True)
     self.opt_step('actor', C_ACTOR)
 
   # ==========================================================================
@@ -1482,7 +1696,7 @@ class PolicyEngine:
     self.enc = Trunk(eng, gm, 'enc', s.enc_layers, E, P) if s.obs_dims else None
     self.enc_cnn = ConvEncoder(eng, gm, P, train=False) if s.cnn_keys else None
     self.init_deter = z(1, D)
-    self.init_trunk = Trunk(eng, gm, 'rssm/initp', s.prior_layers, U, 1)
+    self.init_trunk = Trunk(eng, gm, 'rssm/initp', s.prior_layers, U, 1, names=eng._prior_names)
     self.init_zs, self.init_logit, self.init_stoch = z(1, SC), z(1, SC), z(1, SC)
     self.m_deter, self.m_stoch, self.m_act = z(P, D), z(P, SC), z(P, A)
     self.z_in, self.x_in, self.st_in = z(P, U), z(P, U), z(P, 2)

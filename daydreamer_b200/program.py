@@ -33,9 +33,9 @@ class Seg:
 
 @dataclasses.dataclass
 class Layer:
-  segs: List[Seg]
-  w: torch.Tensor                      # B operand: row-major [wrows, wcols] view
-  w_lo: torch.Tensor
+  segs: List[Seg]                      # empty: epilogue-only layer, its input is `add`
+  w: Optional[torch.Tensor]            # B operand: row-major [wrows, wcols] view
+  w_lo: Optional[torch.Tensor]
   N: int
   epi: int = EPI_PLAIN
   act: int = 0

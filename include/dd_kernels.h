@@ -342,6 +342,10 @@ int dd_program_build(const DdLayer* layers, int nlayers, int rows, void* table_d
 int dd_program_run(const void* table_dev, int nlayers, int rows, dd_stream_t stream);
 /* after a failed run: 1 and the 8 diagnostic words of the stuck wait, else 0 */
 int dd_program_debug(unsigned* out8);
+/* profiling aids: switches that drop parts of the machine's pipeline (garbage results) and
+ * per-CTA wait-cycle totals [cta][16] (index = wait code; 0 = kernel cycles) */
+int dd_set_machine_debug(int flags);
+int dd_machine_prof(int on, unsigned long long* out, int n);
 /* lo[r, c] = tf32(x - top19bits(x)) for a row-strided matrix */
 int dd_split_lo(const float* x, int ldx, float* lo, int ldlo, int rows, int cols,
                 dd_stream_t stream);

@@ -29,6 +29,12 @@ def rel(a, b):
     # image only, continuous actions
     (2, 3, 1, dict(obs_dims={}, cnn_keys={'image': (10, 10, 3)}, cnn_depth=4, enc_kernels=(4, 4),
                    dec_kernels=(4, 4))),
+    # widths that tile across the layer machine's clusters: every trunk, the prior stack and the
+    # rollout cell run as fused programs (operands reconstructed from their (x, x_lo) pairs)
+    (2, 3, 2, dict(obs_dims={'vector': 16}, act_dim=12, deter=256, units=256, stoch=8, classes=32,
+                   enc_units=256, head_units=256, horizon=2)),
+    (2, 3, 1, dict(obs_dims={'vector': 8}, discrete=True, act_dim=8, deter=256, units=256, stoch=8,
+                   classes=32, enc_units=256, head_units=256, horizon=2)),
 ])
 def test_train_step_matches_oracle(B, L, steps, kw):
   torch.manual_seed(0)
@@ -71,7 +77,10 @@ def test_train_step_matches_oracle(B, L, steps, kw):
     # updated parameters
     ep = eng.get_params()
     for k, v in ol.params.items():
-      assert rel(ep[k], v.numpy()) < 1e-5, (it, k)
+      # Adam moves every element by ~lr whatever its gradient: an element whose gradient is at
+      # rounding noise may land a small fraction of lr away
+      assert (rel(ep[k], v.numpy()) < 1e-5 or
+              np.abs(ep[k] - v.numpy()).max() <= 0.05 * ospec.lr), (it, k)
     # metrics
     em = eng.read_metrics()
     for k, v in omets.items():

@@ -33,6 +33,12 @@ def run_both(backends, case, rtol=2e-5, atol=2e-5):
     print('machine debug:', cu.program_debug())
     raise
   for k in ref:
+    if k == 'lo':      # a remainder is only defined relative to the value it belongs to
+      for res in (ref, out):
+        val = next((res[n] for n in ('out', 'dz', 'x') if n in res), None)
+        assert val is not None and torch.equal(P.lo_of(val.cpu()).view(val.shape), res['lo'].cpu()), \
+            'x_lo is not the tf32 remainder of x'
+      continue
     a, b = ref[k].double().cpu().numpy(), out[k].double().cpu().numpy()
     err = np.abs(a - b)
     tol = atol + rtol * np.abs(a)
@@ -43,8 +49,8 @@ def run_both(backends, case, rtol=2e-5, atol=2e-5):
 
 def wt_pair(T, W):
   """Forward B operand of x @ W: the transposed kernel and its remainder."""
-  wt = W.t().contiguous()
-  return T(wt), T(P.lo_of(wt))
+  wt = torch.empty(W.shape[1], W.shape[0]).copy_(W.t())
+  return T(wt), T(P.lo_of(wt).view(wt.shape))
 
 
 def act_pair(T, X):
@@ -189,8 +195,7 @@ def test_trunk_chain(backends, M):
     dg = [T(torch.zeros(U)) for _ in range(4)]
     db = [T(torch.zeros(U)) for _ in range(4)]
     dX = T(rnd(M, D, seed=61))
-    eye, eyelo = T(torch.eye(U)), T(torch.zeros(U, U))
-    back = [P.Layer([P.Seg(dH, dHlo)], eye, eyelo, U, P.EPI_LNBWD, act=1, gamma=gam[3], beta=bet[3],
+    back = [P.Layer([], None, None, U, P.EPI_LNBWD, add=dH, act=1, gamma=gam[3], beta=bet[3],
                     z=Z[3], st=st[3], out=dZ[3], out_lo=dZlo[3], dgamma=dg[3], dbeta=db[3])]
     for i in (2, 1, 0):
       back.append(P.Layer([P.Seg(dZ[i + 1], dZlo[i + 1])], Wb[i + 1][0], Wb[i + 1][1], U, P.EPI_LNBWD,
@@ -205,9 +210,9 @@ def test_trunk_chain(backends, M):
 def test_operand_prep(backends):
   """dd_split_lo on a strided view and dd_transpose_lo over several matrices of a flat buffer."""
   def case(be, T):
-    X = T(rnd(333, 70, seed=1))
+    X = T(rnd(333, 72, seed=1))
     lo = T(torch.zeros(333, 64))
-    be.split_lo(X[:, 3:67], lo)
+    be.split_lo(X[:, 4:68], lo)
     shapes = [(512, 512), (1036, 512), (512, 12), (40, 24)]
     n = sum(r * c for r, c in shapes)
     p = T(rnd(n, seed=2))
@@ -217,5 +222,5 @@ def test_operand_prep(backends):
       jobs.append((off, r, c, off, r if len(jobs) % 2 == 0 else c, len(jobs) % 2))
       off += r * c
     be.transpose_lo(p, pt, ptlo, jobs)
-    return {'lo': lo, 'pt': pt, 'ptlo': ptlo}
+    return {'x': X[:, 4:68].contiguous(), 'lo': lo, 'pt': pt, 'ptlo': ptlo}
   ref, out = run_both(backends, case, rtol=0, atol=0)

@@ -56,8 +56,7 @@ def test_trunk_program_matches_autograd():
   dg = [torch.zeros(U) for _ in range(3)]
   db = [torch.zeros(U) for _ in range(3)]
   dX = torch.zeros(M, D)
-  eye = torch.eye(U)
-  back = [P.Layer([P.Seg(dH, P.lo_of(dH))], eye, torch.zeros(U, U), U, P.EPI_LNBWD, act=1,
+  back = [P.Layer([], None, None, U, P.EPI_LNBWD, act=1, add=dH,
                   gamma=gam[2].detach(), beta=bet[2].detach(), z=Z[2], st=st[2], out=dZ[2],
                   out_lo=dZlo[2], dgamma=dg[2], dbeta=db[2])]
   for i in (1, 0):
