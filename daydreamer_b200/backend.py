@@ -119,8 +119,9 @@ class DdLayer(ctypes.Structure):
   _fields_ = [('nseg', _I), ('seg', DdSeg * 2), ('w', _P), ('w_lo', _P), ('ldw', _I),
               ('wrows', _I), ('wcols', _I), ('wn0', _I), ('N', _I), ('epi', _I), ('act', _I),
               ('add', _P), ('ld_add', _I), ('bias', _P), ('gamma', _P), ('beta', _P), ('z', _P),
-              ('ld_z', _I), ('st', _P), ('out', _P), ('out_lo', _P), ('ld_out', _I),
-              ('dgamma', _P), ('dbeta', _P)]
+              ('ld_z', _I), ('st', _P), ('out', _P), ('out_lo', _P), ('ld_out', _I), ('ld_lo', _I),
+              ('dgamma', _P), ('dbeta', _P), ('x', _P * 3), ('ldx', _I * 3), ('f', _F * 2),
+              ('ipar', _I)]
 
 
 class ProgramHandle:
@@ -589,10 +590,12 @@ class CudaBackend:
       d.st = _ptr(L.st)
       d.out, _, _, d.ld_out = _mat(L.out)
       if L.out_lo is not None:
-        pl, _, _, ldl = _mat(L.out_lo)
-        assert ldl == d.ld_out
-        d.out_lo = pl
+        d.out_lo, _, _, d.ld_lo = _mat(L.out_lo)
       d.dgamma, d.dbeta = _ptr(L.dgamma), _ptr(L.dbeta)
+      for q, t in enumerate((L.x0, L.x1, L.x2)):
+        if t is not None:
+          d.x[q], _, _, d.ldx[q] = _mat(t)
+      d.f[0], d.f[1], d.ipar = float(L.f0), float(L.f1), int(L.ipar)
     nbytes = int(self.lib.dd_program_bytes(n))
     table = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
     torch.cuda.synchronize(self.device)

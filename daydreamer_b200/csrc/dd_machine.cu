@@ -51,9 +51,9 @@ constexpr int STG_LD = 36;
 constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;
 constexpr int OFF_BAR = OFF_STG + 4 * STG_WARP_BYTES;
 constexpr int OFF_EP = OFF_BAR + 128;                      // per-epilogue-warp copy of the layer's epilogue view
-constexpr int EP_BYTES = 160;
+constexpr int EP_BYTES = 208;
 constexpr int SMEM_BYTES = OFF_EP + 4 * EP_BYTES;
-constexpr int THREADS = 192;
+constexpr int THREADS = 224;          // warps: 0 weights, 1 MMA, 2-5 epilogue, 6 activations
 constexpr int TMEM_COLS = 256;        // 2 buffers x (main 64 | cross 64)
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
@@ -66,9 +66,10 @@ struct alignas(64) LmLayer {
   CUtensorMap w_hi, w_lo;         // B operand [n rows, k cols], box {32, bn}
   int nseg, seg_k[2], seg_wk0[2], seg_exact[2];
   int wn0;                        // first row of the B operand used by this layer
+  int w3d;                        // w_hi is a 3-D map over the (w, w_lo) planes: one box per k-block
   int N, bn, nchunk, chunk_stride, nactive;
   int epi, act;
-  int ld_add, ld_out, ld_z;
+  int ld_add, ld_out, ld_z, ld_lo;
   const float* add;               // [M, N] added to the accumulator (beta = 1 / skip input)
   const float* bias;              // [N]
   const float* gamma;             // LayerNorm scale / bias
@@ -79,6 +80,12 @@ struct alignas(64) LmLayer {
   float* out_lo;                  // its tf32 remainder (x_lo), or null
   float* dgamma;                  // LN bwd: parameter gradients (+=), or null
   float* dbeta;
+  // epilogue-specific extras (GRU: x0 = previous deter, x1 = post-norm gates saved for backward;
+  // STATS: x0 = Gumbel noise, x1 = one-hot sample; ACTOR: x0 = eps, x1 = mean, x2 = std)
+  float* x[3];
+  int ldx[3];
+  float f[2];
+  int ipar;
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------
@@ -139,7 +146,7 @@ __device__ __forceinline__ void trace_ev(const Ctx& cx, int role, uint32_t idx) 
   if (cx.trace != nullptr && idx < (uint32_t)TRACE_N && (threadIdx.x & 31) == 0)
     cx.trace[role * TRACE_N + idx] = (unsigned long long)clock64();
 }
-enum { F_NOMMA = 1, F_NOA = 2, F_LOCALA = 4, F_NOB = 8, F_TMFENCE = 16 };
+enum { F_NOMMA = 1, F_NOA = 2, F_LOCALA = 4, F_NOB = 8, F_TMFENCE = 16, F_ONLY1 = 32, F_ONLY2 = 64 };
 __device__ __noinline__ void stuck(const Ctx& cx, int code, uint32_t parity) {
   if (cx.dbg != nullptr) {
     cx.dbg[1] = (unsigned)code;
@@ -212,6 +219,14 @@ __device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* map, i
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
       " [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1,
@@ -365,89 +380,103 @@ __device__ __forceinline__ int layer_kblocks(const LmLayer& L) {
   return kb;
 }
 
-__device__ void producer(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
-                         int cluster_id, int nclusters, int lane, Ctx cx) {
+// Two producer warps share the stage ring: warp 0 streams this CTA's weight tiles (they never
+// depend on the previous layer, so it runs ahead across layer boundaries on its own), warp 6
+// multicasts this CTA's 16-row slice of the activations (it is the one that waits for the previous
+// layer's outputs).  Both arm the stage's `full` barrier with their own byte count.
+__device__ void producer_b(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
+                           int cluster_id, int nclusters, int lane, Ctx cx) {
   const int ntiles = (M + BM - 1) / BM;
   uint32_t it = 0;
   int pair = 0;
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
-    const int m0 = tile * BM;
     for (int l = 0; l < nlayers; ++l, ++pair) {
       const LmLayer& L = layers[l];
       cx.pair = pair;
+      if (L.nseg == 0) continue;
       if (lane == 0) {
-        const bool fence = (cx.flags & F_TMFENCE) != 0;
-        for (int s = 0; s < L.nseg; ++s) {
-          tmap_acquire(&L.a_hi[s], fence);
-          if (!L.seg_exact[s]) tmap_acquire(&L.a_lo[s], fence);
+        tmap_acquire(&L.w_hi, (cx.flags & F_TMFENCE) != 0);
+        if (!L.w3d) tmap_acquire(&L.w_lo, (cx.flags & F_TMFENCE) != 0);
+      }
+      __syncwarp();
+      const int kb0 = (L.seg_k[0] + BK - 1) / BK, kbc = layer_kblocks(L);
+      const int nchunk = L.nchunk, bn = L.bn, chunk_stride = L.chunk_stride, w3d = L.w3d;
+      const int wk0[2] = {L.seg_wk0[0], L.seg_wk0[1]};
+      const bool active = rank < L.nactive && !(cx.flags & F_NOB);
+      const uint32_t bytes = active ? 2u * (uint32_t)bn * BK * 4 : 0u;
+      int n = L.wn0 + rank * bn;
+      for (int c = 0; c < nchunk; ++c, n += chunk_stride) {
+        for (int r = 0; r < kbc; ++r, ++it) {
+          const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          const uint32_t full = sh.bars + BAR_FULL + 8 * s;
+          mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * s, ph ^ 1, cx, 1);   // protects smem reuse only
+          trace_ev(cx, 0, 4 * it);
+          if (lane == 0) {
+            mbar_arrive_tx(full, bytes);
+            if (active) {
+              const uint32_t st = sh.base + s * STAGE_BYTES + 2 * A_BYTES;
+              const int k = wk0[seg] + kb * BK;
+              if (w3d) {             // rows [0, bn) = w, rows [bn, 2 bn) = w_lo: one box
+                tma_load_3d(st, &L.w_hi, k, n, 0, full);
+              } else {
+                tma_load(st, &L.w_hi, k, n, full);
+                tma_load(st + (uint32_t)bn * (BK * 4), &L.w_lo, k, n, full);
+              }
+            }
+          }
+          __syncwarp();
+          trace_ev(cx, 0, 4 * it + 1);
         }
-        if (L.nseg > 0) {
-          tmap_acquire(&L.w_hi, fence);
-          tmap_acquire(&L.w_lo, fence);
+      }
+    }
+  }
+}
+
+__device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
+                           int cluster_id, int nclusters, int lane, Ctx cx) {
+  const int ntiles = (M + BM - 1) / BM;
+  uint32_t it = 0;
+  int pair = 0;
+  for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
+    const int m = tile * BM + rank * SLICE_ROWS;
+    for (int l = 0; l < nlayers; ++l, ++pair) {
+      const LmLayer& L = layers[l];
+      cx.pair = pair;
+      if (L.nseg == 0) continue;
+      if (lane == 0) {
+        for (int g = 0; g < L.nseg; ++g) {
+          tmap_acquire(&L.a_hi[g], (cx.flags & F_TMFENCE) != 0);
+          if (!L.seg_exact[g]) tmap_acquire(&L.a_lo[g], (cx.flags & F_TMFENCE) != 0);
         }
       }
       __syncwarp();
-      const int kb0 = L.nseg > 0 ? (L.seg_k[0] + BK - 1) / BK : 0;
-      const int kbc = layer_kblocks(L);
-      const int total = kbc * L.nchunk;
-      const bool active = rank < L.nactive;
-      bool need_ready = l > 0;
-      int j = 0;
-      while (j < total) {
-        const int batch = need_ready ? min(STAGES, total - j) : 1;
-        // weights first: they do not depend on the previous layer
-        for (int b = 0; b < batch; ++b) {
-          const int jj = j + b, c = jj / kbc, r = jj % kbc;
+      const int kb0 = (L.seg_k[0] + BK - 1) / BK, kbc = layer_kblocks(L);
+      const int nchunk = L.nchunk;
+      const bool exact[2] = {L.seg_exact[0] != 0, L.seg_exact[1] != 0};
+      if (l > 0) {           // the previous layer's outputs of all 8 CTAs are in global memory
+        count_wait(sh.bars + BAR_READY, (uint32_t)pair * CL, cx, 2);
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      for (int c = 0; c < nchunk; ++c) {
+        for (int r = 0; r < kbc; ++r, ++it) {
           const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
-          const uint32_t itb = it + b, s = itb % STAGES, ph = (itb / STAGES) & 1;
-          const uint32_t full = sh.bars + BAR_FULL + 8 * s, empty = sh.bars + BAR_EMPTY + 8 * s;
-          mbar_wait<false>(empty, ph ^ 1, cx, 1);     // protects shared-memory reuse only
-          trace_ev(cx, 0, 4 * itb);
-          if (lane == 0) {
-            const uint32_t bytes = ((cx.flags & F_NOA) ? 0u : (L.seg_exact[seg] ? 1u : 2u) * A_BYTES) +
-                                   ((active && !(cx.flags & F_NOB)) ? 2u * (uint32_t)L.bn * BK * 4 : 0u);
-            mbar_arrive_tx(full, bytes);
-            if (active && !(cx.flags & F_NOB)) {
-              const uint32_t st = sh.base + s * STAGE_BYTES + 2 * A_BYTES;
-              const int k = L.seg_wk0[seg] + kb * BK;
-              const int n = L.wn0 + c * L.chunk_stride + rank * L.bn;
-              tma_load(st, &L.w_hi, k, n, full);
-              tma_load(st + (uint32_t)L.bn * (BK * 4), &L.w_lo, k, n, full);   // rows [bn, 2 bn) of one tile
-            }
-          }
-          __syncwarp();
-          trace_ev(cx, 0, 4 * itb + 1);
-        }
-        if (need_ready) {       // the previous layer's outputs of all 8 CTAs are in global memory
-          count_wait(sh.bars + BAR_READY, (uint32_t)pair * CL, cx, 2);
-          asm volatile("fence.proxy.async;" ::: "memory");
-          need_ready = false;
-        }
-        // activations: my 16-row slice of the tile, multicast to the whole cluster
-        for (int b = 0; b < batch; ++b) {
-          const int jj = j + b, r = jj % kbc;
-          const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
-          const uint32_t itb = it + b, s = itb % STAGES;
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           const uint32_t full = sh.bars + BAR_FULL + 8 * s;
-          if (lane == 0 && !(cx.flags & F_NOA)) {
-            if (cx.flags & F_LOCALA) {       // profiling: every CTA fetches the whole tile itself
-              for (int q = 0; q < CL; ++q) {
-                const uint32_t st = sh.base + s * STAGE_BYTES + q * SLICE_BYTES;
-                tma_load(st, &L.a_hi[seg], kb * BK, m0 + q * SLICE_ROWS, full);
-                if (!L.seg_exact[seg]) tma_load(st + A_BYTES, &L.a_lo[seg], kb * BK, m0 + q * SLICE_ROWS, full);
-              }
-            } else {
+          mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * s, ph ^ 1, cx, 9);
+          trace_ev(cx, 0, 4 * it + 2);
+          if (lane == 0) {
+            const bool noa = (cx.flags & F_NOA) != 0;
+            mbar_arrive_tx(full, noa ? 0u : (exact[seg] ? 1u : 2u) * A_BYTES);
+            if (!noa) {
               const uint32_t st = sh.base + s * STAGE_BYTES + rank * SLICE_BYTES;
-              const int k = kb * BK, m = m0 + rank * SLICE_ROWS;
-              tma_load_mc(st, &L.a_hi[seg], k, m, full, (uint16_t)0xFF);
-              if (!L.seg_exact[seg]) tma_load_mc(st + A_BYTES, &L.a_lo[seg], k, m, full, (uint16_t)0xFF);
+              tma_load_mc(st, &L.a_hi[seg], kb * BK, m, full, (uint16_t)0xFF);
+              if (!exact[seg]) tma_load_mc(st + A_BYTES, &L.a_lo[seg], kb * BK, m, full, (uint16_t)0xFF);
             }
           }
           __syncwarp();
-          trace_ev(cx, 0, 4 * itb + 2);
+          trace_ev(cx, 0, 4 * it + 3);
         }
-        it += batch;
-        j += batch;
       }
     }
   }
@@ -465,16 +494,19 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
       const int kb0 = (L.seg_k[0] + BK - 1) / BK;
       const int kbc = layer_kblocks(L);
       const bool active = rank < L.nactive;
-      const uint32_t idesc = make_idesc(L.bn), idesc2 = make_idesc(2 * L.bn);
+      const int bn = L.bn, nchunk = L.nchunk;
+      const uint32_t idesc = make_idesc(bn), idesc2 = make_idesc(2 * bn);
       if (L.nseg == 0) continue;                 // epilogue-only layer
-      for (int c = 0; c < L.nchunk; ++c) {
+      const int segk[2] = {L.seg_k[0], L.seg_k[1]};
+      const bool sexact[2] = {L.seg_exact[0] != 0, L.seg_exact[1] != 0};
+      for (int c = 0; c < nchunk; ++c) {
         const uint32_t buf = ac & 1;
         if (active) {
           mbar_wait<false>(sh.bars + BAR_ACCE + 8 * buf, ((ac >> 1) & 1) ^ 1, cx, 3);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         // accumulator buffer: columns [0, bn) main (hi.hi), [bn, 2 bn) the small cross terms
-        const uint32_t d_main = tmem_base + buf * 128, d_cross = d_main + (uint32_t)L.bn;
+        const uint32_t d_main = tmem_base + buf * 128, d_cross = d_main + (uint32_t)bn;
         uint32_t acc = 0;
         for (int r = 0; r < kbc; ++r, ++it) {
           const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
@@ -486,16 +518,16 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
             if (active && !(cx.flags & F_NOMMA)) {
               const uint32_t a_hi = sh.base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
               const uint32_t b_hi = a_hi + 2 * A_BYTES;
-              const int kvalid = min(BK, L.seg_k[seg] - kb * BK);
+              const int kvalid = min(BK, segk[seg] - kb * BK);
               const int ksteps = (kvalid + 7) >> 3;
-              const bool exact = L.seg_exact[seg] != 0;
+              const bool exact = sexact[seg];
               for (int ks = 0; ks < ksteps; ++ks) {
                 const uint64_t dah = make_desc(a_hi + ks * 32), dbh = make_desc(b_hi + ks * 32);
                 // B_hi and B_lo are rows [0, bn) and [bn, 2 bn) of ONE K-major tile: a single
                 // N = 2 bn product gives hi.hi (main) and hi.lo (cross) with one read of A_hi
-                mma_tf32(d_main, dah, dbh, idesc2, acc);
+                if (!(cx.flags & F_ONLY2)) mma_tf32(d_main, dah, dbh, idesc2, acc);
                 acc = 1;
-                if (!exact) mma_tf32(d_cross, make_desc(a_lo + ks * 32), dbh, idesc, 1u);
+                if (!exact && !(cx.flags & F_ONLY1)) mma_tf32(d_cross, make_desc(a_lo + ks * 32), dbh, idesc, 1u);
               }
             }
             // this stage may be refilled once every CTA of the cluster has read it
@@ -569,18 +601,24 @@ __device__ __forceinline__ void acc_release(const Shared& sh, EpiState& es, int 
 // the epilogue's view of a layer, copied into shared memory once per (tile, layer) and warp: the
 // descriptor itself lives in global memory and would be re-read after every global store
 struct EP {
-  int nseg, N, bn, nchunk, chunk_stride, nactive, epi, act, ld_add, ld_out, ld_z;
+  int nseg, N, bn, nchunk, chunk_stride, nactive, epi, act, ld_add, ld_out, ld_z, ld_lo;
   const float *add, *bias, *gamma, *beta;
   float *z, *st, *out, *out_lo, *dgamma, *dbeta;
+  float* x[3];
+  int ldx[3];
+  float f[2];
+  int ipar;
 };
 static_assert(sizeof(EP) <= EP_BYTES, "EP slot");
 __device__ __forceinline__ EP load_ep(const LmLayer& L) {
   EP e;
   e.nseg = L.nseg; e.N = L.N; e.bn = L.bn; e.nchunk = L.nchunk; e.chunk_stride = L.chunk_stride;
   e.nactive = L.nactive; e.epi = L.epi; e.act = L.act;
-  e.ld_add = L.ld_add; e.ld_out = L.ld_out; e.ld_z = L.ld_z;
+  e.ld_add = L.ld_add; e.ld_out = L.ld_out; e.ld_z = L.ld_z; e.ld_lo = L.ld_lo;
   e.add = L.add; e.bias = L.bias; e.gamma = L.gamma; e.beta = L.beta;
   e.z = L.z; e.st = L.st; e.out = L.out; e.out_lo = L.out_lo; e.dgamma = L.dgamma; e.dbeta = L.dbeta;
+  for (int i = 0; i < 3; ++i) { e.x[i] = L.x[i]; e.ldx[i] = L.ldx[i]; }
+  e.f[0] = L.f[0]; e.f[1] = L.f[1]; e.ipar = L.ipar;
   return e;
 }
 // 32 consecutive per-column parameters (16-byte aligned: offsets are multiples of 32 floats)
@@ -633,7 +671,7 @@ __device__ __forceinline__ void store_with_lo(const EP& L, float* stg, float (&v
   if (L.out_lo != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = lo_of(v[j]);
-    sub_store(stg, v, L.out_lo + (size_t)wrow0 * L.ld_out + cb, L.ld_out, rows_valid, cols_valid, lane);
+    sub_store(stg, v, L.out_lo + (size_t)wrow0 * L.ld_lo + cb, L.ld_lo, rows_valid, cols_valid, lane);
   }
 }
 
@@ -825,6 +863,165 @@ __device__ void epi_ln_bwd(const Shared& sh, const EP& L, EpiState& es, uint32_t
   }
 }
 
+
+// E_GRU: joint LayerNorm over the 3 D gate pre-activations, then the GRU update (A/nets.py:149-160)
+//   y = LN(z) * gamma + beta; r = sig(y_r); c = tanh(r * y_c); u = sig(y_u - 1); out = u c + (1 - u) prev
+// Chunk g of a CTA holds its column slice of gate g (chunk_stride = D), so a thread has the three
+// gate values of its columns.  z: pre-norm (saved), x1: y (saved), x0: prev.
+__device__ void epi_gru(const Shared& sh, const EP& L, EpiState& es, uint32_t tmem_base, int rank,
+                        int quad, int lane, float* stg, int wrow0, int rows_valid, int trow,
+                        const Ctx& cx) {
+  const int halves = L.bn >> 5;
+  const int D = L.chunk_stride;
+  float mean = 0.f, m2 = 0.f, cnt = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    acc_wait(sh, es, cx, true);
+    const int col0 = c * D + rank * L.bn;
+    for (int h = 0; h < halves; ++h) {
+      const int cb = col0 + h * 32;
+      float v[32];
+      fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, 32, lane, v);
+      sub_store(stg, v, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s += v[j];
+      const float mu = s * (1.f / 32.f);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float d = v[j] - mu; q += d * d; }
+      const float delta = mu - mean, tot = cnt + 32.f;
+      mean += delta * (32.f / tot);
+      m2 += q + delta * delta * (cnt * 32.f / tot);
+      cnt = tot;
+    }
+    acc_release(sh, es, lane, true);
+  }
+  float2 parts[CL];
+  row_exchange(sh, es, rank, trow, 2 + ((quad + 2) & 3), lane, mean, m2, parts, cx);
+  float gm = 0.f;
+  for (int d = 0; d < CL; ++d) gm += parts[d].x;
+  gm *= (1.f / CL);
+  float gq = 0.f;
+  for (int d = 0; d < CL; ++d) { const float dl = parts[d].x - gm; gq += parts[d].y + cnt * dl * dl; }
+  const float rstd = rsqrtf(gq / (float)L.N + DD_LN_EPS);
+  if (L.st != nullptr && rank == 0 && lane < rows_valid) {
+    L.st[(size_t)(wrow0 + lane) * 2] = gm;
+    L.st[(size_t)(wrow0 + lane) * 2 + 1] = rstd;
+  }
+  for (int h = 0; h < halves; ++h) {
+    const int cj = rank * L.bn + h * 32;            // column inside each gate
+    float g[32], v[32];
+    // reset gate
+    sub_load(stg, v, L.z + (size_t)wrow0 * L.ld_z + cj, L.ld_z, rows_valid, 32, lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (v[j] - gm) * rstd * __ldg(L.gamma + cj + j) + __ldg(L.beta + cj + j);
+    if (L.x[1] != nullptr)
+      sub_store(stg, v, L.x[1] + (size_t)wrow0 * L.ldx[1] + cj, L.ldx[1], rows_valid, 32, lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) g[j] = sigmoidf_(v[j]);
+    // candidate
+    sub_load(stg, v, L.z + (size_t)wrow0 * L.ld_z + D + cj, L.ld_z, rows_valid, 32, lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      v[j] = (v[j] - gm) * rstd * __ldg(L.gamma + D + cj + j) + __ldg(L.beta + D + cj + j);
+    if (L.x[1] != nullptr)
+      sub_store(stg, v, L.x[1] + (size_t)wrow0 * L.ldx[1] + D + cj, L.ldx[1], rows_valid, 32, lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) g[j] = tanhf(g[j] * v[j]);
+    // update gate and the new state
+    sub_load(stg, v, L.z + (size_t)wrow0 * L.ld_z + 2 * D + cj, L.ld_z, rows_valid, 32, lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      v[j] = (v[j] - gm) * rstd * __ldg(L.gamma + 2 * D + cj + j) + __ldg(L.beta + 2 * D + cj + j);
+    if (L.x[1] != nullptr)
+      sub_store(stg, v, L.x[1] + (size_t)wrow0 * L.ldx[1] + 2 * D + cj, L.ldx[1], rows_valid, 32, lane);
+    float pv[32];
+    sub_load(stg, pv, L.x[0] + (size_t)wrow0 * L.ldx[0] + cj, L.ldx[0], rows_valid, 32, lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float u = sigmoidf_(v[j] - 1.f);
+      v[j] = u * g[j] + (1.f - u) * pv[j];
+    }
+    store_with_lo(L, stg, v, wrow0, rows_valid, cj, 32, lane);
+  }
+}
+
+// E_STATS: categorical head.  z = acc + bias; logit = log((1 - mix) softmax(z) + mix / C) per group of
+// C classes (A/nets.py:162-171); with noise: idx = argmax(logit + G), one-hot into x1
+// (OneHotDist.sample, A/tfutils.py:368-382).  C == 32: one group per 32-column sub-tile; C < 32: the
+// whole (narrow) layer is one group.  out = logit.
+__device__ void epi_stats(const Shared& sh, const EP& L, EpiState& es, uint32_t tmem_base, int rank,
+                          int quad, int lane, float* stg, int wrow0, int rows_valid, const Ctx& cx) {
+  const int halves = L.bn >> 5;
+  const int C = L.ipar;
+  const float mix = L.f[0], uni = mix / (float)C;
+  for (int c = 0; c < L.nchunk; ++c) {
+    acc_wait(sh, es, cx, L.nseg > 0);
+    const int col0 = c * L.chunk_stride + rank * L.bn;
+    for (int h = 0; h < halves; ++h) {
+      const int cb = col0 + h * 32;
+      const int cols_valid = min(32, L.N - cb);
+      if (cols_valid <= 0) continue;
+      float v[32];
+      fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, cols_valid, lane, v);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (j < C) mx = fmaxf(mx, v[j]);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { v[j] = j < C ? expf(v[j] - mx) : 0.f; sum += v[j]; }
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = logf((1.f - mix) * v[j] * inv + uni);
+      sub_store(stg, v, L.out + (size_t)wrow0 * L.ld_out + cb, L.ld_out, rows_valid, cols_valid, lane);
+      if (L.x[1] != nullptr) {
+        if (L.x[0] != nullptr) {
+          float g[32];
+          sub_load(stg, g, L.x[0] + (size_t)wrow0 * L.ldx[0] + cb, L.ldx[0], rows_valid, cols_valid, lane);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += g[j];
+        }
+        float bv = -INFINITY;
+        int bi = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (j < C && v[j] > bv) { bv = v[j]; bi = j; }   // first maximum
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (j == bi) ? 1.f : 0.f;
+        sub_store(stg, v, L.x[1] + (size_t)wrow0 * L.ldx[1] + cb, L.ldx[1], rows_valid, cols_valid, lane);
+      }
+    }
+    acc_release(sh, es, lane, L.nseg > 0);
+  }
+}
+
+// E_ACTOR: continuous action head (A/nets.py:461-468), N = 2 A columns [mean raw | std raw]:
+// mean = tanh(m); std = (hi - lo) sigmoid(s) + lo; action = mean + std * eps.
+// out = action (+ out_lo), x0 = eps, x1 = mean, x2 = std.
+__device__ void epi_actor(const Shared& sh, const EP& L, EpiState& es, uint32_t tmem_base, int rank,
+                          int quad, int lane, float* stg, int wrow0, int rows_valid, const Ctx& cx) {
+  const int A = L.ipar;
+  acc_wait(sh, es, cx, L.nseg > 0);
+  float v[32];
+  fetch_sub(L, tmem_base, es.ac & 1, quad, 0, stg, wrow0, rows_valid, 0, 2 * A, lane, v);
+  acc_release(sh, es, lane, L.nseg > 0);
+  if (lane < rows_valid) {
+    const size_t row = (size_t)(wrow0 + lane);
+    const float lo = L.f[0], hi = L.f[1];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < A) {
+        const float mu = tanhf(v[j]);
+        const float sd = (hi - lo) * sigmoidf_(v[A + j]) + lo;
+        const float a = mu + sd * L.x[0][row * L.ldx[0] + j];
+        L.x[1][row * L.ldx[1] + j] = mu;
+        L.x[2][row * L.ldx[2] + j] = sd;
+        L.out[row * L.ld_out + j] = a;
+        if (L.out_lo != nullptr) L.out_lo[row * L.ld_lo + j] = lo_of(a);
+      }
+    }
+  }
+}
+
 __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
                          int cluster_id, int nclusters, int warp, int lane, uint32_t tmem_base,
                          Ctx cx) {
@@ -852,8 +1049,14 @@ __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, i
         if (active) epi_plain(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, cx);
       } else if (L.epi == DD_EPI_LN) {
         if (active) epi_ln_fwd(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, trow, cx);
-      } else {
+      } else if (L.epi == DD_EPI_LNBWD) {
         if (active) epi_ln_bwd(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, trow, cx);
+      } else if (L.epi == DD_EPI_GRU) {
+        if (active) epi_gru(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, trow, cx);
+      } else if (L.epi == DD_EPI_STATS) {
+        if (active) epi_stats(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, cx);
+      } else {
+        if (active) epi_actor(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, cx);
       }
       // this CTA's rows of the layer's outputs are written: tell every CTA's producer.  Each
       // writer orders its stores against the async proxy (TMA reads them), the four epilogue warps
@@ -887,7 +1090,7 @@ lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg,
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(sh.bars + BAR_FULL + 8 * s, 1);
+      mbar_init(sh.bars + BAR_FULL + 8 * s, 2);       // one arrive.expect_tx per producer warp
       mbar_init(sh.bars + BAR_EMPTY + 8 * s, CL);
     }
     for (int b = 0; b < 2; ++b) {
@@ -915,14 +1118,16 @@ lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg,
   if ((sh.base & 1023u) != 0u) stuck(cx, 9, sh.base);      // SWIZZLE_128B tiles need 1 KB alignment
 
   if (warp == 0) {
-    producer(sh, layers, nlayers, M, rank, cluster_id, nclusters, lane, cx);
+    producer_b(sh, layers, nlayers, M, rank, cluster_id, nclusters, lane, cx);
+  } else if (warp == 6) {
+    producer_a(sh, layers, nlayers, M, rank, cluster_id, nclusters, lane, cx);
   } else if (warp == 1) {
     mma_issuer(sh, layers, nlayers, M, rank, cluster_id, nclusters, lane, tmem_base, cx);
   } else {
     epilogue(sh, layers, nlayers, M, rank, cluster_id, nclusters, warp, lane, tmem_base, cx);
   }
 
-  if (tid % 32 == 0) trace_ev(cx, 3, 1 + warp);
+  if (tid % 32 == 0 && warp < 6) trace_ev(cx, 3, 1 + warp);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid == 0) trace_ev(cx, 3, 8);
@@ -1013,6 +1218,27 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// 3-D view {cols, rows, 2 planes} of a (w, w_lo) pair whose planes are `plane` bytes apart: one box
+// {32, box_rows, 2} lands w rows then w_lo rows contiguously in shared memory
+static int make_map3(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld,
+                     int64_t plane_bytes, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail("dd_program_build", "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)plane_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[64];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled (3-D) failed (%d)", (int)r);
+    return fail("dd_program_build", msg);
+  }
+  return 0;
+}
+
 // 2-D fp32 tensor [rows, cols], row stride ld floats, box {32 cols, box_rows}, SWIZZLE_128B,
 // out-of-bounds elements read as zero
 static int make_map(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld,
@@ -1064,7 +1290,7 @@ extern "C" int dd_program_build(const DdLayer* layers, int nlayers, int rows, vo
       d.bn = 64; d.nchunk = s.N / (lm::CL * 64); d.nactive = lm::CL;
     } else if (s.N % (lm::CL * 32) == 0) {
       d.bn = 32; d.nchunk = s.N / (lm::CL * 32); d.nactive = lm::CL;
-    } else if (s.N <= 64 && s.epi == DD_EPI_PLAIN) {
+    } else if (s.N <= 64 && (s.epi == DD_EPI_PLAIN || s.epi == DD_EPI_STATS || s.epi == DD_EPI_ACTOR)) {
       d.bn = s.N <= 32 ? 32 : 64; d.nchunk = 1; d.nactive = 1;
     } else {
       rc = fail("dd_program_build", "N must be a multiple of 256 (or <= 64 for plain layers)");
@@ -1086,17 +1312,42 @@ extern "C" int dd_program_build(const DdLayer* layers, int nlayers, int rows, vo
     if (rc != 0) break;
     if (s.nseg > 0) {
       if (s.w == nullptr || s.w_lo == nullptr) { rc = fail("dd_program_build", "B operand needs (w, w_lo)"); break; }
-      rc = lm::make_map(&d.w_hi, s.w, s.wrows, s.wcols, s.ldw, d.bn);
-      if (rc == 0) rc = lm::make_map(&d.w_lo, s.w_lo, s.wrows, s.wcols, s.ldw, d.bn);
+      // (w, w_lo) planes a fixed, 16-byte aligned distance apart: one 3-D descriptor
+      const int64_t plane = reinterpret_cast<const char*>(s.w_lo) - reinterpret_cast<const char*>(s.w);
+      if (plane > 0 && (plane & 15) == 0 && plane >= (int64_t)s.wrows * s.ldw * 4 - (s.ldw - s.wcols) * 4 &&
+          (reinterpret_cast<uintptr_t>(s.w) & 15) == 0 && (s.ldw & 3) == 0) {
+        rc = lm::make_map3(&d.w_hi, s.w, s.wrows, s.wcols, s.ldw, plane, d.bn);
+        d.w3d = 1;
+      } else {
+        rc = lm::make_map(&d.w_hi, s.w, s.wrows, s.wcols, s.ldw, d.bn);
+        if (rc == 0) rc = lm::make_map(&d.w_lo, s.w_lo, s.wrows, s.wcols, s.ldw, d.bn);
+      }
       if (rc != 0) break;
     }
     d.wn0 = s.wn0;
     d.epi = s.epi;
     d.act = s.act;
-    d.ld_add = s.ld_add; d.ld_out = s.ld_out; d.ld_z = s.ld_z;
+    d.ld_add = s.ld_add; d.ld_out = s.ld_out; d.ld_z = s.ld_z; d.ld_lo = s.out_lo != nullptr ? s.ld_lo : 0;
     d.add = s.add; d.bias = s.bias; d.gamma = s.gamma; d.beta = s.beta;
     d.z = s.z; d.st = s.st; d.out = s.out; d.out_lo = s.out_lo;
     d.dgamma = s.dgamma; d.dbeta = s.dbeta;
+    for (int q = 0; q < 3; ++q) { d.x[q] = s.x[q]; d.ldx[q] = s.ldx[q]; }
+    d.f[0] = s.f[0]; d.f[1] = s.f[1]; d.ipar = s.ipar;
+    if (s.epi == DD_EPI_GRU) {
+      if (d.nchunk != 3 || d.nactive != lm::CL || s.gamma == nullptr || s.beta == nullptr ||
+          s.z == nullptr || s.x[0] == nullptr)
+        rc = fail("dd_program_build", "GRU layer: N = 3 D with D a multiple of 256, needs scale, bias, z and prev");
+    }
+    if (s.epi == DD_EPI_STATS) {
+      const bool wide = d.nactive == lm::CL;
+      if ((wide && s.ipar != 32) || (!wide && (s.ipar != s.N || s.N > 32)) || s.nseg == 0)
+        rc = fail("dd_program_build", "STATS layer: groups of 32 classes, or one narrow group of N <= 32");
+    }
+    if (s.epi == DD_EPI_ACTOR) {
+      if (s.N != 2 * s.ipar || s.ipar > 16 || s.x[0] == nullptr || s.x[1] == nullptr || s.x[2] == nullptr)
+        rc = fail("dd_program_build", "ACTOR layer: N = 2 A <= 32 with eps, mean and std buffers");
+    }
+    if (rc != 0) break;
     if (s.out == nullptr) { rc = fail("dd_program_build", "layer without output"); break; }
     if (s.epi == DD_EPI_LN && (s.gamma == nullptr || s.beta == nullptr))
       rc = fail("dd_program_build", "LayerNorm layer without scale / bias");

@@ -304,12 +304,15 @@ class ParamGroup:
       if i == len(decayed) - 1:
         self.n_decay = (off + 3) // 4 * 4
     self.size = (off + 3) // 4 * 4
-    self.p = be.zeros(self.size)
+    self.machine = hasattr(be, 'program_build')
+    # (p, p_lo) as the two planes of one buffer: the machine fetches a weight tile and its
+    # remainder with a single 3-D TMA box
+    self._pp = be.zeros(2 if self.machine else 1, self.size)
+    self.p = self._pp[0]
     self.g = be.zeros(self.size) if opt else None
     self.m = be.zeros(self.size) if opt else None
     self.v = be.zeros(self.size) if opt else None
     self.sumsq = be.zeros(1, dtype=torch.float64) if opt else None
-    self.machine = hasattr(be, 'program_build')
     self.t_off, self.b_off, self.jobs = {}, {}, []
     if self.machine:
       off = 0
@@ -327,9 +330,9 @@ class ParamGroup:
           self.b_off[n] = (off, ldb)
           self.jobs.append((src, K, N, off, ldb, 1))
           off += K * ldb
-      self.p_lo = be.zeros(self.size)
-      self.pt = be.zeros(max(off, 4))
-      self.pt_lo = be.zeros(max(off, 4))
+      self.p_lo = self._pp[1]
+      self._ptt = be.zeros(2, max(_ceil4(off), 4))
+      self.pt, self.pt_lo = self._ptt[0], self._ptt[1]
 
   def view(self, flat, name):
     off, shape = self.offsets[name]
@@ -354,6 +357,21 @@ class ParamGroup:
     off, ldt = self.t_off[name]
     K, N = self.offsets[name][1]
     return _strided(self.pt, off, N, K, ldt), _strided(self.pt_lo, off, N, K, ldt)
+
+  def PT2(self, a, b):
+    """Transposed copies of two kernels with the same input width stacked as one [Na + Nb, K]
+    operand (they are adjacent in `pt` by construction: consecutive kernels, K % 4 == 0)."""
+    (oa, la), (ob, lb) = self.t_off[a], self.t_off[b]
+    Ka, Na = self.offsets[a][1]
+    Kb, Nb = self.offsets[b][1]
+    assert Ka == Kb and la == lb and ob == oa + Na * la, 'kernels are not adjacent'
+    return _strided(self.pt, oa, Na + Nb, Ka, la), _strided(self.pt_lo, oa, Na + Nb, Ka, la)
+
+  def cat(self, a, b):
+    """Two 1-D parameters that lie back to back in the flat buffer, as one vector."""
+    (oa, sa), (ob, sb) = self.offsets[a], self.offsets[b]
+    assert ob == oa + int(np.prod(sa)), 'parameters are not adjacent'
+    return self.p[oa:ob + int(np.prod(sb))]
 
   def PB(self, name):
     """(W, its remainder) as [K, N] views with a 16-byte row stride: the B operand of dY @ W^T."""
@@ -1263,6 +1281,8 @@ class Engine:
     be.copy_(self.tlogit[0], self.post_logit)
     if self.machine:
       be.copy_(self.tfeat_lo[0], self.feat_lo)
+    if actions is None and self._rollout_program():
+      return
     Win = gm.P('rssm/img_in/kernel')
     Wgru = gm.P('rssm/gru_out/kernel')
     if actions is None:
@@ -1287,6 +1307,75 @@ class Engine:
                             Xlo=self.tfeat_lo[t + 1] if self.machine else None)
       if actions is None:
         self._actor_fwd(t + 1)
+
+  def _rollout_program(self):
+    """The whole imagination rollout (A/agent.py:234-261) as ONE machine program: per step
+    actor trunk + action head + sample, img_in, GRU (Linear + joint LayerNorm + gates), the prior
+    stack and the categorical draw -- 11 layers per step, each 128-row tile of start states running
+    through all H steps inside one persistent kernel.  False when a shape does not tile."""
+    s, be = self.spec, self.be
+    gm, ga = self.groups['model'], self.groups['actor']
+    D, U, SC, A, N, H = s.deter, s.units, s.sc, s.act_dim, self.N, self.H
+    if not hasattr(self, '_rollout'):
+      ok = (self.machine and os.environ.get('DD_ROLLOUT', '1') != '0' and not s.discrete and
+            s.classes == 32 and A <= 16 and A % 4 == 0 and D % 256 == 0 and U % 256 == 0 and
+            s.head_units % 256 == 0 and SC % 256 == 0 and self.actor.machine and self.i_prior.machine)
+      self._rollout = None
+      if ok:
+        tf, tlo = self.tfeat, self.tfeat_lo
+        layers = []
+
+        def actor_layers(t):
+          r0, r1 = t * N, (t + 1) * N
+          tr = self.actor
+          for i in range(tr.layers):
+            kn, sn, bn = tr._names(i)
+            wt, wtlo = ga.PT(kn)
+            segs = ([PG.Seg(tf[t][:, :D], tlo[t], 0), PG.Seg(tf[t][:, D:], None, D)] if i == 0 else
+                    [PG.Seg(tr.H[i - 1][r0:r1], tr.Hlo[i - 1][r0:r1], 0)])
+            layers.append(PG.Layer(segs, wt, wtlo, tr.units, PG.EPI_LN, act=1, gamma=ga.P(sn),
+                                   beta=ga.P(bn), z=tr.Z[i][r0:r1], st=tr.st[i][r0:r1],
+                                   out=tr.H[i][r0:r1], out_lo=tr.Hlo[i][r0:r1]))
+          wt, wtlo = ga.PT2('actor/dist_out/out/kernel', 'actor/dist_out/std/kernel')
+          layers.append(PG.Layer([PG.Seg(tr.H[-1][r0:r1], tr.Hlo[-1][r0:r1], 0)], wt, wtlo, 2 * A,
+                                 PG.EPI_ACTOR, bias=ga.cat('actor/dist_out/out/bias', 'actor/dist_out/std/bias'),
+                                 out=self.taction[t], out_lo=self.taction_lo[t], x0=self.eps_act[t],
+                                 x1=self.tmean[t], x2=self.tstd[t], f0=s.actor_minstd,
+                                 f1=s.actor_maxstd, ipar=A))
+
+        actor_layers(0)
+        win, winlo = gm.PT('rssm/img_in/kernel')
+        wg, wglo = gm.PT('rssm/gru_out/kernel')
+        wst, wstlo = gm.PT('rssm/img_stats/kernel')
+        pr = self.i_prior
+        for t in range(H):
+          r0, r1 = t * N, (t + 1) * N
+          layers.append(PG.Layer(
+              [PG.Seg(tf[t][:, D:], None, 0), PG.Seg(self.taction[t], self.taction_lo[t], SC)], win, winlo,
+              U, PG.EPI_LN, act=1, gamma=gm.P('rssm/img_in/norm/scale'), beta=gm.P('rssm/img_in/norm/bias'),
+              z=self.i_zin[t], st=self.i_stin[t], out=self.i_xin[t], out_lo=self.i_xin_lo[t]))
+          layers.append(PG.Layer(
+              [PG.Seg(tf[t][:, :D], tlo[t], 0), PG.Seg(self.i_xin[t], self.i_xin_lo[t], D)], wg, wglo,
+              3 * D, PG.EPI_GRU, gamma=gm.P('rssm/gru_out/norm/scale'), beta=gm.P('rssm/gru_out/norm/bias'),
+              z=self.i_zgru[t], st=self.i_stgru[t], out=tf[t + 1][:, :D], out_lo=tlo[t + 1],
+              x0=tf[t][:, :D], x1=self.i_ygru[t]))
+          for i in range(pr.layers):
+            kn, sn, bn = pr._names(i)
+            wt, wtlo = gm.PT(kn)
+            seg = (PG.Seg(tf[t + 1][:, :D], tlo[t + 1], 0) if i == 0 else
+                   PG.Seg(pr.H[i - 1][r0:r1], pr.Hlo[i - 1][r0:r1], 0))
+            layers.append(PG.Layer([seg], wt, wtlo, U, PG.EPI_LN, act=1, gamma=gm.P(sn), beta=gm.P(bn),
+                                   z=pr.Z[i][r0:r1], st=pr.st[i][r0:r1], out=pr.H[i][r0:r1],
+                                   out_lo=pr.Hlo[i][r0:r1]))
+          layers.append(PG.Layer([PG.Seg(pr.H[-1][r0:r1], pr.Hlo[-1][r0:r1], 0)], wst, wstlo, SC,
+                                 PG.EPI_STATS, bias=gm.P('rssm/img_stats/bias'), out=self.tlogit[t + 1],
+                                 x0=self.g_img[t], x1=tf[t + 1][:, D:], f0=s.rssm_unimix, ipar=s.classes))
+          actor_layers(t + 1)
+        self._rollout = be.program_build(layers, N)
+    if self._rollout is None:
+      return False
+    be.program_run(self._rollout)
+    return True
 
   def _cell_program(self, t, act, own_action):
     """img_in (Linear + LayerNorm + elu over [stoch, action]) and the GRU's Linear + joint

@@ -21,7 +21,7 @@ from typing import List, Optional
 
 import torch
 
-EPI_PLAIN, EPI_LN, EPI_LNBWD = 0, 1, 2
+EPI_PLAIN, EPI_LN, EPI_LNBWD, EPI_GRU, EPI_STATS, EPI_ACTOR = 0, 1, 2, 3, 4, 5
 
 
 @dataclasses.dataclass
@@ -50,11 +50,20 @@ class Layer:
   out_lo: Optional[torch.Tensor] = None
   dgamma: Optional[torch.Tensor] = None
   dbeta: Optional[torch.Tensor] = None
+  # epilogue-specific extras -- GRU: x0 = previous deter [M, D], x1 = post-norm gates [M, 3D] (saved);
+  # STATS: x0 = Gumbel noise (None: logits only), x1 = one-hot sample, f0 = unimix, ipar = classes;
+  # ACTOR: x0 = eps, x1 = mean, x2 = std, f0 / f1 = min / max std, ipar = action dim
+  x0: Optional[torch.Tensor] = None
+  x1: Optional[torch.Tensor] = None
+  x2: Optional[torch.Tensor] = None
+  f0: float = 0.0
+  f1: float = 0.0
+  ipar: int = 0
 
 
 def eligible_width(n: int, epi: int = EPI_LN) -> bool:
   """Column counts the machine tiles across its 8 CTAs (dd_program_build)."""
-  return n % 256 == 0 or (epi == EPI_PLAIN and 1 <= n <= 64)
+  return n % 256 == 0 or (epi in (EPI_PLAIN, EPI_STATS, EPI_ACTOR) and 1 <= n <= 64)
 
 
 def trunc19(x: torch.Tensor) -> torch.Tensor:

@@ -307,6 +307,16 @@ int dd_fill_normal(float* buf, int64_t n, uint64_t seed, uint32_t stream_id,
 #define DD_EPI_PLAIN 0
 #define DD_EPI_LN 1
 #define DD_EPI_LNBWD 2
+/*   DD_EPI_GRU     N = 3 D: y = LN(acc) * gamma + beta over all 3 D columns (z, st, x1 = y saved);
+ *                  out = GRU update of x0 = previous state (A/nets.py:149-160)
+ *   DD_EPI_STATS   z = acc + bias; out = unimix logits per group of ipar classes (f0 = mix); with
+ *                  x0 = Gumbel noise: x1 = one-hot of argmax(logit + noise) (A/nets.py:162-171,
+ *                  A/tfutils.py:368-382)
+ *   DD_EPI_ACTOR   N = 2 ipar columns [mean raw | std raw] (+ bias): x1 = mean = tanh(.), x2 = std =
+ *                  (f1 - f0) sigmoid(.) + f0, out = mean + std * x0 (A/nets.py:461-468) */
+#define DD_EPI_GRU 3
+#define DD_EPI_STATS 4
+#define DD_EPI_ACTOR 5
 #define DD_MAX_TRANSPOSE_JOBS 64
 typedef struct DdSeg {
   const float* a;
@@ -331,8 +341,13 @@ typedef struct DdLayer {
   float* out;
   float* out_lo;
   int ld_out;
+  int ld_lo;        /* row stride of out_lo */
   float* dgamma;
   float* dbeta;
+  float* x[3];      /* epilogue-specific extra operands, see DD_EPI_* */
+  int ldx[3];
+  float f[2];
+  int ipar;
 } DdLayer;
 /* bytes of device memory a compiled program of `nlayers` layers occupies */
 size_t dd_program_bytes(int nlayers);

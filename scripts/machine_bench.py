@@ -31,8 +31,9 @@ def chain(M, K0, U, nl, act=1):
   X = rnd(M, K0)
   Xlo = P.lo_of(X)
   Ws = [rnd(K0 if i == 0 else U, U, scale=(K0 if i == 0 else U) ** -0.5) for i in range(nl)]
-  Wt = [w.t().contiguous() for w in Ws]
-  Wtlo = [P.lo_of(w) for w in Wt]
+  pairs = [torch.stack([w.t().contiguous(), P.lo_of(w.t().contiguous())]) for w in Ws]
+  Wt = [p[0] for p in pairs]
+  Wtlo = [p[1] for p in pairs]
   g, b = torch.ones(U, device=dev), torch.zeros(U, device=dev)
   Z = [torch.zeros(M, U, device=dev) for _ in range(nl)]
   H = [torch.zeros(M, U, device=dev) for _ in range(nl)]
@@ -62,7 +63,7 @@ def chain(M, K0, U, nl, act=1):
 
 def single(M, N, K, epi, act=0):
   X = rnd(M, K); Xlo = P.lo_of(X)
-  W = rnd(K, N, scale=K ** -0.5); Wt = W.t().contiguous(); Wtlo = P.lo_of(Wt)
+  W = rnd(K, N, scale=K ** -0.5); pw = torch.stack([W.t().contiguous(), P.lo_of(W.t().contiguous())]); Wt, Wtlo = pw[0], pw[1]
   g, b = torch.ones(N, device=dev), torch.zeros(N, device=dev)
   z, out, lo, st = (torch.zeros(M, N, device=dev), torch.zeros(M, N, device=dev),
                     torch.zeros(M, N, device=dev), torch.zeros(M, 2, device=dev))

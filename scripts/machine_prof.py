@@ -19,8 +19,9 @@ def build(M, K0, U, nl, epi):
   prev = (X, Xlo)
   for i in range(nl):
     K = K0 if i == 0 else U
-    Wt = (torch.randn(K, U, device=dev) * K ** -0.5).t().contiguous()
-    Wtlo = P.lo_of(Wt)
+    Wt0 = (torch.randn(K, U, device=dev) * K ** -0.5).t().contiguous()
+    pairw = torch.stack([Wt0, P.lo_of(Wt0)])
+    Wt, Wtlo = pairw[0], pairw[1]
     g, b = torch.ones(U, device=dev), torch.zeros(U, device=dev)
     z, out, lo, st = (torch.zeros(M, U, device=dev), torch.zeros(M, U, device=dev),
                       torch.zeros(M, U, device=dev), torch.zeros(M, 2, device=dev))
@@ -56,9 +57,9 @@ def run(tag, h, flags, iters=10, trace=False):
     print('  kernel events: roles end', [rel(x) for x in tr[3, 1:7]], 'after syncthreads', rel(tr[3, 8]),
           'after cluster sync', rel(tr[3, 9]))
     n_it = int((tr[1, ::4] > 0).sum())
-    print('  it: P.empty_ok P.B_issued P.A_issued | M.full_ok M.committed')
-    for it in list(range(min(n_it, 20))) + list(range(max(20, n_it - 4), n_it)):
-      print(f'  {it:3d}: {rel(tr[0, 4 * it]):7d} {rel(tr[0, 4 * it + 1]):7d} {rel(tr[0, 4 * it + 2]):7d} | '
+    print('  it: B.empty_ok B.issued | A.empty_ok A.issued | M.full_ok M.committed')
+    for it in list(range(min(n_it, 10))):
+      print(f'  {it:3d}: {rel(tr[0, 4 * it]):7d} {rel(tr[0, 4 * it + 1]):7d} | {rel(tr[0, 4 * it + 2]):7d} {rel(tr[0, 4 * it + 3]):7d} | '
             f'{rel(tr[1, 4 * it]):7d} {rel(tr[1, 4 * it + 1]):7d}')
     n_p = int((tr[2, ::4] > 0).sum())
     print('  pair: E.start E.accf_ok E.epi_done E.arrived')
@@ -76,5 +77,5 @@ if __name__ == '__main__':
                                    (1024, 512, 512, 4, P.EPI_LN, 'LN chain x4 M=1024'),
                                    (16384, 512, 512, 1, P.EPI_LN, 'LN 16384x512x512')]:
     h = build(M, K0, U, nl, epi)
-    for flags in (0, 1, 2 | 8, 1 | 2 | 8):
-      run(tag, h, flags, trace=(M == 1024))
+    for flags in (0, 1, 32, 64, 32 | 2 | 8, 64 | 2 | 8, 2 | 8):
+      run(tag, h, flags, trace=(M == 1024 and nl == 1))

@@ -123,9 +123,33 @@ class HostSim:
         st = L.st if L.st is not None else torch.zeros(rows, 2)
         out = torch.zeros(rows, L.N)
         self.ln_fwd(acc, L.gamma, L.beta, out, st, L.act)
-      else:
+      elif L.epi == P.EPI_LNBWD:
         out = torch.zeros(rows, L.N)
         self.ln_bwd(acc, L.z, L.st, L.gamma, L.beta, out, L.dgamma, L.dbeta, L.act)
+      elif L.epi == P.EPI_GRU:
+        L.z.copy_(acc)
+        st = L.st if L.st is not None else torch.zeros(rows, 2)
+        y = torch.zeros(rows, L.N)
+        self.ln_fwd(acc, L.gamma, L.beta, y, st, 0)
+        if L.x1 is not None:
+          L.x1.copy_(y)
+        out = torch.zeros(rows, L.N // 3)
+        self.gru_fwd(y, L.x0, out)
+      elif L.epi == P.EPI_STATS:
+        S = L.N // L.ipar
+        out = torch.zeros(rows, L.N)
+        oh = torch.zeros(rows, L.N)
+        self.stats_fwd(acc, L.x0, out, oh, None, S, L.ipar, L.f0,
+                       2 if L.x1 is None else (1 if L.x0 is None else 0))
+        if L.x1 is not None:
+          L.x1.copy_(oh)
+      else:
+        A = L.ipar
+        out, mean, std = torch.zeros(rows, A), torch.zeros(rows, A), torch.zeros(rows, A)
+        self.actor_sample(acc[:, :A].contiguous(), acc[:, A:].contiguous(), L.x0.contiguous(),
+                          L.f0, L.f1, out, mean, std)
+        L.x1.copy_(mean)
+        L.x2.copy_(std)
       L.out.copy_(out)
       if L.out_lo is not None:
         L.out_lo.copy_(P.lo_of(out))

@@ -50,7 +50,8 @@ def run_both(backends, case, rtol=2e-5, atol=2e-5):
 def wt_pair(T, W):
   """Forward B operand of x @ W: the transposed kernel and its remainder."""
   wt = torch.empty(W.shape[1], W.shape[0]).copy_(W.t())
-  return T(wt), T(P.lo_of(wt).view(wt.shape))
+  pair = T(torch.stack([wt, P.lo_of(wt).view(wt.shape)]))     # two planes: one 3-D TMA box per tile
+  return pair[0], pair[1]
 
 
 def act_pair(T, X):
@@ -144,7 +145,7 @@ def test_ln_bwd_layer(backends, M, N, K, act, wgrad):
   def case(be, T):
     dY, dYlo = act_pair(T, rnd(M, K, seed=1))
     W = rnd(N, K, seed=2, scale=K ** -0.5)              # kernel [N_in = N, N_out = K]: dH = dY @ W^T
-    Wd, Wlo = T(W), T(P.lo_of(W))
+    Wd, Wlo = T(W), T(P.lo_of(W))                      # separate allocations: the 2-descriptor path
     z = T(rnd(M, N, seed=3))
     st = T(torch.zeros(M, 2))
     gamma, beta = T(1.0 + 0.1 * rnd(N, seed=4)), T(0.1 * rnd(N, seed=5))
@@ -224,3 +225,73 @@ def test_operand_prep(backends):
     be.transpose_lo(p, pt, ptlo, jobs)
     return {'x': X[:, 4:68].contiguous(), 'lo': lo, 'pt': pt, 'ptlo': ptlo}
   ref, out = run_both(backends, case, rtol=0, atol=0)
+
+
+@pytest.mark.parametrize('M,D', [(1024, 512), (300, 256)])
+def test_gru_layer(backends, M, D):
+  """[deter | x] @ W_gru -> joint LayerNorm over 3 D -> gates -> new deter, as one layer."""
+  def case(be, T):
+    X1, X1lo = act_pair(T, rnd(M, D, seed=1))
+    X2, X2lo = act_pair(T, rnd(M, D, seed=2))
+    Wt, Wtlo = wt_pair(T, rnd(2 * D, 3 * D, seed=3, scale=(2 * D) ** -0.5))
+    gamma, beta = T(1.0 + 0.1 * rnd(3 * D, seed=4)), T(0.1 * rnd(3 * D, seed=5))
+    z, y, st = T(torch.zeros(M, 3 * D)), T(torch.zeros(M, 3 * D)), T(torch.zeros(M, 2))
+    feat = T(torch.zeros(M, D + 64))
+    out, out_lo = feat[:, :D], T(torch.zeros(M, D))
+    L = P.Layer([P.Seg(X1, X1lo, 0), P.Seg(X2, X2lo, D)], Wt, Wtlo, 3 * D, P.EPI_GRU, gamma=gamma,
+                beta=beta, z=z, st=st, out=out, out_lo=out_lo, x0=X1, x1=y)
+    be.program_run(be.program_build([L], M))
+    return {'z': z, 'y': y, 'st': st, 'out': feat, 'lo': out_lo}
+  def fix(res):     # 'lo' belongs to the strided view
+    res['out'] = res['out'][:, :D].contiguous()
+    return res
+  hs, cu = backends
+  ref = fix(case(hs, lambda x: x.clone()))
+  out = fix(case(cu, lambda x: x.clone().to(cu.device)))
+  cu.sync()
+  for k in ('z', 'y', 'st', 'out'):
+    np.testing.assert_allclose(out[k].cpu().numpy(), ref[k].numpy(), rtol=5e-5, atol=5e-5, err_msg=k)
+  assert torch.equal(P.lo_of(out['out'].cpu()), out['lo'].cpu())
+
+
+@pytest.mark.parametrize('M,K,S,C,noise', [(1024, 512, 32, 32, True), (1000, 256, 8, 32, False),
+                                           (1024, 512, 1, 6, True)])
+def test_stats_layer(backends, M, K, S, C, noise):
+  """Linear + bias -> unimix logits -> Gumbel-argmax one-hot per group, fused; sampled indices must
+  agree with the reference except where logit + noise ties to rounding."""
+  def case(be, T):
+    N = S * C
+    X, Xlo = act_pair(T, rnd(M, K, seed=1))
+    Wt, Wtlo = wt_pair(T, rnd(K, N, seed=2, scale=K ** -0.5))
+    bias = T(0.1 * rnd(N, seed=3))
+    g = torch.Generator().manual_seed(4)
+    G = T(-torch.log(-torch.log(torch.rand(M, N, generator=g).clamp(1e-6, 1 - 1e-6))))
+    logit, oh = T(torch.zeros(M, N)), T(torch.zeros(M, N))
+    L = P.Layer([P.Seg(X, Xlo)], Wt, Wtlo, N, P.EPI_STATS, bias=bias, out=logit, x0=G if noise else None,
+                x1=oh, f0=0.01, ipar=C)
+    be.program_run(be.program_build([L], M))
+    return {'logit': logit, 'oh': oh}
+  hs, cu = backends
+  ref = case(hs, lambda x: x.clone())
+  out = case(cu, lambda x: x.clone().to(cu.device))
+  cu.sync()
+  np.testing.assert_allclose(out['logit'].cpu().numpy(), ref['logit'].numpy(), rtol=2e-5, atol=2e-5)
+  a, b = out['oh'].cpu().numpy(), ref['oh'].numpy()
+  assert np.all(a.reshape(M, S, C).sum(-1) == 1.0)
+  bad = int((a != b).any(-1).sum())
+  assert bad <= 2, bad
+
+
+def test_actor_layer(backends):
+  def case(be, T):
+    M, K, A = 1024, 512, 12
+    X, Xlo = act_pair(T, rnd(M, K, seed=1))
+    Wt, Wtlo = wt_pair(T, rnd(K, 2 * A, seed=2, scale=K ** -0.5))
+    bias = T(0.1 * rnd(2 * A, seed=3))
+    eps = T(rnd(M, A, seed=4))
+    act, act_lo, mean, std = (T(torch.zeros(M, A)) for _ in range(4))
+    L = P.Layer([P.Seg(X, Xlo)], Wt, Wtlo, 2 * A, P.EPI_ACTOR, bias=bias, out=act, out_lo=act_lo, x0=eps,
+                x1=mean, x2=std, f0=0.1, f1=1.0, ipar=A)
+    be.program_run(be.program_build([L], M))
+    return {'out': act, 'lo': act_lo, 'mean': mean, 'std': std}
+  run_both(backends, case, rtol=2e-5, atol=2e-5)
