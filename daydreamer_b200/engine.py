@@ -423,7 +423,8 @@ class Trunk:
     """xs: list of (X[r1-r0, k], first weight row[, X_lo]).  heads: (kernel name, bias name, out
     view) output layers applied to the last hidden layer.  Returns H[-1][r0:r1]."""
     be, g = self.eng.be, group or self.group
-    if self._machine_xs(xs) and all(_mview_ok(h[2]) or h[2].shape[1] < 4 for h in heads):
+    if (self._machine_xs(xs) and r1 - r0 <= self.eng.machine_max_rows and
+        all(_mview_ok(h[2]) or h[2].shape[1] < 4 for h in heads)):
       key = ('f', r0, r1, id(g), tuple((x[0].data_ptr(), x[1]) for x in xs),
              tuple((h[0], h[2].data_ptr()) for h in heads))
       prog = self._progs.get(key)
@@ -467,7 +468,7 @@ class Trunk:
     grads to produce.  wgrad: accumulate parameter grads into the group."""
     eng, be, g = self.eng, self.eng.be, group or self.group
     n = r1 - r0
-    if (self.machine and _mview_ok(dH) and
+    if (self.machine and n <= eng.machine_max_rows and _mview_ok(dH) and
         all(_mview_ok(d[0]) and PG.eligible_width(d[0].shape[1], PG.EPI_PLAIN) for d in dxs)):
       key = ('b', r0, r1, id(g), dH.data_ptr(), bool(wgrad),
              tuple((d[0].data_ptr(), d[1], float(d[2])) for d in dxs))
@@ -662,6 +663,10 @@ class Engine:
     # layer machine (csrc/dd_machine.cu): trunks, the prior stack and the rollout's img_in / GRU
     # layers run as fused programs wherever their shapes tile across its 8-CTA clusters
     self.machine = hasattr(be, 'program_build') and os.environ.get('DD_MACHINE', '1') != '0'
+    # measured (profiles/r02_machine_bench.txt): per layer the machine matches dd_gemm + dd_ln at
+    # ~1K rows and loses to the persistent GEMM beyond a few thousand -> big batched trunks stay
+    # on the per-layer kernels
+    self.machine_max_rows = int(os.environ.get('DD_MACHINE_MAXROWS', '2048'))
     s, N, H = spec, self.N, self.H
     D, U, SC, A, E = s.deter, s.units, s.sc, s.act_dim, s.enc_units
     z = be.zeros
