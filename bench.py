@@ -30,20 +30,49 @@ WORKLOAD = 'a1 proprio RSSM deter=512 stoch=32x32 batch=16/GPU seq=64 H=15, synt
 METRIC = 'imagined latent-steps/sec (BxLxH)'
 UNIT = 'latent-steps/s'
 
+# BASELINE.json configs by name.  `a1` (configs[1], B = 16 sequences per GPU, weak scaling) is the
+# default and the line the driver records; the others are run with --config.
+#   batch: sequences per GPU (int) or ('global', B) split over the ranks
+CONFIGS = {
+    'a1': dict(batch=16, L=64, H=15, over={'rssm.deter': 512, 'rssm.units': 512}, block='a1',
+               workload=WORKLOAD),
+    'a1_b256': dict(batch=('global', 256), L=64, H=15, over={'rssm.deter': 512, 'rssm.units': 512},
+                    block='a1', workload='a1 proprio RSSM deter=512 stoch=32x32 global batch=256 '
+                                         'seq=64 H=15 (BASELINE configs[3]), synthetic replay'),
+    'large': dict(batch=('global', 512), L=64, H=20,
+                  over={'rssm.deter': 2048, 'rssm.units': 2048, 'rssm.stoch': 48, 'rssm.classes': 48},
+                  block='a1', workload='large RSSM deter=2048 stoch=48x48 global batch=512 seq=64 H=20 '
+                                       '(BASELINE configs[4]), synthetic replay'),
+    'ur5': dict(batch=32, L=50, H=15, over={}, block='ur5',
+                workload='ur5 64x64 image + proprio fusion encoder batch=32 seq=50 H=15 '
+                         '(BASELINE configs[2]), synthetic replay'),
+}
 
-def synthetic_batch(B, seed):
-  """SURVEY.md 8(d) cfg2 synthetic replay (the unused `image` key is omitted
-  from both arms)."""
+
+def synthetic_batch(B, seed, cfg=None):
+  """SURVEY.md 8(d) synthetic replay of the config's shape (a1: the unused `image` key is omitted
+  from both arms; ur5: uint8 64x64x3 images + 19-dim proprio, one-hot actions)."""
+  cfg = cfg or CONFIGS['a1']
+  Lc = cfg['L']
   rng = np.random.default_rng(seed)
-  first = np.zeros((B, L), bool)
+  first = np.zeros((B, Lc), bool)
   first[:, 0] = True
-  term = rng.uniform(size=(B, L)) < 0.01
-  return {
-      'vector': rng.standard_normal((B, L, 16)).astype(np.float32),
-      'action': rng.uniform(-1, 1, (B, L, 12)).astype(np.float32),
-      'reward': (0.1 * rng.standard_normal((B, L))).astype(np.float32),
-      'is_first': first, 'is_terminal': term, 'is_last': term.copy(),
-  }
+  term = rng.uniform(size=(B, Lc)) < 0.01
+  out = {'reward': (0.1 * rng.standard_normal((B, Lc))).astype(np.float32),
+         'is_first': first, 'is_terminal': term, 'is_last': term.copy()}
+  if cfg['block'] == 'ur5':
+    out['image'] = rng.integers(0, 256, (B, Lc, 64, 64, 3)).astype(np.uint8)
+    for k, d in UR5_VEC.items():
+      out[k] = rng.standard_normal((B, Lc, d)).astype(np.float32)
+    out['action'] = np.eye(6, dtype=np.float32)[rng.integers(0, 6, (B, Lc))]
+  else:
+    out['vector'] = rng.standard_normal((B, Lc, 16)).astype(np.float32)
+    out['action'] = rng.uniform(-1, 1, (B, Lc, 12)).astype(np.float32)
+  return out
+
+
+UR5_VEC = {'cartesian_position': 6, 'joint_positions': 6, 'gripper_pos': 1, 'gripper_side': 3,
+           'grasped_side': 3}
 
 
 class Space:
@@ -51,10 +80,24 @@ class Space:
     self.shape, self.dtype, self.discrete = tuple(shape), np.dtype(dtype), discrete
 
 
-def spaces():
-  obs = {'vector': Space((16,)), 'reward': Space(()), 'is_first': Space((), bool),
-         'is_last': Space((), bool), 'is_terminal': Space((), bool)}
+def spaces(cfg=None):
+  cfg = cfg or CONFIGS['a1']
+  common = {'reward': Space(()), 'is_first': Space((), bool), 'is_last': Space((), bool),
+            'is_terminal': Space((), bool)}
+  if cfg['block'] == 'ur5':
+    obs = {'image': Space((64, 64, 3), np.uint8), **{k: Space((d,)) for k, d in UR5_VEC.items()},
+           **common}
+    return obs, {'action': Space((6,), np.float32, True), 'reset': Space((), bool, True)}
+  obs = {'vector': Space((16,)), **common}
   return obs, {'action': Space((12,)), 'reset': Space((), bool, True)}
+
+
+def per_gpu_batch(cfg, world):
+  b = cfg['batch']
+  if isinstance(b, tuple):
+    assert b[1] % world == 0, f'global batch {b[1]} does not split over {world} GPUs'
+    return b[1] // world
+  return b
 
 
 def load_peaks():
@@ -132,7 +175,7 @@ def best_cpu_threads(make_step, budget_s=25.0):
   torch.set_num_threads(min(16, cores))
   make_step()                                     # first-call costs (allocator, dispatch caches)
   best, best_t = min(16, cores), float('inf')
-  for n in sorted({min(c, cores) for c in (16, 8, 32)}, key=lambda c: abs(c - 16)):
+  for n in sorted({min(c, cores) for c in (16, 8, 32, 64, 128)}, key=lambda c: abs(c - 16)):
     torch.set_num_threads(n)
     t0 = time.perf_counter()
     make_step()
@@ -145,42 +188,66 @@ def best_cpu_threads(make_step, budget_s=25.0):
   return best, cores, best_t
 
 
+def oracle_spec(O, cfg):
+  over = cfg['over']
+  if cfg['block'] == 'ur5':
+    return O.Spec(obs_dims=dict(UR5_VEC), act_dim=6, discrete=True, deter=512, units=512,
+                  cnn_keys={'image': (64, 64, 3)}, horizon=cfg['H'], actent_target=0.4)
+  base = O.a1_spec()
+  import dataclasses
+  return dataclasses.replace(base, deter=over.get('rssm.deter', 512), units=over.get('rssm.units', 512),
+                             stoch=over.get('rssm.stoch', 32), classes=over.get('rssm.classes', 32),
+                             horizon=cfg['H'])
+
+
+def oracle_noise(spec, B, Lc, Hc, seed):
+  rng = np.random.default_rng(seed)
+  gum = lambda *s: (-np.log(-np.log(rng.uniform(1e-6, 1 - 1e-6, s)))).astype(np.float32)
+  act = (gum(Hc + 1, B * Lc, spec.act_dim) if spec.discrete else
+         rng.standard_normal((Hc + 1, B * Lc, spec.act_dim)).astype(np.float32))
+  return {'obs_post': gum(Lc, B, spec.stoch, spec.classes),
+          'img': gum(Hc, B * Lc, spec.stoch, spec.classes), 'act': act}
+
+
 def run_reference(args, rank, world):
+  """The reference learner's CPU path on this box's host cores: the PyTorch-CPU restatement of
+  A/agent.py:67-93 (oracle/), all the threads it can use.  On the default config every step trains
+  on the FULL per-GPU batch (same config as our arm); the larger configs are bounded samples."""
   if rank != 0:
     return
   import torch
   from oracle import dreamer_oracle as O
-  spec = O.a1_spec()
+  cfg = CONFIGS[args.config]
+  Lc, Hc = cfg['L'], cfg['H']
+  spec = oracle_spec(O, cfg)
   learner = O.Learner(spec)
-
-  def noise_for(B, seed):
-    rng = np.random.default_rng(seed)
-    gum = lambda *s: (-np.log(-np.log(rng.uniform(1e-6, 1 - 1e-6, s)))).astype(np.float32)
-    return {'obs_post': gum(L, B, 32, 32), 'img': gum(H, B * L, 32, 32),
-            'act': rng.standard_normal((H + 1, B * L, 12)).astype(np.float32)}
-
   cores, host_cores, t_one = best_cpu_threads(
-      lambda: learner.train_step(synthetic_batch(1, 0), noise_for(1, 0)))
-  # bounded sample: each step trains on B of the 16 sequences, B sized from the measured
-  # one-sequence step so that warm-up + timed steps stay within ~2 minutes of CPU work
-  budget = 120.0
+      lambda: learner.train_step(synthetic_batch(1, 0, cfg), oracle_noise(spec, 1, Lc, Hc, 0)))
+  Bfull = per_gpu_batch(cfg, 1) if args.config != 'a1' else B_PER_GPU
   total = args.steps + args.warmup
-  B = int(max(1, min(B_PER_GPU, budget / (t_one * total))))
+  if args.config == 'a1':
+    B = Bfull                  # same config as our arm: all 16 sequences, every step
+  else:                        # bounded sample: ~4 minutes of CPU work
+    B = int(max(1, min(Bfull, 240.0 / (t_one * total))))
   for i in range(args.warmup):
-    learner.train_step(synthetic_batch(B, i), noise_for(B, i))
+    learner.train_step(synthetic_batch(B, i, cfg), oracle_noise(spec, B, Lc, Hc, i))
   t0 = time.perf_counter()
   for i in range(args.steps):
-    learner.train_step(synthetic_batch(B, 100 + i), noise_for(B, 100 + i))
+    learner.train_step(synthetic_batch(B, 100 + i, cfg), oracle_noise(spec, B, Lc, Hc, 100 + i))
   dt = (time.perf_counter() - t0) / args.steps
-  value = B * L * H / dt
-  sample = f'{B} of 16 sequences x L=64 x H=15 per step, {args.steps} steps, eager PyTorch-CPU fp32'
+  value = B * Lc * Hc / dt
+  sample = (f'{B} of {Bfull} sequences x L={Lc} x H={Hc} per step, {args.steps} steps, '
+            'eager PyTorch-CPU fp32')
   print(json.dumps({
       'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-      'data': 'synthetic', 'config': {'workload': WORKLOAD, 'sample_sequences': B},
+      'data': 'synthetic',
+      'config': {'workload': cfg['workload'], 'global_batch': B, 'seq_len': Lc, 'horizon': Hc,
+                 'sample_sequences': B, 'full_batch': B == Bfull},
       'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                        'sample': sample, 'host_cores': host_cores,
+                       'threads_tried': [c for c in (8, 16, 32, 64, 128) if c <= host_cores],
                        'note': 'reference restated (PyTorch-CPU oracle), not TF2: tensorflow is '
                                'not installable in this image'},
       'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -192,16 +259,17 @@ def run_reference(args, rank, world):
 # ----------------------------------------------------------------------------
 
 class GemmOnly:
-  """Backend view that forwards only dd_gemm launches (and counts their flops);
-  used to time the dominant kernel over exactly the launches of one step.
-  (The fused observe scan is not a dd_gemm launch and is skipped here.)"""
+  """Backend view that forwards only the GEMM-carrying launches -- dd_gemm and the layer-machine
+  programs (dd_program_run: TMA-fed tcgen05 layers with fused epilogues) -- and counts their
+  flops; used to time the dominant kernels over exactly the launches of one step.
+  (The fused observe scans are not among them and are skipped here.)"""
 
   def __init__(self, be):
-    self._be, self.flops, self.calls = be, 0.0, 0
+    self._be, self.flops, self.calls, self.prog_calls = be, 0.0, 0, 0
 
   def __getattr__(self, name):
     attr = getattr(self._be, name)
-    if name in ('zeros', 'upload', 'sync', 'device', 'stream', 'lib', 'launch_count'):
+    if name in ('zeros', 'upload', 'sync', 'device', 'stream', 'lib', 'launch_count', 'program_build'):
       return attr
     if name == 'gemm':
       def gemm(A, B, C, ta=False, tb=False, beta=0.0, bias=None):
@@ -210,6 +278,14 @@ class GemmOnly:
         self.calls += 1
         return attr(A, B, C, ta=ta, tb=tb, beta=beta, bias=bias)
       return gemm
+    if name == 'program_run':
+      def program_run(h):
+        for L in h.layers:
+          self.flops += 2.0 * h.rows * L.N * sum(sg.a.shape[1] for sg in L.segs)
+        self.calls += 1
+        self.prog_calls += 1
+        return attr(h)
+      return program_run
     return (lambda *a, **k: None) if callable(attr) else attr
 
 
@@ -232,12 +308,14 @@ def run_ours(args, rank, world, local_rank):
   from daydreamer_b200.agent import Agent
   from daydreamer_b200.config import make_config
 
-  cfg = make_config('a1', **{'rssm.deter': 512, 'rssm.units': 512, 'batch_size': B_PER_GPU * world,
-                            'replay_chunk': L, 'imag_horizon': H})
-  obs_space, act_space = spaces()
+  bc = CONFIGS[args.config]
+  B_PER_GPU, L, H = per_gpu_batch(bc, world), bc['L'], bc['H']
+  cfg = make_config(bc['block'], **{**bc['over'], 'batch_size': B_PER_GPU * world,
+                                    'replay_chunk': L, 'imag_horizon': H})
+  obs_space, act_space = spaces(bc)
   agent = Agent(obs_space, act_space, None, cfg)
   be = agent.be
-  batches = [synthetic_batch(B_PER_GPU, 1000 * rank + i) for i in range(4)]
+  batches = [synthetic_batch(B_PER_GPU, 1000 * rank + i, bc) for i in range(4)]
 
   def barrier():
     torch.cuda.synchronize()
@@ -334,10 +412,14 @@ def run_ours(args, rank, world, local_rank):
       tj = json.load(open(tpath))
       traffic, traffic_src = tj['dram_bytes_per_launch'], tj['source']
     tf = probe.flops / gemm_s / 1e12
-    scan_bytes = 222.4e6        # fused observe+imagine scan, a1, per GPU
+    # algorithmic HBM bytes of the fused observe + imagine scan per GPU
+    scan_bytes = {'a1': 222.4e6, 'ur5': 350.4e6, 'a1_b256': 420.5e6 * (B_PER_GPU / 32.0),
+                  'large': 2833.9e6 * (B_PER_GPU / 64.0)}[args.config]
     roofline = {
-        'kernel': 'dd::tc::gemm_tc_kernel (tcgen05 kind::tf32 x3 = fp32-accurate) + fp32 SIMT/skinny '
-                  'fallbacks: every dd_gemm launch of one step', 'bound': 'tensor', 'achieved': tf,
+        'kernel': 'every GEMM-carrying launch of one step: dd::lm::lm_kernel (layer machine: TMA-fed '
+                  'tcgen05 kind::tf32 x3 layers with fused LayerNorm / GRU / sampling epilogues) + '
+                  'dd::tc::gemm_tc_kernel (3xTF32) + fp32 SIMT/skinny fallbacks',
+        'bound': 'tensor', 'achieved': tf, 'machine_programs_per_step': probe.prog_calls,
         'peak': peaks['tflops'], 'unit': 'TFLOP/s', 'frac': tf / peaks['tflops'],
         'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peaks['source'],
         'launches_per_step': probe.calls, 'avg_launch_us': gemm_s / probe.calls * 1e6,
@@ -349,7 +431,7 @@ def run_ours(args, rank, world, local_rank):
 
   # ---- CPU baseline on the box's host cores (rank 0, N=1 only) -------------
   cpu = None
-  if rank == 0 and world == 1 and not args.no_cpu:
+  if rank == 0 and world == 1 and not args.no_cpu and args.config == 'a1':
     from oracle import dreamer_oracle as O
     learner = O.Learner(O.a1_spec())
     rng = np.random.default_rng(0)
@@ -379,7 +461,7 @@ def run_ours(args, rank, world, local_rank):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'global_batch': B_PER_GPU * world, 'seq_len': L,
+        'config': {'workload': bc['workload'], 'name': args.config, 'global_batch': B_PER_GPU * world, 'seq_len': L,
                    'horizon': H, 'parallelism': f'dp{world}',
                    'pdl': bool(int(os.environ.get('DD_PDL', '0') or 0)),
                    'l2': 'per-step working set (~2 GB of saved activations) exceeds the 126 MB L2; '
@@ -403,6 +485,8 @@ def main():
   ap.add_argument('--steps', type=int, default=20)
   ap.add_argument('--warmup', type=int, default=5)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--config', default='a1', choices=sorted(CONFIGS),
+                  help='BASELINE.json workload; the default a1 (configs[1]) is the recorded line')
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
   args = ap.parse_args()
   if os.environ.get('DD_BENCH_VERBOSE'):      # where is it, if it ever stalls

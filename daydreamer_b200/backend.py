@@ -111,7 +111,7 @@ class DdObserveBwd(ctypes.Structure):
 
 class DdSeg(ctypes.Structure):
   """Mirror of `struct DdSeg` in include/dd_kernels.h."""
-  _fields_ = [('a', _P), ('a_lo', _P), ('lda', _I), ('k', _I), ('wk0', _I)]
+  _fields_ = [('a', _P), ('a_lo', _P), ('lda', _I), ('k', _I), ('wk0', _I), ('lda_lo', _I)]
 
 
 class DdLayer(ctypes.Structure):
@@ -573,9 +573,8 @@ class CudaBackend:
         assert r == rows, (sg.a.shape, rows)
         d.seg[g].a, d.seg[g].lda, d.seg[g].k, d.seg[g].wk0 = pa, lda, k, int(sg.wk0)
         if sg.a_lo is not None:
-          pl, _, _, ldl = _mat(sg.a_lo)
-          assert ldl == lda and sg.a_lo.shape == sg.a.shape
-          d.seg[g].a_lo = pl
+          assert sg.a_lo.shape == sg.a.shape
+          d.seg[g].a_lo, _, _, d.seg[g].lda_lo = _mat(sg.a_lo)
       if L.segs:
         pw, wrows, wcols, ldw = _mat(L.w)
         pwl, _, _, ldwl = _mat(L.w_lo)

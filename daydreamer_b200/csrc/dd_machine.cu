@@ -587,7 +587,7 @@ __device__ __forceinline__ void acc_wait(const Shared& sh, const EpiState& es, c
                                          bool has_acc) {
   if (!has_acc) return;
   mbar_wait<false>(sh.bars + BAR_ACCF + 8 * (es.ac & 1), (es.ac >> 1) & 1, cx, 6);
-  if ((threadIdx.x >> 5) == 2) trace_ev(cx, 2, 4 * cx.pair + 3);
+  if ((threadIdx.x >> 5) == 2) trace_ev(cx, 2, 16 * cx.pair + 1);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void acc_release(const Shared& sh, EpiState& es, int lane, bool has_acc) {
@@ -711,8 +711,10 @@ __device__ void epi_ln_fwd(const Shared& sh, const EP& L, EpiState& es, uint32_t
         const int cb = col0 + h * 32;
         float v[32];
         fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, 32, lane, v);
+        if (quad == 2 && h == 0 && c == 0) trace_ev(cx, 2, 16 * cx.pair + 2);
         if (L.z != nullptr)
           sub_store(stg, v, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
+        if (quad == 2 && h == 0 && c == 0) trace_ev(cx, 2, 16 * cx.pair + 3);
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) s += v[j];
@@ -733,7 +735,9 @@ __device__ void epi_ln_fwd(const Shared& sh, const EP& L, EpiState& es, uint32_t
     acc_release(sh, es, lane, L.nseg > 0);
   }
   float2 parts[CL];
+  if (quad == 2) trace_ev(cx, 2, 16 * cx.pair + 4);
   row_exchange(sh, es, rank, trow, 2 + ((quad + 2) & 3), lane, mean, m2, parts, cx);
+  if (quad == 2) trace_ev(cx, 2, 16 * cx.pair + 5);
   float gm = 0.f;
   for (int d = 0; d < L.nactive; ++d) gm += parts[d].x;
   gm /= (float)L.nactive;
@@ -765,7 +769,9 @@ __device__ void epi_ln_fwd(const Shared& sh, const EP& L, EpiState& es, uint32_t
           const float y = (v[j] - gm) * rstd * __ldg(gp + j) + __ldg(bp + j);
           v[j] = act ? elu_f(y) : y;
         }
+        if (quad == 2 && h == 0 && c == 0) trace_ev(cx, 2, 16 * cx.pair + 6);
         store_with_lo(L, stg, v, wrow0, rows_valid, cb, 32, lane);
+        if (quad == 2 && h == 0 && c == 0) trace_ev(cx, 2, 16 * cx.pair + 7);
       }
     }
   }
@@ -1044,7 +1050,7 @@ __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, i
       const bool active = rank < L.nactive;
       if (L.nseg == 0 && l > 0)       // no producer wait protects its inputs: wait here
         count_wait(sh.bars + BAR_READY, (uint32_t)pair * CL, cx, 8);
-      if (warp == 2) trace_ev(cx, 2, 4 * pair);
+      if (warp == 2) trace_ev(cx, 2, 16 * pair);
       if (L.epi == DD_EPI_PLAIN) {
         if (active) epi_plain(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, cx);
       } else if (L.epi == DD_EPI_LN) {
@@ -1061,7 +1067,7 @@ __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, i
       // this CTA's rows of the layer's outputs are written: tell every CTA's producer.  Each
       // writer orders its stores against the async proxy (TMA reads them), the four epilogue warps
       // meet at a named barrier, then one thread publishes with a single cluster-scope fence.
-      if (warp == 2) trace_ev(cx, 2, 4 * pair + 1);
+      if (warp == 2) trace_ev(cx, 2, 16 * pair + 9);
       asm volatile("fence.proxy.async;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 2 && lane == 0) {
@@ -1069,7 +1075,7 @@ __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, i
 #pragma unroll
         for (int d = 0; d < CL; ++d) count_add_remote(sh.bars + BAR_READY, d);
       }
-      if (warp == 2) trace_ev(cx, 2, 4 * pair + 2);
+      if (warp == 2) trace_ev(cx, 2, 16 * pair + 11);
       __syncwarp();
     }
   }
@@ -1307,7 +1313,7 @@ extern "C" int dd_program_build(const DdLayer* layers, int nlayers, int rows, vo
       d.seg_exact[g] = sg.a_lo == nullptr ? 1 : 0;
       rc = lm::make_map(&d.a_hi[g], sg.a, rows, sg.k, sg.lda, lm::SLICE_ROWS);
       if (rc == 0 && sg.a_lo != nullptr)
-        rc = lm::make_map(&d.a_lo[g], sg.a_lo, rows, sg.k, sg.lda, lm::SLICE_ROWS);
+        rc = lm::make_map(&d.a_lo[g], sg.a_lo, rows, sg.k, sg.lda_lo, lm::SLICE_ROWS);
     }
     if (rc != 0) break;
     if (s.nseg > 0) {

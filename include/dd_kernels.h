@@ -322,6 +322,7 @@ typedef struct DdSeg {
   const float* a;
   const float* a_lo;
   int lda, k, wk0;
+  int lda_lo;       /* row stride of a_lo */
 } DdSeg;
 typedef struct DdLayer {
   int nseg;
