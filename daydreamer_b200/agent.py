@@ -8,7 +8,9 @@ are plain instance attributes so `embodied.Timer.wrap` can re-bind them
 hand-written sm_100a kernels; this file is host plumbing only (config ->
 Spec, pinned staging, CUDA-graph capture/replay, metric read-back).
 """
+import os
 import re
+import sys
 import threading
 import queue as queuelib
 
@@ -340,9 +342,30 @@ class Agent:
       begin()
 
     saved = main.allreduce
+    torch.cuda.synchronize()
+    if saved is not None and os.environ.get('DD_GRAPH_NCCL', '1') != '0':
+      # data parallel: NCCL all-reduces captured INSIDE the graph (one graph per step, no host
+      # round trip between the segments); falls back to split segments if the capture fails
+      try:
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+          begin()
+          fn()
+          end()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        return segs
+      except Exception as e:     # noqa: BLE001  (any capture failure -> the segmented form)
+        print(f'[daydreamer_b200] NCCL-in-graph capture failed ({type(e).__name__}: {e}); '
+              'using graph segments with eager collectives', file=sys.stderr)
+        try:
+          cur['g'].capture_end()
+        except Exception:        # noqa: BLE001
+          pass
+        segs.clear()
+        torch.cuda.synchronize()
     if saved is not None:
       main.allreduce = hook
-    torch.cuda.synchronize()
     side.wait_stream(torch.cuda.current_stream())
     try:
       with torch.cuda.stream(side):

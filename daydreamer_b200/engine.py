@@ -1487,15 +1487,18 @@ class Engine:
       self.traj_values(slow_only=True)
     be.sub(self.score, self.r_ret, self.r_value[:H])
     self._stat(self.score, 'score')
-    # Normalize EMAs: retnorm/scorenorm are impl 'off' (state only), advnorm used
-    for i, (src, key, decay) in enumerate((
-        (self.score, 'adv_ctrl', s.advnorm_decay), (self.r_ret, 'ret_ctrl', 0.999),
-        (self.score, 'score_ctrl', 0.99))):
-      row = self.mstat[self.midx[key]]
-      be.stats(src, row)
-      if self.allreduce is not None:
-        self.allreduce(row)
-      be.normalize_update(self.norm_state[i], row, decay, s.advnorm_max,
+    # Normalize EMAs: retnorm/scorenorm are impl 'off' (state only), advnorm used.  The three
+    # statistics rows are adjacent in mstat: one collective for all of them under data parallelism.
+    norms = ((self.score, 'adv_ctrl', s.advnorm_decay), (self.r_ret, 'ret_ctrl', 0.999),
+             (self.score, 'score_ctrl', 0.99))
+    i0 = self.midx['adv_ctrl']
+    assert [self.midx[k] for _, k, _ in norms] == [i0, i0 + 1, i0 + 2]
+    for src, key, _ in norms:
+      be.stats(src, self.mstat[self.midx[key]])
+    if self.allreduce is not None:
+      self.allreduce(self.mstat[i0:i0 + 3])
+    for i, (_, key, decay) in enumerate(norms):
+      be.normalize_update(self.norm_state[i], self.mstat[self.midx[key]], decay, s.advnorm_max,
                           self.adv if i == 0 else self.scratch2)
     if s.discrete:
       return self._actor_update_reinforce()
