@@ -82,6 +82,7 @@ SIGNATURES = {
     'dd_fill_normal': [_P, _L, _U64, _U32, _P, _I, _P],
     'dd_program_run': [_P, _I, _I, _P],
     'dd_set_machine_debug': [_I],
+    'dd_set_machine_ks': [_I],
     'dd_machine_prof': [_I, _P, _I],
     'dd_split_lo': [_P, _I, _P, _I, _I, _I, _P],
     'dd_transpose_lo': [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],

@@ -34,31 +34,25 @@
 namespace dd {
 namespace lm {
 
-constexpr int CL = 8;                 // CTAs per cluster = column slices of one row tile
+constexpr int NS = 8;                 // column slices of a row tile (= activation row slices)
 constexpr int BM = 128;               // rows per tile (= TMEM lanes)
 constexpr int BK = 32;                // k-block: 32 fp32 = one 128-byte swizzle row
 constexpr int BNMAX = 64;             // widest per-CTA column chunk
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 4;                       // 16 KB
 constexpr int B_BYTES = BNMAX * BK * 4;                    // 8 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;     // 48 KB: A_hi | A_lo | B_hi | B_lo
-constexpr int SLICE_ROWS = BM / CL;                        // 16 rows of A loaded by each CTA
+constexpr int SLICE_ROWS = BM / NS;                        // 16 rows of A loaded by each CTA
 constexpr int SLICE_BYTES = SLICE_ROWS * BK * 4;           // 2 KB = two 8-row swizzle groups
-constexpr int OFF_STATS = STAGES * STAGE_BYTES;            // float2 [2 parity][CL][BM]
-constexpr int STATS_BYTES = 2 * CL * BM * 8;
-constexpr int OFF_STG = OFF_STATS + STATS_BYTES;           // per-warp 32 x 36 floats
 constexpr int STG_LD = 36;
 constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;
-constexpr int OFF_BAR = OFF_STG + 4 * STG_WARP_BYTES;
-constexpr int OFF_EP = OFF_BAR + 128;                      // per-epilogue-warp copy of the layer's epilogue view
 constexpr int EP_BYTES = 208;
-constexpr int SMEM_BYTES = OFF_EP + 4 * EP_BYTES;
 constexpr int THREADS = 224;          // warps: 0 weights, 1 MMA, 2-5 epilogue, 6 activations
 constexpr int TMEM_COLS = 256;        // 2 buffers x (main 64 | cross 64)
-static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
-enum { BAR_FULL = 0, BAR_EMPTY = 32, BAR_ACCF = 64, BAR_ACCE = 80, BAR_STATS = 96, BAR_READY = 104,
-       BAR_TMEM = 112 };
+// byte-counted barriers (LayerNorm exchange, split-K reduction) come in PAIRS used alternately: a
+// sender that runs one use ahead must not add its bytes to a phase the receiver has not completed
+enum { BAR_FULL = 0, BAR_EMPTY = 32, BAR_ACCF = 64, BAR_ACCE = 80, BAR_STATS = 96, BAR_READY = 112,
+       BAR_TMEM = 120, BAR_RED = 128, BAR_BYTES = 144 };
 
 // device-side layer descriptor (built on the host by dd_program_build)
 struct alignas(64) LmLayer {
@@ -368,6 +362,27 @@ __device__ __forceinline__ void warp_colsum32(float (&a)[32], int lane) {
 }
 
 // ---- roles ------------------------------------------------------------------------------------
+// Geometry.  A row tile is always cut into NS = 8 column slices; with KS = 2 the k-blocks of every
+// layer are additionally split between two CTAs (cluster of 16: rank = kh * 8 + cs), so at ~1K rows
+// (8 tiles) the whole GPU works on a layer instead of 64 SMs.  The two partial accumulators of a
+// slice meet over distributed shared memory: each CTA of the pair sends the 32 columns it does not
+// own and finishes the epilogue of the 32 columns it does -- the split halves the k-loop AND the
+// epilogue of every CTA.
+template <int KS>
+struct Geo {
+  static constexpr int CLS = NS * KS;
+  static constexpr int STAGES = KS == 1 ? 4 : 3;
+  static constexpr int OFF_STATS = STAGES * STAGE_BYTES;            // float2 [2 parity][CLS][BM]
+  static constexpr int STATS_BYTES = 2 * CLS * BM * 8;
+  static constexpr int OFF_RED = OFF_STATS + STATS_BYTES;           // float [2 parity][BM][32], swizzled
+  static constexpr int RED_BYTES = KS == 1 ? 0 : 2 * BM * 32 * 4;
+  static constexpr int OFF_STG = OFF_RED + RED_BYTES;               // per-warp 32 x 36 floats
+  static constexpr int OFF_BAR = OFF_STG + 4 * STG_WARP_BYTES;
+  static constexpr int OFF_EP = OFF_BAR + BAR_BYTES;                // per-epilogue-warp layer view
+  static constexpr int SMEM_BYTES = OFF_EP + 4 * EP_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
 struct Shared {
   char* smem;
   uint32_t base;      // shared-window address of smem
@@ -380,14 +395,28 @@ __device__ __forceinline__ int layer_kblocks(const LmLayer& L) {
   if (L.nseg > 1) kb += (L.seg_k[1] + BK - 1) / BK;
   return kb;
 }
+// k-blocks [lo, hi) of a chunk this CTA works on
+// (only full-width layers, bn = 64, split their k range; a narrow layer runs on the kh = 0 CTAs)
+template <int KS>
+__device__ __forceinline__ void k_range(int kbc, int kh, int bn, int& lo, int& hi) {
+  if (KS == 1) { lo = 0; hi = kbc; return; }
+  if (bn != 64) { lo = 0; hi = kh == 0 ? kbc : 0; return; }
+  const int mid = (kbc + 1) >> 1;
+  lo = kh == 0 ? 0 : mid;
+  hi = kh == 0 ? mid : kbc;
+}
 
 // Two producer warps share the stage ring: warp 0 streams this CTA's weight tiles (they never
 // depend on the previous layer, so it runs ahead across layer boundaries on its own), warp 6
-// multicasts this CTA's 16-row slice of the activations (it is the one that waits for the previous
-// layer's outputs).  Both arm the stage's `full` barrier with their own byte count.
+// multicasts this CTA's 16-row slice of the activations to the 8 CTAs that work on the same
+// k-blocks (it is the one that waits for the previous layer's outputs).  Both arm the stage's
+// `full` barrier with their own byte count.
+template <int KS>
 __device__ void producer_b(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
                            int cluster_id, int nclusters, int lane, Ctx cx) {
+  constexpr int STAGES = Geo<KS>::STAGES;
   const int ntiles = (M + BM - 1) / BM;
+  const int cs = rank % NS, kh = rank / NS;
   uint32_t it = 0;
   int pair = 0;
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
@@ -401,13 +430,15 @@ __device__ void producer_b(const Shared& sh, const LmLayer* layers, int nlayers,
       }
       __syncwarp();
       const int kb0 = (L.seg_k[0] + BK - 1) / BK, kbc = layer_kblocks(L);
+      int k_lo, k_hi;
+      k_range<KS>(kbc, kh, L.bn, k_lo, k_hi);
       const int nchunk = L.nchunk, bn = L.bn, chunk_stride = L.chunk_stride, w3d = L.w3d;
       const int wk0[2] = {L.seg_wk0[0], L.seg_wk0[1]};
-      const bool active = rank < L.nactive && !(cx.flags & F_NOB);
+      const bool active = cs < L.nactive && !(cx.flags & F_NOB);
       const uint32_t bytes = active ? 2u * (uint32_t)bn * BK * 4 : 0u;
-      int n = L.wn0 + rank * bn;
+      int n = L.wn0 + cs * bn;
       for (int c = 0; c < nchunk; ++c, n += chunk_stride) {
-        for (int r = 0; r < kbc; ++r, ++it) {
+        for (int r = k_lo; r < k_hi; ++r, ++it) {
           const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           const uint32_t full = sh.bars + BAR_FULL + 8 * s;
@@ -434,13 +465,17 @@ __device__ void producer_b(const Shared& sh, const LmLayer* layers, int nlayers,
   }
 }
 
+template <int KS>
 __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
                            int cluster_id, int nclusters, int lane, Ctx cx) {
+  constexpr int STAGES = Geo<KS>::STAGES;
   const int ntiles = (M + BM - 1) / BM;
+  const int cs = rank % NS, kh = rank / NS;
+  const uint16_t mask = (uint16_t)(0xFFu << (NS * kh));      // the CTAs sharing my k-blocks
   uint32_t it = 0;
   int pair = 0;
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
-    const int m = tile * BM + rank * SLICE_ROWS;
+    const int m = tile * BM + cs * SLICE_ROWS;
     for (int l = 0; l < nlayers; ++l, ++pair) {
       const LmLayer& L = layers[l];
       cx.pair = pair;
@@ -453,14 +488,16 @@ __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers,
       }
       __syncwarp();
       const int kb0 = (L.seg_k[0] + BK - 1) / BK, kbc = layer_kblocks(L);
+      int k_lo, k_hi;
+      k_range<KS>(kbc, kh, L.bn, k_lo, k_hi);
       const int nchunk = L.nchunk;
       const bool exact[2] = {L.seg_exact[0] != 0, L.seg_exact[1] != 0};
-      if (l > 0) {           // the previous layer's outputs of all 8 CTAs are in global memory
-        count_wait(sh.bars + BAR_READY, (uint32_t)pair * CL, cx, 2);
+      if (l > 0) {           // the previous layer's outputs of every CTA are in global memory
+        count_wait(sh.bars + BAR_READY, (uint32_t)pair * Geo<KS>::CLS, cx, 2);
         asm volatile("fence.proxy.async;" ::: "memory");
       }
       for (int c = 0; c < nchunk; ++c) {
-        for (int r = 0; r < kbc; ++r, ++it) {
+        for (int r = k_lo; r < k_hi; ++r, ++it) {
           const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           const uint32_t full = sh.bars + BAR_FULL + 8 * s;
@@ -470,9 +507,9 @@ __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers,
             const bool noa = (cx.flags & F_NOA) != 0;
             mbar_arrive_tx(full, noa ? 0u : (exact[seg] ? 1u : 2u) * A_BYTES);
             if (!noa) {
-              const uint32_t st = sh.base + s * STAGE_BYTES + rank * SLICE_BYTES;
-              tma_load_mc(st, &L.a_hi[seg], kb * BK, m, full, (uint16_t)0xFF);
-              if (!exact[seg]) tma_load_mc(st + A_BYTES, &L.a_lo[seg], kb * BK, m, full, (uint16_t)0xFF);
+              const uint32_t st = sh.base + s * STAGE_BYTES + cs * SLICE_BYTES;
+              tma_load_mc(st, &L.a_hi[seg], kb * BK, m, full, mask);
+              if (!exact[seg]) tma_load_mc(st + A_BYTES, &L.a_lo[seg], kb * BK, m, full, mask);
             }
           }
           __syncwarp();
@@ -483,21 +520,28 @@ __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers,
   }
 }
 
+template <int KS>
 __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
                            int cluster_id, int nclusters, int lane, uint32_t tmem_base, Ctx cx) {
+  constexpr int STAGES = Geo<KS>::STAGES;
   const int ntiles = (M + BM - 1) / BM;
+  const int cs = rank % NS, kh = rank / NS;
+  const uint16_t mask = (uint16_t)(0xFFu << (NS * kh));
   uint32_t it = 0, ac = 0;
   int pair = 0;
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
     for (int l = 0; l < nlayers; ++l, ++pair) {
       const LmLayer& L = layers[l];
       cx.pair = pair;
+      if (L.nseg == 0) continue;                 // epilogue-only layer
       const int kb0 = (L.seg_k[0] + BK - 1) / BK;
       const int kbc = layer_kblocks(L);
-      const bool active = rank < L.nactive;
+      int k_lo, k_hi;
+      k_range<KS>(kbc, kh, L.bn, k_lo, k_hi);
+      if (k_hi <= k_lo) continue;                // nothing of this layer's k range is mine
+      const bool active = cs < L.nactive;
       const int bn = L.bn, nchunk = L.nchunk;
       const uint32_t idesc = make_idesc(bn), idesc2 = make_idesc(2 * bn);
-      if (L.nseg == 0) continue;                 // epilogue-only layer
       const int segk[2] = {L.seg_k[0], L.seg_k[1]};
       const bool sexact[2] = {L.seg_exact[0] != 0, L.seg_exact[1] != 0};
       for (int c = 0; c < nchunk; ++c) {
@@ -509,7 +553,7 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
         // accumulator buffer: columns [0, bn) main (hi.hi), [bn, 2 bn) the small cross terms
         const uint32_t d_main = tmem_base + buf * 128, d_cross = d_main + (uint32_t)bn;
         uint32_t acc = 0;
-        for (int r = 0; r < kbc; ++r, ++it) {
+        for (int r = k_lo; r < k_hi; ++r, ++it) {
           const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait<false>(sh.bars + BAR_FULL + 8 * s, ph, cx, 4);
@@ -531,9 +575,9 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
                 if (!exact && !(cx.flags & F_ONLY1)) mma_tf32(d_cross, make_desc(a_lo + ks * 32), dbh, idesc, 1u);
               }
             }
-            // this stage may be refilled once every CTA of the cluster has read it
-            umma_commit_mc(sh.bars + BAR_EMPTY + 8 * s, (uint16_t)0xFF);
-            if (active && r == kbc - 1) umma_commit(sh.bars + BAR_ACCF + 8 * buf);
+            // this stage may be refilled once every CTA that received it has read it
+            umma_commit_mc(sh.bars + BAR_EMPTY + 8 * s, mask);
+            if (active && r == k_hi - 1) umma_commit(sh.bars + BAR_ACCF + 8 * buf);
           }
           __syncwarp();
           trace_ev(cx, 1, 4 * it + 1);
@@ -544,61 +588,7 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
   }
 }
 
-struct EpiState {
-  uint32_t ac;        // accumulator buffers consumed
-  uint32_t xc;        // cross-CTA row reductions done
-};
-
-// main + cross accumulator columns [cc*32, cc*32+32) of buffer `buf`, this thread's row
-__device__ __forceinline__ void acc_load32(uint32_t tmem_base, uint32_t buf, int quad, int cc, int bn,
-                                           float (&v)[32]) {
-  uint32_t a[32], b[32];
-  const uint32_t t = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + cc * 32;
-  tmem_ld32_nowait(t, a);
-  tmem_ld32_nowait(t + (uint32_t)bn, b);
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
-}
-
-// publish this thread's pair of row partials to every CTA of the cluster, then collect all 8.
-// The remote stores carry their own completion (st.async ... mbarrier::complete_tx): the destination's
-// barrier counts the bytes, so no fence and no separate arrive is needed.
-__device__ __forceinline__ void row_exchange(const Shared& sh, EpiState& es, int rank, int trow,
-                                             int warp, int lane, float a, float b,
-                                             float2 (&parts)[CL], const Ctx& cx) {
-  const uint32_t par = es.xc & 1;
-  const uint32_t bar = sh.bars + BAR_STATS;
-  if (warp == 2 && lane == 0) mbar_arrive_tx(bar, CL * BM * 8);      // bytes this CTA will receive
-  const uint32_t slot = sh.base + OFF_STATS + ((par * CL + rank) * BM + trow) * 8;
-#pragma unroll
-  for (int d = 0; d < CL; ++d) {
-    const uint32_t ra = mapa(slot, d), rb = mapa(bar, d);
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
-                 ::"r"(ra), "f"(a), "f"(b), "r"(rb) : "memory");
-  }
-  mbar_wait<false>(bar, par, cx, 5);
-  const float2* mine = reinterpret_cast<const float2*>(sh.smem + OFF_STATS) + par * CL * BM + trow;
-#pragma unroll
-  for (int d = 0; d < CL; ++d) parts[d] = mine[d * BM];
-  ++es.xc;
-}
-
-__device__ __forceinline__ void acc_wait(const Shared& sh, const EpiState& es, const Ctx& cx,
-                                         bool has_acc) {
-  if (!has_acc) return;
-  mbar_wait<false>(sh.bars + BAR_ACCF + 8 * (es.ac & 1), (es.ac >> 1) & 1, cx, 6);
-  if ((threadIdx.x >> 5) == 2) trace_ev(cx, 2, 16 * cx.pair + 1);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void acc_release(const Shared& sh, EpiState& es, int lane, bool has_acc) {
-  if (!has_acc) return;
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncwarp();
-  if (lane == 0) mbar_arrive(sh.bars + BAR_ACCE + 8 * (es.ac & 1));
-  ++es.ac;
-}
-
+// ---- epilogue ----------------------------------------------------------------------------------
 // the epilogue's view of a layer, copied into shared memory once per (tile, layer) and warp: the
 // descriptor itself lives in global memory and would be re-read after every global store
 struct EP {
@@ -609,6 +599,7 @@ struct EP {
   int ldx[3];
   float f[2];
   int ipar;
+  int kbc;            // k-blocks per chunk (0: epilogue-only layer)
 };
 static_assert(sizeof(EP) <= EP_BYTES, "EP slot");
 __device__ __forceinline__ EP load_ep(const LmLayer& L) {
@@ -620,6 +611,7 @@ __device__ __forceinline__ EP load_ep(const LmLayer& L) {
   e.z = L.z; e.st = L.st; e.out = L.out; e.out_lo = L.out_lo; e.dgamma = L.dgamma; e.dbeta = L.dbeta;
   for (int i = 0; i < 3; ++i) { e.x[i] = L.x[i]; e.ldx[i] = L.ldx[i]; }
   e.f[0] = L.f[0]; e.f[1] = L.f[1]; e.ipar = L.ipar;
+  e.kbc = layer_kblocks(L);
   return e;
 }
 // 32 consecutive per-column parameters (16-byte aligned: offsets are multiples of 32 floats)
@@ -636,19 +628,156 @@ __device__ __forceinline__ void load32(const float* p, float (&o)[32]) {
   }
 }
 
-// accumulator (+ addend + bias) of one 32-column sub-tile
-__device__ __forceinline__ void fetch_sub(const EP& L, uint32_t tmem_base, uint32_t buf, int quad,
-                                          int half, float* stg, int wrow0, int rows_valid, int cb,
-                                          int cols_valid, int lane, float (&v)[32]) {
-  if (L.nseg > 0) {
-    acc_load32(tmem_base, buf, quad, half, L.bn, v);
-  } else {                                     // epilogue-only layer: the input is `add`
+// per-thread epilogue state: the same for every layer of a tile
+struct Epi {
+  Shared sh;
+  Ctx cx;
+  uint32_t tmem_base;
+  uint32_t ac;        // accumulator buffers consumed
+  uint32_t xc;        // cross-CTA row exchanges done
+  uint32_t rc;        // split-K reductions done
+  int rank, cs, kh, warp, quad, lane;
+  float* stg;
+  int wrow0, rows_valid, trow;
+  uint32_t stats_off, red_off;
+};
+
+// main + cross accumulator columns [cc*32, cc*32+32) of buffer `buf`, this thread's row
+__device__ __forceinline__ void acc_load32(uint32_t tmem_base, uint32_t buf, int quad, int cc, int bn,
+                                           float (&v)[32]) {
+  uint32_t a[32], b[32];
+  const uint32_t t = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + cc * 32;
+  tmem_ld32_nowait(t, a);
+  tmem_ld32_nowait(t + (uint32_t)bn, b);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(a[j]) + __uint_as_float(b[j]);
+}
+
+// Does this CTA finish (own) columns of the layer, how many 32-column sub-tiles per chunk, and
+// where sub-tile h of chunk c starts.  KS = 1: both halves of the slice; KS = 2: one half each
+// (bn = 64) or the whole slice on the kh = 0 CTA (bn = 32).
+template <int KS>
+__device__ __forceinline__ bool owns(const EP& L, const Epi& e) {
+  if (e.cs >= L.nactive) return false;
+  return KS == 1 || L.bn == 64 || e.kh == 0;
+}
+template <int KS>
+__device__ __forceinline__ int nsub(const EP& L) { return KS == 1 ? (L.bn >> 5) : 1; }
+template <int KS>
+__device__ __forceinline__ int sub_col(const EP& L, const Epi& e, int c, int h) {
+  const int base = c * L.chunk_stride + e.cs * L.bn;
+  if (KS == 1) return base + h * 32;
+  return base + (L.bn == 64 ? e.kh * 32 : 0);
+}
+// owners of a wide layer (they exchange the LayerNorm partials), and this CTA's slot among them
+template <int KS>
+__device__ __forceinline__ int n_owners(const EP& L) { return (KS == 2 && L.bn == 64) ? 2 * NS : NS; }
+template <int KS>
+__device__ __forceinline__ int owner_slot(const EP& L, const Epi& e) {
+  return (KS == 2 && L.bn == 64) ? e.rank : e.cs;
+}
+
+__device__ __forceinline__ bool has_k(const EP& L, const Epi& e, int ks) {
+  if (L.kbc == 0) return false;
+  if (ks == 1) return true;
+  if (L.bn != 64) return e.kh == 0;
+  const int mid = (L.kbc + 1) >> 1;
+  return e.kh == 0 ? mid > 0 : L.kbc > mid;
+}
+
+__device__ __forceinline__ void acc_wait(Epi& e) {
+  mbar_wait<false>(e.sh.bars + BAR_ACCF + 8 * (e.ac & 1), (e.ac >> 1) & 1, e.cx, 6);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (e.warp == 2) trace_ev(e.cx, 2, 16 * e.cx.pair + 1);
+}
+__device__ __forceinline__ void acc_release(Epi& e) {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  if (e.lane == 0) mbar_arrive(e.sh.bars + BAR_ACCE + 8 * (e.ac & 1));
+  ++e.ac;
+}
+
+// The sub-tiles of chunk c this thread finishes, as raw sums: accumulator (main + cross) of this
+// CTA's k-blocks, plus -- split-K -- the partner CTA's partial of the same columns, which arrives
+// over distributed shared memory (st.async into a swizzled row buffer, bytes counted by `red`).
+// Must be called by every epilogue thread of every ACTIVE CTA once per chunk, owner or not.
+// vals[h] for h < nsub.
+template <int KS>
+__device__ __forceinline__ void chunk_fetch(const EP& L, Epi& e, float (&v0)[32], float (&v1)[32]) {
+  const bool hk = has_k(L, e, KS);
+  if (KS == 1) {
+    if (hk) {
+      acc_wait(e);
+      acc_load32(e.tmem_base, e.ac & 1, e.quad, 0, L.bn, v0);
+      if (L.bn == 64) acc_load32(e.tmem_base, e.ac & 1, e.quad, 1, L.bn, v1);
+      acc_release(e);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { v0[j] = 0.f; v1[j] = 0.f; }
+    }
+    return;
   }
+  // KS == 2.  Narrow layers (bn = 32) are not split: the kh = 0 CTA has the whole sum.
+  if (L.bn != 64) {
+    if (hk) {
+      acc_wait(e);
+      acc_load32(e.tmem_base, e.ac & 1, e.quad, 0, L.bn, v0);
+      acc_release(e);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v0[j] = 0.f;
+    }
+    return;
+  }
+  // v0 = the 32 columns I keep; the 32 my partner finishes are read first and sent right away
+  // (v1 is only a staging array), so both halves are never live together
+  const uint32_t use = e.rc, par = use & 1;
+  const uint32_t bar = e.sh.bars + BAR_RED + 8 * par;
+  if (e.warp == 2 && e.lane == 0) mbar_arrive_tx(bar, BM * 32 * 4);
+  if (hk) {
+    acc_wait(e);
+    acc_load32(e.tmem_base, e.ac & 1, e.quad, 1 - e.kh, L.bn, v1);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v1[j] = 0.f;
+  }
+  {
+    const uint32_t partner = (uint32_t)(e.rank ^ NS);
+    const uint32_t row = e.sh.base + e.red_off + (par * BM + e.trow) * 128;
+    const uint32_t rrow = mapa(row, partner), rbar = mapa(bar, partner);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t a = rrow + (uint32_t)((q ^ (e.trow & 7)) << 4);
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                   ::"r"(a), "f"(v1[4 * q]), "f"(v1[4 * q + 1]), "f"(v1[4 * q + 2]), "f"(v1[4 * q + 3]), "r"(rbar)
+                   : "memory");
+    }
+  }
+  if (hk) {
+    acc_load32(e.tmem_base, e.ac & 1, e.quad, e.kh, L.bn, v0);
+    acc_release(e);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v0[j] = 0.f;
+  }
+  mbar_wait<false>(bar, (use >> 1) & 1, e.cx, 10);
+  {
+    const char* row = e.sh.smem + e.red_off + (par * BM + e.trow) * 128;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 x = *reinterpret_cast<const float4*>(row + ((q ^ (e.trow & 7)) << 4));
+      v0[4 * q] += x.x; v0[4 * q + 1] += x.y; v0[4 * q + 2] += x.z; v0[4 * q + 3] += x.w;
+    }
+  }
+  ++e.rc;
+}
+
+// + addend + bias on an owned sub-tile
+__device__ __forceinline__ void add_inputs(const EP& L, Epi& e, int cb, int cols_valid, float (&v)[32]) {
   if (L.add != nullptr) {
     float a[32];
-    sub_load(stg, a, L.add + (size_t)wrow0 * L.ld_add + cb, L.ld_add, rows_valid, cols_valid, lane);
+    sub_load(e.stg, a, L.add + (size_t)e.wrow0 * L.ld_add + cb, L.ld_add, e.rows_valid, cols_valid, e.lane);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] += a[j];
   }
@@ -666,120 +795,166 @@ __device__ __forceinline__ void fetch_sub(const EP& L, uint32_t tmem_base, uint3
   }
 }
 
-__device__ __forceinline__ void store_with_lo(const EP& L, float* stg, float (&v)[32], int wrow0,
-                                              int rows_valid, int cb, int cols_valid, int lane) {
-  sub_store(stg, v, L.out + (size_t)wrow0 * L.ld_out + cb, L.ld_out, rows_valid, cols_valid, lane);
+__device__ __forceinline__ void store_with_lo(const EP& L, Epi& e, float (&v)[32], int cb, int cols_valid) {
+  sub_store(e.stg, v, L.out + (size_t)e.wrow0 * L.ld_out + cb, L.ld_out, e.rows_valid, cols_valid, e.lane);
   if (L.out_lo != nullptr) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = lo_of(v[j]);
-    sub_store(stg, v, L.out_lo + (size_t)wrow0 * L.ld_lo + cb, L.ld_lo, rows_valid, cols_valid, lane);
+    sub_store(e.stg, v, L.out_lo + (size_t)e.wrow0 * L.ld_lo + cb, L.ld_lo, e.rows_valid, cols_valid, e.lane);
+  }
+}
+
+// publish this thread's pair of row partials to every owner CTA, then collect all of them.
+// The remote stores carry their own completion (st.async ... mbarrier::complete_tx): the destination's
+// barrier counts the bytes, so no fence and no separate arrive is needed.
+template <int KS>
+__device__ __forceinline__ void row_exchange(const EP& L, Epi& e, float a, float b,
+                                             float2 (&parts)[Geo<KS>::CLS]) {
+  constexpr int CLS = Geo<KS>::CLS;
+  const int nown = n_owners<KS>(L), slot_i = owner_slot<KS>(L, e);
+  const uint32_t par = e.xc & 1;
+  const uint32_t bar = e.sh.bars + BAR_STATS + 8 * par;
+  if (e.warp == 2 && e.lane == 0) mbar_arrive_tx(bar, (uint32_t)nown * BM * 8);   // bytes I will receive
+  const uint32_t slot = e.sh.base + e.stats_off + ((par * CLS + slot_i) * BM + e.trow) * 8;
+#pragma unroll
+  for (int d = 0; d < CLS; ++d) {
+    if (d < nown) {              // owners are ranks 0 .. nown-1 in both geometries
+      const uint32_t ra = mapa(slot, d), rb = mapa(bar, d);
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+                   ::"r"(ra), "f"(a), "f"(b), "r"(rb) : "memory");
+    }
+  }
+  mbar_wait<false>(bar, (e.xc >> 1) & 1, e.cx, 5);
+  const float2* mine = reinterpret_cast<const float2*>(e.sh.smem + e.stats_off) + par * CLS * BM + e.trow;
+#pragma unroll
+  for (int d = 0; d < CLS; ++d)
+    if (d < nown) parts[d] = mine[d * BM];
+  ++e.xc;
+}
+
+// running (count, mean, M2) of a row += one 32-column sub-tile
+__device__ __forceinline__ void welford32(const float (&v)[32], float& mean, float& m2, float& cnt) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) s += v[j];
+  const float mu = s * (1.f / 32.f);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { const float d = v[j] - mu; q += d * d; }
+  const float delta = mu - mean, tot = cnt + 32.f;
+  mean += delta * (32.f / tot);
+  m2 += q + delta * delta * (cnt * 32.f / tot);
+  cnt = tot;
+}
+// merge the owners' equal-count partials into (mean, rstd) of the full row
+template <int KS>
+__device__ __forceinline__ void ln_finish(const EP& L, Epi& e, float mean, float m2, float cnt,
+                                          float& gm, float& rstd) {
+  float2 parts[Geo<KS>::CLS];
+  row_exchange<KS>(L, e, mean, m2, parts);
+  const int nown = n_owners<KS>(L);
+  gm = 0.f;
+  for (int d = 0; d < nown; ++d) gm += parts[d].x;
+  gm /= (float)nown;
+  float gq = 0.f;
+  for (int d = 0; d < nown; ++d) { const float dl = parts[d].x - gm; gq += parts[d].y + cnt * dl * dl; }
+  rstd = rsqrtf(gq / (float)L.N + DD_LN_EPS);
+  if (L.st != nullptr && e.rank == 0 && e.lane < e.rows_valid) {
+    L.st[(size_t)(e.wrow0 + e.lane) * 2] = gm;
+    L.st[(size_t)(e.wrow0 + e.lane) * 2 + 1] = rstd;
+  }
+}
+
+// y = (v - mean) * rstd * gamma + beta (+ elu) on a sub-tile whose columns start at cb
+__device__ __forceinline__ void ln_apply(const EP& L, int cb, float gm, float rstd, int act, float (&v)[32]) {
+  const float4* gp = reinterpret_cast<const float4*>(L.gamma + cb);   // 128-byte aligned slices
+  const float4* bp = reinterpret_cast<const float4*>(L.beta + cb);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 g4 = __ldg(gp + q), b4 = __ldg(bp + q);
+    const float y0 = (v[4 * q] - gm) * rstd * g4.x + b4.x;
+    const float y1 = (v[4 * q + 1] - gm) * rstd * g4.y + b4.y;
+    const float y2 = (v[4 * q + 2] - gm) * rstd * g4.z + b4.z;
+    const float y3 = (v[4 * q + 3] - gm) * rstd * g4.w + b4.w;
+    v[4 * q] = act ? elu_f(y0) : y0;
+    v[4 * q + 1] = act ? elu_f(y1) : y1;
+    v[4 * q + 2] = act ? elu_f(y2) : y2;
+    v[4 * q + 3] = act ? elu_f(y3) : y3;
   }
 }
 
 // E_PLAIN: out = acc (+ add) (+ bias)
-__device__ void epi_plain(const Shared& sh, const EP& L, EpiState& es, uint32_t tmem_base,
-                          int rank, int quad, int lane, float* stg, int wrow0, int rows_valid,
-                          const Ctx& cx) {
-  const int halves = L.bn >> 5;
+template <int KS>
+__device__ void epi_plain(const EP& L, Epi& e) {
+  const bool own = owns<KS>(L, e);
   for (int c = 0; c < L.nchunk; ++c) {
-    acc_wait(sh, es, cx, L.nseg > 0);
-    const int col0 = c * L.chunk_stride + rank * L.bn;
-    for (int h = 0; h < halves; ++h) {
-      const int cb = col0 + h * 32;
-      const int cols_valid = min(32, L.N - cb);
-      float v[32];
-      fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, cols_valid, lane, v);
-      if (cols_valid > 0) store_with_lo(L, stg, v, wrow0, rows_valid, cb, cols_valid, lane);
+    float v[2][32];
+    chunk_fetch<KS>(L, e, v[0], v[1]);
+    if (!own) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h < nsub<KS>(L)) {
+        const int cb = sub_col<KS>(L, e, c, h);
+        const int cols_valid = min(32, L.N - cb);
+        if (cols_valid > 0) {
+          add_inputs(L, e, cb, cols_valid, v[h]);
+          store_with_lo(L, e, v[h], cb, cols_valid);
+        }
+      }
     }
-    acc_release(sh, es, lane, L.nseg > 0);
   }
 }
 
 // E_LN: z = acc (+add)(+bias); out = act(LayerNorm(z) * gamma + beta)   (A/nets.py:585-602)
-__device__ void epi_ln_fwd(const Shared& sh, const EP& L, EpiState& es, uint32_t tmem_base,
-                           int rank, int quad, int lane, float* stg, int wrow0, int rows_valid,
-                           int trow, const Ctx& cx) {
-  const int halves = L.bn >> 5;
-  const bool single = L.nchunk == 1 && halves <= 2;
-  float keep[64];
+template <int KS>
+__device__ void epi_ln_fwd(const EP& L, Epi& e) {
+  const int ns = nsub<KS>(L);
+  const bool own = owns<KS>(L, e);            // a pure split-K contributor only feeds its partner
+  const bool single = L.nchunk == 1;          // values stay in registers between the two passes
+  float keep[2][32];
   float mean = 0.f, m2 = 0.f, cnt = 0.f;
   for (int c = 0; c < L.nchunk; ++c) {
-    acc_wait(sh, es, cx, L.nseg > 0);
-    const int col0 = c * L.chunk_stride + rank * L.bn;
+    float v[2][32];
+    chunk_fetch<KS>(L, e, v[0], v[1]);
+    if (!own) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (h < halves) {
-        const int cb = col0 + h * 32;
-        float v[32];
-        fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, 32, lane, v);
-        if (quad == 2 && h == 0 && c == 0) trace_ev(cx, 2, 16 * cx.pair + 2);
+      if (h < ns) {
+        const int cb = sub_col<KS>(L, e, c, h);
+        add_inputs(L, e, cb, 32, v[h]);
+        if (e.quad == 2 && h == 0 && c == 0) trace_ev(e.cx, 2, 16 * e.cx.pair + 2);
         if (L.z != nullptr)
-          sub_store(stg, v, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
-        if (quad == 2 && h == 0 && c == 0) trace_ev(cx, 2, 16 * cx.pair + 3);
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) s += v[j];
-        const float mu = s * (1.f / 32.f);
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = v[j] - mu; q += d * d; }
-        const float delta = mu - mean, tot = cnt + 32.f;
-        mean += delta * (32.f / tot);
-        m2 += q + delta * delta * (cnt * 32.f / tot);
-        cnt = tot;
+          sub_store(e.stg, v[h], L.z + (size_t)e.wrow0 * L.ld_z + cb, L.ld_z, e.rows_valid, 32, e.lane);
+        if (e.quad == 2 && h == 0 && c == 0) trace_ev(e.cx, 2, 16 * e.cx.pair + 3);
+        welford32(v[h], mean, m2, cnt);
         if (single) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) keep[h * 32 + j] = v[j];
+          for (int j = 0; j < 32; ++j) keep[h][j] = v[h][j];
         }
       }
     }
-    acc_release(sh, es, lane, L.nseg > 0);
   }
-  float2 parts[CL];
-  if (quad == 2) trace_ev(cx, 2, 16 * cx.pair + 4);
-  row_exchange(sh, es, rank, trow, 2 + ((quad + 2) & 3), lane, mean, m2, parts, cx);
-  if (quad == 2) trace_ev(cx, 2, 16 * cx.pair + 5);
-  float gm = 0.f;
-  for (int d = 0; d < L.nactive; ++d) gm += parts[d].x;
-  gm /= (float)L.nactive;
-  float gq = 0.f;
-  for (int d = 0; d < L.nactive; ++d) { const float dl = parts[d].x - gm; gq += parts[d].y + cnt * dl * dl; }
-  const float rstd = rsqrtf(gq / (float)L.N + DD_LN_EPS);
-  if (L.st != nullptr && rank == 0 && lane < rows_valid) {
-    L.st[(size_t)(wrow0 + lane) * 2] = gm;
-    L.st[(size_t)(wrow0 + lane) * 2 + 1] = rstd;
-  }
+  if (!own) return;
+  float gm, rstd;
+  if (e.quad == 2) trace_ev(e.cx, 2, 16 * e.cx.pair + 4);
+  ln_finish<KS>(L, e, mean, m2, cnt, gm, rstd);
+  if (e.quad == 2) trace_ev(e.cx, 2, 16 * e.cx.pair + 5);
   for (int c = 0; c < L.nchunk; ++c) {
-    const int col0 = c * L.chunk_stride + rank * L.bn;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (h < halves) {
-        const int cb = col0 + h * 32;
+      if (h < ns) {
+        const int cb = sub_col<KS>(L, e, c, h);
         float v[32];
         if (single) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = keep[h * 32 + j];
+          for (int j = 0; j < 32; ++j) v[j] = keep[h][j];
         } else {
-          sub_load(stg, v, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
+          sub_load(e.stg, v, L.z + (size_t)e.wrow0 * L.ld_z + cb, L.ld_z, e.rows_valid, 32, e.lane);
         }
-        const float4* gp = reinterpret_cast<const float4*>(L.gamma + cb);   // 128-byte aligned slices
-        const float4* bp = reinterpret_cast<const float4*>(L.beta + cb);
-        const int act = L.act;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 g4 = __ldg(gp + q), b4 = __ldg(bp + q);
-          const float y0 = (v[4 * q] - gm) * rstd * g4.x + b4.x;
-          const float y1 = (v[4 * q + 1] - gm) * rstd * g4.y + b4.y;
-          const float y2 = (v[4 * q + 2] - gm) * rstd * g4.z + b4.z;
-          const float y3 = (v[4 * q + 3] - gm) * rstd * g4.w + b4.w;
-          v[4 * q] = act ? elu_f(y0) : y0;
-          v[4 * q + 1] = act ? elu_f(y1) : y1;
-          v[4 * q + 2] = act ? elu_f(y2) : y2;
-          v[4 * q + 3] = act ? elu_f(y3) : y3;
-        }
-        if (quad == 2 && h == 0 && c == 0) trace_ev(cx, 2, 16 * cx.pair + 6);
-        store_with_lo(L, stg, v, wrow0, rows_valid, cb, 32, lane);
-        if (quad == 2 && h == 0 && c == 0) trace_ev(cx, 2, 16 * cx.pair + 7);
+        ln_apply(L, cb, gm, rstd, L.act, v);
+        if (e.quad == 2 && h == 0 && c == 0) trace_ev(e.cx, 2, 16 * e.cx.pair + 6);
+        store_with_lo(L, e, v, cb, 32);
+        if (e.quad == 2 && h == 0 && c == 0) trace_ev(e.cx, 2, 16 * e.cx.pair + 7);
       }
     }
   }
@@ -787,29 +962,31 @@ __device__ void epi_ln_fwd(const Shared& sh, const EP& L, EpiState& es, uint32_t
 
 // E_LNBWD: dh = acc (+add); dz = LayerNorm'(act'(.) dh) given the saved pre-norm z and (mean, rstd)
 // dgamma += sum_rows dy * xhat, dbeta += sum_rows dy  (optional)
-__device__ void epi_ln_bwd(const Shared& sh, const EP& L, EpiState& es, uint32_t tmem_base,
-                           int rank, int quad, int lane, float* stg, int wrow0, int rows_valid,
-                           int trow, const Ctx& cx) {
-  const int halves = L.bn >> 5;
-  const bool single = L.nchunk == 1 && halves <= 2;
-  const bool rowok = lane < rows_valid;
+template <int KS>
+__device__ void epi_ln_bwd(const EP& L, Epi& e) {
+  const int ns = nsub<KS>(L);
+  const bool own = owns<KS>(L, e);
+  const bool single = L.nchunk == 1;
+  const bool rowok = e.lane < e.rows_valid;
   float mean = 0.f, rstd = 0.f;
-  if (rowok) {
-    mean = L.st[(size_t)(wrow0 + lane) * 2];
-    rstd = L.st[(size_t)(wrow0 + lane) * 2 + 1];
+  if (rowok && own) {
+    mean = L.st[(size_t)(e.wrow0 + e.lane) * 2];
+    rstd = L.st[(size_t)(e.wrow0 + e.lane) * 2 + 1];
   }
-  float keep[64];
+  float keep[2][32];
   float s1 = 0.f, s2 = 0.f;
   for (int c = 0; c < L.nchunk; ++c) {
-    acc_wait(sh, es, cx, L.nseg > 0);
-    const int col0 = c * L.chunk_stride + rank * L.bn;
+    float vv[2][32];
+    chunk_fetch<KS>(L, e, vv[0], vv[1]);
+    if (!own) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (h < halves) {
-        const int cb = col0 + h * 32;
-        float v[32], z[32];
-        fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, 32, lane, v);
-        sub_load(stg, z, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
+      if (h < ns) {
+        float (&v)[32] = vv[h];
+        const int cb = sub_col<KS>(L, e, c, h);
+        add_inputs(L, e, cb, 32, v);
+        float z[32];
+        sub_load(e.stg, z, L.z + (size_t)e.wrow0 * L.ld_z + cb, L.ld_z, e.rows_valid, 32, e.lane);
         float dyv[32];
         const float* gp = L.gamma + cb;
         const float* bp = L.beta + cb;
@@ -831,132 +1008,109 @@ __device__ void epi_ln_bwd(const Shared& sh, const EP& L, EpiState& es, uint32_t
           dyv[j] = dy;
         }
         if (L.dgamma != nullptr) {       // column sums over the warp's rows, one atomic per column
-          warp_colsum32(z, lane);
-          warp_colsum32(dyv, lane);
-          atomicAdd(L.dgamma + cb + lane, z[0]);
-          atomicAdd(L.dbeta + cb + lane, dyv[0]);
+          warp_colsum32(z, e.lane);
+          warp_colsum32(dyv, e.lane);
+          atomicAdd(L.dgamma + cb + e.lane, z[0]);
+          atomicAdd(L.dbeta + cb + e.lane, dyv[0]);
         }
         if (single) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) keep[h * 32 + j] = v[j];
+          for (int j = 0; j < 32; ++j) keep[h][j] = v[j];
         } else {
-          sub_store(stg, v, L.out + (size_t)wrow0 * L.ld_out + cb, L.ld_out, rows_valid, 32, lane);
+          sub_store(e.stg, v, L.out + (size_t)e.wrow0 * L.ld_out + cb, L.ld_out, e.rows_valid, 32, e.lane);
         }
       }
     }
-    acc_release(sh, es, lane, L.nseg > 0);
   }
-  float2 parts[CL];
-  row_exchange(sh, es, rank, trow, 2 + ((quad + 2) & 3), lane, s1, s2, parts, cx);
+  if (!own) return;
+  float2 parts[Geo<KS>::CLS];
+  row_exchange<KS>(L, e, s1, s2, parts);
+  const int nown = n_owners<KS>(L);
   float t1 = 0.f, t2 = 0.f;
-  for (int d = 0; d < L.nactive; ++d) { t1 += parts[d].x; t2 += parts[d].y; }
+  for (int d = 0; d < nown; ++d) { t1 += parts[d].x; t2 += parts[d].y; }
   t1 /= (float)L.N;
   t2 /= (float)L.N;
   for (int c = 0; c < L.nchunk; ++c) {
-    const int col0 = c * L.chunk_stride + rank * L.bn;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (h < halves) {
-        const int cb = col0 + h * 32;
+      if (h < ns) {
+        const int cb = sub_col<KS>(L, e, c, h);
         float v[32], z[32];
         if (single) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = keep[h * 32 + j];
+          for (int j = 0; j < 32; ++j) v[j] = keep[h][j];
         } else {
-          sub_load(stg, v, L.out + (size_t)wrow0 * L.ld_out + cb, L.ld_out, rows_valid, 32, lane);
+          sub_load(e.stg, v, L.out + (size_t)e.wrow0 * L.ld_out + cb, L.ld_out, e.rows_valid, 32, e.lane);
         }
-        sub_load(stg, z, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
+        sub_load(e.stg, z, L.z + (size_t)e.wrow0 * L.ld_z + cb, L.ld_z, e.rows_valid, 32, e.lane);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float xh = (z[j] - mean) * rstd;
           v[j] = rstd * (v[j] - t1 - xh * t2);
         }
-        store_with_lo(L, stg, v, wrow0, rows_valid, cb, 32, lane);
+        store_with_lo(L, e, v, cb, 32);
       }
     }
   }
 }
 
-
 // E_GRU: joint LayerNorm over the 3 D gate pre-activations, then the GRU update (A/nets.py:149-160)
 //   y = LN(z) * gamma + beta; r = sig(y_r); c = tanh(r * y_c); u = sig(y_u - 1); out = u c + (1 - u) prev
 // Chunk g of a CTA holds its column slice of gate g (chunk_stride = D), so a thread has the three
 // gate values of its columns.  z: pre-norm (saved), x1: y (saved), x0: prev.
-__device__ void epi_gru(const Shared& sh, const EP& L, EpiState& es, uint32_t tmem_base, int rank,
-                        int quad, int lane, float* stg, int wrow0, int rows_valid, int trow,
-                        const Ctx& cx) {
-  const int halves = L.bn >> 5;
+template <int KS>
+__device__ void epi_gru(const EP& L, Epi& e) {
+  const int ns = nsub<KS>(L);
+  const bool own = owns<KS>(L, e);
   const int D = L.chunk_stride;
   float mean = 0.f, m2 = 0.f, cnt = 0.f;
   for (int c = 0; c < 3; ++c) {
-    acc_wait(sh, es, cx, true);
-    const int col0 = c * D + rank * L.bn;
-    for (int h = 0; h < halves; ++h) {
-      const int cb = col0 + h * 32;
-      float v[32];
-      fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, 32, lane, v);
-      sub_store(stg, v, L.z + (size_t)wrow0 * L.ld_z + cb, L.ld_z, rows_valid, 32, lane);
-      float s = 0.f;
+    float v[2][32];
+    chunk_fetch<KS>(L, e, v[0], v[1]);
+    if (!own) continue;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) s += v[j];
-      const float mu = s * (1.f / 32.f);
-      float q = 0.f;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) { const float d = v[j] - mu; q += d * d; }
-      const float delta = mu - mean, tot = cnt + 32.f;
-      mean += delta * (32.f / tot);
-      m2 += q + delta * delta * (cnt * 32.f / tot);
-      cnt = tot;
+    for (int h = 0; h < 2; ++h) {
+      if (h < ns) {
+        const int cb = sub_col<KS>(L, e, c, h);
+        add_inputs(L, e, cb, 32, v[h]);
+        sub_store(e.stg, v[h], L.z + (size_t)e.wrow0 * L.ld_z + cb, L.ld_z, e.rows_valid, 32, e.lane);
+        welford32(v[h], mean, m2, cnt);
+      }
     }
-    acc_release(sh, es, lane, true);
   }
-  float2 parts[CL];
-  row_exchange(sh, es, rank, trow, 2 + ((quad + 2) & 3), lane, mean, m2, parts, cx);
-  float gm = 0.f;
-  for (int d = 0; d < CL; ++d) gm += parts[d].x;
-  gm *= (1.f / CL);
-  float gq = 0.f;
-  for (int d = 0; d < CL; ++d) { const float dl = parts[d].x - gm; gq += parts[d].y + cnt * dl * dl; }
-  const float rstd = rsqrtf(gq / (float)L.N + DD_LN_EPS);
-  if (L.st != nullptr && rank == 0 && lane < rows_valid) {
-    L.st[(size_t)(wrow0 + lane) * 2] = gm;
-    L.st[(size_t)(wrow0 + lane) * 2 + 1] = rstd;
-  }
-  for (int h = 0; h < halves; ++h) {
-    const int cj = rank * L.bn + h * 32;            // column inside each gate
+  if (!own) return;
+  float gm, rstd;
+  ln_finish<KS>(L, e, mean, m2, cnt, gm, rstd);
+  for (int h = 0; h < ns; ++h) {
+    const int cj = sub_col<KS>(L, e, 0, h);        // column inside each gate
     float g[32], v[32];
     // reset gate
-    sub_load(stg, v, L.z + (size_t)wrow0 * L.ld_z + cj, L.ld_z, rows_valid, 32, lane);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (v[j] - gm) * rstd * __ldg(L.gamma + cj + j) + __ldg(L.beta + cj + j);
+    sub_load(e.stg, v, L.z + (size_t)e.wrow0 * L.ld_z + cj, L.ld_z, e.rows_valid, 32, e.lane);
+    ln_apply(L, cj, gm, rstd, 0, v);
     if (L.x[1] != nullptr)
-      sub_store(stg, v, L.x[1] + (size_t)wrow0 * L.ldx[1] + cj, L.ldx[1], rows_valid, 32, lane);
+      sub_store(e.stg, v, L.x[1] + (size_t)e.wrow0 * L.ldx[1] + cj, L.ldx[1], e.rows_valid, 32, e.lane);
 #pragma unroll
     for (int j = 0; j < 32; ++j) g[j] = sigmoidf_(v[j]);
     // candidate
-    sub_load(stg, v, L.z + (size_t)wrow0 * L.ld_z + D + cj, L.ld_z, rows_valid, 32, lane);
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      v[j] = (v[j] - gm) * rstd * __ldg(L.gamma + D + cj + j) + __ldg(L.beta + D + cj + j);
+    sub_load(e.stg, v, L.z + (size_t)e.wrow0 * L.ld_z + D + cj, L.ld_z, e.rows_valid, 32, e.lane);
+    ln_apply(L, D + cj, gm, rstd, 0, v);
     if (L.x[1] != nullptr)
-      sub_store(stg, v, L.x[1] + (size_t)wrow0 * L.ldx[1] + D + cj, L.ldx[1], rows_valid, 32, lane);
+      sub_store(e.stg, v, L.x[1] + (size_t)e.wrow0 * L.ldx[1] + D + cj, L.ldx[1], e.rows_valid, 32, e.lane);
 #pragma unroll
     for (int j = 0; j < 32; ++j) g[j] = tanhf(g[j] * v[j]);
     // update gate and the new state
-    sub_load(stg, v, L.z + (size_t)wrow0 * L.ld_z + 2 * D + cj, L.ld_z, rows_valid, 32, lane);
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      v[j] = (v[j] - gm) * rstd * __ldg(L.gamma + 2 * D + cj + j) + __ldg(L.beta + 2 * D + cj + j);
+    sub_load(e.stg, v, L.z + (size_t)e.wrow0 * L.ld_z + 2 * D + cj, L.ld_z, e.rows_valid, 32, e.lane);
+    ln_apply(L, 2 * D + cj, gm, rstd, 0, v);
     if (L.x[1] != nullptr)
-      sub_store(stg, v, L.x[1] + (size_t)wrow0 * L.ldx[1] + 2 * D + cj, L.ldx[1], rows_valid, 32, lane);
+      sub_store(e.stg, v, L.x[1] + (size_t)e.wrow0 * L.ldx[1] + 2 * D + cj, L.ldx[1], e.rows_valid, 32, e.lane);
     float pv[32];
-    sub_load(stg, pv, L.x[0] + (size_t)wrow0 * L.ldx[0] + cj, L.ldx[0], rows_valid, 32, lane);
+    sub_load(e.stg, pv, L.x[0] + (size_t)e.wrow0 * L.ldx[0] + cj, L.ldx[0], e.rows_valid, 32, e.lane);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const float u = sigmoidf_(v[j] - 1.f);
       v[j] = u * g[j] + (1.f - u) * pv[j];
     }
-    store_with_lo(L, stg, v, wrow0, rows_valid, cj, 32, lane);
+    store_with_lo(L, e, v, cj, 32);
   }
 }
 
@@ -964,62 +1118,65 @@ __device__ void epi_gru(const Shared& sh, const EP& L, EpiState& es, uint32_t tm
 // C classes (A/nets.py:162-171); with noise: idx = argmax(logit + G), one-hot into x1
 // (OneHotDist.sample, A/tfutils.py:368-382).  C == 32: one group per 32-column sub-tile; C < 32: the
 // whole (narrow) layer is one group.  out = logit.
-__device__ void epi_stats(const Shared& sh, const EP& L, EpiState& es, uint32_t tmem_base, int rank,
-                          int quad, int lane, float* stg, int wrow0, int rows_valid, const Ctx& cx) {
-  const int halves = L.bn >> 5;
+template <int KS>
+__device__ void epi_stats(const EP& L, Epi& e) {
+  const bool own = owns<KS>(L, e);
   const int C = L.ipar;
   const float mix = L.f[0], uni = mix / (float)C;
   for (int c = 0; c < L.nchunk; ++c) {
-    acc_wait(sh, es, cx, L.nseg > 0);
-    const int col0 = c * L.chunk_stride + rank * L.bn;
-    for (int h = 0; h < halves; ++h) {
-      const int cb = col0 + h * 32;
-      const int cols_valid = min(32, L.N - cb);
-      if (cols_valid <= 0) continue;
-      float v[32];
-      fetch_sub(L, tmem_base, es.ac & 1, quad, h, stg, wrow0, rows_valid, cb, cols_valid, lane, v);
-      float mx = -INFINITY;
+    float vv[2][32];
+    chunk_fetch<KS>(L, e, vv[0], vv[1]);
+    if (!own) continue;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (j < C) mx = fmaxf(mx, v[j]);
-      float sum = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      if (h < nsub<KS>(L)) {
+        float (&v)[32] = vv[h];
+        const int cb = sub_col<KS>(L, e, c, h);
+        const int cols_valid = min(32, L.N - cb);
+        if (cols_valid <= 0) continue;
+        add_inputs(L, e, cb, cols_valid, v);
+        float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { v[j] = j < C ? expf(v[j] - mx) : 0.f; sum += v[j]; }
-      const float inv = 1.f / sum;
+        for (int j = 0; j < 32; ++j) if (j < C) mx = fmaxf(mx, v[j]);
+        float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = logf((1.f - mix) * v[j] * inv + uni);
-      sub_store(stg, v, L.out + (size_t)wrow0 * L.ld_out + cb, L.ld_out, rows_valid, cols_valid, lane);
-      if (L.x[1] != nullptr) {
-        if (L.x[0] != nullptr) {
-          float g[32];
-          sub_load(stg, g, L.x[0] + (size_t)wrow0 * L.ldx[0] + cb, L.ldx[0], rows_valid, cols_valid, lane);
+        for (int j = 0; j < 32; ++j) { v[j] = j < C ? expf(v[j] - mx) : 0.f; sum += v[j]; }
+        const float inv = 1.f / sum;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += g[j];
+        for (int j = 0; j < 32; ++j) v[j] = logf((1.f - mix) * v[j] * inv + uni);
+        sub_store(e.stg, v, L.out + (size_t)e.wrow0 * L.ld_out + cb, L.ld_out, e.rows_valid, cols_valid, e.lane);
+        if (L.x[1] != nullptr) {
+          if (L.x[0] != nullptr) {
+            float g[32];
+            sub_load(e.stg, g, L.x[0] + (size_t)e.wrow0 * L.ldx[0] + cb, L.ldx[0], e.rows_valid, cols_valid, e.lane);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += g[j];
+          }
+          float bv = -INFINITY;
+          int bi = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < C && v[j] > bv) { bv = v[j]; bi = j; }   // first maximum
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (j == bi) ? 1.f : 0.f;
+          sub_store(e.stg, v, L.x[1] + (size_t)e.wrow0 * L.ldx[1] + cb, L.ldx[1], e.rows_valid, cols_valid, e.lane);
         }
-        float bv = -INFINITY;
-        int bi = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (j < C && v[j] > bv) { bv = v[j]; bi = j; }   // first maximum
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (j == bi) ? 1.f : 0.f;
-        sub_store(stg, v, L.x[1] + (size_t)wrow0 * L.ldx[1] + cb, L.ldx[1], rows_valid, cols_valid, lane);
       }
     }
-    acc_release(sh, es, lane, L.nseg > 0);
   }
 }
 
 // E_ACTOR: continuous action head (A/nets.py:461-468), N = 2 A columns [mean raw | std raw]:
 // mean = tanh(m); std = (hi - lo) sigmoid(s) + lo; action = mean + std * eps.
 // out = action (+ out_lo), x0 = eps, x1 = mean, x2 = std.
-__device__ void epi_actor(const Shared& sh, const EP& L, EpiState& es, uint32_t tmem_base, int rank,
-                          int quad, int lane, float* stg, int wrow0, int rows_valid, const Ctx& cx) {
+template <int KS>
+__device__ void epi_actor(const EP& L, Epi& e) {
   const int A = L.ipar;
-  acc_wait(sh, es, cx, L.nseg > 0);
-  float v[32];
-  fetch_sub(L, tmem_base, es.ac & 1, quad, 0, stg, wrow0, rows_valid, 0, 2 * A, lane, v);
-  acc_release(sh, es, lane, L.nseg > 0);
-  if (lane < rows_valid) {
-    const size_t row = (size_t)(wrow0 + lane);
+  float v[32], unused[32];
+  chunk_fetch<KS>(L, e, v, unused);
+  if (!owns<KS>(L, e)) return;
+  add_inputs(L, e, 0, 2 * A, v);
+  if (e.lane < e.rows_valid) {
+    const size_t row = (size_t)(e.wrow0 + e.lane);
     const float lo = L.f[0], hi = L.f[1];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -1036,83 +1193,89 @@ __device__ void epi_actor(const Shared& sh, const EP& L, EpiState& es, uint32_t 
   }
 }
 
+template <int KS>
 __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
                          int cluster_id, int nclusters, int warp, int lane, uint32_t tmem_base,
                          Ctx cx) {
+  constexpr int CLS = Geo<KS>::CLS;
   const int ntiles = (M + BM - 1) / BM;
-  const int quad = warp & 3;                      // TMEM lane quadrant this warp may read
-  float* stg = reinterpret_cast<float*>(sh.smem + OFF_STG + (warp - 2) * STG_WARP_BYTES);
-  EP* ep_slot = reinterpret_cast<EP*>(sh.smem + OFF_EP + (warp - 2) * EP_BYTES);
-  EpiState es = {0u, 0u};
+  Epi e;
+  e.sh = sh; e.cx = cx; e.tmem_base = tmem_base;
+  e.ac = 0; e.xc = 0; e.rc = 0;
+  e.rank = rank; e.cs = rank % NS; e.kh = rank / NS;
+  e.warp = warp; e.quad = warp & 3; e.lane = lane;      // quad: the TMEM lane quadrant this warp may read
+  e.stg = reinterpret_cast<float*>(sh.smem + Geo<KS>::OFF_STG + (warp - 2) * STG_WARP_BYTES);
+  e.stats_off = Geo<KS>::OFF_STATS;
+  e.red_off = Geo<KS>::OFF_RED;
+  EP* ep_slot = reinterpret_cast<EP*>(sh.smem + Geo<KS>::OFF_EP + (warp - 2) * EP_BYTES);
   int pair = 0;
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
-    const int wrow0 = tile * BM + quad * 32;      // first global row of this warp
-    const int rows_valid = max(0, min(32, M - wrow0));
-    const int trow = quad * 32 + lane;
+    e.wrow0 = tile * BM + e.quad * 32;      // first global row of this warp
+    e.rows_valid = max(0, min(32, M - e.wrow0));
+    e.trow = e.quad * 32 + lane;
     for (int l = 0; l < nlayers; ++l, ++pair) {
       __syncwarp();
       if (lane == 0) *ep_slot = load_ep(layers[l]);
       __syncwarp();
       const EP& L = *ep_slot;
-      cx.pair = pair;
-      const bool active = rank < L.nactive;
+      e.cx.pair = pair;
+      const bool active = e.cs < L.nactive && (KS == 1 || L.bn == 64 || e.kh == 0);
       if (L.nseg == 0 && l > 0)       // no producer wait protects its inputs: wait here
-        count_wait(sh.bars + BAR_READY, (uint32_t)pair * CL, cx, 8);
-      if (warp == 2) trace_ev(cx, 2, 16 * pair);
-      if (L.epi == DD_EPI_PLAIN) {
-        if (active) epi_plain(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, cx);
-      } else if (L.epi == DD_EPI_LN) {
-        if (active) epi_ln_fwd(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, trow, cx);
-      } else if (L.epi == DD_EPI_LNBWD) {
-        if (active) epi_ln_bwd(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, trow, cx);
-      } else if (L.epi == DD_EPI_GRU) {
-        if (active) epi_gru(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, trow, cx);
-      } else if (L.epi == DD_EPI_STATS) {
-        if (active) epi_stats(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, cx);
-      } else {
-        if (active) epi_actor(sh, L, es, tmem_base, rank, quad, lane, stg, wrow0, rows_valid, cx);
+        count_wait(sh.bars + BAR_READY, (uint32_t)pair * CLS, e.cx, 8);
+      if (warp == 2) trace_ev(e.cx, 2, 16 * pair);
+      if (active) {
+        if (L.epi == DD_EPI_PLAIN) epi_plain<KS>(L, e);
+        else if (L.epi == DD_EPI_LN) epi_ln_fwd<KS>(L, e);
+        else if (L.epi == DD_EPI_LNBWD) epi_ln_bwd<KS>(L, e);
+        else if (L.epi == DD_EPI_GRU) epi_gru<KS>(L, e);
+        else if (L.epi == DD_EPI_STATS) epi_stats<KS>(L, e);
+        else epi_actor<KS>(L, e);
       }
       // this CTA's rows of the layer's outputs are written: tell every CTA's producer.  Each
       // writer orders its stores against the async proxy (TMA reads them), the four epilogue warps
       // meet at a named barrier, then one thread publishes with a single cluster-scope fence.
-      if (warp == 2) trace_ev(cx, 2, 16 * pair + 9);
+      if (warp == 2) trace_ev(e.cx, 2, 16 * pair + 9);
       asm volatile("fence.proxy.async;" ::: "memory");
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp == 2 && lane == 0) {
         asm volatile("fence.acq_rel.cluster;" ::: "memory");
 #pragma unroll
-        for (int d = 0; d < CL; ++d) count_add_remote(sh.bars + BAR_READY, d);
+        for (int d = 0; d < CLS; ++d) count_add_remote(sh.bars + BAR_READY, d);
       }
-      if (warp == 2) trace_ev(cx, 2, 16 * pair + 11);
-      __syncwarp();
+      if (warp == 2) trace_ev(e.cx, 2, 16 * pair + 11);
     }
   }
 }
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
+template <int KS>
+__global__ void __launch_bounds__(THREADS, 1)
 lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg,
           unsigned long long* prof, int flags) {
+  using G = Geo<KS>;
   extern __shared__ __align__(1024) char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_rank();
-  const int cluster_id = blockIdx.x / CL, nclusters = gridDim.x / CL;
+  const int cluster_id = blockIdx.x / G::CLS, nclusters = gridDim.x / G::CLS;
   Shared sh;
   sh.smem = smem;
   sh.base = smem_u32(smem);
-  sh.bars = sh.base + OFF_BAR;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + BAR_TMEM);
+  sh.bars = sh.base + G::OFF_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + G::OFF_BAR + BAR_TMEM);
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < G::STAGES; ++s) {
       mbar_init(sh.bars + BAR_FULL + 8 * s, 2);       // one arrive.expect_tx per producer warp
-      mbar_init(sh.bars + BAR_EMPTY + 8 * s, CL);
+      mbar_init(sh.bars + BAR_EMPTY + 8 * s, NS);     // the CTAs that receive my activation slices
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(sh.bars + BAR_ACCF + 8 * b, 1);
       mbar_init(sh.bars + BAR_ACCE + 8 * b, 4);
     }
-    mbar_init(sh.bars + BAR_STATS, 1);
-    *reinterpret_cast<volatile unsigned long long*>(smem + OFF_BAR + BAR_READY) = 0ull;
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(sh.bars + BAR_STATS + 8 * b, 1);
+      mbar_init(sh.bars + BAR_RED + 8 * b, 1);
+    }
+    *reinterpret_cast<volatile unsigned long long*>(smem + G::OFF_BAR + BAR_READY) = 0ull;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -1132,13 +1295,13 @@ lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg,
   if ((sh.base & 1023u) != 0u) stuck(cx, 9, sh.base);      // SWIZZLE_128B tiles need 1 KB alignment
 
   if (warp == 0) {
-    producer_b(sh, layers, nlayers, M, rank, cluster_id, nclusters, lane, cx);
+    producer_b<KS>(sh, layers, nlayers, M, rank, cluster_id, nclusters, lane, cx);
   } else if (warp == 6) {
-    producer_a(sh, layers, nlayers, M, rank, cluster_id, nclusters, lane, cx);
+    producer_a<KS>(sh, layers, nlayers, M, rank, cluster_id, nclusters, lane, cx);
   } else if (warp == 1) {
-    mma_issuer(sh, layers, nlayers, M, rank, cluster_id, nclusters, lane, tmem_base, cx);
+    mma_issuer<KS>(sh, layers, nlayers, M, rank, cluster_id, nclusters, lane, tmem_base, cx);
   } else {
-    epilogue(sh, layers, nlayers, M, rank, cluster_id, nclusters, warp, lane, tmem_base, cx);
+    epilogue<KS>(sh, layers, nlayers, M, rank, cluster_id, nclusters, warp, lane, tmem_base, cx);
   }
 
   if (tid % 32 == 0 && warp < 6) trace_ev(cx, 3, 1 + warp);
@@ -1300,10 +1463,10 @@ extern "C" int dd_program_build(const DdLayer* layers, int nlayers, int rows, vo
     if (s.nseg < 0 || s.nseg > 2) { rc = fail("dd_program_build", "0, 1 or 2 A segments"); break; }
     if (s.nseg == 0 && s.add == nullptr) { rc = fail("dd_program_build", "epilogue-only layer without input (add)"); break; }
     // column tiling across the 8 CTAs
-    if (s.N % (lm::CL * 64) == 0) {
-      d.bn = 64; d.nchunk = s.N / (lm::CL * 64); d.nactive = lm::CL;
-    } else if (s.N % (lm::CL * 32) == 0) {
-      d.bn = 32; d.nchunk = s.N / (lm::CL * 32); d.nactive = lm::CL;
+    if (s.N % (lm::NS * 64) == 0) {
+      d.bn = 64; d.nchunk = s.N / (lm::NS * 64); d.nactive = lm::NS;
+    } else if (s.N % (lm::NS * 32) == 0) {
+      d.bn = 32; d.nchunk = s.N / (lm::NS * 32); d.nactive = lm::NS;
     } else if (s.N <= 64 && (s.epi == DD_EPI_PLAIN || s.epi == DD_EPI_STATS || s.epi == DD_EPI_ACTOR)) {
       d.bn = s.N <= 32 ? 32 : 64; d.nchunk = 1; d.nactive = 1;
     } else {
@@ -1348,12 +1511,12 @@ extern "C" int dd_program_build(const DdLayer* layers, int nlayers, int rows, vo
     for (int q = 0; q < 3; ++q) { d.x[q] = s.x[q]; d.ldx[q] = s.ldx[q]; }
     d.f[0] = s.f[0]; d.f[1] = s.f[1]; d.ipar = s.ipar;
     if (s.epi == DD_EPI_GRU) {
-      if (d.nchunk != 3 || d.nactive != lm::CL || s.gamma == nullptr || s.beta == nullptr ||
+      if (d.nchunk != 3 || d.nactive != lm::NS || s.gamma == nullptr || s.beta == nullptr ||
           s.z == nullptr || s.x[0] == nullptr)
         rc = fail("dd_program_build", "GRU layer: N = 3 D with D a multiple of 256, needs scale, bias, z and prev");
     }
     if (s.epi == DD_EPI_STATS) {
-      const bool wide = d.nactive == lm::CL;
+      const bool wide = d.nactive == lm::NS;
       if ((wide && s.ipar != 32) || (!wide && (s.ipar != s.N || s.N > 32)) || s.nseg == 0)
         rc = fail("dd_program_build", "STATS layer: groups of 32 classes, or one narrow group of N <= 32");
     }
@@ -1388,27 +1551,86 @@ extern "C" int dd_program_build(const DdLayer* layers, int nlayers, int rows, vo
   return rc;
 }
 
-extern "C" int dd_program_run(const void* table_dev, int nlayers, int rows, dd_stream_t stream) {
-  static int max_clusters = 0;
-  if (max_clusters == 0) {
-    cudaFuncSetAttribute(lm::lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lm::SMEM_BYTES);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(lm::CL * 16);
-    cfg.blockDim = dim3(lm::THREADS);
-    cfg.dynamicSmemBytes = lm::SMEM_BYTES;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, lm::lm_kernel, &cfg) != cudaSuccess || n < 1) {
-      cudaGetLastError();
-      n = 8;
-    }
-    max_clusters = n;
+namespace dd {
+namespace lm {
+static int g_ks = -1;            // 1: clusters of 8, 2: split-K clusters of 16; -1: not chosen yet
+static int g_max_clusters[3] = {0, 0, 0};
+
+template <int KS>
+static int setup_variant() {
+  using G = Geo<KS>;
+  if (cudaFuncSetAttribute(lm_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
   }
+  if (G::CLS > 8 &&
+      cudaFuncSetAttribute(lm_kernel<KS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(G::CLS * 8);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = G::SMEM_BYTES;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = G::CLS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, lm_kernel<KS>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  return n;
+}
+
+template <int KS>
+static void launch_variant(const LmLayer* table, int nlayers, int rows, int nclusters, cudaStream_t st) {
+  using G = Geo<KS>;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(G::CLS * nclusters);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = G::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = G::CLS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, lm_kernel<KS>, table, nlayers, rows, g_dbg_dev,
+                     g_prof_on ? g_prof_dev : (unsigned long long*)nullptr, g_flags);
+}
+}  // namespace lm
+}  // namespace dd
+
+extern "C" int dd_program_run(const void* table_dev, int nlayers, int rows, dd_stream_t stream) {
+  if (lm::g_max_clusters[1] == 0 && lm::g_max_clusters[2] == 0) {
+    lm::g_max_clusters[1] = lm::setup_variant<1>();
+    lm::g_max_clusters[2] = lm::setup_variant<2>();
+    if (lm::g_ks < 0) {          // split-K clusters of 16 when the device can host at least one
+      const char* e = getenv("DD_MACHINE_KS");
+      lm::g_ks = e != nullptr ? atoi(e) : 2;
+    }
+    if (lm::g_ks == 2 && lm::g_max_clusters[2] < 1) lm::g_ks = 1;
+    if (lm::g_ks != 2) lm::g_ks = 1;
+    if (lm::g_max_clusters[lm::g_ks] < 1) return fail("dd_program_run", "no cluster of the layer machine fits this device");
+  }
+  const int ks = lm::g_ks;
   const int ntiles = (rows + lm::BM - 1) / lm::BM;
-  const int nclusters = ntiles < max_clusters ? ntiles : max_clusters;
-  lm::lm_kernel<<<dim3(lm::CL * nclusters), dim3(lm::THREADS), lm::SMEM_BYTES, S(stream)>>>(
-      static_cast<const lm::LmLayer*>(table_dev), nlayers, rows, lm::g_dbg_dev,
-      lm::g_prof_on ? lm::g_prof_dev : nullptr, lm::g_flags);
+  const int nclusters = ntiles < lm::g_max_clusters[ks] ? ntiles : lm::g_max_clusters[ks];
+  const lm::LmLayer* table = static_cast<const lm::LmLayer*>(table_dev);
+  if (ks == 2) lm::launch_variant<2>(table, nlayers, rows, nclusters, S(stream));
+  else lm::launch_variant<1>(table, nlayers, rows, nclusters, S(stream));
   return launched("dd_program_run");
+}
+
+/* 1: clusters of 8 CTAs; 2: split-K clusters of 16.  Returns the previous choice (0 = unset). */
+extern "C" int dd_set_machine_ks(int ks) {
+  const int prev = lm::g_ks < 0 ? 0 : lm::g_ks;
+  lm::g_ks = ks == 1 ? 1 : 2;
+  if (lm::g_ks == 2 && lm::g_max_clusters[1] + lm::g_max_clusters[2] > 0 && lm::g_max_clusters[2] < 1) lm::g_ks = 1;
+  return prev;
 }
 
 extern "C" int dd_program_debug(unsigned* out8) {

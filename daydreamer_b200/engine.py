@@ -1806,17 +1806,20 @@ class PolicyEngine:
     self.mraw, self.sraw = z(P, A), z(P, A)
     self.action, self.mean, self.std = z(P, A), z(P, A), z(P, A)
 
-  def launch(self):
+  def launch(self, draw=True):
+    """draw=False: the caller has filled self.g (Gumbel [P, SC]) and self.eps ([P, A]) itself
+    (parity tests inject the oracle's noise)."""
     eng, be, s = self.eng, self.be, self.spec
     gm, ga = eng.groups['model'], eng.groups['actor']
     D, SC = s.deter, s.sc
     P = self.P
-    be.fill_gumbel(self.g, eng.seed, STREAM_POL_OBS, eng.counters, C_POLICY)
-    if s.discrete:
-      be.fill_gumbel(self.eps, eng.seed, STREAM_POL_ACT, eng.counters, C_POLICY)
-    else:
-      be.fill_normal(self.eps, eng.seed, STREAM_POL_ACT, eng.counters, C_POLICY)
-    be.counter_inc(eng.counters, C_POLICY)
+    if draw:
+      be.fill_gumbel(self.g, eng.seed, STREAM_POL_OBS, eng.counters, C_POLICY)
+      if s.discrete:
+        be.fill_gumbel(self.eps, eng.seed, STREAM_POL_ACT, eng.counters, C_POLICY)
+      else:
+        be.fill_normal(self.eps, eng.seed, STREAM_POL_ACT, eng.counters, C_POLICY)
+      be.counter_inc(eng.counters, C_POLICY)
     parts = []
     c0 = 0
     for k, shp in s.cnn_keys.items():          # uint8 -> [0,1], channel concat

@@ -356,6 +356,9 @@ size_t dd_program_bytes(int nlayers);
  * outside stream capture).  rows = M of every layer. */
 int dd_program_build(const DdLayer* layers, int nlayers, int rows, void* table_dev);
 int dd_program_run(const void* table_dev, int nlayers, int rows, dd_stream_t stream);
+/* geometry of the machine: 1 = clusters of 8 CTAs (one per column slice), 2 = split-K clusters of
+ * 16 (two CTAs per slice share its k-blocks; default when the device hosts such clusters) */
+int dd_set_machine_ks(int ks);
 /* after a failed run: 1 and the 8 diagnostic words of the stuck wait, else 0 */
 int dd_program_debug(unsigned* out8);
 /* profiling aids: switches that drop parts of the machine's pipeline (garbage results) and

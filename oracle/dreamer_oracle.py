@@ -670,6 +670,41 @@ class Learner:
     data['cont'] = 1.0 - data['is_terminal']
     return data
 
+  # -- acting ------------------------------------------------------------------
+  def policy(self, obs, state, g_post, eps_act, mode='train'):
+    """Agent.policy (A/agent.py:42-65) with expl_noise = eval_noise = 0: preprocess -> encoder
+    -> ONE obs_step from the carried (latent, previous action) -> actor; `train` samples the
+    action, `eval` takes the mode.  Explicit noise: g_post [P, S, C] Gumbel for the posterior draw,
+    eps_act [P, A] standard normal (continuous actor) or Gumbel (one-hot actor).
+    state: None (initial_policy_state: rssm.initial + zero action, A/agent.py:33-38) or the dict
+    returned by the previous call.  Returns ({'action': [P, A]}, state)."""
+    with torch.no_grad():
+      p, spec = self.params, self.spec
+      data = self.preprocess({k: np.asarray(v)[:, None] for k, v in obs.items()})   # [P, 1, ...]
+      P = data['is_first'].shape[0]
+      embed = encoder(data, p, spec)[:, 0]
+      if state is None:
+        latent = initial_state(P, p, spec)
+        action = torch.zeros(P, spec.act_dim)
+      else:
+        latent = {k: torch.as_tensor(np.asarray(state[k])).float() for k in ('deter', 'stoch', 'logit')}
+        latent['stoch'] = latent['stoch'].reshape(P, spec.stoch, spec.classes)
+        latent['logit'] = latent['logit'].reshape(P, spec.stoch, spec.classes)
+        action = torch.as_tensor(np.asarray(state['action'])).float()
+      post, _ = obs_step(latent, action, embed, data['is_first'][:, 0], p, spec,
+                         torch.as_tensor(np.asarray(g_post)).float())
+      dist = actor_dist(feat_of(post, spec), p, spec)
+      if spec.discrete:
+        logit = dist['logit'][:, None, :]
+        eps = torch.as_tensor(np.asarray(eps_act)).float()[:, None, :]
+        act = (mode_onehot(logit)[0] if mode == 'eval' else sample_onehot(logit, eps)[0])[:, 0]
+      else:
+        eps = torch.as_tensor(np.asarray(eps_act)).float()
+        act = dist['mean'] if mode == 'eval' else dist['mean'] + dist['std'] * eps
+      state = {'deter': post['deter'].numpy(), 'stoch': post['stoch'].numpy().reshape(P, -1),
+               'logit': post['logit'].numpy().reshape(P, -1), 'action': act.numpy()}
+      return {'action': act.numpy()}, state
+
   # -- world model ------------------------------------------------------------
   def wm_loss(self, p, data, state, g_post, training=True):
     """A/agent.py:165-212.  Returns loss, aux dict, metrics."""

@@ -12,10 +12,14 @@ from tests.hostsim import HostSim
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope='module')
-def backends():
+@pytest.fixture(scope='module', params=[2, 1], ids=['splitk16', 'cluster8'])
+def backends(request):
+  """Both geometries of the machine: split-K clusters of 16 CTAs (default) and clusters of 8."""
   from daydreamer_b200.backend import CudaBackend
-  return HostSim(), CudaBackend()
+  cu = CudaBackend()
+  cu.lib.dd_set_machine_ks(request.param)
+  yield HostSim(), cu
+  cu.lib.dd_set_machine_ks(2)
 
 
 def rnd(*shape, seed=0, scale=1.0):

@@ -3,6 +3,7 @@ open-loop prediction along recorded actions, imagined rollout with the policy --
 torch-CPU primitive simulator against the oracle restatement of
 WorldModel.report (A/agent.py:266-282) and Greedy.report (A/behaviors.py:32-46)."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import dreamer_oracle as O
@@ -11,14 +12,13 @@ from tests import util
 from tests.hostsim import HostSim
 
 
-def test_report_videos_match_oracle():
+def run_report(be, tol):
   ospec = O.tiny_spec(discrete=True, act_dim=5, cnn_keys={'image': (18, 18, 3), 'depth': (18, 18, 1)},
                       cnn_depth=4, enc_kernels=(4, 4), dec_kernels=(3, 4, 4))
   spec = util.to_engine_spec(ospec)
   B, L, C5 = 3, 8, 5
   T2, H, A = L - C5, ospec.horizon, ospec.act_dim
   params = O.init_params(ospec, seed=1)
-  be = HostSim()
   main = E.Engine(spec, be, B, L)
   main.load_params(params)
   rep = E.VideoReport(main, B, L)
@@ -57,12 +57,14 @@ def test_report_videos_match_oracle():
   ctx = rep.ctx
   sub = {k: v[:, :C5] for k, v in batch.items()}
   util.load_batch(ctx, spec, sub, None, None)
-  ctx.g_obs.copy_(torch.tensor(g_ctx).reshape(C5, B, -1))
-  rep.ol.g_img.copy_(torch.tensor(g_ol).reshape(T2, B, -1))
-  rep.im.g_img.copy_(torch.tensor(g_im).reshape(H, B, -1))
-  rep.im.eps_act.copy_(torch.tensor(g_act))
-  rep.actions.copy_(torch.tensor(batch['action'][:, C5:]).transpose(0, 1))
+  dev = ctx.g_obs.device
+  ctx.g_obs.copy_(torch.tensor(g_ctx).reshape(C5, B, -1).to(dev))
+  rep.ol.g_img.copy_(torch.tensor(g_ol).reshape(T2, B, -1).to(dev))
+  rep.im.g_img.copy_(torch.tensor(g_im).reshape(H, B, -1).to(dev))
+  rep.im.eps_act.copy_(torch.tensor(g_act).to(dev))
+  rep.actions.copy_(torch.tensor(batch['action'][:, C5:]).transpose(0, 1).to(dev))
   rep.launch(draw=False)
+  be.sync()
   truth = {k: np.asarray(batch[k], np.float32) / np.float32(255.0) for k in ospec.cnn_keys}
   vids = rep.videos(truth)
 
@@ -73,9 +75,20 @@ def test_report_videos_match_oracle():
     want = grid(np.concatenate([truth[k], m, (m - truth[k] + 1) / 2], 2))
     got = vids[f'openl_{k}']
     assert got.shape == want.shape == (L, 3 * 18, B * 18, shp[2])
-    assert np.abs(got - want).max() < 2e-5, (k, np.abs(got - want).max())
+    assert np.abs(got - want).max() < tol, (k, np.abs(got - want).max())
     want = grid(imag[..., c0:c0 + shp[2]].numpy())
     got = vids[f'task_imag_{k}']
     assert got.shape == want.shape == (H + 1, 18, B * 18, shp[2])
-    assert np.abs(got - want).max() < 2e-5, (k, np.abs(got - want).max())
+    assert np.abs(got - want).max() < tol, (k, np.abs(got - want).max())
     c0 += shp[2]
+
+
+def test_report_videos_match_oracle():
+  run_report(HostSim(), 2e-5)
+
+
+@pytest.mark.gpu
+def test_report_videos_match_oracle_gpu():
+  """The same comparison with every primitive on the CUDA kernels (pixels in [0, 1])."""
+  from daydreamer_b200.backend import CudaBackend
+  run_report(CudaBackend(), 1e-4)

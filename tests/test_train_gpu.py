@@ -39,7 +39,21 @@ def check_update(new, ref, old, lr, name):
   assert (d > 0.05 * lr).mean() <= 2e-3, (name, (d > 0.05 * lr).mean())
 
 
-def run_pair(ospec, B, L, steps, grad_tol, met_tol=3e-4):
+def grad_distribution(eg, og):
+  """Relative error of the gradient elements that stand above rounding noise (|g| >= 1% of the
+  tensor's max): (count, median, 99th percentile, max).  The 1e-4 bar of BASELINE.json is stated
+  on these; an element far below the tensor's scale carries the absolute rounding error of the
+  K ~ 10^3..10^4 term reductions and has no meaningful relative error."""
+  a, b = np.asarray(eg, np.float64).ravel(), np.asarray(og, np.float64).ravel()
+  scale = np.abs(b).max()
+  if scale == 0.0:
+    return 0, 0.0, 0.0, float(np.abs(a).max())
+  sig = np.abs(b) >= 1e-2 * scale
+  r = np.abs(a[sig] - b[sig]) / np.abs(b[sig])
+  return int(sig.sum()), float(np.median(r)), float(np.percentile(r, 99)), float(r.max())
+
+
+def run_pair(ospec, B, L, steps, grad_tol, met_tol=3e-4, strict=None):
   from daydreamer_b200.backend import CudaBackend
   spec = util.to_engine_spec(ospec)
   params = perturbed_params(ospec)
@@ -76,10 +90,18 @@ def run_pair(ospec, B, L, steps, grad_tol, met_tol=3e-4):
                util.ref_rows_to_tm(traj['weight'].numpy()[..., None], B, L)[..., 0]) < 1e-4
     assert rel(eng.r_ret.cpu().numpy(),
                util.ref_rows_to_tm(aux['ret'].numpy()[..., None], B, L)[..., 0]) < 2e-4
+    worst = (0.0, None)
     for group in ('model', 'critic', 'actor'):
       eg = eng.get_grads(group)
       for k, v in aux[f'{group}_grads'].items():
         assert rel(eg[k], v.numpy()) < grad_tol, (it, group, k, rel(eg[k], v.numpy()))
+        if strict is not None:
+          n, med, p99, mx = grad_distribution(eg[k], v.numpy())
+          if p99 > worst[0]:
+            worst = (p99, (k, n, med, p99, mx))
+          assert med <= strict[0] and p99 <= strict[1], (it, k, n, med, p99, mx)
+    if strict is not None:
+      print(f'step {it}: worst gradient tensor (p99 of rel. error over significant elements): {worst[1]}')
     ep = eng.get_params()
     for k, v in ol.params.items():
       check_update(ep[k], v.numpy(), None, ospec.lr, (it, k))
@@ -131,9 +153,11 @@ def test_image_64x64_reference_geometry_matches_oracle():
   run_pair(spec, 2, 4, 1, grad_tol=1e-3)
 
 
-def test_a1_full_size_one_step_matches_oracle():
-  """BASELINE.json configs[1]: deter=units=512, 32x32 latent, B=16 L=64 H=15."""
-  run_pair(O.a1_spec(), 16, 64, 1, grad_tol=3e-3, met_tol=1e-3)
+def test_a1_full_size_three_steps_match_oracle():
+  """BASELINE.json configs[1]: deter=units=512, 32x32 latent, B=16 L=64 H=15, three consecutive
+  train steps (carried state, Adam moments, controllers).  Per gradient tensor the elements above
+  rounding noise agree with the oracle to a median of 2e-5 and a 99th percentile of 3e-4 relative."""
+  run_pair(O.a1_spec(), 16, 64, 3, grad_tol=3e-3, met_tol=1e-3, strict=(2e-5, 3e-4))
 
 
 @pytest.mark.parametrize('name', ['tiny', 'ragged', 'medium', 'a1'])
