@@ -108,6 +108,16 @@ def spec_from_config(config, obs_space, act_space) -> _engine.Spec:
   for h in ('decoder', 'reward_head', 'cont_head', 'actor', 'critic'):
     if g(f'{h}.act') != 'elu' or g(f'{h}.norm') != 'layer':
       raise NotImplementedError(f'{h}: only act=elu, norm=layer are built')
+    # settings the kernels hard-code: every head reads [deter, stoch] (A/nets.py:612-626) and its
+    # output layer is initialised with outscale 0.1 (A/nets.py:448-450)
+    try:
+      inputs, outscale = list(g(f'{h}.inputs')), float(g(f'{h}.outscale'))
+    except (KeyError, AttributeError, TypeError):
+      continue
+    if inputs != ['deter', 'stoch']:
+      raise NotImplementedError(f'{h}.inputs={inputs} is not built (only [deter, stoch])')
+    if outscale != 0.1:
+      raise NotImplementedError(f'{h}.outscale={outscale} is not built (only 0.1)')
   opts = [tuple(g(f'{o}.{k}') for k in ('lr', 'eps', 'clip', 'wd', 'warmup'))
           for o in ('model_opt', 'actor_opt', 'critic_opt')]
   if len(set(opts)) != 1 or opts[0][4]:

@@ -46,7 +46,6 @@ constexpr int SLICE_BYTES = SLICE_ROWS * BK * 4;           // 2 KB = two 8-row s
 constexpr int STG_LD = 36;
 constexpr int STG_WARP_BYTES = 32 * STG_LD * 4;
 constexpr int EP_BYTES = 208;
-constexpr int THREADS = 224;          // warps: 0 weights, 1 MMA, 2-5 epilogue, 6 activations
 constexpr int TMEM_COLS = 256;        // 2 buffers x (main 64 | cross 64)
 
 // byte-counted barriers (LayerNorm exchange, split-K reduction) come in PAIRS used alternately: a
@@ -371,15 +370,23 @@ __device__ __forceinline__ void warp_colsum32(float (&a)[32], int lane) {
 template <int KS>
 struct Geo {
   static constexpr int CLS = NS * KS;
-  static constexpr int STAGES = KS == 1 ? 4 : 3;
-  static constexpr int OFF_STATS = STAGES * STAGE_BYTES;            // float2 [2 parity][CLS][BM]
-  static constexpr int STATS_BYTES = 2 * CLS * BM * 8;
-  static constexpr int OFF_RED = OFF_STATS + STATS_BYTES;           // float [2 parity][BM][32], swizzled
+  // clusters of 8: EIGHT epilogue warps, two per TMEM lane quadrant, each finishing one 32-column
+  // half of the CTA's 64-column slice (half the serial work per thread, twice the warps to hide the
+  // latency of the tcgen05.ld / staging / global round trips); split-K: one half per CTA, 4 warps
+  static constexpr int EW = KS == 1 ? 8 : 4;
+  static constexpr int THREADS = 32 * (3 + EW);     // + weight producer, MMA issuer, activation producer
+  static constexpr int STAGES = 3;
+  static constexpr int SLOTS = CLS;                 // row partials exchanged per LayerNorm: one per owner CTA
+  static constexpr int OFF_STATS = STAGES * STAGE_BYTES;            // float2 [2 parity][SLOTS][BM]
+  static constexpr int STATS_BYTES = 2 * SLOTS * BM * 8;
+  static constexpr int OFF_LOC = OFF_STATS + STATS_BYTES;           // float2 [BM]: the second warp group's row partials
+  static constexpr int LOC_BYTES = EW == 8 ? BM * 8 : 0;
+  static constexpr int OFF_RED = OFF_LOC + LOC_BYTES;               // float [2 parity][BM][32], swizzled
   static constexpr int RED_BYTES = KS == 1 ? 0 : 2 * BM * 32 * 4;
   static constexpr int OFF_STG = OFF_RED + RED_BYTES;               // per-warp 32 x 36 floats
-  static constexpr int OFF_BAR = OFF_STG + 4 * STG_WARP_BYTES;
+  static constexpr int OFF_BAR = OFF_STG + EW * STG_WARP_BYTES;
   static constexpr int OFF_EP = OFF_BAR + BAR_BYTES;                // per-epilogue-warp layer view
-  static constexpr int SMEM_BYTES = OFF_EP + 4 * EP_BYTES;
+  static constexpr int SMEM_BYTES = OFF_EP + EW * EP_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
@@ -637,9 +644,10 @@ struct Epi {
   uint32_t xc;        // cross-CTA row exchanges done
   uint32_t rc;        // split-K reductions done
   int rank, cs, kh, warp, quad, lane;
+  int ew, grp;        // epilogue warp index 0 .. EW-1; its 32-column half (0 unless EW == 8)
   float* stg;
   int wrow0, rows_valid, trow;
-  uint32_t stats_off, red_off;
+  uint32_t stats_off, red_off, loc_off;
 };
 
 // main + cross accumulator columns [cc*32, cc*32+32) of buffer `buf`, this thread's row
@@ -670,11 +678,18 @@ __device__ __forceinline__ int sub_col(const EP& L, const Epi& e, int c, int h) 
   if (KS == 1) return base + h * 32;
   return base + (L.bn == 64 ? e.kh * 32 : 0);
 }
-// owners of a wide layer (they exchange the LayerNorm partials), and this CTA's slot among them
+// with eight epilogue warps a thread finishes only the half of its warp group
+template <int KS>
+__device__ __forceinline__ bool mine(const Epi& e, int h) { return Geo<KS>::EW == 4 || h == e.grp; }
+// The LayerNorm partials of a row come from `n_slots` threads (one per owned 32-column sub-tile per
+// chunk set): 8 CTAs x 2 halves, or 16 split-K CTAs x 1, or 8 x 1 for 32-wide slices.  Slot of this
+// thread, and the CTAs that own columns (ranks 0 .. n_owners-1).
 template <int KS>
 __device__ __forceinline__ int n_owners(const EP& L) { return (KS == 2 && L.bn == 64) ? 2 * NS : NS; }
 template <int KS>
-__device__ __forceinline__ int owner_slot(const EP& L, const Epi& e) {
+__device__ __forceinline__ int n_slots(const EP& L) { return n_owners<KS>(L); }
+template <int KS>
+__device__ __forceinline__ int my_slot(const EP& L, const Epi& e) {
   return (KS == 2 && L.bn == 64) ? e.rank : e.cs;
 }
 
@@ -698,26 +713,25 @@ __device__ __forceinline__ void acc_release(Epi& e) {
   ++e.ac;
 }
 
-// The sub-tiles of chunk c this thread finishes, as raw sums: accumulator (main + cross) of this
-// CTA's k-blocks, plus -- split-K -- the partner CTA's partial of the same columns, which arrives
-// over distributed shared memory (st.async into a swizzled row buffer, bytes counted by `red`).
-// Must be called by every epilogue thread of every ACTIVE CTA once per chunk, owner or not.
-// vals[h] for h < nsub.
+// Sub-tile h of the current chunk as a raw sum: the accumulator (main + cross) of this CTA's
+// k-blocks, plus -- split-K -- the partner CTA's partial of the same columns, which arrives over
+// distributed shared memory (st.async into a swizzled row buffer, bytes counted by `red`).
+// Called by every epilogue thread of every active CTA for h = 0 .. nsub-1 of every chunk, in order.
 template <int KS>
-__device__ __forceinline__ void chunk_fetch(const EP& L, Epi& e, float (&v0)[32], float (&v1)[32]) {
+__device__ __forceinline__ void sub_fetch(const EP& L, Epi& e, int h, float (&v0)[32]) {
   const bool hk = has_k(L, e, KS);
-  if (KS == 1) {
+  if (KS == 1) {           // this warp's group reads only half h of the accumulator
     if (hk) {
       acc_wait(e);
-      acc_load32(e.tmem_base, e.ac & 1, e.quad, 0, L.bn, v0);
-      if (L.bn == 64) acc_load32(e.tmem_base, e.ac & 1, e.quad, 1, L.bn, v1);
+      acc_load32(e.tmem_base, e.ac & 1, e.quad, h, L.bn, v0);
       acc_release(e);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) { v0[j] = 0.f; v1[j] = 0.f; }
+      for (int j = 0; j < 32; ++j) v0[j] = 0.f;
     }
     return;
   }
+  float v1[32];
   // KS == 2.  Narrow layers (bn = 32) are not split: the kh = 0 CTA has the whole sum.
   if (L.bn != 64) {
     if (hk) {
@@ -807,28 +821,51 @@ __device__ __forceinline__ void store_with_lo(const EP& L, Epi& e, float (&v)[32
 // publish this thread's pair of row partials to every owner CTA, then collect all of them.
 // The remote stores carry their own completion (st.async ... mbarrier::complete_tx): the destination's
 // barrier counts the bytes, so no fence and no separate arrive is needed.
+// `welford`: (a, b) = (mean, M2) over `cnt` columns, merged by Chan's formula; else plain sums.
+// With two warp groups per row the second group's partial is first folded into the first group's
+// through shared memory (a 64-thread named barrier per TMEM quadrant), so one thread per row sends.
 template <int KS>
-__device__ __forceinline__ void row_exchange(const EP& L, Epi& e, float a, float b,
-                                             float2 (&parts)[Geo<KS>::CLS]) {
-  constexpr int CLS = Geo<KS>::CLS;
-  const int nown = n_owners<KS>(L), slot_i = owner_slot<KS>(L, e);
+__device__ __forceinline__ void row_exchange(const EP& L, Epi& e, float a, float b, float& cnt, bool welford,
+                                             float2 (&parts)[Geo<KS>::SLOTS]) {
+  constexpr int SLOTS = Geo<KS>::SLOTS;
+  const bool two = Geo<KS>::EW == 8 && L.bn == 64;
+  if (two) {
+    float2* loc = reinterpret_cast<float2*>(e.sh.smem + e.loc_off) + e.trow;
+    if (e.grp == 1) *loc = make_float2(a, b);
+    asm volatile("bar.sync %0, 64;" ::"r"(2 + e.quad) : "memory");
+    if (e.grp == 0) {
+      const float2 o = *loc;
+      if (welford) {                 // equal counts: mean of means, M2 += cnt/2 * delta^2
+        const float d = o.x - a;
+        a += 0.5f * d;
+        b += o.y + d * d * (cnt * 0.5f);
+      } else {
+        a += o.x;
+        b += o.y;
+      }
+    }
+    cnt *= 2.f;
+  }
+  const int nown = n_owners<KS>(L), nsl = n_slots<KS>(L), slot_i = my_slot<KS>(L, e);
   const uint32_t par = e.xc & 1;
   const uint32_t bar = e.sh.bars + BAR_STATS + 8 * par;
-  if (e.warp == 2 && e.lane == 0) mbar_arrive_tx(bar, (uint32_t)nown * BM * 8);   // bytes I will receive
-  const uint32_t slot = e.sh.base + e.stats_off + ((par * CLS + slot_i) * BM + e.trow) * 8;
+  if (e.warp == 2 && e.lane == 0) mbar_arrive_tx(bar, (uint32_t)nsl * BM * 8);   // bytes I will receive
+  if (!two || e.grp == 0) {
+    const uint32_t slot = e.sh.base + e.stats_off + ((par * SLOTS + slot_i) * BM + e.trow) * 8;
 #pragma unroll
-  for (int d = 0; d < CLS; ++d) {
-    if (d < nown) {              // owners are ranks 0 .. nown-1 in both geometries
-      const uint32_t ra = mapa(slot, d), rb = mapa(bar, d);
-      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
-                   ::"r"(ra), "f"(a), "f"(b), "r"(rb) : "memory");
+    for (int d = 0; d < Geo<KS>::CLS; ++d) {
+      if (d < nown) {              // owners are ranks 0 .. nown-1 in both geometries
+        const uint32_t ra = mapa(slot, d), rb = mapa(bar, d);
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+                     ::"r"(ra), "f"(a), "f"(b), "r"(rb) : "memory");
+      }
     }
   }
   mbar_wait<false>(bar, (e.xc >> 1) & 1, e.cx, 5);
-  const float2* mine = reinterpret_cast<const float2*>(e.sh.smem + e.stats_off) + par * CLS * BM + e.trow;
+  const float2* mine_ = reinterpret_cast<const float2*>(e.sh.smem + e.stats_off) + par * SLOTS * BM + e.trow;
 #pragma unroll
-  for (int d = 0; d < CLS; ++d)
-    if (d < nown) parts[d] = mine[d * BM];
+  for (int d = 0; d < SLOTS; ++d)
+    if (d < nsl) parts[d] = mine_[d * BM];
   ++e.xc;
 }
 
@@ -849,17 +886,17 @@ __device__ __forceinline__ void welford32(const float (&v)[32], float& mean, flo
 // merge the owners' equal-count partials into (mean, rstd) of the full row
 template <int KS>
 __device__ __forceinline__ void ln_finish(const EP& L, Epi& e, float mean, float m2, float cnt,
-                                          float& gm, float& rstd) {
-  float2 parts[Geo<KS>::CLS];
-  row_exchange<KS>(L, e, mean, m2, parts);
-  const int nown = n_owners<KS>(L);
+                                          float& gm, float& rstd) {     // cnt by value: doubled by the local merge
+  float2 parts[Geo<KS>::SLOTS];
+  row_exchange<KS>(L, e, mean, m2, cnt, true, parts);
+  const int nsl = n_slots<KS>(L);
   gm = 0.f;
-  for (int d = 0; d < nown; ++d) gm += parts[d].x;
-  gm /= (float)nown;
+  for (int d = 0; d < nsl; ++d) gm += parts[d].x;
+  gm /= (float)nsl;
   float gq = 0.f;
-  for (int d = 0; d < nown; ++d) { const float dl = parts[d].x - gm; gq += parts[d].y + cnt * dl * dl; }
+  for (int d = 0; d < nsl; ++d) { const float dl = parts[d].x - gm; gq += parts[d].y + cnt * dl * dl; }
   rstd = rsqrtf(gq / (float)L.N + DD_LN_EPS);
-  if (L.st != nullptr && e.rank == 0 && e.lane < e.rows_valid) {
+  if (L.st != nullptr && e.rank == 0 && e.grp == 0 && e.lane < e.rows_valid) {
     L.st[(size_t)(e.wrow0 + e.lane) * 2] = gm;
     L.st[(size_t)(e.wrow0 + e.lane) * 2 + 1] = rstd;
   }
@@ -888,17 +925,17 @@ template <int KS>
 __device__ void epi_plain(const EP& L, Epi& e) {
   const bool own = owns<KS>(L, e);
   for (int c = 0; c < L.nchunk; ++c) {
-    float v[2][32];
-    chunk_fetch<KS>(L, e, v[0], v[1]);
-    if (!own) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (h < nsub<KS>(L)) {
+      if (h < nsub<KS>(L) && mine<KS>(e, h)) {
+        float v[32];
+        sub_fetch<KS>(L, e, h, v);
+        if (!own) continue;
         const int cb = sub_col<KS>(L, e, c, h);
         const int cols_valid = min(32, L.N - cb);
         if (cols_valid > 0) {
-          add_inputs(L, e, cb, cols_valid, v[h]);
-          store_with_lo(L, e, v[h], cb, cols_valid);
+          add_inputs(L, e, cb, cols_valid, v);
+          store_with_lo(L, e, v, cb, cols_valid);
         }
       }
     }
@@ -914,22 +951,22 @@ __device__ void epi_ln_fwd(const EP& L, Epi& e) {
   float keep[2][32];
   float mean = 0.f, m2 = 0.f, cnt = 0.f;
   for (int c = 0; c < L.nchunk; ++c) {
-    float v[2][32];
-    chunk_fetch<KS>(L, e, v[0], v[1]);
-    if (!own) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (h < ns) {
+      if (h < ns && mine<KS>(e, h)) {
+        float v[32];
+        sub_fetch<KS>(L, e, h, v);
+        if (!own) continue;
         const int cb = sub_col<KS>(L, e, c, h);
-        add_inputs(L, e, cb, 32, v[h]);
+        add_inputs(L, e, cb, 32, v);
         if (e.quad == 2 && h == 0 && c == 0) trace_ev(e.cx, 2, 16 * e.cx.pair + 2);
         if (L.z != nullptr)
-          sub_store(e.stg, v[h], L.z + (size_t)e.wrow0 * L.ld_z + cb, L.ld_z, e.rows_valid, 32, e.lane);
+          sub_store(e.stg, v, L.z + (size_t)e.wrow0 * L.ld_z + cb, L.ld_z, e.rows_valid, 32, e.lane);
         if (e.quad == 2 && h == 0 && c == 0) trace_ev(e.cx, 2, 16 * e.cx.pair + 3);
-        welford32(v[h], mean, m2, cnt);
+        welford32(v, mean, m2, cnt);
         if (single) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) keep[h][j] = v[h][j];
+          for (int j = 0; j < 32; ++j) keep[h][j] = v[j];
         }
       }
     }
@@ -942,7 +979,7 @@ __device__ void epi_ln_fwd(const EP& L, Epi& e) {
   for (int c = 0; c < L.nchunk; ++c) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (h < ns) {
+      if (h < ns && mine<KS>(e, h)) {
         const int cb = sub_col<KS>(L, e, c, h);
         float v[32];
         if (single) {
@@ -976,13 +1013,12 @@ __device__ void epi_ln_bwd(const EP& L, Epi& e) {
   float keep[2][32];
   float s1 = 0.f, s2 = 0.f;
   for (int c = 0; c < L.nchunk; ++c) {
-    float vv[2][32];
-    chunk_fetch<KS>(L, e, vv[0], vv[1]);
-    if (!own) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (h < ns) {
-        float (&v)[32] = vv[h];
+      if (h < ns && mine<KS>(e, h)) {
+        float v[32];
+        sub_fetch<KS>(L, e, h, v);
+        if (!own) continue;
         const int cb = sub_col<KS>(L, e, c, h);
         add_inputs(L, e, cb, 32, v);
         float z[32];
@@ -1023,17 +1059,18 @@ __device__ void epi_ln_bwd(const EP& L, Epi& e) {
     }
   }
   if (!own) return;
-  float2 parts[Geo<KS>::CLS];
-  row_exchange<KS>(L, e, s1, s2, parts);
-  const int nown = n_owners<KS>(L);
+  float2 parts[Geo<KS>::SLOTS];
+  float unused_cnt = 0.f;
+  row_exchange<KS>(L, e, s1, s2, unused_cnt, false, parts);
+  const int nsl = n_slots<KS>(L);
   float t1 = 0.f, t2 = 0.f;
-  for (int d = 0; d < nown; ++d) { t1 += parts[d].x; t2 += parts[d].y; }
+  for (int d = 0; d < nsl; ++d) { t1 += parts[d].x; t2 += parts[d].y; }
   t1 /= (float)L.N;
   t2 /= (float)L.N;
   for (int c = 0; c < L.nchunk; ++c) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (h < ns) {
+      if (h < ns && mine<KS>(e, h)) {
         const int cb = sub_col<KS>(L, e, c, h);
         float v[32], z[32];
         if (single) {
@@ -1065,16 +1102,16 @@ __device__ void epi_gru(const EP& L, Epi& e) {
   const int D = L.chunk_stride;
   float mean = 0.f, m2 = 0.f, cnt = 0.f;
   for (int c = 0; c < 3; ++c) {
-    float v[2][32];
-    chunk_fetch<KS>(L, e, v[0], v[1]);
-    if (!own) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (h < ns) {
+      if (h < ns && mine<KS>(e, h)) {
+        float v[32];
+        sub_fetch<KS>(L, e, h, v);
+        if (!own) continue;
         const int cb = sub_col<KS>(L, e, c, h);
-        add_inputs(L, e, cb, 32, v[h]);
-        sub_store(e.stg, v[h], L.z + (size_t)e.wrow0 * L.ld_z + cb, L.ld_z, e.rows_valid, 32, e.lane);
-        welford32(v[h], mean, m2, cnt);
+        add_inputs(L, e, cb, 32, v);
+        sub_store(e.stg, v, L.z + (size_t)e.wrow0 * L.ld_z + cb, L.ld_z, e.rows_valid, 32, e.lane);
+        welford32(v, mean, m2, cnt);
       }
     }
   }
@@ -1082,6 +1119,7 @@ __device__ void epi_gru(const EP& L, Epi& e) {
   float gm, rstd;
   ln_finish<KS>(L, e, mean, m2, cnt, gm, rstd);
   for (int h = 0; h < ns; ++h) {
+    if (!mine<KS>(e, h)) continue;
     const int cj = sub_col<KS>(L, e, 0, h);        // column inside each gate
     float g[32], v[32];
     // reset gate
@@ -1124,13 +1162,12 @@ __device__ void epi_stats(const EP& L, Epi& e) {
   const int C = L.ipar;
   const float mix = L.f[0], uni = mix / (float)C;
   for (int c = 0; c < L.nchunk; ++c) {
-    float vv[2][32];
-    chunk_fetch<KS>(L, e, vv[0], vv[1]);
-    if (!own) continue;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      if (h < nsub<KS>(L)) {
-        float (&v)[32] = vv[h];
+      if (h < nsub<KS>(L) && mine<KS>(e, h)) {
+        float v[32];
+        sub_fetch<KS>(L, e, h, v);
+        if (!own) continue;
         const int cb = sub_col<KS>(L, e, c, h);
         const int cols_valid = min(32, L.N - cb);
         if (cols_valid <= 0) continue;
@@ -1171,8 +1208,8 @@ __device__ void epi_stats(const EP& L, Epi& e) {
 template <int KS>
 __device__ void epi_actor(const EP& L, Epi& e) {
   const int A = L.ipar;
-  float v[32], unused[32];
-  chunk_fetch<KS>(L, e, v, unused);
+  float v[32];
+  sub_fetch<KS>(L, e, 0, v);
   if (!owns<KS>(L, e)) return;
   add_inputs(L, e, 0, 2 * A, v);
   if (e.lane < e.rows_valid) {
@@ -1193,21 +1230,171 @@ __device__ void epi_actor(const EP& L, Epi& e) {
   }
 }
 
+
+// E_STATSBWD: gradient of the straight-through categorical sample back to the raw logits
+// (reverse of E_STATS with dLogit = 0; A/tfutils.py:375-381, A/nets.py:166-170).  input (acc + add) =
+// dStoch, x0 = the unimixed logits saved by the forward pass, f0 = mix, ipar = classes (32).
+//   q = exp(lg); dl = q (ds - sum q ds); dq = dl / q; p = (q - mix/C) / (1 - mix);
+//   dz = p (dp - sum p dp),  dp = (1 - mix) dq
+template <int KS>
+__device__ void epi_stats_bwd(const EP& L, Epi& e) {
+  const bool own = owns<KS>(L, e);
+  const int C = L.ipar;
+  const float mix = L.f[0], uni = mix / (float)C;
+  for (int c = 0; c < L.nchunk; ++c) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h < nsub<KS>(L) && mine<KS>(e, h)) {
+        float v[32];
+        sub_fetch<KS>(L, e, h, v);
+        if (!own) continue;
+        const int cb = sub_col<KS>(L, e, c, h);
+        add_inputs(L, e, cb, 32, v);
+        float lg[32];
+        sub_load(e.stg, lg, L.x[0] + (size_t)e.wrow0 * L.ldx[0] + cb, L.ldx[0], e.rows_valid, 32, e.lane);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { lg[j] = expf(lg[j]); sq += lg[j] * v[j]; }     // lg := q
+        float sp = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float q = lg[j];
+          const float dq = v[j] - sq;                      // dl / q
+          const float pj = (q - uni) / (1.f - mix);
+          const float dp = (1.f - mix) * dq;
+          lg[j] = pj;
+          v[j] = dp;
+          sp += pj * dp;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = lg[j] * (v[j] - sp);
+        store_with_lo(L, e, v, cb, 32);
+      }
+    }
+  }
+}
+
+// E_GRUBWD: reverse of E_GRU.  Layer width N = D: input (acc + add) = dOut, the gradient wrt the new
+// deter.  x0 = previous deter, x1 = y (post-norm gates saved by the forward pass), z / st = the
+// pre-norm gates and their (mean, rstd), gamma / beta over 3 D.  Outputs: out [M, 3 D] = dz of the
+// joint LayerNorm (+ out_lo), x2 [M, D] += dOut (1 - u)  (gradient wrt the previous deter).
+template <int KS>
+__device__ void epi_gru_bwd(const EP& L, Epi& e) {
+  const int ns = nsub<KS>(L);
+  const bool own = owns<KS>(L, e);
+  const int D = L.N;
+  const bool rowok = e.lane < e.rows_valid;
+  float mean = 0.f, rstd = 0.f;
+  if (rowok && own) {
+    mean = L.st[(size_t)(e.wrow0 + e.lane) * 2];
+    rstd = L.st[(size_t)(e.wrow0 + e.lane) * 2 + 1];
+  }
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = 0; c < L.nchunk; ++c) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h < ns && mine<KS>(e, h)) {
+        float v[32];
+        sub_fetch<KS>(L, e, h, v);
+        if (!own) continue;
+        const int cj = sub_col<KS>(L, e, c, h);          // column inside D
+        add_inputs(L, e, cj, 32, v);
+        float yr[32], yc[32], t[32];
+        sub_load(e.stg, yr, L.x[1] + (size_t)e.wrow0 * L.ldx[1] + cj, L.ldx[1], e.rows_valid, 32, e.lane);
+        sub_load(e.stg, yc, L.x[1] + (size_t)e.wrow0 * L.ldx[1] + D + cj, L.ldx[1], e.rows_valid, 32, e.lane);
+        sub_load(e.stg, t, L.x[1] + (size_t)e.wrow0 * L.ldx[1] + 2 * D + cj, L.ldx[1], e.rows_valid, 32, e.lane);
+        float pv[32];
+        sub_load(e.stg, pv, L.x[0] + (size_t)e.wrow0 * L.ldx[0] + cj, L.ldx[0], e.rows_valid, 32, e.lane);
+        // gates: yr := d y_r, yc := d y_c, t := d y_u, pv := d prev
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float dout = rowok ? v[j] : 0.f;
+          const float r = sigmoidf_(yr[j]);
+          const float cc = tanhf(r * yc[j]);
+          const float u = sigmoidf_(t[j] - 1.f);
+          const float du = dout * (cc - pv[j]);
+          const float dpre = dout * u * (1.f - cc * cc);
+          yr[j] = dpre * yc[j] * r * (1.f - r);
+          yc[j] = dpre * r;
+          t[j] = du * u * (1.f - u);
+          pv[j] = dout * (1.f - u);
+        }
+        if (L.x[2] != nullptr) {                     // d prev accumulates into the caller's buffer
+          float old[32];
+          sub_load(e.stg, old, L.x[2] + (size_t)e.wrow0 * L.ldx[2] + cj, L.ldx[2], e.rows_valid, 32, e.lane);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pv[j] += old[j];
+          sub_store(e.stg, pv, L.x[2] + (size_t)e.wrow0 * L.ldx[2] + cj, L.ldx[2], e.rows_valid, 32, e.lane);
+        }
+        // joint LayerNorm backward, pass 1: dx = dy * gamma, row sums; dx parked in `out`
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          float (&dy)[32] = g == 0 ? yr : (g == 1 ? yc : t);
+          float z[32];
+          sub_load(e.stg, z, L.z + (size_t)e.wrow0 * L.ld_z + g * D + cj, L.ld_z, e.rows_valid, 32, e.lane);
+          const float* gp = L.gamma + g * D + cj;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float dx = dy[j] * __ldg(gp + j);
+            const float xh = (z[j] - mean) * rstd;
+            s1 += dx;
+            s2 += dx * xh;
+            dy[j] = dx;
+          }
+          sub_store(e.stg, dy, L.out + (size_t)e.wrow0 * L.ld_out + g * D + cj, L.ld_out, e.rows_valid, 32, e.lane);
+        }
+      }
+    }
+  }
+  if (!own) return;
+  float2 parts[Geo<KS>::SLOTS];
+  float unused_cnt = 0.f;
+  row_exchange<KS>(L, e, s1, s2, unused_cnt, false, parts);
+  const int nsl = n_slots<KS>(L);
+  float t1 = 0.f, t2 = 0.f;
+  for (int d = 0; d < nsl; ++d) { t1 += parts[d].x; t2 += parts[d].y; }
+  t1 /= (float)(3 * D);
+  t2 /= (float)(3 * D);
+  for (int c = 0; c < L.nchunk; ++c) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h < ns && mine<KS>(e, h)) {
+        const int cj = sub_col<KS>(L, e, c, h);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          float v[32], z[32];
+          sub_load(e.stg, v, L.out + (size_t)e.wrow0 * L.ld_out + g * D + cj, L.ld_out, e.rows_valid, 32, e.lane);
+          sub_load(e.stg, z, L.z + (size_t)e.wrow0 * L.ld_z + g * D + cj, L.ld_z, e.rows_valid, 32, e.lane);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float xh = (z[j] - mean) * rstd;
+            v[j] = rstd * (v[j] - t1 - xh * t2);
+          }
+          store_with_lo(L, e, v, g * D + cj, 32);
+        }
+      }
+    }
+  }
+}
+
 template <int KS>
 __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
                          int cluster_id, int nclusters, int warp, int lane, uint32_t tmem_base,
                          Ctx cx) {
-  constexpr int CLS = Geo<KS>::CLS;
+  constexpr int CLS = Geo<KS>::CLS, EW = Geo<KS>::EW;
   const int ntiles = (M + BM - 1) / BM;
   Epi e;
   e.sh = sh; e.cx = cx; e.tmem_base = tmem_base;
   e.ac = 0; e.xc = 0; e.rc = 0;
   e.rank = rank; e.cs = rank % NS; e.kh = rank / NS;
   e.warp = warp; e.quad = warp & 3; e.lane = lane;      // quad: the TMEM lane quadrant this warp may read
-  e.stg = reinterpret_cast<float*>(sh.smem + Geo<KS>::OFF_STG + (warp - 2) * STG_WARP_BYTES);
+  e.ew = warp < 6 ? warp - 2 : warp - 3;                // warps 2-5 -> 0-3, warps 7-10 -> 4-7
+  e.grp = e.ew >> 2;
+  e.stg = reinterpret_cast<float*>(sh.smem + Geo<KS>::OFF_STG + e.ew * STG_WARP_BYTES);
   e.stats_off = Geo<KS>::OFF_STATS;
   e.red_off = Geo<KS>::OFF_RED;
-  EP* ep_slot = reinterpret_cast<EP*>(sh.smem + Geo<KS>::OFF_EP + (warp - 2) * EP_BYTES);
+  e.loc_off = Geo<KS>::OFF_LOC;
+  EP* ep_slot = reinterpret_cast<EP*>(sh.smem + Geo<KS>::OFF_EP + e.ew * EP_BYTES);
   int pair = 0;
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
     e.wrow0 = tile * BM + e.quad * 32;      // first global row of this warp
@@ -1223,20 +1410,27 @@ __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, i
       if (L.nseg == 0 && l > 0)       // no producer wait protects its inputs: wait here
         count_wait(sh.bars + BAR_READY, (uint32_t)pair * CLS, e.cx, 8);
       if (warp == 2) trace_ev(e.cx, 2, 16 * pair);
-      if (active) {
+      if (active && e.grp >= nsub<KS>(L)) {
+        // a 32-wide slice has no second half: this warp group only hands the accumulator back
+        if (has_k(L, e, KS)) {
+          for (int c = 0; c < L.nchunk; ++c) { acc_wait(e); acc_release(e); }
+        }
+      } else if (active) {
         if (L.epi == DD_EPI_PLAIN) epi_plain<KS>(L, e);
         else if (L.epi == DD_EPI_LN) epi_ln_fwd<KS>(L, e);
         else if (L.epi == DD_EPI_LNBWD) epi_ln_bwd<KS>(L, e);
         else if (L.epi == DD_EPI_GRU) epi_gru<KS>(L, e);
         else if (L.epi == DD_EPI_STATS) epi_stats<KS>(L, e);
-        else epi_actor<KS>(L, e);
+        else if (L.epi == DD_EPI_ACTOR) epi_actor<KS>(L, e);
+        else if (L.epi == DD_EPI_STATSBWD) epi_stats_bwd<KS>(L, e);
+        else epi_gru_bwd<KS>(L, e);
       }
       // this CTA's rows of the layer's outputs are written: tell every CTA's producer.  Each
-      // writer orders its stores against the async proxy (TMA reads them), the four epilogue warps
+      // writer orders its stores against the async proxy (TMA reads them), the epilogue warps
       // meet at a named barrier, then one thread publishes with a single cluster-scope fence.
       if (warp == 2) trace_ev(e.cx, 2, 16 * pair + 9);
       asm volatile("fence.proxy.async;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
       if (warp == 2 && lane == 0) {
         asm volatile("fence.acq_rel.cluster;" ::: "memory");
 #pragma unroll
@@ -1248,7 +1442,7 @@ __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, i
 }
 
 template <int KS>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(Geo<KS>::THREADS, 1)
 lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg,
           unsigned long long* prof, int flags) {
   using G = Geo<KS>;
@@ -1269,7 +1463,7 @@ lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg,
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(sh.bars + BAR_ACCF + 8 * b, 1);
-      mbar_init(sh.bars + BAR_ACCE + 8 * b, 4);
+      mbar_init(sh.bars + BAR_ACCE + 8 * b, G::EW);     // one arrive per epilogue warp
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(sh.bars + BAR_STATS + 8 * b, 1);
@@ -1520,6 +1714,15 @@ extern "C" int dd_program_build(const DdLayer* layers, int nlayers, int rows, vo
       if ((wide && s.ipar != 32) || (!wide && (s.ipar != s.N || s.N > 32)) || s.nseg == 0)
         rc = fail("dd_program_build", "STATS layer: groups of 32 classes, or one narrow group of N <= 32");
     }
+    if (s.epi == DD_EPI_STATSBWD) {
+      if (d.nactive != lm::NS || s.ipar != 32 || s.x[0] == nullptr)
+        rc = fail("dd_program_build", "STATSBWD layer: groups of 32 classes over a full-width layer, needs the logits");
+    }
+    if (s.epi == DD_EPI_GRUBWD) {
+      if (d.nactive != lm::NS || s.gamma == nullptr || s.z == nullptr || s.st == nullptr ||
+          s.x[0] == nullptr || s.x[1] == nullptr)
+        rc = fail("dd_program_build", "GRUBWD layer: N = D a multiple of 256, needs scale, z, stats, prev and y");
+    }
     if (s.epi == DD_EPI_ACTOR) {
       if (s.N != 2 * s.ipar || s.ipar > 16 || s.x[0] == nullptr || s.x[1] == nullptr || s.x[2] == nullptr)
         rc = fail("dd_program_build", "ACTOR layer: N = 2 A <= 32 with eps, mean and std buffers");
@@ -1570,7 +1773,7 @@ static int setup_variant() {
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(G::CLS * 8);
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(G::THREADS);
   cfg.dynamicSmemBytes = G::SMEM_BYTES;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1590,7 +1793,7 @@ static void launch_variant(const LmLayer* table, int nlayers, int rows, int nclu
   using G = Geo<KS>;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(G::CLS * nclusters);
-  cfg.blockDim = dim3(THREADS);
+  cfg.blockDim = dim3(G::THREADS);
   cfg.dynamicSmemBytes = G::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -1608,9 +1811,13 @@ extern "C" int dd_program_run(const void* table_dev, int nlayers, int rows, dd_s
   if (lm::g_max_clusters[1] == 0 && lm::g_max_clusters[2] == 0) {
     lm::g_max_clusters[1] = lm::setup_variant<1>();
     lm::g_max_clusters[2] = lm::setup_variant<2>();
-    if (lm::g_ks < 0) {          // split-K clusters of 16 when the device can host at least one
+    if (lm::g_ks < 0) {
+      // default: clusters of 8.  Measured on B200 (profiles/r02_machine_geometry.txt): only 7
+      // clusters of 16 CTAs are co-resident (112 SMs), so the 8 row tiles of the a1 rollout take
+      // two rounds and large batches lose to 16 clusters of 8 (128 SMs); the split-K geometry
+      // stays available (DD_MACHINE_KS=2 / dd_set_machine_ks) for parts that host 8 such clusters.
       const char* e = getenv("DD_MACHINE_KS");
-      lm::g_ks = e != nullptr ? atoi(e) : 2;
+      lm::g_ks = e != nullptr ? atoi(e) : 1;
     }
     if (lm::g_ks == 2 && lm::g_max_clusters[2] < 1) lm::g_ks = 1;
     if (lm::g_ks != 2) lm::g_ks = 1;

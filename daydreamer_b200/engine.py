@@ -468,7 +468,7 @@ class Trunk:
     grads to produce.  wgrad: accumulate parameter grads into the group."""
     eng, be, g = self.eng, self.eng.be, group or self.group
     n = r1 - r0
-    if (self.machine and n <= eng.machine_max_rows and _mview_ok(dH) and
+    if (self.machine and eng.machine_bwd and n <= eng.machine_max_rows and _mview_ok(dH) and
         all(_mview_ok(d[0]) and PG.eligible_width(d[0].shape[1], PG.EPI_PLAIN) for d in dxs)):
       key = ('b', r0, r1, id(g), dH.data_ptr(), bool(wgrad),
              tuple((d[0].data_ptr(), d[1], float(d[2])) for d in dxs))
@@ -667,6 +667,9 @@ class Engine:
     # ~1K rows and loses to the persistent GEMM beyond a few thousand -> big batched trunks stay
     # on the per-layer kernels
     self.machine_max_rows = int(os.environ.get('DD_MACHINE_MAXROWS', '2048'))
+    # reverse chains (LayerNorm-backward epilogue): measured slower than dd_gemm + dd_ln_bwd at
+    # a1 size (profiles/r02_phase_times.txt), so they stay opt-in
+    self.machine_bwd = os.environ.get('DD_MACHINE_BWD', '0') != '0'
     s, N, H = spec, self.N, self.H
     D, U, SC, A, E = s.deter, s.units, s.sc, s.act_dim, s.enc_units
     z = be.zeros
@@ -790,6 +793,11 @@ class Engine:
     self.tfeat_lo = z(T, N, D) if self.machine else None       # deter part; the latent is one-hot
     self.taction_lo = z(T, N, A) if self.machine else None
     self.i_xin_lo = z(H, N, U) if self.machine else None
+    # reverse-rollout program scratch: d(raw prior logits), d(pre-norm GRU gates), d(pre-norm img_in)
+    if self.machine:
+      self.r_dzs, self.r_dzs_lo = z(N, SC), z(N, SC)
+      self.r_dzg, self.r_dzg_lo = z(N, 3 * D), z(N, 3 * D)
+      self.r_dzi, self.r_dzi_lo = z(N, U), z(N, U)
     self.tlogit = z(T, N, SC)
     self.taction = z(T, N, A)
     self.tmean = z(T, N, A)
@@ -1382,6 +1390,68 @@ class Engine:
     be.program_run(self._rollout)
     return True
 
+  def _reverse_program(self):
+    """The reverse pass through the imagined rollout (dynamics backprop of the continuous actor,
+    A/agent.py:351-381 under the persistent tape) as ONE machine program: per step the categorical
+    straight-through backward, the prior stack's reverse (3 x LayerNorm-backward layers), the GRU +
+    joint-LayerNorm backward, and the input gradients of gru_out / img_in accumulated into the
+    trajectory gradient -- 9 layers per step, t = H .. 1.  Parameters are constants here (no weight
+    gradients).  False when a shape does not tile."""
+    s, be, gm = self.spec, self.be, self.groups['model']
+    D, U, SC, A, N, H = s.deter, s.units, s.sc, s.act_dim, self.N, self.H
+    if not hasattr(self, '_reverse'):
+      ok = (self.machine and os.environ.get('DD_REVERSE', '1') != '0' and not s.discrete and
+            s.classes == 32 and D % 256 == 0 and U % 256 == 0 and SC % 256 == 0 and A % 4 == 0 and
+            A <= 64 and self.i_prior.machine and self.i_prior.layers >= 1)
+      self._reverse = None
+      if ok:
+        pr = self.i_prior
+        nl = pr.layers
+        dtf = self.dtfeat
+        wst, wstlo = gm.PB('rssm/img_stats/kernel')
+        wgru, wgrulo = gm.PB('rssm/gru_out/kernel')
+        win, winlo = gm.PB('rssm/img_in/kernel')
+        dZ = [self.dz_buf(i, N, U) for i in range(nl)]
+        layers = []
+        for t in range(H, 0, -1):
+          k = t - 1
+          r0, r1 = k * N, (k + 1) * N
+          # d(one-hot sample) -> d(raw prior logits)
+          layers.append(PG.Layer([], None, None, SC, PG.EPI_STATSBWD, add=dtf[t][:, D:], out=self.r_dzs,
+                                 out_lo=self.r_dzs_lo, x0=self.tlogit[t], f0=s.rssm_unimix, ipar=s.classes))
+          # img_stats and the prior stack, reversed
+          src, w, wlo = (self.r_dzs, self.r_dzs_lo), wst, wstlo
+          for i in reversed(range(nl)):
+            kn, sn, bn = pr._names(i)
+            layers.append(PG.Layer([PG.Seg(src[0], src[1], 0)], w, wlo, U, PG.EPI_LNBWD, act=1,
+                                   gamma=gm.P(sn), beta=gm.P(bn), z=pr.Z[i][r0:r1], st=pr.st[i][r0:r1],
+                                   out=dZ[i][0], out_lo=dZ[i][1]))
+            src = dZ[i]
+            w, wlo = gm.PB(kn)
+          # d(new deter) = d(img_out_0 input) + what the heads put there -> GRU + joint LayerNorm backward
+          layers.append(PG.Layer([PG.Seg(src[0], src[1], 0)], w, wlo, D, PG.EPI_GRUBWD, add=dtf[t][:, :D],
+                                 gamma=gm.P('rssm/gru_out/norm/scale'), beta=gm.P('rssm/gru_out/norm/bias'),
+                                 z=self.i_zgru[k], st=self.i_stgru[k], out=self.r_dzg, out_lo=self.r_dzg_lo,
+                                 x0=self.tfeat[k][:, :D], x1=self.i_ygru[k], x2=dtf[k][:, :D]))
+          gseg = [PG.Seg(self.r_dzg, self.r_dzg_lo, 0)]
+          # gru_out input gradients: x part -> img_in's LayerNorm backward, deter part -> trajectory
+          layers.append(PG.Layer(gseg, wgru, wgrulo, U, PG.EPI_LNBWD, act=1, wn0=D,
+                                 gamma=gm.P('rssm/img_in/norm/scale'), beta=gm.P('rssm/img_in/norm/bias'),
+                                 z=self.i_zin[k], st=self.i_stin[k], out=self.r_dzi, out_lo=self.r_dzi_lo))
+          if k > 0:
+            layers.append(PG.Layer(gseg, wgru, wgrulo, D, PG.EPI_PLAIN, wn0=0, add=dtf[k][:, :D],
+                                   out=dtf[k][:, :D]))
+          iseg = [PG.Seg(self.r_dzi, self.r_dzi_lo, 0)]
+          if k > 0:
+            layers.append(PG.Layer(iseg, win, winlo, SC, PG.EPI_PLAIN, wn0=0, add=dtf[k][:, D:],
+                                   out=dtf[k][:, D:]))
+          layers.append(PG.Layer(iseg, win, winlo, A, PG.EPI_PLAIN, wn0=SC, out=self.da[r0:r1]))
+        self._reverse = be.program_build(layers, N)
+    if self._reverse is None:
+      return False
+    be.program_run(self._reverse)
+    return True
+
   def _cell_program(self, t, act, own_action):
     """img_in (Linear + LayerNorm + elu over [stoch, action]) and the GRU's Linear + joint
     LayerNorm of rollout step t as one 2-layer machine program (A/nets.py:129, :153-154).
@@ -1533,7 +1603,7 @@ class Engine:
     # reverse through the rollout: t = H .. 1
     Win = gm.P('rssm/img_in/kernel')
     Wgru = gm.P('rssm/gru_out/kernel')
-    for t in range(H, 0, -1):
+    for t in ([] if self._reverse_program() else range(H, 0, -1)):
       k = t - 1
       dzs = self.tmp(2, N, SC)
       be.stats_bwd(self.dtfeat[t][:, D:], None, self.tlogit[t], dzs, s.stoch,

@@ -21,7 +21,7 @@ from typing import List, Optional
 
 import torch
 
-EPI_PLAIN, EPI_LN, EPI_LNBWD, EPI_GRU, EPI_STATS, EPI_ACTOR = 0, 1, 2, 3, 4, 5
+EPI_PLAIN, EPI_LN, EPI_LNBWD, EPI_GRU, EPI_STATS, EPI_ACTOR, EPI_STATSBWD, EPI_GRUBWD = range(8)
 
 
 @dataclasses.dataclass
@@ -52,7 +52,9 @@ class Layer:
   dbeta: Optional[torch.Tensor] = None
   # epilogue-specific extras -- GRU: x0 = previous deter [M, D], x1 = post-norm gates [M, 3D] (saved);
   # STATS: x0 = Gumbel noise (None: logits only), x1 = one-hot sample, f0 = unimix, ipar = classes;
-  # ACTOR: x0 = eps, x1 = mean, x2 = std, f0 / f1 = min / max std, ipar = action dim
+  # ACTOR: x0 = eps, x1 = mean, x2 = std, f0 / f1 = min / max std, ipar = action dim;
+  # STATSBWD: x0 = forward logits, f0 = unimix, ipar = classes; GRUBWD: x0 = previous deter, x1 = y,
+  # x2 = buffer that accumulates d(previous deter), z / st / gamma of the forward GRU layer
   x0: Optional[torch.Tensor] = None
   x1: Optional[torch.Tensor] = None
   x2: Optional[torch.Tensor] = None

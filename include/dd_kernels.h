@@ -314,9 +314,15 @@ int dd_fill_normal(float* buf, int64_t n, uint64_t seed, uint32_t stream_id,
  *                  A/tfutils.py:368-382)
  *   DD_EPI_ACTOR   N = 2 ipar columns [mean raw | std raw] (+ bias): x1 = mean = tanh(.), x2 = std =
  *                  (f1 - f0) sigmoid(.) + f0, out = mean + std * x0 (A/nets.py:461-468) */
+/*   DD_EPI_STATSBWD input = d(one-hot sample) through the straight-through estimator, x0 = the
+ *                  unimix logits of the forward pass: out = d(raw logits)
+ *   DD_EPI_GRUBWD  N = D: input = d(new deter); x0 = previous deter, x1 = y, z / st of the forward GRU
+ *                  layer: out [M, 3 D] = d(pre-norm gates), x2 [M, D] += d(previous deter) */
 #define DD_EPI_GRU 3
 #define DD_EPI_STATS 4
 #define DD_EPI_ACTOR 5
+#define DD_EPI_STATSBWD 6
+#define DD_EPI_GRUBWD 7
 #define DD_MAX_TRANSPOSE_JOBS 64
 typedef struct DdSeg {
   const float* a;

@@ -143,6 +143,18 @@ class HostSim:
                        2 if L.x1 is None else (1 if L.x0 is None else 0))
         if L.x1 is not None:
           L.x1.copy_(oh)
+      elif L.epi == P.EPI_STATSBWD:
+        out = torch.zeros(rows, L.N)
+        self.stats_bwd(acc, None, L.x0, out, L.N // L.ipar, L.ipar, L.f0)
+      elif L.epi == P.EPI_GRUBWD:
+        D = L.N
+        dy, dprev = torch.zeros(rows, 3 * D), torch.zeros(rows, D)
+        self.gru_bwd(acc, L.x1, L.x0, dy, dprev, False)
+        if L.x2 is not None:
+          L.x2.copy_(L.x2 + dprev)
+        out = torch.zeros(rows, 3 * D)
+        self.ln_bwd(dy, L.z, L.st, L.gamma, L.beta if L.beta is not None else torch.zeros(3 * D), out,
+                    None, None, 0)
       else:
         A = L.ipar
         out, mean, std = torch.zeros(rows, A), torch.zeros(rows, A), torch.zeros(rows, A)

@@ -1,9 +1,13 @@
 """Host logic check (no GPU): the product's orchestration (engine.py, hand-written
 backward) running on the torch-CPU primitive simulator must reproduce the
 oracle's autograd train step."""
+import os
+
 import numpy as np
 import pytest
 import torch
+
+os.environ.setdefault('DD_MACHINE_BWD', '1')      # the CPU tests cover the reverse programs too
 
 from oracle import dreamer_oracle as O
 from daydreamer_b200 import engine as E

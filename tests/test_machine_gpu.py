@@ -12,14 +12,14 @@ from tests.hostsim import HostSim
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope='module', params=[2, 1], ids=['splitk16', 'cluster8'])
+@pytest.fixture(scope='module', params=[1, 2], ids=['cluster8', 'splitk16'])
 def backends(request):
-  """Both geometries of the machine: split-K clusters of 16 CTAs (default) and clusters of 8."""
+  """Both geometries of the machine: clusters of 8 CTAs (default) and split-K clusters of 16."""
   from daydreamer_b200.backend import CudaBackend
   cu = CudaBackend()
   cu.lib.dd_set_machine_ks(request.param)
   yield HostSim(), cu
-  cu.lib.dd_set_machine_ks(2)
+  cu.lib.dd_set_machine_ks(1)
 
 
 def rnd(*shape, seed=0, scale=1.0):
@@ -299,3 +299,45 @@ def test_actor_layer(backends):
     be.program_run(be.program_build([L], M))
     return {'out': act, 'lo': act_lo, 'mean': mean, 'std': std}
   run_both(backends, case, rtol=2e-5, atol=2e-5)
+
+
+def test_stats_bwd_layer(backends):
+  """Epilogue-only layer: straight-through categorical gradient back to the raw logits."""
+  def case(be, T):
+    M, S, C = 1024, 32, 32
+    N = S * C
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(M, S, C, generator=g)
+    lg = torch.log(0.99 * torch.softmax(z, -1) + 0.01 / C).reshape(M, N)
+    feat = T(rnd(M, 512 + N, seed=4))            # d(stoch) is a column slice of a wider buffer
+    dzs, dzs_lo = T(torch.zeros(M, N)), T(torch.zeros(M, N))
+    L = P.Layer([], None, None, N, P.EPI_STATSBWD, add=feat[:, 512:], out=dzs, out_lo=dzs_lo, x0=T(lg),
+                f0=0.01, ipar=C)
+    be.program_run(be.program_build([L], M))
+    return {'out': dzs, 'lo': dzs_lo}
+  run_both(backends, case, rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize('M,D', [(1024, 512), (300, 256)])
+def test_gru_bwd_layer(backends, M, D):
+  """dZ0 @ W0^T + head gradient -> GRU gates backward -> joint LayerNorm backward over 3 D, and the
+  gradient wrt the previous deter accumulated into a strided slice."""
+  def case(be, T):
+    U = D
+    dZ0, dZ0lo = act_pair(T, rnd(M, U, seed=1, scale=0.1))
+    W0 = rnd(D, U, seed=2, scale=U ** -0.5)                 # kernel [D, U]: d deter = dZ0 @ W0^T
+    pw = T(torch.stack([W0, P.lo_of(W0)]))
+    z = rnd(M, 3 * D, seed=3)
+    gamma, beta = 1.0 + 0.1 * rnd(3 * D, seed=4), 0.1 * rnd(3 * D, seed=5)
+    y, st = torch.zeros(M, 3 * D), torch.zeros(M, 2)
+    HostSim().ln_fwd(z, gamma, beta, y, st, 0)
+    prev = rnd(M, D, seed=6)
+    dtf_t = T(rnd(M, D + 64, seed=7, scale=0.1))            # head gradients at step t (strided view)
+    dtf_k = T(rnd(M, D + 64, seed=8, scale=0.1))            # accumulates d prev
+    dzg, dzg_lo = T(torch.zeros(M, 3 * D)), T(torch.zeros(M, 3 * D))
+    L = P.Layer([P.Seg(dZ0, dZ0lo)], pw[0], pw[1], D, P.EPI_GRUBWD, add=dtf_t[:, :D], gamma=T(gamma),
+                beta=T(beta), z=T(z), st=T(st), out=dzg, out_lo=dzg_lo, x0=T(prev), x1=T(y),
+                x2=dtf_k[:, :D])
+    be.program_run(be.program_build([L], M))
+    return {'out': dzg, 'lo': dzg_lo, 'dprev': dtf_k}
+  run_both(backends, case, rtol=1e-4, atol=2e-5)
