@@ -1396,11 +1396,12 @@ class Engine:
     straight-through backward, the prior stack's reverse (3 x LayerNorm-backward layers), the GRU +
     joint-LayerNorm backward, and the input gradients of gru_out / img_in accumulated into the
     trajectory gradient -- 9 layers per step, t = H .. 1.  Parameters are constants here (no weight
-    gradients).  False when a shape does not tile."""
+    gradients).  False when a shape does not tile.  Opt-in (DD_REVERSE=1): measured at a1 size it
+    takes 6.1 ms against 5.0 ms of the per-op launches it replaces (profiles/r02_phase_times.txt)."""
     s, be, gm = self.spec, self.be, self.groups['model']
     D, U, SC, A, N, H = s.deter, s.units, s.sc, s.act_dim, self.N, self.H
     if not hasattr(self, '_reverse'):
-      ok = (self.machine and os.environ.get('DD_REVERSE', '1') != '0' and not s.discrete and
+      ok = (self.machine and os.environ.get('DD_REVERSE', '0') != '0' and not s.discrete and
             s.classes == 32 and D % 256 == 0 and U % 256 == 0 and SC % 256 == 0 and A % 4 == 0 and
             A <= 64 and self.i_prior.machine and self.i_prior.layers >= 1)
       self._reverse = None

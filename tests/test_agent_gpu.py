@@ -144,11 +144,14 @@ def test_a1_full_size_properties():
   assert int(eng.counters[0]) == 6 and int(eng.counters[4]) == 6
 
 
-def test_segmented_graph_capture_around_collectives():
-  """Data-parallel launch path on one GPU: with a collective hook installed the step is
-  captured as graph segments split at every all-reduce (NCCL never runs inside a graph);
-  with an identity collective the results must equal the single-graph agent."""
+@pytest.mark.parametrize('in_graph', [False, True])
+def test_graph_capture_around_collectives(in_graph, monkeypatch):
+  """Data-parallel launch path on one GPU.  DD_GRAPH_NCCL=0: with a collective hook installed the
+  step is captured as graph segments split at every all-reduce and the collectives run eagerly
+  between the replays; default: the collectives are captured INSIDE one graph (torch.distributed
+  NCCL calls are capturable).  With an identity collective both must equal the single-graph agent."""
   from daydreamer_b200.agent import Agent
+  monkeypatch.setenv('DD_GRAPH_NCCL', '1' if in_graph else '0')
   obs, act = spaces()
   cfg = small_config()
   a1 = Agent(obs, act, None, cfg)
@@ -169,8 +172,13 @@ def test_segmented_graph_capture_around_collectives():
         assert abs(m1[k] - m2[k]) <= 1e-4 * max(1.0, abs(m1[k])), (it, k, m1[k], m2[k])
   segs = a2._graphs[(id(a2._main), 'train')]
   kinds = [k for k, _ in segs]
-  assert kinds.count('allreduce') == 8 and kinds.count('graph') >= 8, kinds
-  assert len(calls) == 8 * 5                     # 5 steps x 8 collectives (eager, capture replay, replays)
+  # collectives per step: kl statistic, model grads, the three normalizer rows (one call), entropy
+  # statistic, critic grads, actor grads
+  if in_graph:
+    assert kinds == ['graph'], kinds
+  else:
+    assert kinds.count('allreduce') == 6 and kinds.count('graph') >= 6, kinds
+    assert len(calls) == 6 * 5                   # 5 steps x 6 collectives (eager, capture replay, replays)
 
 
 def xarm_like_spaces(act_dim=6):

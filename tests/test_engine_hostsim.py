@@ -8,6 +8,7 @@ import pytest
 import torch
 
 os.environ.setdefault('DD_MACHINE_BWD', '1')      # the CPU tests cover the reverse programs too
+os.environ.setdefault('DD_REVERSE', '1')
 
 from oracle import dreamer_oracle as O
 from daydreamer_b200 import engine as E
