@@ -165,27 +165,41 @@ class ClockSampler:
 # ----------------------------------------------------------------------------
 
 def best_cpu_threads(make_step, budget_s=25.0):
-  """Eager PyTorch-CPU oversubscribes badly on many-core hosts (128 threads on
-  tiny ops is ~25x slower than 16): give the CPU arm the best of a few thread
-  counts, measured on a one-sequence sample under a time bound, and report the
-  count used.  Returns (threads, host cores, seconds of the best sample step)."""
+  """Eager PyTorch-CPU oversubscribes badly on many-core hosts (measured on the 128-core B200 host:
+  one step at 128 threads takes minutes, at 16 threads under a second): give the CPU arm the best
+  thread count of a sweep on a one-sequence sample.  The sweep starts at 16 threads and only moves
+  further in a direction (8 | 32, 64, 128) while that direction keeps getting faster, so it never
+  runs the pathological counts, and it stops at `budget_s`.  Returns (threads, host cores, seconds
+  of the best sample step, {threads: seconds} of every count tried)."""
   import torch
   cores = os.cpu_count() or 1
   t_start = time.perf_counter()
-  torch.set_num_threads(min(16, cores))
-  make_step()                                     # first-call costs (allocator, dispatch caches)
-  best, best_t = min(16, cores), float('inf')
-  for n in sorted({min(c, cores) for c in (16, 8, 32, 64, 128)}, key=lambda c: abs(c - 16)):
+  tried = {}
+
+  def trial(n):
     torch.set_num_threads(n)
     t0 = time.perf_counter()
     make_step()
-    t = time.perf_counter() - t0
-    if t < best_t:
-      best, best_t = n, t
-    if time.perf_counter() - t_start > budget_s:
-      break
+    tried[n] = time.perf_counter() - t0
+    return tried[n]
+
+  base = min(16, cores)
+  torch.set_num_threads(base)
+  make_step()                                     # first-call costs (allocator, dispatch caches)
+  best, best_t = base, trial(base)
+  for direction in ((8,), (32, 64, 128)):
+    prev = tried[base]
+    for n in direction:
+      if n > cores or n in tried or time.perf_counter() - t_start > budget_s:
+        break
+      t = trial(n)
+      if t < best_t:
+        best, best_t = n, t
+      if t > prev:                                # getting slower this way: stop here
+        break
+      prev = t
   torch.set_num_threads(best)
-  return best, cores, best_t
+  return best, cores, best_t, {str(k): round(v, 3) for k, v in sorted(tried.items())}
 
 
 def oracle_spec(O, cfg):
@@ -221,7 +235,7 @@ def run_reference(args, rank, world):
   Lc, Hc = cfg['L'], cfg['H']
   spec = oracle_spec(O, cfg)
   learner = O.Learner(spec)
-  cores, host_cores, t_one = best_cpu_threads(
+  cores, host_cores, t_one, sweep = best_cpu_threads(
       lambda: learner.train_step(synthetic_batch(1, 0, cfg), oracle_noise(spec, 1, Lc, Hc, 0)))
   Bfull = per_gpu_batch(cfg, 1) if args.config != 'a1' else B_PER_GPU
   total = args.steps + args.warmup
@@ -247,7 +261,7 @@ def run_reference(args, rank, world):
                  'sample_sequences': B, 'full_batch': B == Bfull},
       'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                        'sample': sample, 'host_cores': host_cores,
-                       'threads_tried': [c for c in (8, 16, 32, 64, 128) if c <= host_cores],
+                       'thread_sweep_s': sweep,
                        'note': 'reference restated (PyTorch-CPU oracle), not TF2: tensorflow is '
                                'not installable in this image'},
       'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -439,7 +453,7 @@ def run_ours(args, rank, world, local_rank):
     n1 = {'obs_post': gum(L, 1, 32, 32), 'img': gum(H, L, 32, 32),
           'act': rng.standard_normal((H + 1, L, 12)).astype(np.float32)}
     b1 = synthetic_batch(1, 0)
-    cores, host_cores, t_one = best_cpu_threads(lambda: learner.train_step(b1, n1))
+    cores, host_cores, t_one, sweep = best_cpu_threads(lambda: learner.train_step(b1, n1))
     # bounded sample (~20 s of CPU work): 2 timed steps on Bc of the 16 sequences
     Bc = int(max(1, min(B_PER_GPU, 20.0 / (2 * t_one))))
     noise = {'obs_post': gum(L, Bc, 32, 32), 'img': gum(H, Bc * L, 32, 32),
@@ -452,7 +466,7 @@ def run_ours(args, rank, world, local_rank):
     cpu = {'value': Bc * L * H / cdt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
            'sample': f'{n_cpu} train steps on {Bc} of the 16 sequences (L=64, H=15), '
                      'eager PyTorch-CPU fp32 oracle',
-           'ms_per_step': cdt * 1e3, 'host_cores': host_cores}
+           'ms_per_step': cdt * 1e3, 'host_cores': host_cores, 'thread_sweep_s': sweep}
 
   if rank == 0:
     units = B_PER_GPU * world * L * H

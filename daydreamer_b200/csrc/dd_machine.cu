@@ -7,8 +7,11 @@
 // chain independently of every other tile.  So a cluster of CL = 8 CTAs owns a row tile: CTA r
 // computes column slice r of every layer (tcgen05 kind::tf32 tiles 128 x bn, accumulators in
 // TMEM), the 8 CTAs exchange the per-row LayerNorm partials through distributed shared memory,
-// and the only synchronisation between consecutive layers is cluster-local (mbarriers with
-// release/acquire at cluster scope) -- no grid barrier, no kernel boundary.
+// and the only synchronisation between consecutive layers is cluster-local -- no grid barrier, no
+// kernel boundary.  Nothing on that path is a cluster-scope release/acquire: those compile to
+// MEMBAR.ALL.GPU / CCTL.IVALL on sm_100a (measured: 10x the layer time).  Row partials travel as
+// st.async ... mbarrier::complete_tx (the bytes ARE the signal), "my activations are written" is a
+// relaxed remote add on a monotonic counter after ONE fence.acq_rel.cluster per layer per CTA.
 //
 // Operands reach the tensor core straight from TMA (cp.async.bulk.tensor, SWIZZLE_128B K-major
 // tiles; SASS: UTMALDG): fp32-accurate 3xTF32 needs x = hi + lo with both halves in shared
@@ -18,13 +21,22 @@
 // activations, identical for the 8 column-slice CTAs) is fetched ONCE per cluster: each CTA
 // loads a 16-row slice and multicasts it to all 8; weights (B) are private column slices.
 //
-//   warp 0    TMA producer (one lane issues): 4-stage ring {A_hi, A_lo, B_hi, B_lo}
-//   warp 1    TMEM allocator + MMA issuer (one lane): per k-step hi.hi -> main accumulator,
-//             lo.hi + hi.lo -> cross accumulator (separate TMEM columns), tcgen05.commit
-//             multicast to the `empty` barrier of all 8 CTAs (they all receive my A slices)
-//   warps 2-5 epilogue, one accumulator row per thread: tcgen05.ld, bias / addend, LayerNorm
-//             forward (+elu) or backward with the cross-CTA row reduction over DSMEM, writes x and
-//             x_lo for the next layer through a per-warp transposing staging buffer (coalesced)
+// Warp roles (Geo<KS>; KS = 1: clusters of 8, 352 threads; KS = 2: split-K clusters of 16, 224):
+//   warp 0    weight producer (one lane issues): ring of 3 stages {A_hi, A_lo, B_hi, B_lo}; the
+//             (w, w_lo) planes of a k-block are ONE 3-D box, so one TMA instruction per k-block
+//   warp 6    activation producer: waits for the producing layer's `ready` count, then multicasts
+//             its 16-row slice of A_hi / A_lo to the cluster (TMA issue costs ~250 cycles per
+//             instruction, so A and B are issued by different warps)
+//   warp 1    TMEM allocator + MMA issuer (one lane): per k-step  A_hi x [B_hi; B_lo]  (N = 2 bn)
+//             and  A_lo x B_hi  (N = bn) -- two instructions for the three tf32 products --
+//             then tcgen05.commit multicast to the `empty` barrier of every CTA in the cluster
+//   others    epilogue warps (8 for KS = 1: two per TMEM lane quarter, each takes half the
+//             columns): tcgen05.ld, bias / addend, the epilogue proper (LN forward / backward, GRU
+//             cell and its reverse, latent statistics + Gumbel sample, actor head) with the
+//             cross-CTA row reduction over DSMEM, and x / x_lo for the next layer written through
+//             a per-warp transposing staging buffer (coalesced 128-byte rows)
+// A 2-second watchdog in every wait writes (role, barrier, layer) to mapped host memory and traps,
+// so a protocol bug is a diagnosable error instead of a hung GPU.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -582,9 +594,11 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
                 if (!exact && !(cx.flags & F_ONLY1)) mma_tf32(d_cross, make_desc(a_lo + ks * 32), dbh, idesc, 1u);
               }
             }
+            if (cx.trace != nullptr && 4 * it + 2 < (uint32_t)TRACE_N) cx.trace[TRACE_N + 4 * it + 2] = (unsigned long long)clock64();
             // this stage may be refilled once every CTA that received it has read it
             umma_commit_mc(sh.bars + BAR_EMPTY + 8 * s, mask);
             if (active && r == k_hi - 1) umma_commit(sh.bars + BAR_ACCF + 8 * buf);
+            if (cx.trace != nullptr && 4 * it + 3 < (uint32_t)TRACE_N) cx.trace[TRACE_N + 4 * it + 3] = (unsigned long long)clock64();
           }
           __syncwarp();
           trace_ev(cx, 1, 4 * it + 1);

@@ -57,10 +57,10 @@ def run(tag, h, flags, iters=10, trace=False):
     print('  kernel events: roles end', [rel(x) for x in tr[3, 1:7]], 'after syncthreads', rel(tr[3, 8]),
           'after cluster sync', rel(tr[3, 9]))
     n_it = int((tr[1, ::4] > 0).sum())
-    print('  it: B.empty_ok B.issued | A.empty_ok A.issued | M.full_ok M.committed')
+    print('  it: B.empty_ok B.issued | A.empty_ok A.issued | M.full_ok M.mmas_issued M.commit_issued M.syncwarp')
     for it in list(range(min(n_it, 10))):
       print(f'  {it:3d}: {rel(tr[0, 4 * it]):7d} {rel(tr[0, 4 * it + 1]):7d} | {rel(tr[0, 4 * it + 2]):7d} {rel(tr[0, 4 * it + 3]):7d} | '
-            f'{rel(tr[1, 4 * it]):7d} {rel(tr[1, 4 * it + 1]):7d}')
+            f'{rel(tr[1, 4 * it]):7d} {rel(tr[1, 4 * it + 2]):7d} {rel(tr[1, 4 * it + 3]):7d} {rel(tr[1, 4 * it + 1]):7d}')
     n_p = int((tr[2, ::16] > 0).sum())
     print('  pair: start accf_ok acc0_loaded z0_stored exch_in exch_out norm0_done h0_stored | epi_done arrived')
     for pr in range(min(n_p, 12)):
