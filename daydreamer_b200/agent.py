@@ -334,7 +334,8 @@ class Agent:
     main = getattr(eng, 'eng', eng)            # PolicyEngine shares the learner's hooks
     be = self.be
     segs, cur = [], {}
-    side = torch.cuda.Stream(device=be.device)
+    # above the default priority: launches of a concurrent branch (Engine.launch_step) fill in behind
+    side = torch.cuda.Stream(device=be.device, priority=-1)
 
     def begin():
       cur['g'] = torch.cuda.CUDAGraph()
@@ -374,8 +375,10 @@ class Agent:
           pass
         segs.clear()
         torch.cuda.synchronize()
+    overlap = getattr(main, 'overlap', False)
     if saved is not None:
       main.allreduce = hook
+      main.overlap = False       # a segment cannot end while a second stream is still forked
     side.wait_stream(torch.cuda.current_stream())
     try:
       with torch.cuda.stream(side):
@@ -384,6 +387,8 @@ class Agent:
         end()
     finally:
       main.allreduce = saved
+      if saved is not None:
+        main.overlap = overlap
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     return segs

@@ -6,6 +6,7 @@ any primitive.  torch is used for device memory and streams only; every method
 enqueues hand-written CUDA kernels through the C-ABI on torch's current stream
 (so a torch.cuda.graph capture records them).
 """
+import contextlib
 import ctypes
 import os
 import pathlib
@@ -223,6 +224,21 @@ class CudaBackend:
   def _ck(self, rc):
     if rc != 0:
       raise RuntimeError(self.lib.dd_last_error().decode())
+
+  @contextlib.contextmanager
+  def branch(self):
+    """Launches issued inside run on a second stream, ordered after everything issued so far on
+    the current one; `join()` orders the current stream after them.  Under stream capture both
+    become edges of the graph, so the two branches replay concurrently."""
+    cur = torch.cuda.current_stream(self.device)
+    if getattr(self, '_side', None) is None:
+      self._side = torch.cuda.Stream(device=self.device)      # default (lowest) priority
+    self._side.wait_stream(cur)
+    with torch.cuda.stream(self._side):
+      yield
+
+  def join(self):
+    torch.cuda.current_stream(self.device).wait_stream(self._side)
 
   def set_gemm_tc(self, on):
     return self.lib.dd_set_gemm_tc(int(on))

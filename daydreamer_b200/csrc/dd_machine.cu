@@ -151,7 +151,7 @@ __device__ __forceinline__ void trace_ev(const Ctx& cx, int role, uint32_t idx) 
   if (cx.trace != nullptr && idx < (uint32_t)TRACE_N && (threadIdx.x & 31) == 0)
     cx.trace[role * TRACE_N + idx] = (unsigned long long)clock64();
 }
-enum { F_NOMMA = 1, F_NOA = 2, F_LOCALA = 4, F_NOB = 8, F_TMFENCE = 16, F_ONLY1 = 32, F_ONLY2 = 64 };
+enum { F_NOMMA = 1, F_NOA = 2, F_LOCALA = 4, F_NOB = 8, F_TMFENCE = 16 };
 __device__ __noinline__ void stuck(const Ctx& cx, int code, uint32_t parity) {
   if (cx.dbg != nullptr) {
     cx.dbg[1] = (unsigned)code;
@@ -430,12 +430,27 @@ __device__ __forceinline__ void k_range(int kbc, int kh, int bn, int& lo, int& h
 // multicasts this CTA's 16-row slice of the activations to the 8 CTAs that work on the same
 // k-blocks (it is the one that waits for the previous layer's outputs).  Both arm the stage's
 // `full` barrier with their own byte count.
+// The three single-lane roles below are written for the instruction latency of ONE thread: a lone
+// warp issues a dependent instruction every ~5 cycles, so 40 instructions of index arithmetic per
+// k-step cost more than the MMA they feed (r02 trace: 920 cycles to issue 8 MMAs the tensor pipe
+// retires in 600, plus ~600 of ring bookkeeping per k-block).  Hence: stage index / phase are
+// counters (no % or /), shared-memory addresses and UMMA descriptors advance by constants, the
+// four k-steps of a full k-block are unrolled, and only lane 0 runs the loop at all.
+struct Ring {
+  uint32_t s, ph;                        // stage, phase parity of its `full` barrier
+  __device__ __forceinline__ void next(int stages) {
+    if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
+  }
+};
+
 template <int KS>
 __device__ void producer_b(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
                            int cluster_id, int nclusters, int lane, Ctx cx) {
   constexpr int STAGES = Geo<KS>::STAGES;
+  if (lane != 0) return;
   const int ntiles = (M + BM - 1) / BM;
   const int cs = rank % NS, kh = rank / NS;
+  Ring rg = {0u, 0u};
   uint32_t it = 0;
   int pair = 0;
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
@@ -443,41 +458,36 @@ __device__ void producer_b(const Shared& sh, const LmLayer* layers, int nlayers,
       const LmLayer& L = layers[l];
       cx.pair = pair;
       if (L.nseg == 0) continue;
-      if (lane == 0) {
-        tmap_acquire(&L.w_hi, (cx.flags & F_TMFENCE) != 0);
-        if (!L.w3d) tmap_acquire(&L.w_lo, (cx.flags & F_TMFENCE) != 0);
-      }
-      __syncwarp();
+      tmap_acquire(&L.w_hi, (cx.flags & F_TMFENCE) != 0);
+      if (!L.w3d) tmap_acquire(&L.w_lo, (cx.flags & F_TMFENCE) != 0);
       const int kb0 = (L.seg_k[0] + BK - 1) / BK, kbc = layer_kblocks(L);
       int k_lo, k_hi;
       k_range<KS>(kbc, kh, L.bn, k_lo, k_hi);
       const int nchunk = L.nchunk, bn = L.bn, chunk_stride = L.chunk_stride, w3d = L.w3d;
-      const int wk0[2] = {L.seg_wk0[0], L.seg_wk0[1]};
+      const int wk0 = L.seg_wk0[0], wk1 = L.seg_wk0[1] - kb0 * BK;     // k = wk + r * BK
       const bool active = cs < L.nactive && !(cx.flags & F_NOB);
       const uint32_t bytes = active ? 2u * (uint32_t)bn * BK * 4 : 0u;
+      const CUtensorMap* whi = &L.w_hi;
+      const CUtensorMap* wlo = &L.w_lo;
       int n = L.wn0 + cs * bn;
       for (int c = 0; c < nchunk; ++c, n += chunk_stride) {
         for (int r = k_lo; r < k_hi; ++r, ++it) {
-          const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
-          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-          const uint32_t full = sh.bars + BAR_FULL + 8 * s;
-          mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * s, ph ^ 1, cx, 1);   // protects smem reuse only
+          const uint32_t full = sh.bars + BAR_FULL + 8 * rg.s;
+          mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * rg.s, rg.ph ^ 1u, cx, 1);   // smem reuse only
           trace_ev(cx, 0, 4 * it);
-          if (lane == 0) {
-            mbar_arrive_tx(full, bytes);
-            if (active) {
-              const uint32_t st = sh.base + s * STAGE_BYTES + 2 * A_BYTES;
-              const int k = wk0[seg] + kb * BK;
-              if (w3d) {             // rows [0, bn) = w, rows [bn, 2 bn) = w_lo: one box
-                tma_load_3d(st, &L.w_hi, k, n, 0, full);
-              } else {
-                tma_load(st, &L.w_hi, k, n, full);
-                tma_load(st + (uint32_t)bn * (BK * 4), &L.w_lo, k, n, full);
-              }
+          mbar_arrive_tx(full, bytes);
+          if (active) {
+            const uint32_t st = sh.base + rg.s * STAGE_BYTES + 2 * A_BYTES;
+            const int k = (r < kb0 ? wk0 : wk1) + r * BK;
+            if (w3d) {               // rows [0, bn) = w, rows [bn, 2 bn) = w_lo: one box
+              tma_load_3d(st, whi, k, n, 0, full);
+            } else {
+              tma_load(st, whi, k, n, full);
+              tma_load(st + (uint32_t)bn * (BK * 4), wlo, k, n, full);
             }
           }
-          __syncwarp();
           trace_ev(cx, 0, 4 * it + 1);
+          rg.next(STAGES);
         }
       }
     }
@@ -488,9 +498,12 @@ template <int KS>
 __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
                            int cluster_id, int nclusters, int lane, Ctx cx) {
   constexpr int STAGES = Geo<KS>::STAGES;
+  if (lane != 0) return;
   const int ntiles = (M + BM - 1) / BM;
   const int cs = rank % NS, kh = rank / NS;
   const uint16_t mask = (uint16_t)(0xFFu << (NS * kh));      // the CTAs sharing my k-blocks
+  const bool noa = (cx.flags & F_NOA) != 0;
+  Ring rg = {0u, 0u};
   uint32_t it = 0;
   int pair = 0;
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
@@ -499,40 +512,39 @@ __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers,
       const LmLayer& L = layers[l];
       cx.pair = pair;
       if (L.nseg == 0) continue;
-      if (lane == 0) {
-        for (int g = 0; g < L.nseg; ++g) {
-          tmap_acquire(&L.a_hi[g], (cx.flags & F_TMFENCE) != 0);
-          if (!L.seg_exact[g]) tmap_acquire(&L.a_lo[g], (cx.flags & F_TMFENCE) != 0);
-        }
+      for (int g = 0; g < L.nseg; ++g) {
+        tmap_acquire(&L.a_hi[g], (cx.flags & F_TMFENCE) != 0);
+        if (!L.seg_exact[g]) tmap_acquire(&L.a_lo[g], (cx.flags & F_TMFENCE) != 0);
       }
-      __syncwarp();
       const int kb0 = (L.seg_k[0] + BK - 1) / BK, kbc = layer_kblocks(L);
       int k_lo, k_hi;
       k_range<KS>(kbc, kh, L.bn, k_lo, k_hi);
       const int nchunk = L.nchunk;
-      const bool exact[2] = {L.seg_exact[0] != 0, L.seg_exact[1] != 0};
+      const bool exact0 = L.seg_exact[0] != 0, exact1 = L.seg_exact[1] != 0;
+      const CUtensorMap* ah0 = &L.a_hi[0];
+      const CUtensorMap* al0 = &L.a_lo[0];
+      const CUtensorMap* ah1 = &L.a_hi[1];
+      const CUtensorMap* al1 = &L.a_lo[1];
       if (l > 0) {           // the previous layer's outputs of every CTA are in global memory
         count_wait(sh.bars + BAR_READY, (uint32_t)pair * Geo<KS>::CLS, cx, 2);
         asm volatile("fence.proxy.async;" ::: "memory");
       }
       for (int c = 0; c < nchunk; ++c) {
         for (int r = k_lo; r < k_hi; ++r, ++it) {
-          const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
-          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-          const uint32_t full = sh.bars + BAR_FULL + 8 * s;
-          mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * s, ph ^ 1, cx, 9);
+          const bool s1 = r >= kb0;
+          const bool exact = s1 ? exact1 : exact0;
+          const uint32_t full = sh.bars + BAR_FULL + 8 * rg.s;
+          mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * rg.s, rg.ph ^ 1u, cx, 9);
           trace_ev(cx, 0, 4 * it + 2);
-          if (lane == 0) {
-            const bool noa = (cx.flags & F_NOA) != 0;
-            mbar_arrive_tx(full, noa ? 0u : (exact[seg] ? 1u : 2u) * A_BYTES);
-            if (!noa) {
-              const uint32_t st = sh.base + s * STAGE_BYTES + cs * SLICE_BYTES;
-              tma_load_mc(st, &L.a_hi[seg], kb * BK, m, full, mask);
-              if (!exact[seg]) tma_load_mc(st + A_BYTES, &L.a_lo[seg], kb * BK, m, full, mask);
-            }
+          mbar_arrive_tx(full, noa ? 0u : (exact ? 1u : 2u) * A_BYTES);
+          if (!noa) {
+            const uint32_t st = sh.base + rg.s * STAGE_BYTES + cs * SLICE_BYTES;
+            const int k = (s1 ? r - kb0 : r) * BK;
+            tma_load_mc(st, s1 ? ah1 : ah0, k, m, full, mask);
+            if (!exact) tma_load_mc(st + A_BYTES, s1 ? al1 : al0, k, m, full, mask);
           }
-          __syncwarp();
           trace_ev(cx, 0, 4 * it + 3);
+          rg.next(STAGES);
         }
       }
     }
@@ -543,9 +555,16 @@ template <int KS>
 __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
                            int cluster_id, int nclusters, int lane, uint32_t tmem_base, Ctx cx) {
   constexpr int STAGES = Geo<KS>::STAGES;
+  if (lane != 0) return;
   const int ntiles = (M + BM - 1) / BM;
   const int cs = rank % NS, kh = rank / NS;
   const uint16_t mask = (uint16_t)(0xFFu << (NS * kh));
+  const bool nomma = (cx.flags & F_NOMMA) != 0;
+  // descriptors of stage 0; stage s adds s * STAGE_BYTES and k-step ks adds 32 bytes, both in the
+  // descriptor's 16-byte units (the address field cannot carry: every sum is a valid smem address)
+  const uint64_t d_ahi0 = make_desc(sh.base), d_alo0 = make_desc(sh.base + A_BYTES);
+  const uint64_t d_b0 = make_desc(sh.base + 2 * A_BYTES);
+  Ring rg = {0u, 0u};
   uint32_t it = 0, ac = 0;
   int pair = 0;
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
@@ -561,8 +580,12 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
       const bool active = cs < L.nactive;
       const int bn = L.bn, nchunk = L.nchunk;
       const uint32_t idesc = make_idesc(bn), idesc2 = make_idesc(2 * bn);
-      const int segk[2] = {L.seg_k[0], L.seg_k[1]};
-      const bool sexact[2] = {L.seg_exact[0] != 0, L.seg_exact[1] != 0};
+      // k-steps of the last (possibly partial) k-block of each segment
+      const int last0 = kb0 - 1, last1 = kbc - 1;
+      const int ks_last0 = ((L.seg_k[0] - last0 * BK) + 7) >> 3;
+      const int ks_last1 = L.nseg > 1 ? ((L.seg_k[1] - (last1 - kb0) * BK) + 7) >> 3 : 4;
+      const bool exact0 = L.seg_exact[0] != 0, exact1 = L.seg_exact[1] != 0;
+      const bool issue = active && !nomma;
       for (int c = 0; c < nchunk; ++c) {
         const uint32_t buf = ac & 1;
         if (active) {
@@ -573,35 +596,43 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
         const uint32_t d_main = tmem_base + buf * 128, d_cross = d_main + (uint32_t)bn;
         uint32_t acc = 0;
         for (int r = k_lo; r < k_hi; ++r, ++it) {
-          const int seg = r < kb0 ? 0 : 1, kb = seg ? r - kb0 : r;
-          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-          mbar_wait<false>(sh.bars + BAR_FULL + 8 * s, ph, cx, 4);
+          const bool s1 = r >= kb0;
+          const bool exact = s1 ? exact1 : exact0;
+          const int ksteps = r == last0 ? ks_last0 : (r == last1 ? ks_last1 : 4);
+          mbar_wait<false>(sh.bars + BAR_FULL + 8 * rg.s, rg.ph, cx, 4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           trace_ev(cx, 1, 4 * it);
-          if (lane == 0) {
-            if (active && !(cx.flags & F_NOMMA)) {
-              const uint32_t a_hi = sh.base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
-              const uint32_t b_hi = a_hi + 2 * A_BYTES;
-              const int kvalid = min(BK, segk[seg] - kb * BK);
-              const int ksteps = (kvalid + 7) >> 3;
-              const bool exact = sexact[seg];
+          if (issue) {
+            const uint64_t so = (uint64_t)(rg.s * (STAGE_BYTES >> 4));
+            const uint64_t dah = d_ahi0 + so, dal = d_alo0 + so, dbh = d_b0 + so;
+            // B_hi and B_lo are rows [0, bn) and [bn, 2 bn) of ONE K-major tile: a single
+            // N = 2 bn product gives hi.hi (main) and hi.lo (cross) with one read of A_hi
+            if (ksteps == 4 && !exact) {
+              mma_tf32(d_main, dah, dbh, idesc2, acc);
+              mma_tf32(d_cross, dal, dbh, idesc, 1u);
+#pragma unroll
+              for (int ks = 1; ks < 4; ++ks) {
+                mma_tf32(d_main, dah + 2 * ks, dbh + 2 * ks, idesc2, 1u);
+                mma_tf32(d_cross, dal + 2 * ks, dbh + 2 * ks, idesc, 1u);
+              }
+            } else if (ksteps == 4) {
+              mma_tf32(d_main, dah, dbh, idesc2, acc);
+#pragma unroll
+              for (int ks = 1; ks < 4; ++ks) mma_tf32(d_main, dah + 2 * ks, dbh + 2 * ks, idesc2, 1u);
+            } else {
               for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t dah = make_desc(a_hi + ks * 32), dbh = make_desc(b_hi + ks * 32);
-                // B_hi and B_lo are rows [0, bn) and [bn, 2 bn) of ONE K-major tile: a single
-                // N = 2 bn product gives hi.hi (main) and hi.lo (cross) with one read of A_hi
-                if (!(cx.flags & F_ONLY2)) mma_tf32(d_main, dah, dbh, idesc2, acc);
-                acc = 1;
-                if (!exact && !(cx.flags & F_ONLY1)) mma_tf32(d_cross, make_desc(a_lo + ks * 32), dbh, idesc, 1u);
+                mma_tf32(d_main, dah + 2 * ks, dbh + 2 * ks, idesc2, ks == 0 ? acc : 1u);
+                if (!exact) mma_tf32(d_cross, dal + 2 * ks, dbh + 2 * ks, idesc, 1u);
               }
             }
-            if (cx.trace != nullptr && 4 * it + 2 < (uint32_t)TRACE_N) cx.trace[TRACE_N + 4 * it + 2] = (unsigned long long)clock64();
-            // this stage may be refilled once every CTA that received it has read it
-            umma_commit_mc(sh.bars + BAR_EMPTY + 8 * s, mask);
-            if (active && r == k_hi - 1) umma_commit(sh.bars + BAR_ACCF + 8 * buf);
-            if (cx.trace != nullptr && 4 * it + 3 < (uint32_t)TRACE_N) cx.trace[TRACE_N + 4 * it + 3] = (unsigned long long)clock64();
+            acc = 1;
           }
-          __syncwarp();
+          trace_ev(cx, 1, 4 * it + 2);
+          // this stage may be refilled once every CTA that received it has read it
+          umma_commit_mc(sh.bars + BAR_EMPTY + 8 * rg.s, mask);
+          if (active && r == k_hi - 1) umma_commit(sh.bars + BAR_ACCF + 8 * buf);
           trace_ev(cx, 1, 4 * it + 1);
+          rg.next(STAGES);
         }
         if (active) ++ac;
       }

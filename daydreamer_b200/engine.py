@@ -716,11 +716,15 @@ class Engine:
     R = (H + 1) * N
     wide = max(3 * D, SC, U, s.head_units, s.trunk('dec')[1], E)
     self._tmp = [z(R * wide) for _ in range(3)]
+    # second pool for the launches of a concurrent branch (launch_step: critic next to actor)
+    self.overlap = os.environ.get('DD_OVERLAP', '1') != '0'
+    self._tmp_alt = [z(R * max(s.head_units, 1)) for _ in range(3)] if self.overlap else None
     # machine: per-layer dZ (+ remainder) of the trunk being differentiated (trunks run one after
     # another, so one pool serves them all), remainders of the GEMM-operand activations
     umax = max(U, s.head_units, s.trunk('dec')[1], E)
     nl = max(s.head_layers, s.enc_layers, s.prior_layers, s.trunk('dec')[0])
     self._dzp = [z(R * umax) for _ in range(2 * nl)] if self.machine else []
+    self._dzp_alt = [z(R * umax) for _ in range(2 * nl)] if self.machine_bwd and self.overlap else []
     self.obs_lo = z(N, s.obs_total) if self.machine and s.obs_total else None
     self.feat_lo = z(N, D) if self.machine else None
 
@@ -1384,6 +1388,7 @@ class Engine:
                                  PG.EPI_STATS, bias=gm.P('rssm/img_stats/bias'), out=self.tlogit[t + 1],
                                  x0=self.g_img[t], x1=tf[t + 1][:, D:], f0=s.rssm_unimix, ipar=s.classes))
           actor_layers(t + 1)
+        self._rollout_layers = layers            # kept for scripts/rollout_prof.py
         self._rollout = be.program_build(layers, N)
     if self._rollout is None:
       return False
@@ -1519,6 +1524,13 @@ class Engine:
                   self.r_reward, self.r_value, self.r_cont, self.r_weight, self.r_ret)
 
   def critic_update(self):
+    self.critic_grads()
+    self.critic_apply()
+
+  def critic_grads(self):
+    """Critic loss, its gradients and metrics (A/agent.py:417-442).  Reads the trajectory and the
+    lambda-returns only and writes nothing the actor update reads, so launch_step may issue it on a
+    second stream next to the reverse rollout (whose 800-row products leave most SMs idle)."""
     s, be, gc = self.spec, self.be, self.groups['critic']
     N, H = self.N, self.H
     M = H * N
@@ -1538,6 +1550,9 @@ class Engine:
     self._stat(self.vsym, 'imag_critic')
     self._stat(self.r_ret, 'imag_return')
     self._stat(self.closs_row, 'closs')
+
+  def critic_apply(self):
+    s, be, gc = self.spec, self.be, self.groups['critic']
     self.opt_step('critic', C_CRITIC)
     be.slow_sync(gc.p, self.groups['slow_critic'].p, self.counters, C_SLOW, s.slow_every)
     self.groups['slow_critic'].prep(be)
@@ -1703,8 +1718,24 @@ class Engine:
     self.be.copy_(self.cont0.view(-1, 1), self.cont)
     self.imagine()
     self.traj_values()
-    self.critic_update()
-    self.actor_update(slow_refreshed)
+    if self.overlap and not slow_refreshed and hasattr(self.be, 'branch'):
+      # the slow critic the actor scores with is not refreshed this step: critic and actor updates
+      # are independent until their optimizers.  No collective is issued on the second stream (one
+      # communicator must not run on two streams at once): the critic's all-reduce follows the join.
+      with self.be.branch():
+        self._tmp, self._tmp_alt = self._tmp_alt, self._tmp
+        self._dzp, self._dzp_alt = self._dzp_alt, self._dzp
+        try:
+          self.critic_grads()
+        finally:
+          self._tmp, self._tmp_alt = self._tmp_alt, self._tmp
+          self._dzp, self._dzp_alt = self._dzp_alt, self._dzp
+      self.actor_update(False)
+      self.be.join()
+      self.critic_apply()
+    else:
+      self.critic_update()
+      self.actor_update(slow_refreshed)
 
   def launch_report(self, draw=True):
     """WorldModel.report's scalar part (A/agent.py:266-268): the loss metrics of

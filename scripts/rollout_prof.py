@@ -39,9 +39,23 @@ for name, fn in (('imagine', eng.imagine),):
   be.lib.dd_machine_prof(1, None, 0)
   fn()
   torch.cuda.synchronize()
-  buf = (ctypes.c_ulonglong * (148 * 16))()
-  be.lib.dd_machine_prof(0, buf, 148 * 16)
-  arr = np.array(buf[:], dtype=np.float64).reshape(148, 16)
+  TN = 2048
+  buf = (ctypes.c_ulonglong * (148 * 16 + 4 * TN))()
+  be.lib.dd_machine_prof(0, buf, 148 * 16 + 4 * TN)
+  arr = np.array(buf[:148 * 16], dtype=np.float64).reshape(148, 16)
+  tr = np.array(buf[148 * 16:], dtype=np.float64).reshape(4, TN)
+  # CTA 0's timeline of the first layers: epilogue events per (tile, layer) pair, relative cycles
+  EPI = ['PLAIN', 'LN', 'LNBWD', 'GRU', 'STATS', 'ACTOR', 'STATSBWD', 'GRUBWD']
+  layers = getattr(eng, '_rollout_layers', [])
+  t0 = tr[3, 0]
+  rel = lambda x: int(x - t0) if x > 0 else -1
+  print('  pair epi    N  kblk | k-loop  epilogue  publish  to-next-start   (cycles; k-loop = start -> accumulator full)')
+  for pr in range(min(len(layers), 40)):
+    e = [rel(tr[2, 16 * pr + k]) for k in range(12)]
+    nxt = rel(tr[2, 16 * (pr + 1)]) if pr + 1 < len(layers) else -1
+    L = layers[pr]
+    kb = sum((sg.a.shape[1] + 31) // 32 for sg in L.segs) * max(1, L.N // 512)
+    print(f'  {pr:4d} {EPI[L.epi]:6s} {L.N:4d} {kb:5d} | {e[1] - e[0]:6d} {e[9] - e[1]:9d} {e[11] - e[9]:8d} {nxt - e[11]:8d}')
   used = arr[arr[:, 0] > 0]
   avg = used.mean(0)
   print(f'{name}: {ms:.3f} ms, {len(used)} CTAs, kernel {avg[0]:.0f} cycles/CTA -> effective clock '

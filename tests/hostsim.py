@@ -13,6 +13,7 @@ The product never imports this file: daydreamer_b200.backend.CudaBackend is the
 only backend the Agent constructs, and it raises if the .so or the GPU is
 missing.
 """
+import contextlib
 import math
 
 import numpy as np
@@ -34,6 +35,14 @@ class HostSim:
 
   def upload(self, array, dtype=torch.float32):
     return torch.as_tensor(np.ascontiguousarray(array)).to(dtype).clone()
+
+  @contextlib.contextmanager
+  def branch(self):
+    """CudaBackend.branch: a second stream.  Here: the same launch order, issued serially."""
+    yield
+
+  def join(self):
+    pass
 
   def sync(self):
     pass
