@@ -78,6 +78,12 @@ __device__ __forceinline__ void warp_mbar_arrive(uint32_t bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
@@ -260,7 +266,8 @@ gemm_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index broadcast from lane 0: the role dispatch compiles as warp-uniform control flow
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int kbeg = blockIdx.z * klen;
   const int kend = min(K, kbeg + klen);
@@ -439,7 +446,10 @@ gemm_tc_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B
       const uint32_t ph = (kb / STAGES) & 1;
       mbar_wait(full0 + 8 * s, ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
+      // all lanes walk the loop; only the MMA / commit instructions are predicated on the elected
+      // lane, so their operands stay in uniform registers (with `if (lane == 0)` around a diverged
+      // region every tcgen05.mma was wrapped in an ELECT + R2UR waterfall: ~80 cycles per MMA)
+      if (elect_one()) {
         const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
         const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
@@ -505,7 +515,8 @@ gemm_tc_persistent_kernel(const float* __restrict__ A, int lda, const float* __r
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index broadcast from lane 0: the role dispatch compiles as warp-uniform control flow
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int tiles_n = (N + BN - 1) / BN, tiles_m = (M + BM - 1) / BM;
   const int ntiles = tiles_m * tiles_n;
   const int nkb = (K + BK - 1) / BK;
@@ -652,7 +663,7 @@ gemm_tc_persistent_kernel(const float* __restrict__ A, int lda, const float* __r
         const uint32_t ph = (uint32_t)((it / STAGES) & 1);
         mbar_wait(full0 + 8 * s, ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + A_BYTES;
           const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll

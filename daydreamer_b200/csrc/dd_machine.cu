@@ -165,24 +165,30 @@ __device__ __noinline__ void stuck(const Ctx& cx, int code, uint32_t parity) {
   __trap();
 }
 template <bool CLUSTER>
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const Ctx& cx, int code) {
-  uint32_t done = 0;
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  if (CLUSTER)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
+// the waiting path (watchdog, wait-cycle accounting) sits behind the first poll: a wait that is
+// already satisfied -- the common case in the single-lane roles -- costs one poll and one branch
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, const Ctx& cx, int code) {
   unsigned long long t0 = 0;
   const long long c0 = cx.prof != nullptr ? clock64() : 0;
   for (uint32_t spin = 0;; ++spin) {
-    if (CLUSTER)
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.b32 %0, 1, 0, p;\n\t}"
-          : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    else
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.b32 %0, 1, 0, p;\n\t}"
-          : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) {
+    if (mbar_try<CLUSTER>(bar, parity)) {
       if (cx.prof != nullptr && (threadIdx.x & 31) == 0)
         atomicAdd(cx.prof + code, (unsigned long long)(clock64() - c0));
       return;
@@ -194,6 +200,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const C
       else if (t - t0 > 2000000000ull) stuck(cx, code, parity);
     }
   }
+}
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, const Ctx& cx, int code) {
+  if (mbar_try<CLUSTER>(bar, parity)) return;
+  mbar_wait_slow<CLUSTER>(bar, parity, cx, code);
 }
 
 __device__ __forceinline__ void count_wait(uint32_t addr, uint32_t target, const Ctx& cx, int code) {
@@ -430,24 +441,43 @@ __device__ __forceinline__ void k_range(int kbc, int kh, int bn, int& lo, int& h
 // multicasts this CTA's 16-row slice of the activations to the 8 CTAs that work on the same
 // k-blocks (it is the one that waits for the previous layer's outputs).  Both arm the stage's
 // `full` barrier with their own byte count.
-// The three single-lane roles below are written for the instruction latency of ONE thread: a lone
-// warp issues a dependent instruction every ~5 cycles, so 40 instructions of index arithmetic per
-// k-step cost more than the MMA they feed (r02 trace: 920 cycles to issue 8 MMAs the tensor pipe
-// retires in 600, plus ~600 of ring bookkeeping per k-block).  Hence: stage index / phase are
-// counters (no % or /), shared-memory addresses and UMMA descriptors advance by constants, the
-// four k-steps of a full k-block are unrolled, and only lane 0 runs the loop at all.
+// The producer and issuer roles run WARP-UNIFORM: all 32 lanes walk the loops with values the
+// compiler can prove identical across the warp (shuffle-broadcast layer fields, counters), and only
+// the TMA / MMA / commit instructions themselves sit under an elected-lane predicate.  Those
+// instructions take their operands from uniform registers: when the loop ran on one lane of a
+// diverged warp instead, every one of them was wrapped in an ELECT + 7 x R2UR + branch "waterfall"
+// and a lone thread at ~5 cycles per dependent instruction needed 80 cycles per MMA and ~470
+// cycles of ring bookkeeping per k-block (r02 trace), more than the tensor pipe needs for the
+// MMAs themselves.  Stage index / phase are counters (no % or /), descriptors advance by constants.
 struct Ring {
   uint32_t s, ph;                        // stage, phase parity of its `full` barrier
   __device__ __forceinline__ void next(int stages) {
     if (++s == (uint32_t)stages) { s = 0; ph ^= 1u; }
   }
 };
+__device__ __forceinline__ int ubc(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// the scalar fields of a layer the single-issue roles steer by, made warp-uniform
+struct LayerU {
+  int nseg, k0, k1, wk0, wk1, wn0, bn, nchunk, chunk_stride, nactive, w3d, exact0, exact1;
+  __device__ __forceinline__ void load(const LmLayer& L) {
+    nseg = ubc(L.nseg); k0 = ubc(L.seg_k[0]); k1 = ubc(L.seg_k[1]);
+    wk0 = ubc(L.seg_wk0[0]); wk1 = ubc(L.seg_wk0[1]); wn0 = ubc(L.wn0); bn = ubc(L.bn);
+    nchunk = ubc(L.nchunk); chunk_stride = ubc(L.chunk_stride); nactive = ubc(L.nactive);
+    w3d = ubc(L.w3d); exact0 = ubc(L.seg_exact[0]); exact1 = ubc(L.seg_exact[1]);
+  }
+  __device__ __forceinline__ int kb0() const { return (k0 + BK - 1) / BK; }
+  __device__ __forceinline__ int kbc() const { return kb0() + (nseg > 1 ? (k1 + BK - 1) / BK : 0); }
+};
 
 template <int KS>
 __device__ void producer_b(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
                            int cluster_id, int nclusters, int lane, Ctx cx) {
   constexpr int STAGES = Geo<KS>::STAGES;
-  if (lane != 0) return;
   const int ntiles = (M + BM - 1) / BM;
   const int cs = rank % NS, kh = rank / NS;
   Ring rg = {0u, 0u};
@@ -456,34 +486,40 @@ __device__ void producer_b(const Shared& sh, const LmLayer* layers, int nlayers,
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
     for (int l = 0; l < nlayers; ++l, ++pair) {
       const LmLayer& L = layers[l];
+      LayerU u;
+      u.load(L);
       cx.pair = pair;
-      if (L.nseg == 0) continue;
-      tmap_acquire(&L.w_hi, (cx.flags & F_TMFENCE) != 0);
-      if (!L.w3d) tmap_acquire(&L.w_lo, (cx.flags & F_TMFENCE) != 0);
-      const int kb0 = (L.seg_k[0] + BK - 1) / BK, kbc = layer_kblocks(L);
+      if (u.nseg == 0) continue;
+      if (elect_one()) {
+        tmap_acquire(&L.w_hi, (cx.flags & F_TMFENCE) != 0);
+        if (!u.w3d) tmap_acquire(&L.w_lo, (cx.flags & F_TMFENCE) != 0);
+      }
+      const int kb0 = u.kb0(), kbc = u.kbc();
       int k_lo, k_hi;
-      k_range<KS>(kbc, kh, L.bn, k_lo, k_hi);
-      const int nchunk = L.nchunk, bn = L.bn, chunk_stride = L.chunk_stride, w3d = L.w3d;
-      const int wk0 = L.seg_wk0[0], wk1 = L.seg_wk0[1] - kb0 * BK;     // k = wk + r * BK
-      const bool active = cs < L.nactive && !(cx.flags & F_NOB);
+      k_range<KS>(kbc, kh, u.bn, k_lo, k_hi);
+      const int bn = u.bn;
+      const int wk0 = u.wk0, wk1 = u.wk1 - kb0 * BK;     // k = wk + r * BK
+      const bool active = cs < u.nactive && !(cx.flags & F_NOB);
       const uint32_t bytes = active ? 2u * (uint32_t)bn * BK * 4 : 0u;
       const CUtensorMap* whi = &L.w_hi;
       const CUtensorMap* wlo = &L.w_lo;
-      int n = L.wn0 + cs * bn;
-      for (int c = 0; c < nchunk; ++c, n += chunk_stride) {
+      int n = u.wn0 + cs * bn;
+      for (int c = 0; c < u.nchunk; ++c, n += u.chunk_stride) {
         for (int r = k_lo; r < k_hi; ++r, ++it) {
           const uint32_t full = sh.bars + BAR_FULL + 8 * rg.s;
           mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * rg.s, rg.ph ^ 1u, cx, 1);   // smem reuse only
           trace_ev(cx, 0, 4 * it);
-          mbar_arrive_tx(full, bytes);
-          if (active) {
-            const uint32_t st = sh.base + rg.s * STAGE_BYTES + 2 * A_BYTES;
-            const int k = (r < kb0 ? wk0 : wk1) + r * BK;
-            if (w3d) {               // rows [0, bn) = w, rows [bn, 2 bn) = w_lo: one box
-              tma_load_3d(st, whi, k, n, 0, full);
-            } else {
-              tma_load(st, whi, k, n, full);
-              tma_load(st + (uint32_t)bn * (BK * 4), wlo, k, n, full);
+          if (elect_one()) {
+            mbar_arrive_tx(full, bytes);
+            if (active) {
+              const uint32_t st = sh.base + rg.s * STAGE_BYTES + 2 * A_BYTES;
+              const int k = (r < kb0 ? wk0 : wk1) + r * BK;
+              if (u.w3d) {               // rows [0, bn) = w, rows [bn, 2 bn) = w_lo: one box
+                tma_load_3d(st, whi, k, n, 0, full);
+              } else {
+                tma_load(st, whi, k, n, full);
+                tma_load(st + (uint32_t)bn * (BK * 4), wlo, k, n, full);
+              }
             }
           }
           trace_ev(cx, 0, 4 * it + 1);
@@ -498,7 +534,6 @@ template <int KS>
 __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
                            int cluster_id, int nclusters, int lane, Ctx cx) {
   constexpr int STAGES = Geo<KS>::STAGES;
-  if (lane != 0) return;
   const int ntiles = (M + BM - 1) / BM;
   const int cs = rank % NS, kh = rank / NS;
   const uint16_t mask = (uint16_t)(0xFFu << (NS * kh));      // the CTAs sharing my k-blocks
@@ -510,17 +545,20 @@ __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers,
     const int m = tile * BM + cs * SLICE_ROWS;
     for (int l = 0; l < nlayers; ++l, ++pair) {
       const LmLayer& L = layers[l];
+      LayerU u;
+      u.load(L);
       cx.pair = pair;
-      if (L.nseg == 0) continue;
-      for (int g = 0; g < L.nseg; ++g) {
-        tmap_acquire(&L.a_hi[g], (cx.flags & F_TMFENCE) != 0);
-        if (!L.seg_exact[g]) tmap_acquire(&L.a_lo[g], (cx.flags & F_TMFENCE) != 0);
+      if (u.nseg == 0) continue;
+      if (elect_one()) {
+        for (int g = 0; g < u.nseg; ++g) {
+          tmap_acquire(&L.a_hi[g], (cx.flags & F_TMFENCE) != 0);
+          if (!(g ? u.exact1 : u.exact0)) tmap_acquire(&L.a_lo[g], (cx.flags & F_TMFENCE) != 0);
+        }
       }
-      const int kb0 = (L.seg_k[0] + BK - 1) / BK, kbc = layer_kblocks(L);
+      const int kb0 = u.kb0(), kbc = u.kbc();
       int k_lo, k_hi;
-      k_range<KS>(kbc, kh, L.bn, k_lo, k_hi);
-      const int nchunk = L.nchunk;
-      const bool exact0 = L.seg_exact[0] != 0, exact1 = L.seg_exact[1] != 0;
+      k_range<KS>(kbc, kh, u.bn, k_lo, k_hi);
+      const bool exact0 = u.exact0 != 0, exact1 = u.exact1 != 0;
       const CUtensorMap* ah0 = &L.a_hi[0];
       const CUtensorMap* al0 = &L.a_lo[0];
       const CUtensorMap* ah1 = &L.a_hi[1];
@@ -529,19 +567,21 @@ __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers,
         count_wait(sh.bars + BAR_READY, (uint32_t)pair * Geo<KS>::CLS, cx, 2);
         asm volatile("fence.proxy.async;" ::: "memory");
       }
-      for (int c = 0; c < nchunk; ++c) {
+      for (int c = 0; c < u.nchunk; ++c) {
         for (int r = k_lo; r < k_hi; ++r, ++it) {
           const bool s1 = r >= kb0;
           const bool exact = s1 ? exact1 : exact0;
           const uint32_t full = sh.bars + BAR_FULL + 8 * rg.s;
           mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * rg.s, rg.ph ^ 1u, cx, 9);
           trace_ev(cx, 0, 4 * it + 2);
-          mbar_arrive_tx(full, noa ? 0u : (exact ? 1u : 2u) * A_BYTES);
-          if (!noa) {
-            const uint32_t st = sh.base + rg.s * STAGE_BYTES + cs * SLICE_BYTES;
-            const int k = (s1 ? r - kb0 : r) * BK;
-            tma_load_mc(st, s1 ? ah1 : ah0, k, m, full, mask);
-            if (!exact) tma_load_mc(st + A_BYTES, s1 ? al1 : al0, k, m, full, mask);
+          if (elect_one()) {
+            mbar_arrive_tx(full, noa ? 0u : (exact ? 1u : 2u) * A_BYTES);
+            if (!noa) {
+              const uint32_t st = sh.base + rg.s * STAGE_BYTES + cs * SLICE_BYTES;
+              const int k = (s1 ? r - kb0 : r) * BK;
+              tma_load_mc(st, s1 ? ah1 : ah0, k, m, full, mask);
+              if (!exact) tma_load_mc(st + A_BYTES, s1 ? al1 : al0, k, m, full, mask);
+            }
           }
           trace_ev(cx, 0, 4 * it + 3);
           rg.next(STAGES);
@@ -555,7 +595,6 @@ template <int KS>
 __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers, int M, int rank,
                            int cluster_id, int nclusters, int lane, uint32_t tmem_base, Ctx cx) {
   constexpr int STAGES = Geo<KS>::STAGES;
-  if (lane != 0) return;
   const int ntiles = (M + BM - 1) / BM;
   const int cs = rank % NS, kh = rank / NS;
   const uint16_t mask = (uint16_t)(0xFFu << (NS * kh));
@@ -569,24 +608,24 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
   int pair = 0;
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
     for (int l = 0; l < nlayers; ++l, ++pair) {
-      const LmLayer& L = layers[l];
+      LayerU u;
+      u.load(layers[l]);
       cx.pair = pair;
-      if (L.nseg == 0) continue;                 // epilogue-only layer
-      const int kb0 = (L.seg_k[0] + BK - 1) / BK;
-      const int kbc = layer_kblocks(L);
+      if (u.nseg == 0) continue;                 // epilogue-only layer
+      const int kb0 = u.kb0(), kbc = u.kbc();
       int k_lo, k_hi;
-      k_range<KS>(kbc, kh, L.bn, k_lo, k_hi);
+      k_range<KS>(kbc, kh, u.bn, k_lo, k_hi);
       if (k_hi <= k_lo) continue;                // nothing of this layer's k range is mine
-      const bool active = cs < L.nactive;
-      const int bn = L.bn, nchunk = L.nchunk;
+      const bool active = cs < u.nactive;
+      const int bn = u.bn;
       const uint32_t idesc = make_idesc(bn), idesc2 = make_idesc(2 * bn);
       // k-steps of the last (possibly partial) k-block of each segment
       const int last0 = kb0 - 1, last1 = kbc - 1;
-      const int ks_last0 = ((L.seg_k[0] - last0 * BK) + 7) >> 3;
-      const int ks_last1 = L.nseg > 1 ? ((L.seg_k[1] - (last1 - kb0) * BK) + 7) >> 3 : 4;
-      const bool exact0 = L.seg_exact[0] != 0, exact1 = L.seg_exact[1] != 0;
+      const int ks_last0 = ((u.k0 - last0 * BK) + 7) >> 3;
+      const int ks_last1 = u.nseg > 1 ? ((u.k1 - (last1 - kb0) * BK) + 7) >> 3 : 4;
+      const bool exact0 = u.exact0 != 0, exact1 = u.exact1 != 0;
       const bool issue = active && !nomma;
-      for (int c = 0; c < nchunk; ++c) {
+      for (int c = 0; c < u.nchunk; ++c) {
         const uint32_t buf = ac & 1;
         if (active) {
           mbar_wait<false>(sh.bars + BAR_ACCE + 8 * buf, ((ac >> 1) & 1) ^ 1, cx, 3);
@@ -602,35 +641,36 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
           mbar_wait<false>(sh.bars + BAR_FULL + 8 * rg.s, rg.ph, cx, 4);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           trace_ev(cx, 1, 4 * it);
-          if (issue) {
-            const uint64_t so = (uint64_t)(rg.s * (STAGE_BYTES >> 4));
-            const uint64_t dah = d_ahi0 + so, dal = d_alo0 + so, dbh = d_b0 + so;
-            // B_hi and B_lo are rows [0, bn) and [bn, 2 bn) of ONE K-major tile: a single
-            // N = 2 bn product gives hi.hi (main) and hi.lo (cross) with one read of A_hi
-            if (ksteps == 4 && !exact) {
-              mma_tf32(d_main, dah, dbh, idesc2, acc);
-              mma_tf32(d_cross, dal, dbh, idesc, 1u);
+          if (elect_one()) {
+            if (issue) {
+              const uint64_t so = (uint64_t)(rg.s * (STAGE_BYTES >> 4));
+              const uint64_t dah = d_ahi0 + so, dal = d_alo0 + so, dbh = d_b0 + so;
+              // B_hi and B_lo are rows [0, bn) and [bn, 2 bn) of ONE K-major tile: a single
+              // N = 2 bn product gives hi.hi (main) and hi.lo (cross) with one read of A_hi
+              if (ksteps == 4 && !exact) {
+                mma_tf32(d_main, dah, dbh, idesc2, acc);
+                mma_tf32(d_cross, dal, dbh, idesc, 1u);
 #pragma unroll
-              for (int ks = 1; ks < 4; ++ks) {
-                mma_tf32(d_main, dah + 2 * ks, dbh + 2 * ks, idesc2, 1u);
-                mma_tf32(d_cross, dal + 2 * ks, dbh + 2 * ks, idesc, 1u);
-              }
-            } else if (ksteps == 4) {
-              mma_tf32(d_main, dah, dbh, idesc2, acc);
+                for (int ks = 1; ks < 4; ++ks) {
+                  mma_tf32(d_main, dah + 2 * ks, dbh + 2 * ks, idesc2, 1u);
+                  mma_tf32(d_cross, dal + 2 * ks, dbh + 2 * ks, idesc, 1u);
+                }
+              } else if (ksteps == 4) {
+                mma_tf32(d_main, dah, dbh, idesc2, acc);
 #pragma unroll
-              for (int ks = 1; ks < 4; ++ks) mma_tf32(d_main, dah + 2 * ks, dbh + 2 * ks, idesc2, 1u);
-            } else {
-              for (int ks = 0; ks < ksteps; ++ks) {
-                mma_tf32(d_main, dah + 2 * ks, dbh + 2 * ks, idesc2, ks == 0 ? acc : 1u);
-                if (!exact) mma_tf32(d_cross, dal + 2 * ks, dbh + 2 * ks, idesc, 1u);
+                for (int ks = 1; ks < 4; ++ks) mma_tf32(d_main, dah + 2 * ks, dbh + 2 * ks, idesc2, 1u);
+              } else {
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  mma_tf32(d_main, dah + 2 * ks, dbh + 2 * ks, idesc2, ks == 0 ? acc : 1u);
+                  if (!exact) mma_tf32(d_cross, dal + 2 * ks, dbh + 2 * ks, idesc, 1u);
+                }
               }
             }
-            acc = 1;
+            // this stage may be refilled once every CTA that received it has read it
+            umma_commit_mc(sh.bars + BAR_EMPTY + 8 * rg.s, mask);
+            if (active && r == k_hi - 1) umma_commit(sh.bars + BAR_ACCF + 8 * buf);
           }
-          trace_ev(cx, 1, 4 * it + 2);
-          // this stage may be refilled once every CTA that received it has read it
-          umma_commit_mc(sh.bars + BAR_EMPTY + 8 * rg.s, mask);
-          if (active && r == k_hi - 1) umma_commit(sh.bars + BAR_ACCF + 8 * buf);
+          acc = 1;
           trace_ev(cx, 1, 4 * it + 1);
           rg.next(STAGES);
         }
@@ -1492,8 +1532,10 @@ lm_kernel(const LmLayer* __restrict__ layers, int nlayers, int M, unsigned* dbg,
           unsigned long long* prof, int flags) {
   using G = Geo<KS>;
   extern __shared__ __align__(1024) char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rank = (int)cluster_rank();
+  // warp index and cluster rank broadcast from lane 0: the role dispatch and everything steered by
+  // them compiles as warp-uniform control flow
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const int rank = __shfl_sync(0xffffffffu, (int)cluster_rank(), 0);
   const int cluster_id = blockIdx.x / G::CLS, nclusters = gridDim.x / G::CLS;
   Shared sh;
   sh.smem = smem;

@@ -245,12 +245,6 @@ int main() {
       {1, M_COMMIT | M_ONLY1, "4 MMAs N=128 + local commit"},
       {1, M_COMMIT | M_ONLY1 | M_WAIT, "4 MMAs N=128 + local commit, ring waits"},
       {1, M_COMMIT | M_N256, "4 MMAs N=256 + local commit"},
-      {8, M_COMMIT | M_MC, "8 MMAs + multicast commit (cluster 8)"},
-      {8, M_COMMIT | M_MC | M_WAIT, "8 MMAs + multicast commit, ring of 3 waits (cluster 8)"},
-      {8, M_COMMIT | M_MC | M_WAIT | M_ONLY1, "4 MMAs N=128 + multicast commit, ring waits (cluster 8)"},
-      {8, M_COMMIT | M_MC | M_WAIT | M_SEPARATE, "8 MMAs separate + multicast commit, ring waits (cluster 8)"},
-      {8, M_COMMIT | M_MC | M_WAIT | M_N256, "4 MMAs N=256 + multicast commit, ring waits (cluster 8)"},
-      {8, M_COMMIT | M_WAIT, "8 MMAs + local commit, ring waits (cluster 8 launch)"},
   };
   for (int grid : {8, 56})
     for (auto& c : cases) {
@@ -266,9 +260,6 @@ int main() {
     report_fast<M_FAST | M_COMMIT | M_WAIT>(1, grid, "lean: 8 MMAs + local commit, ring waits", out);
     report_fast<M_FAST | M_COMMIT | M_WAIT | M_ONLY1>(1, grid, "lean: 4 MMAs N=128 + local commit, ring waits", out);
     report_fast<M_FAST | M_COMMIT | M_WAIT | M_UNIFORM>(1, grid, "lean: 8 MMAs all N=128 (4 products) + local commit, ring waits", out);
-    report_fast<M_FAST | M_COMMIT | M_MC | M_WAIT>(8, grid, "lean: 8 MMAs + multicast commit, ring waits (cluster 8)", out);
-    report_fast<M_FAST | M_COMMIT | M_MC | M_WAIT | M_UNIFORM>(8, grid, "lean: 8 MMAs all N=128 + multicast commit, ring waits (cluster 8)", out);
-    report_fast<M_FAST | M_COMMIT | M_MC | M_WAIT | M_ONLY1>(8, grid, "lean: 4 MMAs N=128 + multicast commit, ring waits (cluster 8)", out);
   }
   return 0;
 }
