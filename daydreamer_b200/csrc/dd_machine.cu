@@ -322,10 +322,29 @@ __device__ __forceinline__ float elu_f(float y) { return y > 0.f ? y : __expf(y)
 // Thread `lane` owns row `lane` of the sub-tile in registers; global rows are `ld` floats apart.
 // Vector path (ld % 4 == 0, 16-byte aligned, all 32 columns valid): each global access covers 4
 // rows x 128 contiguous bytes.  Otherwise a guarded scalar path (narrow heads, N = 1 ... 31).
+// r02 A/B (profiles/r02_machine_epilogue_io.txt): loads are fastest row-per-lane (the second 16 bytes
+// of every 32-byte sector hit L1), stores are fastest through the staging buffer -- a row-per-lane
+// store touches 32 lines per instruction (256 LSU wavefronts per sub-tile against ~100 staged) and
+// made every forward epilogue 40 % longer.
+#ifndef DD_LM_STAGED_STORE
+#define DD_LM_STAGED_STORE 1
+#endif
+#ifndef DD_LM_STAGED_LOAD
+#define DD_LM_STAGED_LOAD 0
+#endif
 __device__ __forceinline__ void sub_store(float* stg, const float (&v)[32], float* g, int ld,
                                           int rows_valid, int cols_valid, int lane) {
   const bool vec = cols_valid >= 32 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
-  if (vec) {
+  if (vec && !DD_LM_STAGED_STORE) {
+    // every lane writes the 128 contiguous bytes of its own row: eight 16-byte stores, no trip
+    // through shared memory and no warp barriers (the sectors are half-filled per instruction, and
+    // the L2 write path is nowhere near a limit here)
+    if (lane < rows_valid) {
+      float4* row = reinterpret_cast<float4*>(g + (size_t)lane * ld);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) row[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  } else if (vec) {
     float4* srow = reinterpret_cast<float4*>(stg + lane * STG_LD);
 #pragma unroll
     for (int j = 0; j < 8; ++j) srow[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -346,7 +365,15 @@ __device__ __forceinline__ void sub_store(float* stg, const float (&v)[32], floa
 __device__ __forceinline__ void sub_load(float* stg, float (&v)[32], const float* g, int ld,
                                          int rows_valid, int cols_valid, int lane) {
   const bool vec = cols_valid >= 32 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0;
-  if (vec) {
+  if (vec && !DD_LM_STAGED_LOAD) {
+    const float4* row = reinterpret_cast<const float4*>(g + (size_t)(lane < rows_valid ? lane : 0) * ld);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < rows_valid) x = row[j];
+      v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+    }
+  } else if (vec) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = it * 4 + (lane >> 3), c4 = (lane & 7) * 4;
@@ -910,8 +937,7 @@ __device__ __forceinline__ void store_with_lo(const EP& L, Epi& e, float (&v)[32
 // With two warp groups per row the second group's partial is first folded into the first group's
 // through shared memory (a 64-thread named barrier per TMEM quadrant), so one thread per row sends.
 template <int KS>
-__device__ __forceinline__ void row_exchange(const EP& L, Epi& e, float a, float b, float& cnt, bool welford,
-                                             float2 (&parts)[Geo<KS>::SLOTS]) {
+__device__ __forceinline__ void row_send(const EP& L, Epi& e, float a, float b, float& cnt, bool welford) {
   constexpr int SLOTS = Geo<KS>::SLOTS;
   const bool two = Geo<KS>::EW == 8 && L.bn == 64;
   if (two) {
@@ -946,12 +972,27 @@ __device__ __forceinline__ void row_exchange(const EP& L, Epi& e, float a, float
       }
     }
   }
+}
+// ... and the other half: wait for every owner's partials of my rows (work that does not need them
+// -- storing the pre-norm values -- goes between row_send and row_recv)
+template <int KS>
+__device__ __forceinline__ void row_recv(const EP& L, Epi& e, float2 (&parts)[Geo<KS>::SLOTS]) {
+  constexpr int SLOTS = Geo<KS>::SLOTS;
+  const int nsl = n_slots<KS>(L);
+  const uint32_t par = e.xc & 1;
+  const uint32_t bar = e.sh.bars + BAR_STATS + 8 * par;
   mbar_wait<false>(bar, (e.xc >> 1) & 1, e.cx, 5);
   const float2* mine_ = reinterpret_cast<const float2*>(e.sh.smem + e.stats_off) + par * SLOTS * BM + e.trow;
 #pragma unroll
   for (int d = 0; d < SLOTS; ++d)
     if (d < nsl) parts[d] = mine_[d * BM];
   ++e.xc;
+}
+template <int KS>
+__device__ __forceinline__ void row_exchange(const EP& L, Epi& e, float a, float b, float& cnt, bool welford,
+                                             float2 (&parts)[Geo<KS>::SLOTS]) {
+  row_send<KS>(L, e, a, b, cnt, welford);
+  row_recv<KS>(L, e, parts);
 }
 
 // running (count, mean, M2) of a row += one 32-column sub-tile
@@ -968,12 +1009,19 @@ __device__ __forceinline__ void welford32(const float (&v)[32], float& mean, flo
   m2 += q + delta * delta * (cnt * 32.f / tot);
   cnt = tot;
 }
+template <int KS>
+__device__ __forceinline__ void ln_recv(const EP& L, Epi& e, float cnt, float& gm, float& rstd);
 // merge the owners' equal-count partials into (mean, rstd) of the full row
 template <int KS>
 __device__ __forceinline__ void ln_finish(const EP& L, Epi& e, float mean, float m2, float cnt,
                                           float& gm, float& rstd) {     // cnt by value: doubled by the local merge
+  row_send<KS>(L, e, mean, m2, cnt, true);
+  ln_recv<KS>(L, e, cnt, gm, rstd);
+}
+template <int KS>
+__device__ __forceinline__ void ln_recv(const EP& L, Epi& e, float cnt, float& gm, float& rstd) {
   float2 parts[Geo<KS>::SLOTS];
-  row_exchange<KS>(L, e, mean, m2, cnt, true, parts);
+  row_recv<KS>(L, e, parts);
   const int nsl = n_slots<KS>(L);
   gm = 0.f;
   for (int d = 0; d < nsl; ++d) gm += parts[d].x;
@@ -1045,7 +1093,7 @@ __device__ void epi_ln_fwd(const EP& L, Epi& e) {
         const int cb = sub_col<KS>(L, e, c, h);
         add_inputs(L, e, cb, 32, v);
         if (e.quad == 2 && h == 0 && c == 0) trace_ev(e.cx, 2, 16 * e.cx.pair + 2);
-        if (L.z != nullptr)
+        if (L.z != nullptr && !single)
           sub_store(e.stg, v, L.z + (size_t)e.wrow0 * L.ld_z + cb, L.ld_z, e.rows_valid, 32, e.lane);
         if (e.quad == 2 && h == 0 && c == 0) trace_ev(e.cx, 2, 16 * e.cx.pair + 3);
         welford32(v, mean, m2, cnt);
@@ -1059,7 +1107,15 @@ __device__ void epi_ln_fwd(const EP& L, Epi& e) {
   if (!own) return;
   float gm, rstd;
   if (e.quad == 2) trace_ev(e.cx, 2, 16 * e.cx.pair + 4);
-  ln_finish<KS>(L, e, mean, m2, cnt, gm, rstd);
+  row_send<KS>(L, e, mean, m2, cnt, true);
+  if (single && L.z != nullptr) {        // the pre-norm values go out while the partials travel
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (h < ns && mine<KS>(e, h))
+        sub_store(e.stg, keep[h], L.z + (size_t)e.wrow0 * L.ld_z + sub_col<KS>(L, e, 0, h), L.ld_z,
+                  e.rows_valid, 32, e.lane);
+  }
+  ln_recv<KS>(L, e, cnt, gm, rstd);
   if (e.quad == 2) trace_ev(e.cx, 2, 16 * e.cx.pair + 5);
   for (int c = 0; c < L.nchunk; ++c) {
 #pragma unroll

@@ -667,9 +667,9 @@ class Engine:
     # ~1K rows and loses to the persistent GEMM beyond a few thousand -> big batched trunks stay
     # on the per-layer kernels
     self.machine_max_rows = int(os.environ.get('DD_MACHINE_MAXROWS', '2048'))
-    # reverse chains (LayerNorm-backward epilogue): measured slower than dd_gemm + dd_ln_bwd at
-    # a1 size (profiles/r02_phase_times.txt), so they stay opt-in
-    self.machine_bwd = os.environ.get('DD_MACHINE_BWD', '0') != '0'
+    # reverse chains (LayerNorm-backward epilogue) of the same trunks; DD_MACHINE_BWD=0 keeps
+    # dd_gemm + dd_ln_bwd (r02 A/B at a1 size: 0.15 ms per step slower)
+    self.machine_bwd = os.environ.get('DD_MACHINE_BWD', '1') != '0'
     s, N, H = spec, self.N, self.H
     D, U, SC, A, E = s.deter, s.units, s.sc, s.act_dim, s.enc_units
     z = be.zeros
@@ -1401,12 +1401,12 @@ class Engine:
     straight-through backward, the prior stack's reverse (3 x LayerNorm-backward layers), the GRU +
     joint-LayerNorm backward, and the input gradients of gru_out / img_in accumulated into the
     trajectory gradient -- 9 layers per step, t = H .. 1.  Parameters are constants here (no weight
-    gradients).  False when a shape does not tile.  Opt-in (DD_REVERSE=1): measured at a1 size it
-    takes 6.1 ms against 5.0 ms of the per-op launches it replaces (profiles/r02_phase_times.txt)."""
+    gradients).  False when a shape does not tile.  DD_REVERSE=0 keeps the per-op launches (the
+    r02 A/B: 81 vs 303 launches and 8.5 vs 9.5 ms for the actor update at a1 size)."""
     s, be, gm = self.spec, self.be, self.groups['model']
     D, U, SC, A, N, H = s.deter, s.units, s.sc, s.act_dim, self.N, self.H
     if not hasattr(self, '_reverse'):
-      ok = (self.machine and os.environ.get('DD_REVERSE', '0') != '0' and not s.discrete and
+      ok = (self.machine and os.environ.get('DD_REVERSE', '1') != '0' and not s.discrete and
             s.classes == 32 and D % 256 == 0 and U % 256 == 0 and SC % 256 == 0 and A % 4 == 0 and
             A <= 64 and self.i_prior.machine and self.i_prior.layers >= 1)
       self._reverse = None
