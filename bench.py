@@ -488,9 +488,22 @@ def run_ours(args, rank, world, local_rank):
         'roofline': roofline, 'cpu_baseline': cpu,
         'last_metrics': {k: mets[k] for k in ('model_loss', 'actor_loss', 'extr_critic_loss')},
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
   if world > 1:
+    # the step graphs hold NCCL kernels: release them while the communicator is alive, and never let
+    # a stuck teardown keep the launcher waiting after the result line is out
+    import threading
+    sys.stdout.flush()
+    guard = threading.Timer(30.0, lambda: os._exit(0))
+    guard.daemon = True
+    guard.start()
+    agent.close()
+    dist.barrier()
     dist.destroy_process_group()
+    guard.cancel()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)          # skip interpreter teardown of CUDA / NCCL state: the line is printed
 
 
 def main():

@@ -330,6 +330,16 @@ class Agent:
       else:
         self._allreduce(item)
 
+  def close(self):
+    """Drop the captured CUDA graphs.  Under data parallelism the graphs hold NCCL kernels of the
+    default process group: call this BEFORE torch.distributed.destroy_process_group() (tearing the
+    communicator down first left the process hanging at exit on 2 x B200, r02)."""
+    torch.cuda.synchronize()
+    self._graphs.clear()
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+
   def _capture(self, eng, fn):
     main = getattr(eng, 'eng', eng)            # PolicyEngine shares the learner's hooks
     be = self.be

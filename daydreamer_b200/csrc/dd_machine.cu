@@ -317,6 +317,12 @@ __device__ __forceinline__ float lo_of(float x) {
 }
 // elu with the hardware exponential: |error| <= ~2e-7 absolute on (-1, 0], far inside the 1e-4 parity bar
 __device__ __forceinline__ float elu_f(float y) { return y > 0.f ? y : __expf(y) - 1.f; }
+// gate non-linearities on the hardware exponential / reciprocal: sigmoid to ~1e-6 relative, tanh to
+// ~2e-7 absolute (r02 trace: the precise expf / tanhf / divide chains were 40 of the 65 K cycles of a
+// GRU epilogue -- two warps per scheduler cannot hide their dependent-instruction latency).  The
+// categorical head keeps the precise expf / logf: its argmax must reproduce the oracle's indices.
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_f(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 // ---- 32 x 32 sub-tile I/O through the warp's staging buffer ----------------------------------
 // Thread `lane` owns row `lane` of the sub-tile in registers; global rows are `ld` floats apart.
@@ -1258,7 +1264,9 @@ __device__ void epi_gru(const EP& L, Epi& e) {
   }
   if (!own) return;
   float gm, rstd;
+  if (e.warp == 2) trace_ev(e.cx, 2, 16 * e.cx.pair + 12);
   ln_finish<KS>(L, e, mean, m2, cnt, gm, rstd);
+  if (e.warp == 2) trace_ev(e.cx, 2, 16 * e.cx.pair + 13);
   for (int h = 0; h < ns; ++h) {
     if (!mine<KS>(e, h)) continue;
     const int cj = sub_col<KS>(L, e, 0, h);        // column inside each gate
@@ -1269,14 +1277,16 @@ __device__ void epi_gru(const EP& L, Epi& e) {
     if (L.x[1] != nullptr)
       sub_store(e.stg, v, L.x[1] + (size_t)e.wrow0 * L.ldx[1] + cj, L.ldx[1], e.rows_valid, 32, e.lane);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) g[j] = sigmoidf_(v[j]);
+    for (int j = 0; j < 32; ++j) g[j] = sigmoid_f(v[j]);
+    if (e.warp == 2) trace_ev(e.cx, 2, 16 * e.cx.pair + 14);
     // candidate
     sub_load(e.stg, v, L.z + (size_t)e.wrow0 * L.ld_z + D + cj, L.ld_z, e.rows_valid, 32, e.lane);
     ln_apply(L, D + cj, gm, rstd, 0, v);
     if (L.x[1] != nullptr)
       sub_store(e.stg, v, L.x[1] + (size_t)e.wrow0 * L.ldx[1] + D + cj, L.ldx[1], e.rows_valid, 32, e.lane);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) g[j] = tanhf(g[j] * v[j]);
+    for (int j = 0; j < 32; ++j) g[j] = tanh_f(g[j] * v[j]);
+    if (e.warp == 2) trace_ev(e.cx, 2, 16 * e.cx.pair + 15);
     // update gate and the new state
     sub_load(e.stg, v, L.z + (size_t)e.wrow0 * L.ld_z + 2 * D + cj, L.ld_z, e.rows_valid, 32, e.lane);
     ln_apply(L, 2 * D + cj, gm, rstd, 0, v);
@@ -1286,7 +1296,7 @@ __device__ void epi_gru(const EP& L, Epi& e) {
     sub_load(e.stg, pv, L.x[0] + (size_t)e.wrow0 * L.ldx[0] + cj, L.ldx[0], e.rows_valid, 32, e.lane);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      const float u = sigmoidf_(v[j] - 1.f);
+      const float u = sigmoid_f(v[j] - 1.f);
       v[j] = u * g[j] + (1.f - u) * pv[j];
     }
     store_with_lo(L, e, v, cj, 32);
@@ -1313,6 +1323,7 @@ __device__ void epi_stats(const EP& L, Epi& e) {
         const int cols_valid = min(32, L.N - cb);
         if (cols_valid <= 0) continue;
         add_inputs(L, e, cb, cols_valid, v);
+        if (e.warp == 2 && c == 0) trace_ev(e.cx, 2, 16 * e.cx.pair + 12);
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (j < C) mx = fmaxf(mx, v[j]);
@@ -1322,7 +1333,9 @@ __device__ void epi_stats(const EP& L, Epi& e) {
         const float inv = 1.f / sum;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = logf((1.f - mix) * v[j] * inv + uni);
+        if (e.warp == 2 && c == 0) trace_ev(e.cx, 2, 16 * e.cx.pair + 13);
         sub_store(e.stg, v, L.out + (size_t)e.wrow0 * L.ld_out + cb, L.ld_out, e.rows_valid, cols_valid, e.lane);
+        if (e.warp == 2 && c == 0) trace_ev(e.cx, 2, 16 * e.cx.pair + 14);
         if (L.x[1] != nullptr) {
           if (L.x[0] != nullptr) {
             float g[32];
@@ -1337,9 +1350,33 @@ __device__ void epi_stats(const EP& L, Epi& e) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = (j == bi) ? 1.f : 0.f;
           sub_store(e.stg, v, L.x[1] + (size_t)e.wrow0 * L.ldx[1] + cb, L.ldx[1], e.rows_valid, cols_valid, e.lane);
+          if (e.warp == 2 && c == 0) trace_ev(e.cx, 2, 16 * e.cx.pair + 15);
         }
       }
     }
+  }
+}
+
+// one row of the action head with compile-time width (register indices stay static)
+template <int A>
+__device__ __forceinline__ void actor_row_vec(const float (&v)[32], float lo, float hi, const float* pe,
+                                              float* pm, float* ps, float* po, float* pl) {
+#pragma unroll
+  for (int q = 0; q < A / 4; ++q) {
+    const float4 ep = *reinterpret_cast<const float4*>(pe + 4 * q);
+    const float epv[4] = {ep.x, ep.y, ep.z, ep.w};
+    float mu[4], sd[4], a[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mu[i] = tanh_f(v[4 * q + i]);
+      sd[i] = (hi - lo) * sigmoid_f(v[A + 4 * q + i]) + lo;
+      a[i] = mu[i] + sd[i] * epv[i];
+      al[i] = lo_of(a[i]);
+    }
+    *reinterpret_cast<float4*>(pm + 4 * q) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+    *reinterpret_cast<float4*>(ps + 4 * q) = make_float4(sd[0], sd[1], sd[2], sd[3]);
+    *reinterpret_cast<float4*>(po + 4 * q) = make_float4(a[0], a[1], a[2], a[3]);
+    if (pl != nullptr) *reinterpret_cast<float4*>(pl + 4 * q) = make_float4(al[0], al[1], al[2], al[3]);
   }
 }
 
@@ -1356,16 +1393,35 @@ __device__ void epi_actor(const EP& L, Epi& e) {
   if (e.lane < e.rows_valid) {
     const size_t row = (size_t)(e.wrow0 + e.lane);
     const float lo = L.f[0], hi = L.f[1];
+    float* po = L.out + row * L.ld_out;
+    float* pl = L.out_lo != nullptr ? L.out_lo + row * L.ld_lo : nullptr;
+    float* pm = L.x[1] + row * L.ldx[1];
+    float* ps = L.x[2] + row * L.ldx[2];
+    const float* pe = L.x[0] + row * L.ldx[0];
+    const bool vec = (A & 3) == 0 && ((L.ld_out | L.ldx[0] | L.ldx[1] | L.ldx[2] | (pl ? L.ld_lo : 0)) & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(L.out) | reinterpret_cast<uintptr_t>(L.x[0]) |
+                       reinterpret_cast<uintptr_t>(L.x[1]) | reinterpret_cast<uintptr_t>(L.x[2]) |
+                       reinterpret_cast<uintptr_t>(L.out_lo)) & 15) == 0;
+    if (vec) {                       // 16-byte accesses: a row of the head is 48 bytes at A = 12
+      if (A == 4) actor_row_vec<4>(v, lo, hi, pe, pm, ps, po, pl);
+      else if (A == 8) actor_row_vec<8>(v, lo, hi, pe, pm, ps, po, pl);
+      else if (A == 12) actor_row_vec<12>(v, lo, hi, pe, pm, ps, po, pl);
+      else actor_row_vec<16>(v, lo, hi, pe, pm, ps, po, pl);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (j < A) {
-        const float mu = tanhf(v[j]);
-        const float sd = (hi - lo) * sigmoidf_(v[A + j]) + lo;
-        const float a = mu + sd * L.x[0][row * L.ldx[0] + j];
-        L.x[1][row * L.ldx[1] + j] = mu;
-        L.x[2][row * L.ldx[2] + j] = sd;
-        L.out[row * L.ld_out + j] = a;
-        if (L.out_lo != nullptr) L.out_lo[row * L.ld_lo + j] = lo_of(a);
+      for (int j = 0; j < 16; ++j) {
+        if (j < A) {
+          const float mu = tanh_f(v[j]);
+          float sraw = 0.f;
+#pragma unroll
+          for (int t = 0; t < 32; ++t) if (t == A + j) sraw = v[t];
+          const float sd = (hi - lo) * sigmoid_f(sraw) + lo;
+          const float a = mu + sd * pe[j];
+          pm[j] = mu;
+          ps[j] = sd;
+          po[j] = a;
+          if (pl != nullptr) pl[j] = lo_of(a);
+        }
       }
     }
   }
@@ -1450,9 +1506,9 @@ __device__ void epi_gru_bwd(const EP& L, Epi& e) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float dout = rowok ? v[j] : 0.f;
-          const float r = sigmoidf_(yr[j]);
-          const float cc = tanhf(r * yc[j]);
-          const float u = sigmoidf_(t[j] - 1.f);
+          const float r = sigmoid_f(yr[j]);
+          const float cc = tanh_f(r * yc[j]);
+          const float u = sigmoid_f(t[j] - 1.f);
           const float du = dout * (cc - pv[j]);
           const float dpre = dout * u * (1.f - cc * cc);
           yr[j] = dpre * yc[j] * r * (1.f - r);

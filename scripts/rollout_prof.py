@@ -55,7 +55,9 @@ for name, fn in (('imagine', eng.imagine),):
     nxt = rel(tr[2, 16 * (pr + 1)]) if pr + 1 < len(layers) else -1
     L = layers[pr]
     kb = sum((sg.a.shape[1] + 31) // 32 for sg in L.segs) * max(1, L.N // 512)
-    print(f'  {pr:4d} {EPI[L.epi]:6s} {L.N:4d} {kb:5d} | {e[1] - e[0]:6d} {e[9] - e[1]:9d} {e[11] - e[9]:8d} {nxt - e[11]:8d}')
+    x = [rel(tr[2, 16 * pr + k]) for k in range(12, 16)]
+    extra = '' if x[0] < 0 else '   marks (from start): ' + ' '.join(str(v - e[0]) for v in x) + f'  accf {e[1] - e[0]} done {e[9] - e[0]}'
+    print(f'  {pr:4d} {EPI[L.epi]:6s} {L.N:4d} {kb:5d} | {e[1] - e[0]:6d} {e[9] - e[1]:9d} {e[11] - e[9]:8d} {nxt - e[11]:8d}{extra}')
   used = arr[arr[:, 0] > 0]
   avg = used.mean(0)
   print(f'{name}: {ms:.3f} ms, {len(used)} CTAs, kernel {avg[0]:.0f} cycles/CTA -> effective clock '
