@@ -158,6 +158,8 @@ def load_library(path=LIB_PATH):
   lib.dd_program_bytes.restype = ctypes.c_size_t
   lib.dd_program_build.argtypes = [ctypes.POINTER(DdLayer), _I, _I, _P]
   lib.dd_program_build.restype = ctypes.c_int
+  lib.dd_program_deps.argtypes = [ctypes.POINTER(DdLayer), _I, _I, ctypes.POINTER(ctypes.c_int)]
+  lib.dd_program_deps.restype = ctypes.c_int
   lib.dd_program_debug.argtypes = [ctypes.POINTER(ctypes.c_uint)]
   lib.dd_program_debug.restype = ctypes.c_int
   lib.dd_version.restype = ctypes.c_int
@@ -188,6 +190,55 @@ def _flat(t):
   return t.data_ptr(), t.numel()
 
 
+def encode_layers(layers, rows):
+  """program.Layer list -> the DdLayer array of the C-ABI (pointers and strides of torch views)."""
+  n = len(layers)
+  arr = (DdLayer * n)()
+  for i, L in enumerate(layers):
+    d = arr[i]
+    d.nseg = len(L.segs)
+    assert 0 <= d.nseg <= 2
+    for g, sg in enumerate(L.segs):
+      pa, r, k, lda = _mat(sg.a)
+      assert r == rows, (sg.a.shape, rows)
+      d.seg[g].a, d.seg[g].lda, d.seg[g].k, d.seg[g].wk0 = pa, lda, k, int(sg.wk0)
+      if sg.a_lo is not None:
+        assert sg.a_lo.shape == sg.a.shape
+        d.seg[g].a_lo, _, _, d.seg[g].lda_lo = _mat(sg.a_lo)
+    if L.segs:
+      pw, wrows, wcols, ldw = _mat(L.w)
+      pwl, _, _, ldwl = _mat(L.w_lo)
+      assert ldwl == ldw and L.w_lo.shape == L.w.shape
+      d.w, d.w_lo, d.ldw, d.wrows, d.wcols, d.wn0 = pw, pwl, ldw, wrows, wcols, int(L.wn0)
+    d.N, d.epi, d.act = int(L.N), int(L.epi), int(L.act)
+    if L.add is not None:
+      d.add, _, _, d.ld_add = _mat(L.add)
+    d.bias, d.gamma, d.beta = _ptr(L.bias), _ptr(L.gamma), _ptr(L.beta)
+    if L.z is not None:
+      d.z, _, _, d.ld_z = _mat(L.z)
+    d.st = _ptr(L.st)
+    d.out, _, _, d.ld_out = _mat(L.out)
+    if L.out_lo is not None:
+      d.out_lo, _, _, d.ld_lo = _mat(L.out_lo)
+    d.dgamma, d.dbeta = _ptr(L.dgamma), _ptr(L.dbeta)
+    for q, t in enumerate((L.x0, L.x1, L.x2)):
+      if t is not None:
+        d.x[q], _, _, d.ldx[q] = _mat(t)
+    d.f[0], d.f[1], d.ipar = float(L.f0), float(L.f1), int(L.ipar)
+  return arr
+
+
+def program_deps(lib, layers, rows):
+  """[(dep of segment 0, dep of segment 1)] per layer: how many leading layers of the program write
+  the segment (dd_program_deps; host only, works on CPU tensors)."""
+  n = len(layers)
+  out = (ctypes.c_int * (2 * n))()
+  rc = lib.dd_program_deps(encode_layers(layers, rows), n, int(rows), out)
+  if rc != 0:
+    raise RuntimeError(lib.dd_last_error().decode())
+  return [(out[2 * i], out[2 * i + 1]) for i in range(n)]
+
+
 class CudaBackend:
   name = 'cuda-sm100a'
 
@@ -212,6 +263,8 @@ class CudaBackend:
       self.lib.dd_set_gemm_tc_staged(int(os.environ['DD_GEMM_TC_STAGED']))
     if os.environ.get('DD_GEMM_TC_PERSISTENT', '') != '':
       self.lib.dd_set_gemm_tc_persistent(int(os.environ['DD_GEMM_TC_PERSISTENT']))
+    if os.environ.get('DD_MACHINE_DEBUG', '') != '':        # dd_machine.cu F_* switches (A/B runs)
+      self.lib.dd_set_machine_debug(int(os.environ['DD_MACHINE_DEBUG']))
 
   def set_pdl(self, on):
     return self.lib.dd_set_pdl(int(on))
@@ -580,38 +633,7 @@ class CudaBackend:
     """Compile a list of program.Layer into a device table (TMA descriptors are encoded here:
     synchronous, call outside stream capture)."""
     n = len(layers)
-    arr = (DdLayer * n)()
-    for i, L in enumerate(layers):
-      d = arr[i]
-      d.nseg = len(L.segs)
-      assert 0 <= d.nseg <= 2
-      for g, sg in enumerate(L.segs):
-        pa, r, k, lda = _mat(sg.a)
-        assert r == rows, (sg.a.shape, rows)
-        d.seg[g].a, d.seg[g].lda, d.seg[g].k, d.seg[g].wk0 = pa, lda, k, int(sg.wk0)
-        if sg.a_lo is not None:
-          assert sg.a_lo.shape == sg.a.shape
-          d.seg[g].a_lo, _, _, d.seg[g].lda_lo = _mat(sg.a_lo)
-      if L.segs:
-        pw, wrows, wcols, ldw = _mat(L.w)
-        pwl, _, _, ldwl = _mat(L.w_lo)
-        assert ldwl == ldw and L.w_lo.shape == L.w.shape
-        d.w, d.w_lo, d.ldw, d.wrows, d.wcols, d.wn0 = pw, pwl, ldw, wrows, wcols, int(L.wn0)
-      d.N, d.epi, d.act = int(L.N), int(L.epi), int(L.act)
-      if L.add is not None:
-        d.add, _, _, d.ld_add = _mat(L.add)
-      d.bias, d.gamma, d.beta = _ptr(L.bias), _ptr(L.gamma), _ptr(L.beta)
-      if L.z is not None:
-        d.z, _, _, d.ld_z = _mat(L.z)
-      d.st = _ptr(L.st)
-      d.out, _, _, d.ld_out = _mat(L.out)
-      if L.out_lo is not None:
-        d.out_lo, _, _, d.ld_lo = _mat(L.out_lo)
-      d.dgamma, d.dbeta = _ptr(L.dgamma), _ptr(L.dbeta)
-      for q, t in enumerate((L.x0, L.x1, L.x2)):
-        if t is not None:
-          d.x[q], _, _, d.ldx[q] = _mat(t)
-      d.f[0], d.f[1], d.ipar = float(L.f0), float(L.f1), int(L.ipar)
+    arr = encode_layers(layers, rows)
     nbytes = int(self.lib.dd_program_bytes(n))
     table = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
     torch.cuda.synchronize(self.device)

@@ -70,6 +70,8 @@ struct alignas(64) LmLayer {
   CUtensorMap a_hi[2], a_lo[2];   // per A segment: [rows, k] fp32, box {32, 16}, SWIZZLE_128B
   CUtensorMap w_hi, w_lo;         // B operand [n rows, k cols], box {32, bn}
   int nseg, seg_k[2], seg_wk0[2], seg_exact[2];
+  int seg_dep[2];                 // leading layers of the program that must be complete before the segment's
+                                  // first k-block (0: an external input); the last k-block waits for all of them
   int wn0;                        // first row of the B operand used by this layer
   int w3d;                        // w_hi is a 3-D map over the (w, w_lo) planes: one box per k-block
   int N, bn, nchunk, chunk_stride, nactive;
@@ -151,7 +153,7 @@ __device__ __forceinline__ void trace_ev(const Ctx& cx, int role, uint32_t idx) 
   if (cx.trace != nullptr && idx < (uint32_t)TRACE_N && (threadIdx.x & 31) == 0)
     cx.trace[role * TRACE_N + idx] = (unsigned long long)clock64();
 }
-enum { F_NOMMA = 1, F_NOA = 2, F_LOCALA = 4, F_NOB = 8, F_TMFENCE = 16 };
+enum { F_NOMMA = 1, F_NOA = 2, F_LOCALA = 4, F_NOB = 8, F_TMFENCE = 16, F_NORELAX = 32 };
 __device__ __noinline__ void stuck(const Ctx& cx, int code, uint32_t parity) {
   if (cx.dbg != nullptr) {
     cx.dbg[1] = (unsigned)code;
@@ -496,12 +498,13 @@ __device__ __forceinline__ bool elect_one() {
 }
 // the scalar fields of a layer the single-issue roles steer by, made warp-uniform
 struct LayerU {
-  int nseg, k0, k1, wk0, wk1, wn0, bn, nchunk, chunk_stride, nactive, w3d, exact0, exact1;
+  int nseg, k0, k1, wk0, wk1, wn0, bn, nchunk, chunk_stride, nactive, w3d, exact0, exact1, dep0, dep1;
   __device__ __forceinline__ void load(const LmLayer& L) {
     nseg = ubc(L.nseg); k0 = ubc(L.seg_k[0]); k1 = ubc(L.seg_k[1]);
     wk0 = ubc(L.seg_wk0[0]); wk1 = ubc(L.seg_wk0[1]); wn0 = ubc(L.wn0); bn = ubc(L.bn);
     nchunk = ubc(L.nchunk); chunk_stride = ubc(L.chunk_stride); nactive = ubc(L.nactive);
     w3d = ubc(L.w3d); exact0 = ubc(L.seg_exact[0]); exact1 = ubc(L.seg_exact[1]);
+    dep0 = ubc(L.seg_dep[0]); dep1 = ubc(L.seg_dep[1]);
   }
   __device__ __forceinline__ int kb0() const { return (k0 + BK - 1) / BK; }
   __device__ __forceinline__ int kbc() const { return kb0() + (nseg > 1 ? (k1 + BK - 1) / BK : 0); }
@@ -571,9 +574,10 @@ __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers,
   const int cs = rank % NS, kh = rank / NS;
   const uint16_t mask = (uint16_t)(0xFFu << (NS * kh));      // the CTAs sharing my k-blocks
   const bool noa = (cx.flags & F_NOA) != 0;
+  const int relax = (cx.flags & F_NORELAX) ? 0 : 1;
   Ring rg = {0u, 0u};
   uint32_t it = 0;
-  int pair = 0;
+  int pair = 0, have = 0;                  // `have`: pairs known complete on every CTA of the cluster
   for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
     const int m = tile * BM + cs * SLICE_ROWS;
     for (int l = 0; l < nlayers; ++l, ++pair) {
@@ -596,15 +600,24 @@ __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers,
       const CUtensorMap* al0 = &L.a_lo[0];
       const CUtensorMap* ah1 = &L.a_hi[1];
       const CUtensorMap* al1 = &L.a_lo[1];
-      if (l > 0) {           // the previous layer's outputs of every CTA are in global memory
-        count_wait(sh.bars + BAR_READY, (uint32_t)pair * Geo<KS>::CLS, cx, 2);
-        asm volatile("fence.proxy.async;" ::: "memory");
-      }
+      // A segment is fetched as soon as the layers that WRITE it are complete on every CTA
+      // (seg_dep, found by dd_program_build), not when the previous layer is: the k-blocks of an
+      // early operand (the carried deter of the GRU, the latent of img_in / the actor) run while
+      // the previous layer's epilogue is still busy.  The last k-block of the first chunk waits
+      // for everything before this layer, so no accumulator of layer l is complete -- and no
+      // epilogue of layer l starts anywhere -- before layer l - 1 is published, exactly as before.
+      const int base = pair - l;           // pairs of the tiles this cluster has finished
       for (int c = 0; c < u.nchunk; ++c) {
         for (int r = k_lo; r < k_hi; ++r, ++it) {
           const bool s1 = r >= kb0;
           const bool exact = s1 ? exact1 : exact0;
           const uint32_t full = sh.bars + BAR_FULL + 8 * rg.s;
+          const int rel = ((c == 0 && r == k_hi - 1) || relax == 0) ? l : (s1 ? u.dep1 : u.dep0);
+          if (rel > 0 && base + rel > have) {          // rel == 0: inputs of the program, no wait
+            have = base + rel;
+            count_wait(sh.bars + BAR_READY, (uint32_t)have * Geo<KS>::CLS, cx, 2);
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
           mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * rg.s, rg.ph ^ 1u, cx, 9);
           trace_ev(cx, 0, 4 * it + 2);
           if (elect_one()) {
@@ -1845,6 +1858,76 @@ using namespace dd;
 
 extern "C" size_t dd_program_bytes(int nlayers) { return sizeof(lm::LmLayer) * (size_t)nlayers; }
 
+namespace dd {
+namespace lm {
+// ---- which earlier layers write an A segment ---------------------------------------------------
+// A rectangle of floats: `rows` rows of `w` floats, `ld` apart.
+struct Rect { const float* p; int64_t w, ld; };
+static bool rect_overlap(const Rect& a, const Rect& b, int64_t rows) {
+  if (a.p == nullptr || b.p == nullptr || a.w <= 0 || b.w <= 0) return false;
+  if (a.ld == b.ld && a.ld > 0) {
+    // same pitch: express a's origin in b's (row, column) grid
+    const int64_t d = a.p - b.p, ld = a.ld;
+    int64_t q = d / ld, rem = d % ld;
+    if (rem < 0) { rem += ld; q -= 1; }
+    if (rem + a.w <= ld) {                               // a's rows do not wrap in b's grid
+      if (q <= -rows || q >= rows) return false;          // no row in common
+      return rem < b.w;                                  // column intervals [rem, rem + a.w) and [0, b.w)
+    }
+    return q > -rows - 1 && q < rows + 1;                // wrapping: be conservative
+  }
+  const float* a_end = a.p + (rows - 1) * a.ld + a.w;
+  const float* b_end = b.p + (rows - 1) * b.ld + b.w;
+  return a.p < b_end && b.p < a_end;
+}
+// everything layer s writes that a later layer could read as a GEMM operand (generous widths)
+static int written_rects(const DdLayer& s, Rect* out) {
+  int n = 0;
+  const int64_t N = s.N;
+  const int64_t ow = s.epi == DD_EPI_GRU ? N / 3 : (s.epi == DD_EPI_GRUBWD ? 3 * N : (s.epi == DD_EPI_ACTOR ? s.ipar : N));
+  out[n++] = {s.out, ow, s.ld_out};
+  if (s.out_lo != nullptr) out[n++] = {s.out_lo, ow, s.ld_lo};
+  if (s.z != nullptr && (s.epi == DD_EPI_LN || s.epi == DD_EPI_GRU || s.epi == DD_EPI_PLAIN))
+    out[n++] = {s.z, N, s.ld_z};
+  if (s.st != nullptr && (s.epi == DD_EPI_LN || s.epi == DD_EPI_GRU)) out[n++] = {s.st, 2, 2};
+  if (s.x[1] != nullptr && (s.epi == DD_EPI_GRU || s.epi == DD_EPI_STATS || s.epi == DD_EPI_ACTOR))
+    out[n++] = {s.x[1], s.epi == DD_EPI_ACTOR ? (int64_t)s.ipar : N, s.ldx[1]};
+  if (s.x[2] != nullptr && (s.epi == DD_EPI_ACTOR || s.epi == DD_EPI_GRUBWD))
+    out[n++] = {s.x[2], s.epi == DD_EPI_ACTOR ? (int64_t)s.ipar : N, s.ldx[2]};
+  return n;
+}
+// seg_dep[g] of layer l = 1 + the last earlier layer that writes any part of segment g (0: none)
+static void find_segment_deps(const DdLayer* layers, int nlayers, int rows, LmLayer* host) {
+  for (int l = 0; l < nlayers; ++l) {
+    for (int g = 0; g < layers[l].nseg; ++g) {
+      const DdSeg& sg = layers[l].seg[g];
+      const Rect a = {sg.a, sg.k, sg.lda}, alo = {sg.a_lo, sg.a_lo != nullptr ? sg.k : 0, sg.lda_lo};
+      int dep = 0;
+      for (int j = l - 1; j >= 0 && dep == 0; --j) {
+        Rect w[8];
+        const int n = written_rects(layers[j], w);
+        for (int i = 0; i < n; ++i)
+          if (rect_overlap(a, w[i], rows) || rect_overlap(alo, w[i], rows)) { dep = j + 1; break; }
+      }
+      host[l].seg_dep[g] = dep;
+    }
+  }
+}
+}  // namespace lm
+}  // namespace dd
+
+// Host-only view of the dependency analysis (tests / tooling): deps[2 * l + g] = number of leading
+// layers that must be complete before segment g of layer l may be fetched (0: a program input).
+extern "C" int dd_program_deps(const DdLayer* layers, int nlayers, int rows, int* deps) {
+  if (nlayers < 1 || rows < 1 || deps == nullptr) return fail("dd_program_deps", "empty program");
+  lm::LmLayer* host = static_cast<lm::LmLayer*>(calloc(nlayers, sizeof(lm::LmLayer)));
+  if (host == nullptr) return fail("dd_program_deps", "out of host memory");
+  lm::find_segment_deps(layers, nlayers, rows, host);
+  for (int l = 0; l < nlayers; ++l) { deps[2 * l] = host[l].seg_dep[0]; deps[2 * l + 1] = host[l].seg_dep[1]; }
+  free(host);
+  return 0;
+}
+
 extern "C" int dd_program_build(const DdLayer* layers, int nlayers, int rows, void* table_dev) {
   if (nlayers < 1 || rows < 1) return fail("dd_program_build", "empty program");
   lm::LmLayer* host = static_cast<lm::LmLayer*>(calloc(nlayers, sizeof(lm::LmLayer)));
@@ -1939,6 +2022,7 @@ extern "C" int dd_program_build(const DdLayer* layers, int nlayers, int rows, vo
     if ((s.dgamma == nullptr) != (s.dbeta == nullptr))
       rc = fail("dd_program_build", "dgamma and dbeta come together");
   }
+  if (rc == 0) lm::find_segment_deps(layers, nlayers, rows, host);
   if (rc == 0) {
     cudaError_t e = cudaMemcpy(table_dev, host, sizeof(lm::LmLayer) * (size_t)nlayers, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) rc = fail("dd_program_build", cudaGetErrorString(e));

@@ -1452,6 +1452,7 @@ class Engine:
             layers.append(PG.Layer(iseg, win, winlo, SC, PG.EPI_PLAIN, wn0=0, add=dtf[k][:, D:],
                                    out=dtf[k][:, D:]))
           layers.append(PG.Layer(iseg, win, winlo, A, PG.EPI_PLAIN, wn0=SC, out=self.da[r0:r1]))
+        self._reverse_layers = layers            # kept for tests / profiling scripts
         self._reverse = be.program_build(layers, N)
     if self._reverse is None:
       return False

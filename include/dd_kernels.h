@@ -361,6 +361,11 @@ size_t dd_program_bytes(int nlayers);
 /* encodes the TMA descriptors and copies the program into table_dev (synchronous; call once,
  * outside stream capture).  rows = M of every layer. */
 int dd_program_build(const DdLayer* layers, int nlayers, int rows, void* table_dev);
+/* Host only (no device work): for every A segment the number of leading layers of the program that
+ * write it, i.e. that must be complete before its first k-block is fetched; deps[2 * l + g], 0 for a
+ * program input.  dd_program_build uses the same analysis to let early operands of a layer stream
+ * while the previous layer's epilogue is still running. */
+int dd_program_deps(const DdLayer* layers, int nlayers, int rows, int* deps);
 int dd_program_run(const void* table_dev, int nlayers, int rows, dd_stream_t stream);
 /* geometry of the machine: 1 = clusters of 8 CTAs (one per column slice), 2 = split-K clusters of
  * 16 (two CTAs per slice share its k-blocks; default when the device hosts such clusters) */

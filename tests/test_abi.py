@@ -35,7 +35,7 @@ def test_binding_covers_header(lib_path):
   typed = set(backend.SIGNATURES) | {'dd_version', 'dd_last_error', 'dd_launch_count',
                                      'dd_observe_fwd', 'dd_observe_fwd_grid',
                                      'dd_observe_bwd', 'dd_observe_bwd_grid', 'dd_program_bytes',
-                                     'dd_program_build', 'dd_program_debug'}
+                                     'dd_program_build', 'dd_program_deps', 'dd_program_debug'}
   assert typed == set(declared_symbols())
   assert lib.dd_version() >= 100
   assert lib.dd_launch_count() == 0

@@ -99,3 +99,78 @@ def test_transpose_jobs():
   got = pt[100:100 + 4 * 4 + 3].as_strided((5, 3), (4, 1))
   assert torch.equal(got, p[96:111].view(5, 3))
   assert torch.equal(ptlo[:96].view(12, 8), P.lo_of(p[:96].view(8, 12).t().contiguous()))
+
+
+# ---- dd_program_deps: which earlier layers write an A segment (host-only entry point of the .so) ----
+def _brute_force_deps(layers, rows):
+  """The same question answered element by element: addresses (in floats) every layer writes, the
+  last earlier layer whose set meets a segment's."""
+  def cells(t, width=None):
+    if t is None:
+      return set()
+    t2 = t if t.dim() == 2 else t.view(-1, 1) if t.dim() == 1 else t.reshape(-1, t.shape[-1])
+    w = t2.shape[1] if width is None else width
+    base, ld = t2.data_ptr() // 4, (t2.stride(0) if t2.shape[0] > 1 else w)
+    return {base + r * ld + c for r in range(rows) for c in range(w)}
+  written = []
+  for L in layers:
+    ow = L.N // 3 if L.epi == P.EPI_GRU else 3 * L.N if L.epi == P.EPI_GRUBWD else L.ipar if L.epi == P.EPI_ACTOR else L.N
+    w = cells(L.out, ow) | cells(L.out_lo, ow)
+    if L.epi in (P.EPI_LN, P.EPI_GRU, P.EPI_PLAIN):
+      w |= cells(L.z, L.N if L.z is not None else None)
+    if L.epi in (P.EPI_LN, P.EPI_GRU):
+      w |= cells(L.st)
+    if L.epi in (P.EPI_GRU, P.EPI_STATS, P.EPI_ACTOR):
+      w |= cells(L.x1, L.ipar if L.epi == P.EPI_ACTOR else L.N)
+    if L.epi in (P.EPI_ACTOR, P.EPI_GRUBWD):
+      w |= cells(L.x2, L.ipar if L.epi == P.EPI_ACTOR else L.N)
+    written.append(w)
+  out = []
+  for l, L in enumerate(layers):
+    deps = [0, 0]
+    for g, sg in enumerate(L.segs):
+      need = cells(sg.a) | cells(sg.a_lo)
+      for j in range(l - 1, -1, -1):
+        if need & written[j]:
+          deps[g] = j + 1
+          break
+    out.append(tuple(deps))
+  return out
+
+
+def test_segment_dependencies_of_the_rollout_programs():
+  """The engine's real rollout / reverse programs (small widths, CPU tensors): dd_program_deps agrees
+  with the element-wise answer, and the early operands really are early: the latent of img_in does not
+  wait for the actor head before it, the carried deter of the GRU does not wait for img_in."""
+  import os
+  from daydreamer_b200 import backend, engine as E
+  from oracle import dreamer_oracle as O
+  from tests import util
+  lib = backend.load_library()
+  os.environ['DD_REVERSE'] = '1'
+  ospec = O.tiny_spec(obs_dims={'vector': 16}, act_dim=12, deter=256, units=256, stoch=8, classes=32,
+                      enc_units=256, head_units=256, horizon=2)
+  eng = E.Engine(util.to_engine_spec(ospec), HostSim(), 2, 3)
+  eng.load_params(O.init_params(ospec, seed=1))
+  util.load_batch(eng, util.to_engine_spec(ospec), util.make_batch(ospec, 2, 3, seed=1), util.make_noise(ospec, 2, 3, seed=2))
+  eng.launch_step(draw=False, slow_refreshed=True)
+  fwd = eng._rollout_layers
+  rows = eng.N
+  got = backend.program_deps(lib, fwd, rows)
+  assert got == _brute_force_deps(fwd, rows)
+  rev = eng._reverse_layers
+  assert backend.program_deps(lib, rev, rows) == _brute_force_deps(rev, rows)
+  kinds = [L.epi for L in fwd]
+  for l, L in enumerate(fwd):
+    if len(L.segs) == 1:
+      assert got[l][0] in (0, l)                 # a chain: the layer before (or a program input)
+      continue
+    d0, d1 = got[l]
+    if L.epi == P.EPI_GRU:                       # [carried deter | x_in]: x_in is the layer before
+      assert d1 == l and d0 < l
+    elif l > 0 and kinds[l - 1] == P.EPI_ACTOR:  # img_in: [latent | action]: the action is the layer before
+      assert d1 == l and d0 <= l - 2           # ... and the latent was sampled before the actor ran
+    elif l == 0:                                 # first actor call: the start states are inputs
+      assert (d0, d1) == (0, 0)
+    else:                                        # actor layer 1: [deter (GRU, 5 back) | latent (STATS, before)]
+      assert d1 == l and 0 < d0 < l
