@@ -153,7 +153,15 @@ __device__ __forceinline__ void trace_ev(const Ctx& cx, int role, uint32_t idx) 
   if (cx.trace != nullptr && idx < (uint32_t)TRACE_N && (threadIdx.x & 31) == 0)
     cx.trace[role * TRACE_N + idx] = (unsigned long long)clock64();
 }
-enum { F_NOMMA = 1, F_NOA = 2, F_LOCALA = 4, F_NOB = 8, F_TMFENCE = 16, F_NORELAX = 32 };
+enum { F_NOMMA = 1, F_NOA = 2, F_LOCALA = 4, F_NOB = 8, F_TMFENCE = 16, F_NORELAX = 32, F_NODUAL = 64 };
+// Two row tiles per cluster, interleaved layer by layer ("dual"): when a cluster has several tiles to
+// process, it runs them in pairs -- (layer l, tile A), (layer l, tile B), (layer l + 1, tile A), ... --
+// so the k-loop of one tile runs during the epilogue of the other (a tile's own layers are dependent and
+// leave the tensor pipe idle during every epilogue).  Every role walks the same sequence; each of the two
+// chains has its own `ready` counter (a chain is strictly ordered, so its counter stays unambiguous).
+__device__ __forceinline__ bool dual_mode(int ntiles, int nclusters, int flags) {
+  return ntiles > nclusters && !(flags & F_NODUAL);
+}
 __device__ __noinline__ void stuck(const Ctx& cx, int code, uint32_t parity) {
   if (cx.dbg != nullptr) {
     cx.dbg[1] = (unsigned)code;
@@ -519,13 +527,15 @@ __device__ void producer_b(const Shared& sh, const LmLayer* layers, int nlayers,
   Ring rg = {0u, 0u};
   uint32_t it = 0;
   int pair = 0;
-  for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
-    for (int l = 0; l < nlayers; ++l, ++pair) {
+  const bool dual = dual_mode(ntiles, nclusters, cx.flags);
+  const int tstep = dual ? 2 * nclusters : nclusters;
+  for (int t0 = cluster_id; t0 < ntiles; t0 += tstep) {
+    const int ng = (dual && t0 + nclusters < ntiles) ? 2 : 1;      // tiles of this group
+    for (int l = 0; l < nlayers; ++l) {
       const LmLayer& L = layers[l];
       LayerU u;
       u.load(L);
-      cx.pair = pair;
-      if (u.nseg == 0) continue;
+      if (u.nseg == 0) { pair += ng; continue; }
       if (elect_one()) {
         tmap_acquire(&L.w_hi, (cx.flags & F_TMFENCE) != 0);
         if (!u.w3d) tmap_acquire(&L.w_lo, (cx.flags & F_TMFENCE) != 0);
@@ -539,27 +549,30 @@ __device__ void producer_b(const Shared& sh, const LmLayer* layers, int nlayers,
       const uint32_t bytes = active ? 2u * (uint32_t)bn * BK * 4 : 0u;
       const CUtensorMap* whi = &L.w_hi;
       const CUtensorMap* wlo = &L.w_lo;
-      int n = u.wn0 + cs * bn;
-      for (int c = 0; c < u.nchunk; ++c, n += u.chunk_stride) {
-        for (int r = k_lo; r < k_hi; ++r, ++it) {
-          const uint32_t full = sh.bars + BAR_FULL + 8 * rg.s;
-          mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * rg.s, rg.ph ^ 1u, cx, 1);   // smem reuse only
-          trace_ev(cx, 0, 4 * it);
-          if (elect_one()) {
-            mbar_arrive_tx(full, bytes);
-            if (active) {
-              const uint32_t st = sh.base + rg.s * STAGE_BYTES + 2 * A_BYTES;
-              const int k = (r < kb0 ? wk0 : wk1) + r * BK;
-              if (u.w3d) {               // rows [0, bn) = w, rows [bn, 2 bn) = w_lo: one box
-                tma_load_3d(st, whi, k, n, 0, full);
-              } else {
-                tma_load(st, whi, k, n, full);
-                tma_load(st + (uint32_t)bn * (BK * 4), wlo, k, n, full);
+      for (int sub = 0; sub < ng; ++sub, ++pair) {       // the same weight tiles for both row tiles
+        cx.pair = pair;
+        int n = u.wn0 + cs * bn;
+        for (int c = 0; c < u.nchunk; ++c, n += u.chunk_stride) {
+          for (int r = k_lo; r < k_hi; ++r, ++it) {
+            const uint32_t full = sh.bars + BAR_FULL + 8 * rg.s;
+            mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * rg.s, rg.ph ^ 1u, cx, 1);   // smem reuse only
+            trace_ev(cx, 0, 4 * it);
+            if (elect_one()) {
+              mbar_arrive_tx(full, bytes);
+              if (active) {
+                const uint32_t st = sh.base + rg.s * STAGE_BYTES + 2 * A_BYTES;
+                const int k = (r < kb0 ? wk0 : wk1) + r * BK;
+                if (u.w3d) {               // rows [0, bn) = w, rows [bn, 2 bn) = w_lo: one box
+                  tma_load_3d(st, whi, k, n, 0, full);
+                } else {
+                  tma_load(st, whi, k, n, full);
+                  tma_load(st + (uint32_t)bn * (BK * 4), wlo, k, n, full);
+                }
               }
             }
+            trace_ev(cx, 0, 4 * it + 1);
+            rg.next(STAGES);
           }
-          trace_ev(cx, 0, 4 * it + 1);
-          rg.next(STAGES);
         }
       }
     }
@@ -577,15 +590,18 @@ __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers,
   const int relax = (cx.flags & F_NORELAX) ? 0 : 1;
   Ring rg = {0u, 0u};
   uint32_t it = 0;
-  int pair = 0, have = 0;                  // `have`: pairs known complete on every CTA of the cluster
-  for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
-    const int m = tile * BM + cs * SLICE_ROWS;
-    for (int l = 0; l < nlayers; ++l, ++pair) {
+  int pair = 0;
+  int have0 = 0, have1 = 0;                // layers of chain 0 / 1 known complete on every CTA
+  int base0 = 0, base1 = 0;                // layers the chains completed in earlier tile groups
+  const bool dual = dual_mode(ntiles, nclusters, cx.flags);
+  const int tstep = dual ? 2 * nclusters : nclusters;
+  for (int t0 = cluster_id; t0 < ntiles; t0 += tstep) {
+    const int ng = (dual && t0 + nclusters < ntiles) ? 2 : 1;
+    for (int l = 0; l < nlayers; ++l) {
       const LmLayer& L = layers[l];
       LayerU u;
       u.load(L);
-      cx.pair = pair;
-      if (u.nseg == 0) continue;
+      if (u.nseg == 0) { pair += ng; continue; }
       if (elect_one()) {
         for (int g = 0; g < u.nseg; ++g) {
           tmap_acquire(&L.a_hi[g], (cx.flags & F_TMFENCE) != 0);
@@ -606,34 +622,41 @@ __device__ void producer_a(const Shared& sh, const LmLayer* layers, int nlayers,
       // the previous layer's epilogue is still busy.  The last k-block of the first chunk waits
       // for everything before this layer, so no accumulator of layer l is complete -- and no
       // epilogue of layer l starts anywhere -- before layer l - 1 is published, exactly as before.
-      const int base = pair - l;           // pairs of the tiles this cluster has finished
-      for (int c = 0; c < u.nchunk; ++c) {
-        for (int r = k_lo; r < k_hi; ++r, ++it) {
-          const bool s1 = r >= kb0;
-          const bool exact = s1 ? exact1 : exact0;
-          const uint32_t full = sh.bars + BAR_FULL + 8 * rg.s;
-          const int rel = ((c == 0 && r == k_hi - 1) || relax == 0) ? l : (s1 ? u.dep1 : u.dep0);
-          if (rel > 0 && base + rel > have) {          // rel == 0: inputs of the program, no wait
-            have = base + rel;
-            count_wait(sh.bars + BAR_READY, (uint32_t)have * Geo<KS>::CLS, cx, 2);
-            asm volatile("fence.proxy.async;" ::: "memory");
-          }
-          mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * rg.s, rg.ph ^ 1u, cx, 9);
-          trace_ev(cx, 0, 4 * it + 2);
-          if (elect_one()) {
-            mbar_arrive_tx(full, noa ? 0u : (exact ? 1u : 2u) * A_BYTES);
-            if (!noa) {
-              const uint32_t st = sh.base + rg.s * STAGE_BYTES + cs * SLICE_BYTES;
-              const int k = (s1 ? r - kb0 : r) * BK;
-              tma_load_mc(st, s1 ? ah1 : ah0, k, m, full, mask);
-              if (!exact) tma_load_mc(st + A_BYTES, s1 ? al1 : al0, k, m, full, mask);
+      for (int sub = 0; sub < ng; ++sub, ++pair) {
+        cx.pair = pair;
+        const int m = (t0 + sub * nclusters) * BM + cs * SLICE_ROWS;
+        const int base = sub ? base1 : base0;          // this chain's layers before the current tile
+        const uint32_t ready = sh.bars + BAR_READY + 4 * sub;
+        for (int c = 0; c < u.nchunk; ++c) {
+          for (int r = k_lo; r < k_hi; ++r, ++it) {
+            const bool s1 = r >= kb0;
+            const bool exact = s1 ? exact1 : exact0;
+            const uint32_t full = sh.bars + BAR_FULL + 8 * rg.s;
+            const int rel = ((c == 0 && r == k_hi - 1) || relax == 0) ? l : (s1 ? u.dep1 : u.dep0);
+            if (rel > 0 && base + rel > (sub ? have1 : have0)) {   // rel == 0: inputs of the program
+              if (sub) have1 = base + rel; else have0 = base + rel;
+              count_wait(ready, (uint32_t)(base + rel) * Geo<KS>::CLS, cx, 2);
+              asm volatile("fence.proxy.async;" ::: "memory");
             }
+            mbar_wait<false>(sh.bars + BAR_EMPTY + 8 * rg.s, rg.ph ^ 1u, cx, 9);
+            trace_ev(cx, 0, 4 * it + 2);
+            if (elect_one()) {
+              mbar_arrive_tx(full, noa ? 0u : (exact ? 1u : 2u) * A_BYTES);
+              if (!noa) {
+                const uint32_t st = sh.base + rg.s * STAGE_BYTES + cs * SLICE_BYTES;
+                const int k = (s1 ? r - kb0 : r) * BK;
+                tma_load_mc(st, s1 ? ah1 : ah0, k, m, full, mask);
+                if (!exact) tma_load_mc(st + A_BYTES, s1 ? al1 : al0, k, m, full, mask);
+              }
+            }
+            trace_ev(cx, 0, 4 * it + 3);
+            rg.next(STAGES);
           }
-          trace_ev(cx, 0, 4 * it + 3);
-          rg.next(STAGES);
         }
       }
     }
+    base0 += nlayers;
+    if (ng == 2) base1 += nlayers;
   }
 }
 
@@ -652,16 +675,18 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
   Ring rg = {0u, 0u};
   uint32_t it = 0, ac = 0;
   int pair = 0;
-  for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
-    for (int l = 0; l < nlayers; ++l, ++pair) {
+  const bool dual = dual_mode(ntiles, nclusters, cx.flags);
+  const int tstep = dual ? 2 * nclusters : nclusters;
+  for (int t0 = cluster_id; t0 < ntiles; t0 += tstep) {
+    const int ng = (dual && t0 + nclusters < ntiles) ? 2 : 1;
+    for (int l = 0; l < nlayers; ++l) {
       LayerU u;
       u.load(layers[l]);
-      cx.pair = pair;
-      if (u.nseg == 0) continue;                 // epilogue-only layer
+      if (u.nseg == 0) { pair += ng; continue; }   // epilogue-only layer
       const int kb0 = u.kb0(), kbc = u.kbc();
       int k_lo, k_hi;
       k_range<KS>(kbc, kh, u.bn, k_lo, k_hi);
-      if (k_hi <= k_lo) continue;                // nothing of this layer's k range is mine
+      if (k_hi <= k_lo) { pair += ng; continue; }  // nothing of this layer's k range is mine
       const bool active = cs < u.nactive;
       const int bn = u.bn;
       const uint32_t idesc = make_idesc(bn), idesc2 = make_idesc(2 * bn);
@@ -671,6 +696,8 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
       const int ks_last1 = u.nseg > 1 ? ((u.k1 - (last1 - kb0) * BK) + 7) >> 3 : 4;
       const bool exact0 = u.exact0 != 0, exact1 = u.exact1 != 0;
       const bool issue = active && !nomma;
+      for (int sub = 0; sub < ng; ++sub, ++pair) {
+      cx.pair = pair;
       for (int c = 0; c < u.nchunk; ++c) {
         const uint32_t buf = ac & 1;
         if (active) {
@@ -721,6 +748,7 @@ __device__ void mma_issuer(const Shared& sh, const LmLayer* layers, int nlayers,
           rg.next(STAGES);
         }
         if (active) ++ac;
+      }
       }
     }
   }
@@ -1606,11 +1634,17 @@ __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, i
   e.loc_off = Geo<KS>::OFF_LOC;
   EP* ep_slot = reinterpret_cast<EP*>(sh.smem + Geo<KS>::OFF_EP + e.ew * EP_BYTES);
   int pair = 0;
-  for (int tile = cluster_id; tile < ntiles; tile += nclusters) {
-    e.wrow0 = tile * BM + e.quad * 32;      // first global row of this warp
-    e.rows_valid = max(0, min(32, M - e.wrow0));
-    e.trow = e.quad * 32 + lane;
-    for (int l = 0; l < nlayers; ++l, ++pair) {
+  int base0 = 0, base1 = 0;                 // layers the two chains completed in earlier tile groups
+  const bool dual = dual_mode(ntiles, nclusters, cx.flags);
+  const int tstep = dual ? 2 * nclusters : nclusters;
+  e.trow = e.quad * 32 + lane;
+  for (int t0 = cluster_id; t0 < ntiles; t0 += tstep) {
+    const int ng = (dual && t0 + nclusters < ntiles) ? 2 : 1;
+    for (int l = 0; l < nlayers; ++l) {
+     for (int sub = 0; sub < ng; ++sub, ++pair) {
+      e.wrow0 = (t0 + sub * nclusters) * BM + e.quad * 32;      // first global row of this warp
+      e.rows_valid = max(0, min(32, M - e.wrow0));
+      const uint32_t ready = sh.bars + BAR_READY + 4 * sub;     // this chain's counter
       __syncwarp();
       if (lane == 0) *ep_slot = load_ep(layers[l]);
       __syncwarp();
@@ -1618,7 +1652,7 @@ __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, i
       e.cx.pair = pair;
       const bool active = e.cs < L.nactive && (KS == 1 || L.bn == 64 || e.kh == 0);
       if (L.nseg == 0 && l > 0)       // no producer wait protects its inputs: wait here
-        count_wait(sh.bars + BAR_READY, (uint32_t)pair * CLS, e.cx, 8);
+        count_wait(ready, (uint32_t)((sub ? base1 : base0) + l) * CLS, e.cx, 8);
       if (warp == 2) trace_ev(e.cx, 2, 16 * pair);
       if (active && e.grp >= nsub<KS>(L)) {
         // a 32-wide slice has no second half: this warp group only hands the accumulator back
@@ -1644,10 +1678,13 @@ __device__ void epilogue(const Shared& sh, const LmLayer* layers, int nlayers, i
       if (warp == 2 && lane == 0) {
         asm volatile("fence.acq_rel.cluster;" ::: "memory");
 #pragma unroll
-        for (int d = 0; d < CLS; ++d) count_add_remote(sh.bars + BAR_READY, d);
+        for (int d = 0; d < CLS; ++d) count_add_remote(ready, d);
       }
       if (warp == 2) trace_ev(e.cx, 2, 16 * pair + 11);
+     }
     }
+    base0 += nlayers;
+    if (ng == 2) base1 += nlayers;
   }
 }
 

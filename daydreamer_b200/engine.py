@@ -663,10 +663,10 @@ class Engine:
     # layer machine (csrc/dd_machine.cu): trunks, the prior stack and the rollout's img_in / GRU
     # layers run as fused programs wherever their shapes tile across its 8-CTA clusters
     self.machine = hasattr(be, 'program_build') and os.environ.get('DD_MACHINE', '1') != '0'
-    # measured (profiles/r02_machine_bench.txt): per layer the machine matches dd_gemm + dd_ln at
-    # ~1K rows and loses to the persistent GEMM beyond a few thousand -> big batched trunks stay
-    # on the per-layer kernels
-    self.machine_max_rows = int(os.environ.get('DD_MACHINE_MAXROWS', '2048'))
+    # measured (profiles/r02_machine_bench.txt): a chain of 4 layers is 1.7x faster than dd_gemm + dd_ln
+    # launches at 1K rows and still 5 % faster at 16K rows (two interleaved tiles per cluster); beyond
+    # that it is unmeasured and the per-layer kernels stay
+    self.machine_max_rows = int(os.environ.get('DD_MACHINE_MAXROWS', '32768'))
     # reverse chains (LayerNorm-backward epilogue) of the same trunks; DD_MACHINE_BWD=0 keeps
     # dd_gemm + dd_ln_bwd (r02 A/B at a1 size: 0.15 ms per step slower)
     self.machine_bwd = os.environ.get('DD_MACHINE_BWD', '1') != '0'

@@ -166,7 +166,7 @@ def test_ln_bwd_layer(backends, M, N, K, act, wgrad):
   run_both(backends, case, rtol=1e-4, atol=1e-4 * np.sqrt(M / 128))
 
 
-@pytest.mark.parametrize('M', [1024, 16384, 1600])
+@pytest.mark.parametrize('M', [1024, 16384, 1600, 4800])    # 16384 / 4800 rows: two interleaved tiles per cluster
 def test_trunk_chain(backends, M):
   """A 4-layer MLP trunk + its output layer as ONE program: layer i+1 reads what layer i wrote
   (x and x_lo) after a cluster-local handshake; then the reverse chain as a second program."""
@@ -231,7 +231,7 @@ def test_operand_prep(backends):
   ref, out = run_both(backends, case, rtol=0, atol=0)
 
 
-@pytest.mark.parametrize('M,D', [(1024, 512), (300, 256)])
+@pytest.mark.parametrize('M,D', [(1024, 512), (300, 256), (4800, 256)])
 def test_gru_layer(backends, M, D):
   """[deter | x] @ W_gru -> joint LayerNorm over 3 D -> gates -> new deter, as one layer."""
   def case(be, T):
