@@ -35,6 +35,10 @@
 //             cell and its reverse, latent statistics + Gumbel sample, actor head) with the
 //             cross-CTA row reduction over DSMEM, and x / x_lo for the next layer written through
 //             a per-warp transposing staging buffer (coalesced 128-byte rows)
+// Scheduling across layers: the activation producer waits per A SEGMENT for the last layer that writes
+// it (dd_program_build finds that from the pointers), so early operands of layer l stream during the
+// epilogue of layer l - 1; a cluster with several row tiles runs them in interleaved pairs (dual_mode),
+// each chain with its own `ready` counter, so one tile's k-loop fills the other's epilogue.
 // A 2-second watchdog in every wait writes (role, barrier, layer) to mapped host memory and traps,
 // so a protocol bug is a diagnosable error instead of a hung GPU.
 #include <cuda.h>
