@@ -63,8 +63,24 @@ DEFAULTS = dict(
     actent=dict(impl='mult', scale=3e-3, target=0.5, min=1e-5, max=1.0, vel=0.1),
     actent_norm=True, advnorm=_norm('mean_std', 0.99), retnorm=_norm('off', 0.999),
     scorenorm=_norm('off', 0.99), critic_type='vfunction',
-    # exploration (only `expl_behavior: None` is built; keys kept for flag parity)
+    # exploration (only `expl_behavior: None | Random` is built; the keys of A/configs.yaml:91-112 are
+    # kept so that reference command lines which set them still parse)
     expl_rewards=dict(extr=0.0, disag=0.0, vae=0.0, ctrl=0.0, pbe=0.0),
+    expl_discount=0.99, expl_retnorm=_norm('std', 0.999), expl_scorenorm=_norm('off', 0.999),
+    expl_opt=dict(opt='adam', lr=1e-4, eps=1e-6, clip=100.0, wd=1e-2, warmup=0),
+    disag_head=dict(layers=4, units=512, act='elu', norm='layer', dist='mse', outscale=1.0,
+                    inputs=['deter', 'stoch', 'action']),
+    disag_target=['stoch'], disag_models=8,
+    ctrl_embed=dict(layers=3, units=512, act='elu', norm='layer', dist='mse', inputs=['deter', 'stoch']),
+    ctrl_head=dict(layers=1, units=128, act='elu', norm='layer', dist='mse', inputs=['current', 'next']),
+    ctrl_size=32, ctrl_opt=dict(opt='adam', lr=1e-4, eps=1e-6, clip=100.0, wd=1e-2, warmup=0),
+    pbe_inputs=['deter'], pbe_knn=16,
+    expl_enc=dict(layers=4, units=512, act='elu', norm='layer', dist='onehot', outscale=0.1,
+                  inputs=['deter'], shape=[8, 8]),
+    expl_dec=dict(layers=4, units=512, act='elu', norm='layer', dist='mse', outscale=0.1),
+    expl_kl=dict(impl='mult', scale=0.1, target=10.0, min=1e-2, max=1.0, vel=0.1),
+    expl_vae_elbo=False, expl_when_buffer=1e4, expl_when_frac=0.1, expl_when_every=50,
+    expl_when_random=False,
 )
 
 _robot = {
